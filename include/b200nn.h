@@ -1,0 +1,203 @@
+/*
+ * b200nn.h -- C ABI of libb200nn.so, the B200 (sm_100a) implementation of
+ * Seurat's FindNeighbors hot path: exact Euclidean kNN + nn Graph + SNN graph.
+ *
+ * Plain pointers and sizes only: this is what the R package's `.Call` shim
+ * (shim/b200nn_r.c), Python's ctypes (seurat_b200/_lib.py) or any other FFI
+ * binds.  Every entry point returns 0 on success or a B200NN_ERR_* code;
+ * b200nn_last_error() gives the message.  Nothing here throws or long-jumps.
+ * There is NO CPU fallback: without a CUDA device every compute call fails
+ * with B200NN_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the Seurat tree):
+ *   b200nn_knn              RANN::nn2(data, query, k, searchtype="standard",
+ *                           eps=0) as called by NNHelper, R/clustering.R:1664-1667
+ *   b200nn_snn_*            ComputeSNN(nn_ranked, prune): src/snn.cpp:14-38,
+ *                           glue R/RcppExports.R:96-98, src/RcppExports.cpp:313-323
+ *   b200nn_nn_graph_*       the sparseMatrix() nn Graph, R/clustering.R:664-670
+ *   b200nn_find_neighbors_* the body of FindNeighbors.default,
+ *                           R/clustering.R:633-682, fused so that the kNN index
+ *                           never leaves the device between the stages
+ *   b200nn_dev_*            the same stages on buffers already resident in
+ *                           HBM (used by the multi-GPU host code, which shards
+ *                           query rows over one process per GPU and all-gathers
+ *                           the index between the kNN and the SNN stage)
+ */
+#ifndef B200NN_H
+#define B200NN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NN_VERSION 1
+
+#if defined(__GNUC__)
+#define B200NN_API __attribute__((visibility("default")))
+#else
+#define B200NN_API
+#endif
+
+enum {
+  B200NN_OK = 0,
+  B200NN_ERR_INVALID = 1,      /* bad argument (NULL, d<=0, k<=0, ...)               */
+  B200NN_ERR_K_TOO_LARGE = 2,  /* k > number of reference points (nn2's stop())     */
+  B200NN_ERR_CUDA = 3,         /* CUDA runtime / driver failure, or no device       */
+  B200NN_ERR_INDEX_RANGE = 4,  /* neighbour index outside [1, n]                    */
+  B200NN_ERR_NNZ_OVERFLOW = 5, /* result does not fit a dgCMatrix (nnz >= 2^31)     */
+  B200NN_ERR_NOMEM = 6,        /* device allocation failed                          */
+  B200NN_ERR_STATE = 7         /* *_fill called without a matching *_count          */
+};
+
+/* memory layout of embedding inputs and of idx/dist/nn_ranked matrices */
+enum {
+  B200NN_COL_MAJOR = 0, /* R matrices: element (row, col) at [col * nrow + row]    */
+  B200NN_ROW_MAJOR = 1  /* C / numpy:  element (row, col) at [row * ncol + col]    */
+};
+
+/* kNN algorithm selection */
+enum {
+  B200NN_KNN_AUTO = 0,   /* tensor-core path when applicable, else exact scan       */
+  B200NN_KNN_EXACT = 1,  /* FP64 exhaustive scan (reference arithmetic everywhere)  */
+  B200NN_KNN_TENSOR = 2  /* tcgen05 FP16 candidate generation + FP64 re-rank with a
+                            per-row exactness certificate and FP64 fallback rows     */
+};
+
+typedef struct b200nn_ctx b200nn_ctx;
+
+typedef struct b200nn_opts {
+  int32_t layout;      /* B200NN_COL_MAJOR (default, R) or B200NN_ROW_MAJOR          */
+  int32_t knn_algo;    /* B200NN_KNN_*                                               */
+  int32_t n_cand;      /* widened candidate count k' of the tensor path, 0 = auto    */
+  int32_t reserved;
+} b200nn_opts;
+
+typedef struct b200nn_stats {
+  double ms_h2d;          /* host->device copies                                     */
+  double ms_prep;         /* layout / precision conversion of the embedding          */
+  double ms_knn_cand;     /* tensor-core candidate generation (K1)                   */
+  double ms_knn_rerank;   /* FP64 re-rank + certificate (K2)                         */
+  double ms_knn_fallback; /* FP64 exhaustive scan (all rows, or uncertified rows)    */
+  double ms_nn_graph;     /* transpose / nn Graph (K3)                               */
+  double ms_snn;          /* SNN rows (K4)                                           */
+  double ms_d2h;          /* device->host copies                                     */
+  int64_t n_uncertified;  /* query rows that needed the FP64 fallback scan           */
+  int64_t nnz_nn;         /* entries of the nn Graph                                 */
+  int64_t nnz_snn;        /* entries of the SNN graph                                */
+  int64_t snn_expanded;   /* sum over rows of expanded candidates (sum_c indeg^2)    */
+  int64_t max_indegree;   /* longest reverse-neighbour list                          */
+  int64_t gpu_launches;   /* kernels launched by this call                           */
+} b200nn_stats;
+
+/* ---- context ---------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` (owns one stream and a growable
+ * workspace; buffers are reused across calls). */
+B200NN_API int b200nn_ctx_create(int device, b200nn_ctx **ctx_out);
+B200NN_API void b200nn_ctx_destroy(b200nn_ctx *ctx);
+/* Blocks until all work queued on the context's stream has finished. */
+B200NN_API int b200nn_ctx_sync(b200nn_ctx *ctx);
+/* The context's cudaStream_t (as void*), e.g. to record timing events on. */
+B200NN_API void *b200nn_ctx_stream(b200nn_ctx *ctx);
+/* Message of the last error raised on the calling thread. */
+B200NN_API const char *b200nn_last_error(void);
+B200NN_API int b200nn_version(void);
+/* Number of CUDA devices visible (0 when there is none / no driver). */
+B200NN_API int b200nn_device_count(void);
+
+/* ---- host-buffer entry points (what the R shim binds) ------------------ */
+
+/*
+ * Exact k nearest reference rows of every query row (Euclidean).
+ *   ref  [nr x d], qry [nq x d] doubles in opts->layout; qry == NULL means
+ *   qry = ref (self search: column 1 is the point itself unless duplicates).
+ *   idx_out  [nq x k] int32, 1-based reference row numbers, opts->layout
+ *   dist_out [nq x k] double, ascending Euclidean distances,  opts->layout
+ * Ties in distance are ordered by lower index.
+ */
+B200NN_API int b200nn_knn(b200nn_ctx *ctx, const double *ref, int64_t nr, const double *qry,
+               int64_t nq, int32_t d, int32_t k, int32_t *idx_out, double *dist_out,
+               const b200nn_opts *opts, b200nn_stats *stats);
+
+/*
+ * ComputeSNN in two phases so that the caller (R) can allocate the result.
+ *   nn_ranked [n x k] int32, 1-based, opts->layout.  count: computes the graph
+ *   on the device and reports nnz.  fill: copies p[n+1], i[nnz] (0-based,
+ *   ascending within each column), x[nnz] -- the slots of a dgCMatrix.
+ */
+B200NN_API int b200nn_snn_count(b200nn_ctx *ctx, const int32_t *nn_ranked, int64_t n, int32_t k,
+                     double prune, const b200nn_opts *opts, int64_t *nnz_out,
+                     b200nn_stats *stats);
+B200NN_API int b200nn_snn_fill(b200nn_ctx *ctx, int32_t *p, int32_t *i, double *x);
+
+/*
+ * nn Graph: sparseMatrix(i = row, j = nn_ranked, x = 1, dims = c(n, n)) with
+ * duplicates summed.  nn_ranked is [n_rows x k]; n_rows may differ from n
+ * (the reference's query != object quirk); indices must lie in [1, n].
+ */
+B200NN_API int b200nn_nn_graph_count(b200nn_ctx *ctx, const int32_t *nn_ranked, int64_t n_rows,
+                          int32_t k, int64_t n, const b200nn_opts *opts,
+                          int64_t *nnz_out, b200nn_stats *stats);
+B200NN_API int b200nn_nn_graph_fill(b200nn_ctx *ctx, int32_t *p, int32_t *i, double *x);
+
+/*
+ * FindNeighbors.default for query == object: kNN, nn Graph and (optionally)
+ * SNN with the index kept on the device between stages.  idx_out / dist_out
+ * may be NULL when the caller only wants the graphs.
+ */
+B200NN_API int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, int32_t d,
+                                int32_t k, double prune, int32_t compute_snn,
+                                int32_t *idx_out, double *dist_out,
+                                const b200nn_opts *opts, int64_t *nnz_nn_out,
+                                int64_t *nnz_snn_out, b200nn_stats *stats);
+B200NN_API int b200nn_find_neighbors_fill(b200nn_ctx *ctx, int32_t *nn_p, int32_t *nn_i, double *nn_x,
+                               int32_t *snn_p, int32_t *snn_i, double *snn_x);
+
+/* ---- device-buffer entry points ---------------------------------------- */
+/* All pointers are device pointers on the context's device.  Work is queued
+ * on the context's stream; calls that return sizes synchronise internally. */
+
+/*
+ * kNN on resident data.  d_ref [nr x d], d_qry [nq x d] (NULL = self) doubles,
+ * ROW-MAJOR.  Outputs, both ROW-MAJOR [nq x k]: d_idx0 int32 **0-based**
+ * reference rows (the form the SNN stage consumes), d_dist double.
+ */
+B200NN_API int b200nn_dev_knn(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                   int64_t nq, int32_t d, int32_t k, int32_t *d_idx0, double *d_dist,
+                   const b200nn_opts *opts, b200nn_stats *stats);
+
+/*
+ * nn Graph + SNN rows [row_begin, row_end) from the FULL 0-based index
+ * d_idx0 [n x k] (row-major).  Results stay on the device inside the context:
+ * fetch pointers with b200nn_dev_result.  With compute_snn == 0 only the nn
+ * Graph is built.  The nn Graph is always the full n x n matrix.
+ */
+B200NN_API int b200nn_dev_graphs(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n, int32_t k,
+                      double prune, int32_t compute_snn, int64_t row_begin,
+                      int64_t row_end, int64_t *nnz_nn_out, int64_t *nnz_snn_out,
+                      b200nn_stats *stats);
+
+typedef struct b200nn_dev_csr {
+  int64_t n_rows;      /* rows (== columns for the symmetric SNN block)             */
+  int64_t nnz;
+  const int64_t *p;    /* [n_rows + 1] offsets (64-bit on the device)               */
+  const int32_t *i;    /* [nnz] 0-based, ascending within a row/column              */
+  const double *x;     /* [nnz]                                                     */
+} b200nn_dev_csr;
+
+/* which: 0 = nn Graph (CSC of the n x n matrix), 1 = SNN rows of the last
+ * b200nn_dev_graphs call (row-compressed block; column indices are global). */
+B200NN_API int b200nn_dev_result(b200nn_ctx *ctx, int32_t which, b200nn_dev_csr *out);
+
+/* Device-to-device copy of a result into caller-owned device buffers
+ * (d_p: int64[n_rows + 1], d_i: int32[nnz], d_x: double[nnz]; NULL = skip).
+ * Queued on the context's stream and synchronised before returning. */
+B200NN_API int b200nn_dev_copy_result(b200nn_ctx *ctx, int32_t which, int64_t *d_p, int32_t *d_i,
+                                      double *d_x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NN_H */

@@ -1,0 +1,142 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of oracle.c.  The product package
+``seurat_b200`` never imports this module; only ``tests/``,
+``__graft_entry__.smoke()`` and the CPU legs of ``bench.py`` do.
+
+Parity status: unpinned against the real reference (no R / RANN / Eigen in the
+container); pinned against the SURVEY.md 8c known-answer vectors in
+``tests/golden`` and cross-checked against scipy / sklearn in ``tests/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc, OpenMP)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        i64, i32, dbl, vp = C.c_int64, C.c_int, C.c_double, C.c_void_p
+        L.oracle_knn_brute.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, i32]
+        L.oracle_knn_brute.restype = i32
+        L.oracle_knn_kdtree.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, i32, vp, vp]
+        L.oracle_knn_kdtree.restype = i32
+        L.oracle_nn_graph.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp]
+        L.oracle_nn_graph.restype = i32
+        L.oracle_compute_snn.argtypes = [vp, i64, i32, dbl, i32, vp, vp]
+        L.oracle_compute_snn.restype = i32
+        L.oracle_snn_fetch.argtypes = [vp, vp, vp, vp]
+        L.oracle_snn_fetch.restype = None
+        L.oracle_l2norm.argtypes = [vp, i64, i32]
+        L.oracle_l2norm.restype = None
+        L.oracle_num_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def _mat(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def knn(data, query=None, k: int = 20, method: str = "brute", nthreads: int = 0,
+        timings: dict | None = None):
+    """Exact kNN as ``RANN::nn2(data, query, k)`` returns it.
+
+    Returns ``(nn_idx int32 [nq,k] 1-based, nn_dists float64 [nq,k])``.
+    ``method`` is "brute" (ties by lower index; the parity reference) or
+    "kdtree" (ANN-style, the timed CPU baseline).
+    """
+    ref = _mat(data)
+    qry = ref if query is None else _mat(query)
+    nr, d = ref.shape
+    nq = qry.shape[0]
+    if qry.shape[1] != d:
+        raise ValueError("query and data must have the same number of columns")
+    idx = np.empty((nq, k), dtype=np.int32)
+    dist = np.empty((nq, k), dtype=np.float64)
+    if method == "brute":
+        rc = lib().oracle_knn_brute(_p(ref), nr, _p(qry), nq, d, k, _p(idx), _p(dist), nthreads)
+    elif method == "kdtree":
+        tb, ts = C.c_double(0), C.c_double(0)
+        rc = lib().oracle_knn_kdtree(_p(ref), nr, _p(qry), nq, d, k, _p(idx), _p(dist), nthreads,
+                                     C.byref(tb), C.byref(ts))
+        if timings is not None:
+            timings["build_s"], timings["search_s"] = tb.value, ts.value
+    else:
+        raise ValueError(method)
+    if rc == 1:
+        raise ValueError("Cannot find more nearest neighbours than there are points")
+    if rc:
+        raise RuntimeError(f"oracle kNN failed rc={rc}")
+    return idx, dist
+
+
+def nn_graph(nn_idx, n: int | None = None):
+    """nn Graph of R/clustering.R:664-670 as dgCMatrix arrays (p, i, x)."""
+    nn = np.ascontiguousarray(np.asarray(nn_idx, dtype=np.int32))
+    rows, k = nn.shape
+    n = rows if n is None else n
+    nnz = C.c_int64(0)
+    rc = lib().oracle_nn_graph(_p(nn), rows, k, n, C.byref(nnz), None, None, None)
+    if rc:
+        raise ValueError("neighbour index out of range")
+    p = np.empty(n + 1, dtype=np.int32)
+    i = np.empty(nnz.value, dtype=np.int32)
+    x = np.empty(nnz.value, dtype=np.float64)
+    lib().oracle_nn_graph(_p(nn), rows, k, n, C.byref(nnz), _p(p), _p(i), _p(x))
+    return p, i, x
+
+
+def compute_snn(nn_ranked, prune: float, nthreads: int = 0):
+    """``ComputeSNN(nn_ranked, prune)`` (src/snn.cpp:14-38) -> (p int64, i int32, x float64)."""
+    nn = np.ascontiguousarray(np.asarray(nn_ranked, dtype=np.int32))
+    n, k = nn.shape
+    h = C.c_void_p()
+    nnz = C.c_int64(0)
+    rc = lib().oracle_compute_snn(_p(nn), n, k, float(prune), nthreads, C.byref(h), C.byref(nnz))
+    if rc:
+        raise ValueError("neighbour index out of range")
+    p = np.empty(n + 1, dtype=np.int64)
+    i = np.empty(nnz.value, dtype=np.int32)
+    x = np.empty(nnz.value, dtype=np.float64)
+    lib().oracle_snn_fetch(h, _p(p), _p(i), _p(x))
+    return p, i, x
+
+
+def l2norm(mat) -> np.ndarray:
+    m = _mat(mat).copy()
+    lib().oracle_l2norm(_p(m), m.shape[0], m.shape[1])
+    return m
+
+
+def find_neighbors(data, k: int = 20, prune: float = 1.0 / 15.0, nthreads: int = 0,
+                   method: str = "brute"):
+    """kNN + nn Graph + SNN on one matrix: what FindNeighbors.default computes."""
+    idx, dist = knn(data, None, k, method=method, nthreads=nthreads)
+    return {"nn_idx": idx, "nn_dist": dist, "nn": nn_graph(idx), "snn": compute_snn(idx, prune, nthreads)}
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())

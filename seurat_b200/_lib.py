@@ -1,0 +1,265 @@
+"""ctypes binding of libb200nn.so -- the only compute back end of this package.
+
+There is deliberately no CPU fallback: if the CUDA library is missing or no
+B200 is visible, every compute call raises :class:`B200Error`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200nn.so")
+
+OK, ERR_INVALID, ERR_K_TOO_LARGE, ERR_CUDA, ERR_INDEX_RANGE, ERR_NNZ_OVERFLOW, ERR_NOMEM, ERR_STATE = range(8)
+COL_MAJOR, ROW_MAJOR = 0, 1
+KNN_AUTO, KNN_EXACT, KNN_TENSOR = 0, 1, 2
+
+# every symbol include/b200nn.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "b200nn_ctx_create", "b200nn_ctx_destroy", "b200nn_ctx_sync", "b200nn_ctx_stream",
+    "b200nn_last_error", "b200nn_version", "b200nn_device_count",
+    "b200nn_knn", "b200nn_snn_count", "b200nn_snn_fill",
+    "b200nn_nn_graph_count", "b200nn_nn_graph_fill",
+    "b200nn_find_neighbors_count", "b200nn_find_neighbors_fill",
+    "b200nn_dev_knn", "b200nn_dev_graphs", "b200nn_dev_result", "b200nn_dev_copy_result",
+]
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libb200nn error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class Opts(C.Structure):
+    _fields_ = [("layout", C.c_int32), ("knn_algo", C.c_int32), ("n_cand", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("ms_h2d", "ms_prep", "ms_knn_cand", "ms_knn_rerank", "ms_knn_fallback",
+                 "ms_nn_graph", "ms_snn", "ms_d2h")] + \
+               [(n, C.c_int64) for n in
+                ("n_uncertified", "nnz_nn", "nnz_snn", "snn_expanded", "max_indegree",
+                 "gpu_launches")]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class DevCsr(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("p", C.c_void_p), ("i", C.c_void_p),
+                ("x", C.c_void_p)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libb200nn.so, failing loudly when it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(ERR_CUDA, f"{LIB_PATH} is missing: build it with "
+                                      "`python -m seurat_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+        L.b200nn_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.b200nn_ctx_destroy.argtypes = [vp]
+        L.b200nn_ctx_destroy.restype = None
+        L.b200nn_ctx_sync.argtypes = [vp]
+        L.b200nn_ctx_stream.argtypes = [vp]
+        L.b200nn_ctx_stream.restype = vp
+        L.b200nn_last_error.restype = C.c_char_p
+        L.b200nn_knn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
+        L.b200nn_snn_count.argtypes = [vp, vp, i64, i32, dbl, C.POINTER(Opts), C.POINTER(i64), C.POINTER(Stats)]
+        L.b200nn_snn_fill.argtypes = [vp, vp, vp, vp]
+        L.b200nn_nn_graph_count.argtypes = [vp, vp, i64, i32, i64, C.POINTER(Opts), C.POINTER(i64), C.POINTER(Stats)]
+        L.b200nn_nn_graph_fill.argtypes = [vp, vp, vp, vp]
+        L.b200nn_find_neighbors_count.argtypes = [vp, vp, i64, i32, i32, dbl, i32, vp, vp, C.POINTER(Opts),
+                                                  C.POINTER(i64), C.POINTER(i64), C.POINTER(Stats)]
+        L.b200nn_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.b200nn_dev_knn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
+        L.b200nn_dev_graphs.argtypes = [vp, vp, i64, i32, dbl, i32, i64, i64, C.POINTER(i64), C.POINTER(i64),
+                                        C.POINTER(Stats)]
+        L.b200nn_dev_result.argtypes = [vp, i32, C.POINTER(DevCsr)]
+        L.b200nn_dev_copy_result.argtypes = [vp, i32, vp, vp, vp]
+        _lib = L
+        return L
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise B200Error(rc, load().b200nn_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return int(load().b200nn_device_count())
+
+
+def _ptr(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(None)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class Context:
+    """One library context = one CUDA device, one stream, one reusable workspace."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p(None)
+        self.device = device
+        L = load()
+        check(L.b200nn_ctx_create(int(device), C.byref(self._h)))
+        self._L = L
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.b200nn_ctx_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self) -> None:
+        check(self._L.b200nn_ctx_sync(self._h))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._L.b200nn_ctx_stream(self._h) or 0)
+
+    # ---- host-buffer calls ------------------------------------------------
+    def knn(self, ref, qry, k: int, layout: int, algo: int = KNN_AUTO, n_cand: int = 0):
+        """ref/qry: float64 arrays [n, d] stored in `layout`.  Returns (idx, dist, stats)."""
+        nr, d = ref.shape
+        nq = nr if qry is None else qry.shape[0]
+        order = "C" if layout == ROW_MAJOR else "F"
+        idx = np.empty((nq, k), dtype=np.int32, order=order)
+        dist = np.empty((nq, k), dtype=np.float64, order=order)
+        o = Opts(layout, algo, n_cand, 0)
+        st = Stats()
+        check(self._L.b200nn_knn(self._h, _ptr(ref), nr, _ptr(qry), nq, d, k, _ptr(idx), _ptr(dist),
+                                 C.byref(o), C.byref(st)))
+        return idx, dist, st.as_dict()
+
+    def compute_snn(self, nn_ranked, prune: float, layout: int):
+        n, k = nn_ranked.shape
+        o = Opts(layout, 0, 0, 0)
+        st = Stats()
+        nnz = C.c_int64(0)
+        check(self._L.b200nn_snn_count(self._h, _ptr(nn_ranked), n, k, float(prune), C.byref(o),
+                                       C.byref(nnz), C.byref(st)))
+        p = np.empty(n + 1, dtype=np.int32)
+        i = np.empty(nnz.value, dtype=np.int32)
+        x = np.empty(nnz.value, dtype=np.float64)
+        check(self._L.b200nn_snn_fill(self._h, _ptr(p), _ptr(i), _ptr(x)))
+        return p, i, x, st.as_dict()
+
+    def nn_graph(self, nn_ranked, n: int, layout: int):
+        rows, k = nn_ranked.shape
+        o = Opts(layout, 0, 0, 0)
+        st = Stats()
+        nnz = C.c_int64(0)
+        check(self._L.b200nn_nn_graph_count(self._h, _ptr(nn_ranked), rows, k, n, C.byref(o),
+                                            C.byref(nnz), C.byref(st)))
+        p = np.empty(n + 1, dtype=np.int32)
+        i = np.empty(nnz.value, dtype=np.int32)
+        x = np.empty(nnz.value, dtype=np.float64)
+        check(self._L.b200nn_nn_graph_fill(self._h, _ptr(p), _ptr(i), _ptr(x)))
+        return p, i, x, st.as_dict()
+
+    def find_neighbors(self, data, k: int, prune: float, compute_snn: bool, layout: int,
+                       algo: int = KNN_AUTO, n_cand: int = 0, want_knn: bool = True,
+                       out: dict | None = None):
+        """Fused kNN + nn Graph (+ SNN) on host buffers.  `out` may carry
+        preallocated (pinned) result arrays keyed idx/dist/nn_p/nn_i/nn_x/snn_p/snn_i/snn_x."""
+        n, d = data.shape
+        order = "C" if layout == ROW_MAJOR else "F"
+        out = out or {}
+        idx = dist = None
+        if want_knn:
+            idx = out.get("idx")
+            dist = out.get("dist")
+            if idx is None:
+                idx = np.empty((n, k), dtype=np.int32, order=order)
+            if dist is None:
+                dist = np.empty((n, k), dtype=np.float64, order=order)
+        o = Opts(layout, algo, n_cand, 0)
+        st = Stats()
+        nnz_nn, nnz_snn = C.c_int64(0), C.c_int64(0)
+        check(self._L.b200nn_find_neighbors_count(self._h, _ptr(data), n, d, k, float(prune),
+                                                  1 if compute_snn else 0, _ptr(idx), _ptr(dist),
+                                                  C.byref(o), C.byref(nnz_nn), C.byref(nnz_snn),
+                                                  C.byref(st)))
+
+        def buf(name, count, dtype):
+            a = out.get(name)
+            if a is not None and a.size >= count:
+                return a[:count] if a.size != count else a
+            return np.empty(count, dtype=dtype)
+
+        nn_p, nn_i, nn_x = buf("nn_p", n + 1, np.int32), buf("nn_i", nnz_nn.value, np.int32), \
+            buf("nn_x", nnz_nn.value, np.float64)
+        snn = (None, None, None)
+        if compute_snn:
+            snn = (buf("snn_p", n + 1, np.int32), buf("snn_i", nnz_snn.value, np.int32),
+                   buf("snn_x", nnz_snn.value, np.float64))
+        check(self._L.b200nn_find_neighbors_fill(self._h, _ptr(nn_p), _ptr(nn_i), _ptr(nn_x),
+                                                 _ptr(snn[0]), _ptr(snn[1]), _ptr(snn[2])))
+        return {"idx": idx, "dist": dist, "nn": (nn_p, nn_i, nn_x), "snn": snn if compute_snn else None,
+                "stats": st.as_dict()}
+
+    # ---- device-buffer calls (pointers or torch CUDA tensors) --------------
+    def dev_knn(self, d_ref, nr: int, d_qry, nq: int, d: int, k: int, d_idx0, d_dist,
+                algo: int = KNN_AUTO, n_cand: int = 0) -> dict:
+        o = Opts(ROW_MAJOR, algo, n_cand, 0)
+        st = Stats()
+        check(self._L.b200nn_dev_knn(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, k, _ptr(d_idx0),
+                                     _ptr(d_dist), C.byref(o), C.byref(st)))
+        return st.as_dict()
+
+    def dev_graphs(self, d_idx0, n: int, k: int, prune: float, compute_snn: bool, row_begin: int,
+                   row_end: int) -> dict:
+        st = Stats()
+        nnz_nn, nnz_snn = C.c_int64(0), C.c_int64(0)
+        check(self._L.b200nn_dev_graphs(self._h, _ptr(d_idx0), n, k, float(prune),
+                                        1 if compute_snn else 0, row_begin, row_end,
+                                        C.byref(nnz_nn), C.byref(nnz_snn), C.byref(st)))
+        r = st.as_dict()
+        r["nnz_nn"], r["nnz_snn"] = nnz_nn.value, nnz_snn.value
+        return r
+
+    def dev_result(self, which: int) -> DevCsr:
+        r = DevCsr()
+        check(self._L.b200nn_dev_result(self._h, which, C.byref(r)))
+        return r
+
+    def dev_copy_result(self, which: int, d_p, d_i, d_x) -> None:
+        """Device-to-device copy of a result into caller buffers (p is int64)."""
+        check(self._L.b200nn_dev_copy_result(self._h, which, _ptr(d_p), _ptr(d_i), _ptr(d_x)))
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

@@ -1,0 +1,94 @@
+"""Builds libb200nn.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m seurat_b200.build [--force]
+
+The library is written to seurat_b200/libb200nn.so so that it travels to the
+GPU box with the repository snapshot.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libb200nn.so")
+SOURCES = ["util.cu", "knn_exact.cu", "knn_tc.cu", "snn.cu", "api.cu"]
+HEADERS = [os.path.join(CSRC, "internal.cuh"), os.path.join(HERE, "..", "include", "b200nn.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libb200nn.so cannot be built")
+
+
+def _digest(paths) -> str:
+    h = hashlib.sha256()
+    for p in paths:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _extra_headers():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = sorted(set(HEADERS + _extra_headers()))
+    objs, jobs = [], []
+    for src in SOURCES:
+        sp = os.path.join(CSRC, src)
+        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
+        stamp = obj + ".sha"
+        dig = _digest([sp] + hdrs)
+        objs.append(obj)
+        if (not force and os.path.exists(obj) and os.path.exists(stamp)
+                and open(stamp).read() == dig):
+            continue
+        jobs.append((sp, obj, stamp, dig))
+
+    def compile_one(job):
+        sp, obj, stamp, dig = job
+        cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", sp, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {sp}:\n{r.stdout}\n{r.stderr}")
+        with open(obj + ".ptxas.log", "w") as f:
+            f.write(r.stderr)
+        with open(stamp, "w") as f:
+            f.write(dig)
+        return sp
+
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for done in ex.map(compile_one, jobs):
+                if verbose:
+                    print("compiled", os.path.basename(done), file=sys.stderr)
+    if jobs or force or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,493 @@
+// api.cu -- the C ABI of libb200nn.so (see include/b200nn.h).
+#include <string.h>
+
+#include <new>
+
+#include "internal.cuh"
+
+namespace {
+
+struct Timer {
+  b200nn_ctx *ctx;
+  cudaEvent_t a, b;
+  Timer(b200nn_ctx *c, int slot) : ctx(c), a(c->ev[slot]), b(c->ev[slot + 1]) {}
+  int start() {
+    CU_TRY(cudaEventRecord(a, ctx->stream));
+    return B200NN_OK;
+  }
+  int stop(double *ms_out) {
+    CU_TRY(cudaEventRecord(b, ctx->stream));
+    CU_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, a, b));
+    if (ms_out) *ms_out += ms;
+    return B200NN_OK;
+  }
+};
+
+b200nn_opts default_opts() {
+  b200nn_opts o;
+  memset(&o, 0, sizeof(o));
+  o.layout = B200NN_COL_MAJOR;
+  o.knn_algo = B200NN_KNN_AUTO;
+  return o;
+}
+
+int check_ctx(b200nn_ctx *ctx) {
+  if (!ctx) {
+    b200nn_set_error("NULL context");
+    return B200NN_ERR_INVALID;
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  return B200NN_OK;
+}
+
+// host matrix [rows x cols] doubles in `layout` -> device row-major
+int upload_matrix_f64(b200nn_ctx *ctx, const double *h, int64_t rows, int64_t cols, int layout,
+                      WsSlot stage, WsSlot dst_slot, double **d_out) {
+  size_t cnt = (size_t)rows * (size_t)cols;
+  double *dst;
+  RC_TRY(ws_get(ctx, dst_slot, cnt, &dst));
+  if (layout == B200NN_ROW_MAJOR) {
+    CU_TRY(cudaMemcpyAsync(dst, h, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    double *raw;
+    RC_TRY(ws_get(ctx, stage, cnt, &raw));
+    CU_TRY(cudaMemcpyAsync(raw, h, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    RC_TRY(transpose_f64(ctx, raw, dst, rows, cols));
+  }
+  *d_out = dst;
+  return B200NN_OK;
+}
+
+// host nn_ranked [rows x k] int32 1-based in `layout` -> device row-major 0-based
+int upload_nn_ranked(b200nn_ctx *ctx, const int32_t *h, int64_t rows, int k, int layout,
+                     int32_t **d_out) {
+  size_t cnt = (size_t)rows * (size_t)k;
+  int32_t *raw, *dst;
+  RC_TRY(ws_get(ctx, WS_STAGE_A, cnt, &raw));
+  RC_TRY(ws_get(ctx, WS_IDX0, cnt, &dst));
+  CU_TRY(cudaMemcpyAsync(raw, h, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (layout == B200NN_ROW_MAJOR)
+    RC_TRY(add_i32(ctx, raw, dst, (int64_t)cnt, -1));
+  else
+    RC_TRY(transpose_i32_add(ctx, raw, dst, rows, k, -1));
+  *d_out = dst;
+  return B200NN_OK;
+}
+
+// device row-major idx0 / dist [nq x k] -> host buffers in `layout`, idx 1-based
+int download_knn(b200nn_ctx *ctx, const int32_t *d_idx0, const double *d_dist, int64_t nq, int k,
+                 int layout, int32_t *h_idx, double *h_dist) {
+  size_t cnt = (size_t)nq * (size_t)k;
+  if (h_idx) {
+    int32_t *o;
+    RC_TRY(ws_get(ctx, WS_OUT_IDX, cnt, &o));
+    if (layout == B200NN_ROW_MAJOR)
+      RC_TRY(add_i32(ctx, d_idx0, o, (int64_t)cnt, 1));
+    else  // row-major [nq x k] == column-major [k x nq]; transposing that gives col-major [nq x k]
+      RC_TRY(transpose_i32_add(ctx, d_idx0, o, k, nq, 1));
+    CU_TRY(cudaMemcpyAsync(h_idx, o, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (h_dist) {
+    const double *src = d_dist;
+    if (layout != B200NN_ROW_MAJOR) {
+      double *o;
+      RC_TRY(ws_get(ctx, WS_OUT_DIST, cnt, &o));
+      RC_TRY(transpose_f64(ctx, d_dist, o, k, nq));
+      src = o;
+    }
+    CU_TRY(cudaMemcpyAsync(h_dist, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+int download_csr(b200nn_ctx *ctx, const CsrResult &r, int32_t *p, int32_t *i, double *x) {
+  if (!r.valid) {
+    b200nn_set_error("no result pending: call the matching *_count entry point first");
+    return B200NN_ERR_STATE;
+  }
+  if (r.nnz >= 0x7fffffffLL) {
+    b200nn_set_error("graph has %lld entries, more than a dgCMatrix can hold", (long long)r.nnz);
+    return B200NN_ERR_NNZ_OVERFLOW;
+  }
+  if (p) {
+    int32_t *p32;
+    RC_TRY(ws_get(ctx, WS_OUT_P32, (size_t)r.n_rows + 1, &p32));
+    RC_TRY(narrow_i64_to_i32(ctx, r.p, p32, r.n_rows + 1));
+    CU_TRY(cudaMemcpyAsync(p, p32, sizeof(int32_t) * ((size_t)r.n_rows + 1), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  }
+  if (i && r.nnz)
+    CU_TRY(cudaMemcpyAsync(i, r.i, sizeof(int32_t) * (size_t)r.nnz, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  if (x && r.nnz)
+    CU_TRY(cudaMemcpyAsync(x, r.x, sizeof(double) * (size_t)r.nnz, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
+                 int d, int k, const b200nn_opts &o, int32_t *d_idx0, double *d_dist,
+                 b200nn_stats *stats) {
+  if (!d_ref || nr <= 0 || nq < 0 || d <= 0 || k <= 0 || !d_idx0 || !d_dist) {
+    b200nn_set_error("knn: invalid argument (nr=%lld nq=%lld d=%d k=%d)", (long long)nr,
+                     (long long)nq, d, k);
+    return B200NN_ERR_INVALID;
+  }
+  if ((int64_t)k > nr) {
+    b200nn_set_error("Cannot find more nearest neighbours than there are points");
+    return B200NN_ERR_K_TOO_LARGE;
+  }
+  if (nr >= 0x7fffffffLL || nq >= 0x7fffffffLL) {
+    b200nn_set_error("knn: more than 2^31-1 points are not supported");
+    return B200NN_ERR_INVALID;
+  }
+  if (nq == 0) return B200NN_OK;
+  const double *q = d_qry ? d_qry : d_ref;
+  int algo = o.knn_algo;
+  if (algo == B200NN_KNN_AUTO)
+    algo = knn_tc_applicable(nr, nq, d, k) ? B200NN_KNN_TENSOR : B200NN_KNN_EXACT;
+  if (algo == B200NN_KNN_TENSOR) {
+    if (!knn_tc_applicable(nr, nq, d, k)) {
+      b200nn_set_error("tensor-core kNN path does not cover nr=%lld d=%d k=%d", (long long)nr, d, k);
+      return B200NN_ERR_INVALID;
+    }
+    return knn_tc_launch(ctx, d_ref, nr, q, nq, d, k, o.n_cand, d_idx0, d_dist, stats);
+  }
+  Timer t(ctx, 4);
+  RC_TRY(t.start());
+  RC_TRY(knn_exact_launch(ctx, d_ref, nr, q, nq, d, k, nullptr, 0, d_idx0, d_dist));
+  RC_TRY(t.stop(stats ? &stats->ms_knn_fallback : nullptr));
+  return B200NN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200nn_version(void) { return B200NN_VERSION; }
+
+int b200nn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int b200nn_ctx_create(int device, b200nn_ctx **ctx_out) {
+  if (!ctx_out) {
+    b200nn_set_error("ctx_out is NULL");
+    return B200NN_ERR_INVALID;
+  }
+  *ctx_out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    b200nn_set_error("no CUDA device available (%s); libb200nn has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return B200NN_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    b200nn_set_error("device %d out of range (%d visible)", device, n);
+    return B200NN_ERR_INVALID;
+  }
+  CU_TRY(cudaSetDevice(device));
+  b200nn_ctx *ctx = new (std::nothrow) b200nn_ctx();
+  if (!ctx) return B200NN_ERR_NOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    b200nn_set_error("device %d is sm_%d%d; libb200nn is built for sm_100a (B200) only", device,
+                     prop.major, prop.minor);
+    delete ctx;
+    return B200NN_ERR_CUDA;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto &ev : ctx->ev) CU_TRY(cudaEventCreate(&ev));
+  CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(DevInfo)));
+  *ctx_out = ctx;
+  return B200NN_OK;
+}
+
+void b200nn_ctx_destroy(b200nn_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto &b : ctx->ws)
+    if (b.p) cudaFree(b.p);
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  (void)cudaGetLastError();
+  delete ctx;
+}
+
+int b200nn_ctx_sync(b200nn_ctx *ctx) {
+  RC_TRY(check_ctx(ctx));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+void *b200nn_ctx_stream(b200nn_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ---- device-buffer entry points -------------------------------------------
+
+int b200nn_dev_knn(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                   int64_t nq, int32_t d, int32_t k, int32_t *d_idx0, double *d_dist,
+                   const b200nn_opts *opts, b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  int64_t l0 = ctx->launches;
+  int rc = knn_dispatch(ctx, d_ref, nr, d_qry, nq, d, k, o, d_idx0, d_dist, stats);
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  return rc;
+}
+
+int b200nn_dev_graphs(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n, int32_t k, double prune,
+                      int32_t compute_snn, int64_t row_begin, int64_t row_end,
+                      int64_t *nnz_nn_out, int64_t *nnz_snn_out, b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  if (!d_idx0) {
+    b200nn_set_error("d_idx0 is NULL");
+    return B200NN_ERR_INVALID;
+  }
+  if (stats) memset(stats, 0, sizeof(*stats));
+  int64_t l0 = ctx->launches;
+  int rc = graphs_launch(ctx, d_idx0, n, k, n, prune, true, compute_snn != 0, row_begin, row_end,
+                         stats);
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  if (rc != B200NN_OK) return rc;
+  if (nnz_nn_out) *nnz_nn_out = ctx->nn_graph.nnz;
+  if (nnz_snn_out) *nnz_snn_out = compute_snn ? ctx->snn.nnz : 0;
+  return B200NN_OK;
+}
+
+int b200nn_dev_result(b200nn_ctx *ctx, int32_t which, b200nn_dev_csr *out) {
+  if (!ctx || !out) {
+    b200nn_set_error("NULL argument");
+    return B200NN_ERR_INVALID;
+  }
+  const CsrResult &r = which == 0 ? ctx->nn_graph : ctx->snn;
+  if (!r.valid) {
+    b200nn_set_error("no %s result in this context", which == 0 ? "nn Graph" : "SNN");
+    return B200NN_ERR_STATE;
+  }
+  out->n_rows = r.n_rows;
+  out->nnz = r.nnz;
+  out->p = r.p;
+  out->i = r.i;
+  out->x = r.x;
+  return B200NN_OK;
+}
+
+int b200nn_dev_copy_result(b200nn_ctx *ctx, int32_t which, int64_t *d_p, int32_t *d_i,
+                           double *d_x) {
+  RC_TRY(check_ctx(ctx));
+  const CsrResult &r = which == 0 ? ctx->nn_graph : ctx->snn;
+  if (!r.valid) {
+    b200nn_set_error("no %s result in this context", which == 0 ? "nn Graph" : "SNN");
+    return B200NN_ERR_STATE;
+  }
+  if (d_p)
+    CU_TRY(cudaMemcpyAsync(d_p, r.p, sizeof(int64_t) * ((size_t)r.n_rows + 1),
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d_i && r.nnz)
+    CU_TRY(cudaMemcpyAsync(d_i, r.i, sizeof(int32_t) * (size_t)r.nnz, cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  if (d_x && r.nnz)
+    CU_TRY(cudaMemcpyAsync(d_x, r.x, sizeof(double) * (size_t)r.nnz, cudaMemcpyDeviceToDevice,
+                           ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+// ---- host-buffer entry points ----------------------------------------------
+
+int b200nn_knn(b200nn_ctx *ctx, const double *ref, int64_t nr, const double *qry, int64_t nq,
+               int32_t d, int32_t k, int32_t *idx_out, double *dist_out, const b200nn_opts *opts,
+               b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!ref || nr <= 0 || d <= 0 || k <= 0 || (!idx_out && !dist_out)) {
+    b200nn_set_error("knn: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  if ((int64_t)k > nr) {
+    b200nn_set_error("Cannot find more nearest neighbours than there are points");
+    return B200NN_ERR_K_TOO_LARGE;
+  }
+  if (!qry) nq = nr;
+  int64_t l0 = ctx->launches;
+  Timer th(ctx, 6);
+  RC_TRY(th.start());
+  double *d_ref, *d_qry = nullptr;
+  RC_TRY(upload_matrix_f64(ctx, ref, nr, d, o.layout, WS_STAGE_A, WS_REF64, &d_ref));
+  if (qry) RC_TRY(upload_matrix_f64(ctx, qry, nq, d, o.layout, WS_STAGE_B, WS_QRY64, &d_qry));
+  RC_TRY(th.stop(stats ? &stats->ms_h2d : nullptr));
+  int32_t *d_idx0;
+  double *d_dist;
+  RC_TRY(ws_get(ctx, WS_IDX0, (size_t)nq * k, &d_idx0));
+  RC_TRY(ws_get(ctx, WS_DIST, (size_t)nq * k, &d_dist));
+  RC_TRY(knn_dispatch(ctx, d_ref, nr, d_qry, nq, d, k, o, d_idx0, d_dist, stats));
+  RC_TRY(th.start());
+  RC_TRY(download_knn(ctx, d_idx0, d_dist, nq, k, o.layout, idx_out, dist_out));
+  RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  return B200NN_OK;
+}
+
+int b200nn_snn_count(b200nn_ctx *ctx, const int32_t *nn_ranked, int64_t n, int32_t k, double prune,
+                     const b200nn_opts *opts, int64_t *nnz_out, b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  ctx->pending_snn = false;
+  if (!nn_ranked || n <= 0 || k <= 0 || !nnz_out) {
+    b200nn_set_error("snn: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  int64_t l0 = ctx->launches;
+  Timer th(ctx, 6);
+  RC_TRY(th.start());
+  int32_t *d_idx0;
+  RC_TRY(upload_nn_ranked(ctx, nn_ranked, n, k, o.layout, &d_idx0));
+  RC_TRY(th.stop(stats ? &stats->ms_h2d : nullptr));
+  RC_TRY(graphs_launch(ctx, d_idx0, n, k, n, prune, false, true, 0, n, stats));
+  if (ctx->snn.nnz >= 0x7fffffffLL) {
+    b200nn_set_error("SNN graph has %lld entries, more than a dgCMatrix can hold",
+                     (long long)ctx->snn.nnz);
+    return B200NN_ERR_NNZ_OVERFLOW;
+  }
+  *nnz_out = ctx->snn.nnz;
+  ctx->pending_snn = true;
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  return B200NN_OK;
+}
+
+int b200nn_snn_fill(b200nn_ctx *ctx, int32_t *p, int32_t *i, double *x) {
+  RC_TRY(check_ctx(ctx));
+  if (!ctx->pending_snn) {
+    b200nn_set_error("b200nn_snn_fill without a successful b200nn_snn_count");
+    return B200NN_ERR_STATE;
+  }
+  return download_csr(ctx, ctx->snn, p, i, x);
+}
+
+int b200nn_nn_graph_count(b200nn_ctx *ctx, const int32_t *nn_ranked, int64_t n_rows, int32_t k,
+                          int64_t n, const b200nn_opts *opts, int64_t *nnz_out,
+                          b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  ctx->pending_nn = false;
+  if (!nn_ranked || n_rows <= 0 || n <= 0 || k <= 0 || !nnz_out) {
+    b200nn_set_error("nn_graph: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  int64_t l0 = ctx->launches;
+  int32_t *d_idx0;
+  RC_TRY(upload_nn_ranked(ctx, nn_ranked, n_rows, k, o.layout, &d_idx0));
+  RC_TRY(graphs_launch(ctx, d_idx0, n_rows, k, n, 0.0, true, false, 0, n_rows, stats));
+  *nnz_out = ctx->nn_graph.nnz;
+  ctx->pending_nn = true;
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  return B200NN_OK;
+}
+
+int b200nn_nn_graph_fill(b200nn_ctx *ctx, int32_t *p, int32_t *i, double *x) {
+  RC_TRY(check_ctx(ctx));
+  if (!ctx->pending_nn) {
+    b200nn_set_error("b200nn_nn_graph_fill without a successful b200nn_nn_graph_count");
+    return B200NN_ERR_STATE;
+  }
+  return download_csr(ctx, ctx->nn_graph, p, i, x);
+}
+
+int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, int32_t d,
+                                int32_t k, double prune, int32_t compute_snn, int32_t *idx_out,
+                                double *dist_out, const b200nn_opts *opts, int64_t *nnz_nn_out,
+                                int64_t *nnz_snn_out, b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  ctx->pending_nn = ctx->pending_snn = false;
+  if (!data || n <= 0 || d <= 0 || k <= 0) {
+    b200nn_set_error("find_neighbors: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  if ((int64_t)k > n) {
+    b200nn_set_error("Cannot find more nearest neighbours than there are points");
+    return B200NN_ERR_K_TOO_LARGE;
+  }
+  int64_t l0 = ctx->launches;
+  Timer th(ctx, 6);
+  RC_TRY(th.start());
+  double *d_ref;
+  RC_TRY(upload_matrix_f64(ctx, data, n, d, o.layout, WS_STAGE_A, WS_REF64, &d_ref));
+  RC_TRY(th.stop(stats ? &stats->ms_h2d : nullptr));
+  int32_t *d_idx0;
+  double *d_dist;
+  RC_TRY(ws_get(ctx, WS_IDX0, (size_t)n * k, &d_idx0));
+  RC_TRY(ws_get(ctx, WS_DIST, (size_t)n * k, &d_dist));
+  RC_TRY(knn_dispatch(ctx, d_ref, n, nullptr, n, d, k, o, d_idx0, d_dist, stats));
+  b200nn_stats gs;
+  memset(&gs, 0, sizeof(gs));
+  RC_TRY(graphs_launch(ctx, d_idx0, n, k, n, prune, true, compute_snn != 0, 0, n, &gs));
+  if (stats) {
+    stats->ms_nn_graph = gs.ms_nn_graph;
+    stats->ms_snn = gs.ms_snn;
+    stats->nnz_nn = gs.nnz_nn;
+    stats->nnz_snn = gs.nnz_snn;
+    stats->snn_expanded = gs.snn_expanded;
+    stats->max_indegree = gs.max_indegree;
+  }
+  if (idx_out || dist_out) {
+    RC_TRY(th.start());
+    RC_TRY(download_knn(ctx, d_idx0, d_dist, n, k, o.layout, idx_out, dist_out));
+    RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));
+  }
+  if (compute_snn && ctx->snn.nnz >= 0x7fffffffLL) {
+    b200nn_set_error("SNN graph has %lld entries, more than a dgCMatrix can hold",
+                     (long long)ctx->snn.nnz);
+    return B200NN_ERR_NNZ_OVERFLOW;
+  }
+  if (nnz_nn_out) *nnz_nn_out = ctx->nn_graph.nnz;
+  if (nnz_snn_out) *nnz_snn_out = compute_snn ? ctx->snn.nnz : 0;
+  ctx->pending_nn = true;
+  ctx->pending_snn = compute_snn != 0;
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  return B200NN_OK;
+}
+
+int b200nn_find_neighbors_fill(b200nn_ctx *ctx, int32_t *nn_p, int32_t *nn_i, double *nn_x,
+                               int32_t *snn_p, int32_t *snn_i, double *snn_x) {
+  RC_TRY(check_ctx(ctx));
+  if (!ctx->pending_nn) {
+    b200nn_set_error("b200nn_find_neighbors_fill without a successful _count");
+    return B200NN_ERR_STATE;
+  }
+  Timer th(ctx, 6);
+  RC_TRY(th.start());
+  if (nn_p || nn_i || nn_x) RC_TRY(download_csr(ctx, ctx->nn_graph, nn_p, nn_i, nn_x));
+  if (snn_p || snn_i || snn_x) {
+    if (!ctx->pending_snn) {
+      b200nn_set_error("SNN was not computed by the last b200nn_find_neighbors_count");
+      return B200NN_ERR_STATE;
+    }
+    RC_TRY(download_csr(ctx, ctx->snn, snn_p, snn_i, snn_x));
+  }
+  return B200NN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// internal.cuh -- shared declarations of libb200nn (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nn.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing: every internal function returns a B200NN_* code
+// ---------------------------------------------------------------------------
+void b200nn_set_error(const char *fmt, ...);
+
+#define CU_TRY(expr)                                                              \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      b200nn_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),        \
+                       __FILE__, __LINE__, cudaGetErrorString(_e));               \
+      (void)cudaGetLastError();                                                   \
+      return _e == cudaErrorMemoryAllocation ? B200NN_ERR_NOMEM : B200NN_ERR_CUDA; \
+    }                                                                             \
+  } while (0)
+
+#define RC_TRY(expr)           \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != B200NN_OK) return _rc; \
+  } while (0)
+
+#define KERNEL_CHECK(ctx)            \
+  do {                               \
+    (ctx)->launches++;               \
+    CU_TRY(cudaGetLastError());      \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// context: one stream + a slot-addressed workspace that only ever grows
+// ---------------------------------------------------------------------------
+enum WsSlot {
+  WS_STAGE_A = 0,  // raw host copies (embedding / nn_ranked) before re-layout
+  WS_STAGE_B,
+  WS_REF64,        // reference embedding, row-major fp64
+  WS_QRY64,        // query embedding, row-major fp64
+  WS_IDX0,         // kNN index, row-major 0-based int32
+  WS_DIST,         // kNN distances, row-major fp64
+  WS_OUT_IDX,      // idx in caller layout (1-based)
+  WS_OUT_DIST,     // dist in caller layout
+  WS_INDEG,        // in-degree per column (int32, n+1)
+  WS_COLPTR,       // exclusive scan of in-degree (int64, n+1)
+  WS_CURSOR,       // scatter cursors (int32, n)
+  WS_REV,          // reverse lists = rows of each column (int32, n_rows*k)
+  WS_UNIQ,         // unique entries per column (int32, n+1)
+  WS_NN_P,         // nn Graph CSC: p (int64, n+1)
+  WS_NN_I,         //               i (int32)
+  WS_NN_X,         //               x (fp64)
+  WS_ROW_E,        // expanded candidates per row (int32)
+  WS_ROW_BOUND,    // survivor bound per row (int32)
+  WS_TMP_OFF,      // exclusive scan of bounds (int64)
+  WS_TMP,          // packed survivors (uint32 or uint64 words)
+  WS_ROW_NNZ,      // survivors per row (int32)
+  WS_SNN_P,        // SNN CSR: p (int64, rows+1)
+  WS_SNN_I,
+  WS_SNN_X,
+  WS_CLASS_LIST,   // row ids grouped by work class (int32, 4 * rows)
+  WS_SCAN_TMP,     // block sums of the scan
+  WS_INFO,         // small device struct with counters / flags
+  WS_LUT_KEEP,     // keep[s] bytes
+  WS_LUT_JAC,      // jaccard[s] doubles
+  WS_HUGE_TABLE,   // global-memory hash tables of the "huge row" path
+  WS_OUT_P32,      // int32 copies of p for dgCMatrix
+  WS_LONG_LIST,    // columns handled by the block-level sort
+  // tensor-core kNN path
+  WS_TC_REF16,     // fp16 operand matrix of the reference set (K-padded, augmented)
+  WS_TC_QRY16,     // fp16 operand matrix of the queries
+  WS_TC_REFERR,    // per-point fp16 rounding residual norms
+  WS_TC_QRYERR,
+  WS_TC_CAND,      // candidate indices (int32, nq * k')
+  WS_TC_CANDKEY,   // candidate keys (fp32, nq * k')
+  WS_TC_FLAGS,     // per-query certificate flags / fallback list
+  WS_TC_MISC,
+  WS_NUM
+};
+
+struct WsBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+// host mirror of the device-side info block (one D2H per phase)
+struct DevInfo {
+  int32_t err_index_range;   // some neighbour index was outside [0, n)
+  int32_t has_dups;          // some row lists the same neighbour twice
+  int32_t max_indegree;
+  int32_t max_row_e;         // largest expanded-candidate count of a row
+  int64_t sum_row_e;
+  int64_t sum_bound;
+  int64_t nnz_nn;
+  int64_t nnz_snn;
+  int32_t class_count[4];    // rows per work class
+  int32_t n_uncertified;
+  int32_t n_long;            // columns too long for the warp-level sort
+};
+
+struct CsrResult {
+  bool valid = false;
+  int64_t n_rows = 0;
+  int64_t nnz = 0;
+  const int64_t *p = nullptr;
+  const int32_t *i = nullptr;
+  const double *x = nullptr;
+};
+
+struct b200nn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[16] = {};
+  WsBuf ws[WS_NUM];
+  DevInfo *h_info = nullptr;  // pinned
+  int sm_count = 148;
+  int64_t launches = 0;
+  CsrResult nn_graph, snn;
+  // pending host-buffer results (between *_count and *_fill)
+  bool pending_nn = false, pending_snn = false;
+};
+
+// grow-only workspace allocation; returns nullptr + error code via rc
+int ws_reserve(b200nn_ctx *ctx, WsSlot slot, size_t bytes, void **out);
+
+template <typename T>
+static inline int ws_get(b200nn_ctx *ctx, WsSlot slot, size_t count, T **out) {
+  void *p = nullptr;
+  int rc = ws_reserve(ctx, slot, count * sizeof(T), &p);
+  *out = static_cast<T *>(p);
+  return rc;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// stage entry points implemented in the other translation units
+// ---------------------------------------------------------------------------
+
+// util.cu
+int scan_exclusive_i32_to_i64(b200nn_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n);
+// out[r * ncol + c] = in[c * nrow + r] (+ add)   (column-major -> row-major)
+int transpose_f64(b200nn_ctx *ctx, const double *d_in, double *d_out, int64_t nrow, int64_t ncol);
+int transpose_i32_add(b200nn_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t nrow,
+                      int64_t ncol, int32_t add);
+int add_i32(b200nn_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int32_t add);
+int narrow_i64_to_i32(b200nn_ctx *ctx, const int64_t *d_in, int32_t *d_out, int64_t n);
+
+// knn_exact.cu : FP64 exhaustive scan.  d_qsel == nullptr: queries 0..nq-1;
+// otherwise the kernel processes the n_sel query rows listed in d_qsel
+// (count read from the device at launch-time upper bound n_sel).
+int knn_exact_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                     int64_t nq, int d, int k, const int32_t *d_qsel, int64_t n_sel,
+                     int32_t *d_idx0, double *d_dist);
+
+// knn_tc.cu : tcgen05 candidate generation + FP64 re-rank + certificate
+bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k);
+int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                  int64_t nq, int d, int k, int n_cand, int32_t *d_idx0, double *d_dist,
+                  b200nn_stats *stats);
+
+// snn.cu
+int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k, int64_t n,
+                  double prune, bool want_nn_graph, bool compute_snn, int64_t row_begin,
+                  int64_t row_end, b200nn_stats *stats);

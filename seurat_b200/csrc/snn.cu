@@ -1,0 +1,801 @@
+// snn.cu -- nn Graph (K3) and shared-nearest-neighbour graph (K4).
+//
+// Replaces, bit for bit:
+//   * the nn Graph of /root/reference/R/clustering.R:664-670
+//       sparseMatrix(i = row, j = nn.ranked, x = 1, dims = c(n, n)), duplicates summed
+//   * ComputeSNN, /root/reference/src/snn.cpp:14-38
+//       A[i, nn(i,j)] += 1;  S = A * A^T;  v <- v / (k + (k - v));
+//       v < prune -> 0 (strict);  exact zeros dropped;  column-compressed, sorted.
+//
+// K3 (transpose): histogram of neighbour ids -> scan -> scatter of row ids ->
+//     per-column sort.  The sorted reverse lists R(c) = {i : c in N(i)} ARE
+//     the nn Graph in CSC form.
+// K4 (SNN rows): S[i, j] = sum over the k listed neighbours c of row i of the
+//     multiplicity of j in R(c).  A row-group of threads walks the k reverse
+//     lists (coalesced reads of sorted runs), counts every candidate j in a
+//     shared-memory hash table (packed key|count words), keeps the entries
+//     whose count passes the prune cut-off (a 2k-entry lookup table built from
+//     the exact double expression), sorts the survivors by column and emits the
+//     row.  The n x n pre-prune product is never materialised.  Because S is
+//     symmetric the row-compressed arrays equal the column-compressed ones.
+//
+// Rows are binned by expanded work E_i = sum_c |R(c)| into classes that differ
+// only in table size / threads per row; the "huge" class hashes in HBM.
+#include <limits.h>
+
+#include <algorithm>
+
+#include "internal.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int warp_sum_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_i64(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Ascending sort of a[0..m) by `nthr` cooperating threads (thread id g).
+// Bitonic network written with ascending comparators only (first step of each
+// stage mirrors the partner), so that the virtual +inf padding up to the next
+// power of two never has to move: comparators touching index >= m are skipped.
+template <typename T, typename SyncFn>
+__device__ __forceinline__ void bitonic_sort_asc(T *a, int m, int g, int nthr, SyncFn sync) {
+  if (m <= 1) {
+    return;
+  }
+  int P = 1;
+  while (P < m) P <<= 1;
+  const int half = P >> 1;
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    // mirrored step
+    {
+      const int hk = kk >> 1;
+      for (int t = g; t < half; t += nthr) {
+        int blk = t / hk, off = t - blk * hk;
+        int lo = blk * kk + off, hi = blk * kk + kk - 1 - off;
+        if (hi < m) {
+          T x = a[lo], y = a[hi];
+          if (x > y) {
+            a[lo] = y;
+            a[hi] = x;
+          }
+        }
+      }
+      sync();
+    }
+    for (int j = kk >> 2; j > 0; j >>= 1) {
+      for (int t = g; t < half; t += nthr) {
+        int blk = t / j, off = t - blk * j;
+        int lo = blk * 2 * j + off, hi = lo + j;
+        if (hi < m) {
+          T x = a[lo], y = a[hi];
+          if (x > y) {
+            a[lo] = y;
+            a[hi] = x;
+          }
+        }
+      }
+      sync();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: transpose
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_hist(const int32_t *__restrict__ idx0, int64_t total, int64_t n, int32_t *__restrict__ indeg,
+       DevInfo *__restrict__ info) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int32_t c = idx0[t];
+  if (c < 0 || (int64_t)c >= n)
+    info->err_index_range = 1;
+  else
+    atomicAdd(&indeg[c], 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter(const int32_t *__restrict__ idx0, int64_t total, int k, int64_t n,
+          const int64_t *__restrict__ colptr, int32_t *__restrict__ cursor,
+          int32_t *__restrict__ rev) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int32_t c = idx0[t];
+  if (c < 0 || (int64_t)c >= n) return;
+  int pos = atomicAdd(&cursor[c], 1);
+  rev[colptr[c] + pos] = (int32_t)(t / k);
+}
+
+constexpr int SORT_WARPS = 8;
+constexpr int SORT_WARP_CAP = 1024;  // elements a warp sorts in shared memory
+
+// one warp per column: sort the reverse list, count distinct rows
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+k_sort_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr, int64_t n,
+               int32_t *__restrict__ uniq, int32_t *__restrict__ long_list,
+               DevInfo *__restrict__ info) {
+  __shared__ int32_t sbuf[SORT_WARPS][SORT_WARP_CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * SORT_WARPS + w;
+  if (c >= n) return;
+  const int64_t beg = colptr[c];
+  const int64_t len64 = colptr[c + 1] - beg;
+  const int len = (int)len64;
+  if (lane == 0 && len > info->max_indegree) atomicMax(&info->max_indegree, len);
+  if (len <= 1) {
+    if (lane == 0) uniq[c] = len;
+    return;
+  }
+  int ndup = 0;
+  if (len <= 32) {
+    int32_t v = lane < len ? rev[beg + lane] : INT_MAX;
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        int32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+        bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+        v = (lower == up) ? min(v, o) : max(v, o);
+      }
+    }
+    int32_t prev = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane < len) rev[beg + lane] = v;
+    ndup = (lane > 0 && lane < len && v == prev) ? 1 : 0;
+  } else if (len <= SORT_WARP_CAP) {
+    int32_t *a = sbuf[w];
+    for (int t = lane; t < len; t += 32) a[t] = rev[beg + t];
+    __syncwarp();
+    bitonic_sort_asc(a, len, lane, 32, [] { __syncwarp(); });
+    for (int t = lane; t < len; t += 32) {
+      int32_t v = a[t];
+      rev[beg + t] = v;
+      if (t > 0 && a[t - 1] == v) ndup++;
+    }
+  } else {
+    if (lane == 0) {
+      int pos = atomicAdd(&info->n_long, 1);
+      long_list[pos] = (int32_t)c;
+    }
+    return;  // uniq[c] is written by k_sort_long_columns
+  }
+  ndup = warp_sum_i32(ndup);
+  if (lane == 0) {
+    uniq[c] = len - ndup;
+    if (ndup) info->has_dups = 1;
+  }
+}
+
+constexpr int LONG_THREADS = 1024;
+constexpr int LONG_SMEM_CAP = 32768;  // elements (128 KB)
+
+// one CTA per long column (hubs)
+__global__ void __launch_bounds__(LONG_THREADS)
+k_sort_long_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr,
+                    int32_t *__restrict__ uniq, const int32_t *__restrict__ long_list,
+                    DevInfo *__restrict__ info) {
+  extern __shared__ int32_t lbuf[];
+  __shared__ int red[32];
+  const int n_long = info->n_long;
+  for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const int64_t c = long_list[li];
+    const int64_t beg = colptr[c];
+    const int len = (int)(colptr[c + 1] - beg);
+    int32_t *a;
+    if (len <= LONG_SMEM_CAP) {
+      a = lbuf;
+      for (int t = threadIdx.x; t < len; t += LONG_THREADS) a[t] = rev[beg + t];
+    } else {
+      a = rev + beg;  // in place in HBM (block-scope visibility via __syncthreads)
+    }
+    __syncthreads();
+    bitonic_sort_asc(a, len, (int)threadIdx.x, LONG_THREADS, [] { __syncthreads(); });
+    int ndup = 0;
+    for (int t = threadIdx.x; t < len; t += LONG_THREADS) {
+      int32_t v = a[t];
+      if (t > 0 && a[t - 1] == v) ndup++;
+    }
+    __syncthreads();
+    if (len <= LONG_SMEM_CAP)
+      for (int t = threadIdx.x; t < len; t += LONG_THREADS) rev[beg + t] = a[t];
+    ndup = warp_sum_i32(ndup);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ndup;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int v = warp_sum_i32(red[threadIdx.x]);
+      if (threadIdx.x == 0) {
+        uniq[c] = len - v;
+        if (v) info->has_dups = 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// nn Graph emission: column c gets its distinct rows and their multiplicities
+__global__ void __launch_bounds__(256)
+k_emit_nn_graph(const int32_t *__restrict__ rev, const int64_t *__restrict__ colptr,
+                const int32_t *__restrict__ uniq, const int64_t *__restrict__ nn_p, int64_t n,
+                int32_t *__restrict__ nn_i, double *__restrict__ nn_x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= n) return;
+  const int64_t beg = colptr[c];
+  const int len = (int)(colptr[c + 1] - beg);
+  const int64_t ob = nn_p[c];
+  if (uniq[c] == len) {
+    for (int t = lane; t < len; t += 32) {
+      nn_i[ob + t] = rev[beg + t];
+      nn_x[ob + t] = 1.0;
+    }
+  } else if (lane == 0) {  // duplicated neighbours: rare, sequential
+    int64_t o = ob - 1;
+    int32_t prev = -1;
+    for (int t = 0; t < len; ++t) {
+      int32_t v = rev[beg + t];
+      if (t == 0 || v != prev) {
+        ++o;
+        nn_i[o] = v;
+        nn_x[o] = 1.0;
+      } else {
+        nn_x[o] += 1.0;
+      }
+      prev = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: SNN rows
+// ---------------------------------------------------------------------------
+struct SnnParams {
+  const int32_t *idx0;     // [n x k] 0-based
+  const int64_t *colptr;   // [n + 1]
+  const int32_t *rev;      // reverse lists
+  const uint8_t *keep;     // keep[count]
+  const int32_t *row_list; // rows of this class (local row numbers)
+  int32_t n_rows_class;
+  int32_t k;
+  int32_t cbits;           // low bits of a word hold the count
+  int64_t row_begin;       // global row of local row 0
+  const int64_t *tmp_off;  // [rows + 1]
+  void *tmp;               // packed survivors
+  int32_t *row_nnz;        // [rows]
+  void *huge_tables;       // HBM hash tables (huge class)
+  int32_t huge_log_t;
+};
+
+template <typename Word>
+struct WordTraits;
+template <>
+struct WordTraits<uint32_t> {
+  static constexpr uint32_t EMPTY = 0xffffffffu;
+  typedef unsigned int atomic_t;
+};
+template <>
+struct WordTraits<uint64_t> {
+  static constexpr uint64_t EMPTY = 0xffffffffffffffffull;
+  typedef unsigned long long atomic_t;
+};
+
+template <typename Word>
+__device__ __forceinline__ void hash_insert(Word *tab, uint32_t mask, int log_t, int cbits,
+                                            uint32_t j) {
+  typedef typename WordTraits<Word>::atomic_t A;
+  const Word EMPTY = WordTraits<Word>::EMPTY;
+  uint32_t h = (j * 2654435761u) >> (32 - log_t);
+  const Word fresh = ((Word)j << cbits) | (Word)1;
+  volatile Word *vt = tab;
+  while (true) {
+    Word cur = vt[h];
+    if (cur == EMPTY) {
+      Word old = (Word)atomicCAS(reinterpret_cast<A *>(tab + h), (A)EMPTY, (A)fresh);
+      if (old == EMPTY) return;
+      cur = old;
+    }
+    if ((uint32_t)(cur >> cbits) == j) {
+      atomicAdd(reinterpret_cast<A *>(tab + h), (A)1);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// G threads cooperate on one row.  LOG_T > 0: table of 2^LOG_T words in shared
+// memory (+ a survivor buffer of half that size when G > 32);  LOG_T == 0: table
+// in HBM, survivors written straight to their slot in `tmp` and sorted there.
+template <typename Word, int LOG_T, int G, int RPB>
+__global__ void __launch_bounds__(G *RPB) k_snn_rows(SnnParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Word EMPTY = WordTraits<Word>::EMPTY;
+  constexpr bool HUGE = (LOG_T == 0);
+  constexpr bool INPLACE = (G == 32) && !HUGE;
+  const int grp = threadIdx.x / G;
+  const int g = threadIdx.x - grp * G;
+  const int lane = threadIdx.x & 31;
+  const int log_t = HUGE ? P.huge_log_t : LOG_T;
+  const uint32_t T = 1u << log_t;
+  const uint32_t mask = T - 1;
+
+  Word *tab;
+  Word *surv = nullptr;
+  if (HUGE) {
+    tab = reinterpret_cast<Word *>(P.huge_tables) + (size_t)blockIdx.x * T;
+  } else {
+    constexpr size_t per_group = ((size_t)1 << LOG_T) + (INPLACE ? 0 : ((size_t)1 << LOG_T) / 2);
+    tab = reinterpret_cast<Word *>(smem_raw) + (size_t)grp * per_group;
+    if (!INPLACE) surv = tab + T;
+  }
+  __shared__ int s_count[RPB];
+
+  auto gsync = [&]() {
+    if (G == 32) {
+      __syncwarp();
+    } else if (RPB == 1) {
+      __syncthreads();
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(G) : "memory");
+    }
+  };
+
+  const int n_groups = gridDim.x * RPB;
+  for (int r = blockIdx.x * RPB + grp; r < P.n_rows_class; r += n_groups) {
+    const int row_l = P.row_list[r];
+    const int64_t row = P.row_begin + row_l;
+    // 1. clear
+    for (uint32_t s = g; s < T; s += G) tab[s] = EMPTY;
+    if (g == 0) s_count[grp] = 0;
+    gsync();
+    // 2. count every candidate j of the k reverse lists
+    const int32_t *nbr = P.idx0 + row * P.k;
+    for (int p = 0; p < P.k; ++p) {
+      const int32_t c = nbr[p];
+      const int64_t beg = P.colptr[c];
+      const int len = (int)(P.colptr[c + 1] - beg);
+      for (int t = g; t < len; t += G)
+        hash_insert<Word>(tab, mask, log_t, P.cbits, (uint32_t)P.rev[beg + t]);
+    }
+    gsync();
+    // 3. keep the entries that pass the prune cut-off
+    const Word cmask = (((Word)1) << P.cbits) - 1;
+    int m = 0;
+    Word *out;
+    if (INPLACE) {
+      out = tab;
+      for (uint32_t base = 0; base < T; base += 32) {
+        Word wv = tab[base + lane];
+        bool kp = (wv != EMPTY) && P.keep[(uint32_t)(wv & cmask)];
+        unsigned bal = __ballot_sync(0xffffffffu, kp);
+        __syncwarp();  // every lane has read its slot of this round
+        if (kp) tab[m + __popc(bal & ((1u << lane) - 1))] = wv;
+        m += __popc(bal);
+      }
+      __syncwarp();
+    } else {
+      out = HUGE ? reinterpret_cast<Word *>(P.tmp) + P.tmp_off[row_l] : surv;
+      for (uint32_t base = 0; base < T; base += G) {
+        uint32_t s = base + g;
+        Word wv = s < T ? tab[s] : EMPTY;
+        bool kp = (wv != EMPTY) && P.keep[(uint32_t)(wv & cmask)];
+        unsigned bal = __ballot_sync(0xffffffffu, kp);
+        int wbase = 0;
+        if (lane == 0 && bal) wbase = atomicAdd(&s_count[grp], __popc(bal));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (kp) out[wbase + __popc(bal & ((1u << lane) - 1))] = wv;
+      }
+      gsync();
+      m = s_count[grp];
+    }
+    // 4. ascending column order (keys are distinct, so word order == key order)
+    bitonic_sort_asc(out, m, g, G, gsync);
+    // 5. emit
+    if (!HUGE) {
+      Word *dst = reinterpret_cast<Word *>(P.tmp) + P.tmp_off[row_l];
+      for (int t = g; t < m; t += G) dst[t] = out[t];
+    }
+    if (g == 0) P.row_nnz[row_l] = m;
+    gsync();
+  }
+}
+
+// expanded work, survivor bound and work class of every row
+struct RowWorkParams {
+  const int32_t *idx0;
+  const int64_t *colptr;
+  int64_t row_begin;
+  int32_t n_rows;  // rows in [row_begin, row_end)
+  int32_t k;
+  int32_t s_min;   // smallest kept count (0: nothing is ever kept)
+  int64_t n;
+  int32_t class_lim[3];
+  int32_t *row_bound;
+  int32_t *class_list;  // 4 x n_rows
+  DevInfo *info;
+};
+
+__global__ void __launch_bounds__(256) k_row_work(RowWorkParams P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = rl < P.n_rows;
+  int64_t e = 0;
+  if (act) {
+    const int32_t *nbr = P.idx0 + (P.row_begin + rl) * P.k;
+    for (int p = 0; p < P.k; ++p) {
+      int32_t c = nbr[p];
+      e += P.colptr[c + 1] - P.colptr[c];
+    }
+  }
+  int64_t bound = 0;
+  if (act && P.s_min > 0) {
+    bound = e / P.s_min;
+    if (bound > P.n) bound = P.n;
+  }
+  if (act) P.row_bound[rl] = (int32_t)bound;
+  int cls = -1;
+  if (act) cls = e <= P.class_lim[0] ? 0 : e <= P.class_lim[1] ? 1 : e <= P.class_lim[2] ? 2 : 3;
+  // warp-aggregated append to the class lists
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    unsigned bal = __ballot_sync(0xffffffffu, cls == q);
+    if (bal) {
+      int base = 0;
+      if (lane == __ffs(bal) - 1) base = atomicAdd(&P.info->class_count[q], __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+      if (cls == q)
+        P.class_list[(int64_t)q * P.n_rows + base + __popc(bal & ((1u << lane) - 1))] = (int32_t)rl;
+    }
+  }
+  int emax = warp_max_i32((int)(e > INT_MAX ? INT_MAX : e));
+  long long esum = warp_sum_i64(e), bsum = warp_sum_i64(bound);
+  if (lane == 0) {
+    if (emax > P.info->max_row_e) atomicMax(&P.info->max_row_e, emax);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&P.info->sum_row_e), (unsigned long long)esum);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&P.info->sum_bound), (unsigned long long)bsum);
+  }
+}
+
+// unpack survivors into the final CSR arrays
+template <typename Word>
+__global__ void __launch_bounds__(256)
+k_snn_fill(const Word *__restrict__ tmp, const int64_t *__restrict__ tmp_off,
+           const int64_t *__restrict__ snn_p, const double *__restrict__ jac, int cbits,
+           int32_t n_rows, int32_t *__restrict__ snn_i, double *__restrict__ snn_x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const int64_t ob = snn_p[r];
+  const int m = (int)(snn_p[r + 1] - ob);
+  const Word *src = tmp + tmp_off[r];
+  const Word cmask = (((Word)1) << cbits) - 1;
+  for (int t = lane; t < m; t += 32) {
+    Word w = src[t];
+    snn_i[ob + t] = (int32_t)(w >> cbits);
+    snn_x[ob + t] = jac[(uint32_t)(w & cmask)];
+  }
+}
+
+template <typename Word, int LOG_T, int G, int RPB>
+int launch_class(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm) {
+  if (P.n_rows_class <= 0) return B200NN_OK;
+  constexpr bool HUGE = (LOG_T == 0);
+  constexpr bool INPLACE = (G == 32) && !HUGE;
+  size_t smem = 0;
+  if (!HUGE) {
+    size_t per_group = ((size_t)1 << LOG_T) + (INPLACE ? 0 : ((size_t)1 << LOG_T) / 2);
+    smem = per_group * sizeof(Word) * RPB;
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows<Word, LOG_T, G, RPB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int64_t want = ceil_div64(P.n_rows_class, RPB);
+  int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
+  int blocks = (int)std::min<int64_t>(want, cap);
+  k_snn_rows<Word, LOG_T, G, RPB><<<blocks, G * RPB, smem, ctx->stream>>>(P);
+  KERNEL_CHECK(ctx);
+  return B200NN_OK;
+}
+
+struct WordCfg32 {
+  typedef uint32_t Word;
+  static constexpr int L0 = 11, L1 = 13, L2 = 15;
+};
+struct WordCfg64 {
+  typedef uint64_t Word;
+  static constexpr int L0 = 10, L1 = 12, L2 = 14;
+};
+
+constexpr int HUGE_BLOCKS_PER_SM = 1;
+
+template <typename Cfg>
+int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int32_t n_rows,
+                    const int32_t class_count[4], int max_row_e) {
+  typedef typename Cfg::Word Word;
+  P.row_list = class_list + 0 * (int64_t)n_rows;
+  P.n_rows_class = class_count[0];
+  RC_TRY((launch_class<Word, Cfg::L0, 32, 8>(ctx, P, 3)));
+  P.row_list = class_list + 1 * (int64_t)n_rows;
+  P.n_rows_class = class_count[1];
+  RC_TRY((launch_class<Word, Cfg::L1, 128, 2>(ctx, P, 2)));
+  P.row_list = class_list + 2 * (int64_t)n_rows;
+  P.n_rows_class = class_count[2];
+  RC_TRY((launch_class<Word, Cfg::L2, 256, 1>(ctx, P, 1)));
+  if (class_count[3] > 0) {
+    int log_t = 1;
+    while (((int64_t)1 << log_t) < 2 * (int64_t)max_row_e) ++log_t;
+    int64_t blocks = std::min<int64_t>(class_count[3], (int64_t)ctx->sm_count * HUGE_BLOCKS_PER_SM);
+    Word *tables;
+    RC_TRY(ws_get(ctx, WS_HUGE_TABLE, (size_t)blocks << log_t, &tables));
+    P.huge_tables = tables;
+    P.huge_log_t = log_t;
+    P.row_list = class_list + 3 * (int64_t)n_rows;
+    P.n_rows_class = class_count[3];
+    RC_TRY((launch_class<Word, 0, 256, 1>(ctx, P, HUGE_BLOCKS_PER_SM)));
+  }
+  return B200NN_OK;
+}
+
+int fetch_info(b200nn_ctx *ctx, const DevInfo *d_info) {
+  CU_TRY(cudaMemcpyAsync(ctx->h_info, d_info, sizeof(DevInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+}  // namespace
+
+// host-side evaluation of the reference's per-entry expression (snn.cpp:30-33,36)
+static inline double jaccard_of(double s, double k) { return s / (k + (k - s)); }
+
+int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k, int64_t n,
+                  double prune, bool want_nn_graph, bool compute_snn, int64_t row_begin,
+                  int64_t row_end, b200nn_stats *stats) {
+  cudaStream_t st = ctx->stream;
+  ctx->nn_graph.valid = false;
+  ctx->snn.valid = false;
+  if (n_rows < 0 || n <= 0 || k <= 0) {
+    b200nn_set_error("graphs: invalid shape n_rows=%lld n=%lld k=%d", (long long)n_rows,
+                     (long long)n, k);
+    return B200NN_ERR_INVALID;
+  }
+  const int64_t total = n_rows * (int64_t)k;
+  if (total >= 0x7fffffffLL || n >= 0x7fffffffLL) {
+    b200nn_set_error("nn Graph with %lld entries does not fit a dgCMatrix", (long long)total);
+    return B200NN_ERR_NNZ_OVERFLOW;
+  }
+  if (compute_snn && n_rows != n) {
+    b200nn_set_error("ComputeSNN needs a square neighbour matrix (n_rows=%lld, n=%lld)",
+                     (long long)n_rows, (long long)n);
+    return B200NN_ERR_INVALID;
+  }
+  if (row_begin < 0 || row_end > n_rows || row_begin > row_end) {
+    b200nn_set_error("graphs: invalid row range [%lld, %lld)", (long long)row_begin,
+                     (long long)row_end);
+    return B200NN_ERR_INVALID;
+  }
+
+  cudaEvent_t e0 = ctx->ev[0], e1 = ctx->ev[1], e2 = ctx->ev[2];
+  CU_TRY(cudaEventRecord(e0, st));
+
+  DevInfo *d_info;
+  int32_t *indeg, *cursor, *rev, *uniq, *long_list;
+  int64_t *colptr;
+  RC_TRY(ws_get(ctx, WS_INFO, 1, &d_info));
+  RC_TRY(ws_get(ctx, WS_INDEG, (size_t)n + 1, &indeg));
+  RC_TRY(ws_get(ctx, WS_CURSOR, (size_t)n + 1, &cursor));
+  RC_TRY(ws_get(ctx, WS_COLPTR, (size_t)n + 1, &colptr));
+  RC_TRY(ws_get(ctx, WS_REV, (size_t)total + 1, &rev));
+  RC_TRY(ws_get(ctx, WS_UNIQ, (size_t)n + 1, &uniq));
+  RC_TRY(ws_get(ctx, WS_LONG_LIST, (size_t)(total / SORT_WARP_CAP) + 2, &long_list));
+  CU_TRY(cudaMemsetAsync(d_info, 0, sizeof(DevInfo), st));
+  CU_TRY(cudaMemsetAsync(indeg, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+  CU_TRY(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+
+  // ---- K3 ----
+  if (total > 0) {
+    k_hist<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(d_idx0, total, n, indeg, d_info);
+    KERNEL_CHECK(ctx);
+  }
+  RC_TRY(scan_exclusive_i32_to_i64(ctx, indeg, colptr, n));
+  if (total > 0) {
+    k_scatter<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(d_idx0, total, k, n, colptr, cursor,
+                                                                 rev);
+    KERNEL_CHECK(ctx);
+  }
+  k_sort_columns<<<(unsigned)ceil_div64(n, SORT_WARPS), SORT_WARPS * 32, 0, st>>>(
+      rev, colptr, n, uniq, long_list, d_info);
+  KERNEL_CHECK(ctx);
+  {
+    size_t smem = sizeof(int32_t) * LONG_SMEM_CAP;
+    CU_TRY(cudaFuncSetAttribute(k_sort_long_columns, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+    k_sort_long_columns<<<ctx->sm_count, LONG_THREADS, smem, st>>>(rev, colptr, uniq, long_list,
+                                                                   d_info);
+    KERNEL_CHECK(ctx);
+  }
+
+  int64_t *nn_p = nullptr;
+  if (want_nn_graph) {
+    RC_TRY(ws_get(ctx, WS_NN_P, (size_t)n + 1, &nn_p));
+    RC_TRY(scan_exclusive_i32_to_i64(ctx, uniq, nn_p, n));
+  }
+  // sync #1: flags of the transpose
+  RC_TRY(fetch_info(ctx, d_info));
+  DevInfo hi = *ctx->h_info;
+  if (hi.err_index_range) {
+    b200nn_set_error("neighbour index out of range: every entry must lie in [1, %lld]",
+                     (long long)n);
+    return B200NN_ERR_INDEX_RANGE;
+  }
+  if (want_nn_graph) {
+    int64_t nnz_nn = 0;
+    CU_TRY(cudaMemcpyAsync(&nnz_nn, nn_p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    int32_t *nn_i;
+    double *nn_x;
+    RC_TRY(ws_get(ctx, WS_NN_I, (size_t)nnz_nn + 1, &nn_i));
+    RC_TRY(ws_get(ctx, WS_NN_X, (size_t)nnz_nn + 1, &nn_x));
+    k_emit_nn_graph<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, st>>>(rev, colptr, uniq, nn_p, n,
+                                                                        nn_i, nn_x);
+    KERNEL_CHECK(ctx);
+    ctx->nn_graph.valid = true;
+    ctx->nn_graph.n_rows = n;
+    ctx->nn_graph.nnz = nnz_nn;
+    ctx->nn_graph.p = nn_p;
+    ctx->nn_graph.i = nn_i;
+    ctx->nn_graph.x = nn_x;
+    if (stats) stats->nnz_nn = nnz_nn;
+  }
+  if (stats) stats->max_indegree = hi.max_indegree;
+  CU_TRY(cudaEventRecord(e1, st));
+
+  // ---- K4 ----
+  if (compute_snn) {
+    const int64_t rows = row_end - row_begin;
+    if (rows >= 0x7fffffffLL) return B200NN_ERR_INVALID;
+    // count range: without duplicates |N(i) ∩ N(j)| <= k; with duplicates <= k^2
+    int64_t smax = hi.has_dups ? (int64_t)k * k : (int64_t)k;
+    if (smax > (1 << 20)) {
+      b200nn_set_error("k = %d with duplicated neighbours exceeds the supported count range", k);
+      return B200NN_ERR_INVALID;
+    }
+    // lookup tables from the exact double expression of the reference
+    std::vector<uint8_t> h_keep((size_t)smax + 1);
+    std::vector<double> h_jac((size_t)smax + 1);
+    int32_t s_min = 0;
+    for (int64_t s = 0; s <= smax; ++s) {
+      double v = jaccard_of((double)s, (double)k);
+      if (v < prune) v = 0;
+      bool kp = (s > 0) && (v != 0);  // s == 0 entries are never stored by the product
+      h_keep[(size_t)s] = kp ? 1 : 0;
+      h_jac[(size_t)s] = v;
+      if (kp && s_min == 0) s_min = (int32_t)s;
+    }
+    uint8_t *d_keep;
+    double *d_jac;
+    RC_TRY(ws_get(ctx, WS_LUT_KEEP, (size_t)smax + 1, &d_keep));
+    RC_TRY(ws_get(ctx, WS_LUT_JAC, (size_t)smax + 1, &d_jac));
+    CU_TRY(cudaMemcpyAsync(d_keep, h_keep.data(), h_keep.size(), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_jac, h_jac.data(), h_jac.size() * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));  // the host vectors go out of scope below
+
+    // word format
+    int kbits = 1;
+    while (((int64_t)1 << kbits) < n) ++kbits;
+    bool use32 = kbits < 32 && smax <= (((int64_t)1 << (32 - kbits)) - 2);
+    const int cbits = use32 ? 32 - kbits : 32;
+    const size_t wbytes = use32 ? 4 : 8;
+
+    int32_t *row_bound, *class_list, *row_nnz;
+    int64_t *tmp_off, *snn_p;
+    RC_TRY(ws_get(ctx, WS_ROW_BOUND, (size_t)rows + 1, &row_bound));
+    RC_TRY(ws_get(ctx, WS_CLASS_LIST, (size_t)rows * 4 + 4, &class_list));
+    RC_TRY(ws_get(ctx, WS_ROW_NNZ, (size_t)rows + 1, &row_nnz));
+    RC_TRY(ws_get(ctx, WS_TMP_OFF, (size_t)rows + 1, &tmp_off));
+    RC_TRY(ws_get(ctx, WS_SNN_P, (size_t)rows + 1, &snn_p));
+
+    RowWorkParams rw;
+    rw.idx0 = d_idx0;
+    rw.colptr = colptr;
+    rw.row_begin = row_begin;
+    rw.n_rows = (int32_t)rows;
+    rw.k = k;
+    rw.s_min = s_min;
+    rw.n = n;
+    const int L0 = use32 ? WordCfg32::L0 : WordCfg64::L0;
+    const int L1 = use32 ? WordCfg32::L1 : WordCfg64::L1;
+    const int L2 = use32 ? WordCfg32::L2 : WordCfg64::L2;
+    rw.class_lim[0] = (1 << L0) / 2;
+    rw.class_lim[1] = (1 << L1) / 2;
+    rw.class_lim[2] = (1 << L2) / 2;
+    rw.row_bound = row_bound;
+    rw.class_list = class_list;
+    rw.info = d_info;
+    if (rows > 0) {
+      k_row_work<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(rw);
+      KERNEL_CHECK(ctx);
+    }
+    RC_TRY(scan_exclusive_i32_to_i64(ctx, row_bound, tmp_off, rows));
+    // sync #2: class sizes and the survivor-buffer bound
+    RC_TRY(fetch_info(ctx, d_info));
+    hi = *ctx->h_info;
+    void *tmp;
+    RC_TRY(ws_reserve(ctx, WS_TMP, ((size_t)hi.sum_bound + 1) * wbytes, &tmp));
+    CU_TRY(cudaMemsetAsync(row_nnz, 0, sizeof(int32_t) * ((size_t)rows + 1), st));
+
+    SnnParams P;
+    P.idx0 = d_idx0;
+    P.colptr = colptr;
+    P.rev = rev;
+    P.keep = d_keep;
+    P.row_list = nullptr;
+    P.n_rows_class = 0;
+    P.k = k;
+    P.cbits = cbits;
+    P.row_begin = row_begin;
+    P.tmp_off = tmp_off;
+    P.tmp = tmp;
+    P.row_nnz = row_nnz;
+    P.huge_tables = nullptr;
+    P.huge_log_t = 0;
+    if (use32)
+      RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, hi.class_count,
+                                        hi.max_row_e));
+    else
+      RC_TRY(run_snn_classes<WordCfg64>(ctx, P, class_list, (int32_t)rows, hi.class_count,
+                                        hi.max_row_e));
+    RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
+    // sync #3: nnz
+    int64_t nnz = 0;
+    CU_TRY(cudaMemcpyAsync(&nnz, snn_p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    int32_t *snn_i;
+    double *snn_x;
+    RC_TRY(ws_get(ctx, WS_SNN_I, (size_t)nnz + 1, &snn_i));
+    RC_TRY(ws_get(ctx, WS_SNN_X, (size_t)nnz + 1, &snn_x));
+    if (rows > 0) {
+      unsigned blocks = (unsigned)ceil_div64(rows * 32, 256);
+      if (use32)
+        k_snn_fill<uint32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t *>(tmp), tmp_off,
+                                                     snn_p, d_jac, cbits, (int32_t)rows, snn_i,
+                                                     snn_x);
+      else
+        k_snn_fill<uint64_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint64_t *>(tmp), tmp_off,
+                                                     snn_p, d_jac, cbits, (int32_t)rows, snn_i,
+                                                     snn_x);
+      KERNEL_CHECK(ctx);
+    }
+    ctx->snn.valid = true;
+    ctx->snn.n_rows = rows;
+    ctx->snn.nnz = nnz;
+    ctx->snn.p = snn_p;
+    ctx->snn.i = snn_i;
+    ctx->snn.x = snn_x;
+    if (stats) {
+      stats->nnz_snn = nnz;
+      stats->snn_expanded = hi.sum_row_e;
+    }
+  }
+  CU_TRY(cudaEventRecord(e2, st));
+  CU_TRY(cudaEventSynchronize(e2));
+  if (stats) {
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    stats->ms_nn_graph = ms;
+    CU_TRY(cudaEventElapsedTime(&ms, e1, e2));
+    stats->ms_snn = ms;
+  }
+  return B200NN_OK;
+}
