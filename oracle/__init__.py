@@ -43,6 +43,8 @@ def lib() -> C.CDLL:
         L.oracle_nn_graph.restype = i32
         L.oracle_compute_snn.argtypes = [vp, i64, i32, dbl, i32, vp, vp]
         L.oracle_compute_snn.restype = i32
+        L.oracle_compute_snn_rows.argtypes = [vp, i64, i32, dbl, i64, i64, i32, vp, vp, vp]
+        L.oracle_compute_snn_rows.restype = i32
         L.oracle_snn_fetch.argtypes = [vp, vp, vp, vp]
         L.oracle_snn_fetch.restype = None
         L.oracle_l2norm.argtypes = [vp, i64, i32]
@@ -122,6 +124,28 @@ def compute_snn(nn_ranked, prune: float, nthreads: int = 0):
     i = np.empty(nnz.value, dtype=np.int32)
     x = np.empty(nnz.value, dtype=np.float64)
     lib().oracle_snn_fetch(h, _p(p), _p(i), _p(x))
+    return p, i, x
+
+
+def compute_snn_rows(nn_ranked, prune: float, row_begin: int, row_end: int, nthreads: int = 0,
+                     timings: dict | None = None):
+    """SNN rows [row_begin, row_end) only (local offsets); used for bounded CPU baselines."""
+    nn = np.ascontiguousarray(np.asarray(nn_ranked, dtype=np.int32))
+    n, k = nn.shape
+    h = C.c_void_p()
+    nnz = C.c_int64(0)
+    sec = (C.c_double * 2)()
+    rc = lib().oracle_compute_snn_rows(_p(nn), n, k, float(prune), row_begin, row_end, nthreads,
+                                       C.byref(h), C.byref(nnz), sec)
+    if rc:
+        raise ValueError("neighbour index out of range")
+    rows = row_end - row_begin
+    p = np.empty(rows + 1, dtype=np.int64)
+    i = np.empty(nnz.value, dtype=np.int32)
+    x = np.empty(nnz.value, dtype=np.float64)
+    lib().oracle_snn_fetch(h, _p(p), _p(i), _p(x))
+    if timings is not None:
+        timings["transpose_s"], timings["rows_s"] = sec[0], sec[1]
     return p, i, x
 
 

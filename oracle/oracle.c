@@ -463,23 +463,31 @@ typedef struct {
  * dropped (snn.cpp:30-36).  Result rows == columns (S is symmetric), indices
  * ascending.  Returns an opaque handle; fetch with oracle_snn_fetch.
  */
-ORACLE_API int oracle_compute_snn(const int32_t *nn, int64_t n, int k, double prune,
-                                  int nthreads, void **handle, int64_t *nnz_out) {
+/* rows [row_begin, row_end) only (the transpose is always built in full);
+ * seconds[0] = transpose, seconds[1] = rows, for sub-sampled baselines. */
+ORACLE_API int oracle_compute_snn_rows(const int32_t *nn, int64_t n, int k, double prune,
+                                       int64_t row_begin, int64_t row_end, int nthreads,
+                                       void **handle, int64_t *nnz_out, double *seconds) {
+#ifdef _OPENMP
+  double t0 = omp_get_wtime();
+#endif
   int64_t *colptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
   int32_t *crow; double *cval;
   int rc = build_csc(nn, n, k, n, colptr, &crow, &cval);
   if (rc) { free(colptr); return rc; }
 #ifdef _OPENMP
+  double t1 = omp_get_wtime();
   if (nthreads > 0) omp_set_num_threads(nthreads);
   int nt = omp_get_max_threads();
 #else
   int nt = 1;
 #endif
+  const int64_t nrows = row_end - row_begin;
   snn_result *res = (snn_result *)calloc(1, sizeof(snn_result));
-  res->n = n;
-  res->p = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+  res->n = nrows;
+  res->p = (int64_t *)calloc((size_t)nrows + 1, sizeof(int64_t));
   /* per-thread output chunks over contiguous row blocks */
-  int64_t nblk = nt * 8; if (nblk > n) nblk = n > 0 ? n : 1;
+  int64_t nblk = nt * 8; if (nblk > nrows) nblk = nrows > 0 ? nrows : 1;
   int32_t **bi = (int32_t **)calloc((size_t)nblk, sizeof(int32_t *));
   double **bx = (double **)calloc((size_t)nblk, sizeof(double *));
   int64_t *bn = (int64_t *)calloc((size_t)nblk, sizeof(int64_t));
@@ -490,7 +498,7 @@ ORACLE_API int oracle_compute_snn(const int32_t *nn, int64_t n, int k, double pr
     int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
 #pragma omp for schedule(dynamic, 1)
     for (int64_t b = 0; b < nblk; ++b) {
-      int64_t r0 = n * b / nblk, r1 = n * (b + 1) / nblk;
+      int64_t r0 = row_begin + nrows * b / nblk, r1 = row_begin + nrows * (b + 1) / nblk;
       int64_t cap = (r1 - r0) * 64 + 64, cnt = 0;
       int32_t *oi = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap);
       double *ox = (double *)malloc(sizeof(double) * (size_t)cap);
@@ -534,14 +542,14 @@ ORACLE_API int oracle_compute_snn(const int32_t *nn, int64_t n, int k, double pr
             oi[cnt] = r; ox[cnt] = v; cnt++; row_n++;
           }
         }
-        res->p[i + 1] = row_n;
+        res->p[i - row_begin + 1] = row_n;
       }
       bi[b] = oi; bx[b] = ox; bn[b] = cnt;
     }
     free(acc); free(touched);
   }
-  for (int64_t i = 0; i < n; ++i) res->p[i + 1] += res->p[i];
-  res->nnz = res->p[n];
+  for (int64_t i = 0; i < nrows; ++i) res->p[i + 1] += res->p[i];
+  res->nnz = res->p[nrows];
   res->i = (int32_t *)malloc(sizeof(int32_t) * (size_t)(res->nnz ? res->nnz : 1));
   res->x = (double *)malloc(sizeof(double) * (size_t)(res->nnz ? res->nnz : 1));
   int64_t off = 0;
@@ -557,7 +565,17 @@ ORACLE_API int oracle_compute_snn(const int32_t *nn, int64_t n, int k, double pr
   free(colptr); free(crow); free(cval);
   *handle = res;
   *nnz_out = res->nnz;
+#ifdef _OPENMP
+  if (seconds) { seconds[0] = t1 - t0; seconds[1] = omp_get_wtime() - t1; }
+#else
+  if (seconds) { seconds[0] = 0; seconds[1] = 0; }
+#endif
   return 0;
+}
+
+ORACLE_API int oracle_compute_snn(const int32_t *nn, int64_t n, int k, double prune,
+                                  int nthreads, void **handle, int64_t *nnz_out) {
+  return oracle_compute_snn_rows(nn, n, k, prune, 0, n, nthreads, handle, nnz_out, NULL);
 }
 
 /* copy out (p as int64 so that callers can detect dgCMatrix overflow) and free */
