@@ -179,6 +179,20 @@ B200NN_API int b200nn_dev_graphs(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t
                       int64_t row_end, int64_t *nnz_nn_out, int64_t *nnz_snn_out,
                       b200nn_stats *stats);
 
+/*
+ * Candidate stage of the tensor-core kNN path alone (diagnostics / profiling):
+ * prep + tcgen05 candidate kernel, no re-rank.  d_ref/d_qry as in b200nn_dev_knn
+ * (d <= 61).  Outputs (device, any may be NULL): d_cand [nq x n_cand] int32
+ * 0-based candidate rows (unordered), d_tau [nq] float selection thresholds,
+ * d_keys [256 x 128] float raw accumulator keys of the first 256 queries against
+ * the first 128 reference rows.  h_scale_mu (host, 65 doubles, may be NULL)
+ * receives the power-of-two scale and the centring vector of the prep stage.
+ */
+B200NN_API int b200nn_dev_knn_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr,
+                                         const double *d_qry, int64_t nq, int32_t d,
+                                         int32_t n_cand, int32_t *d_cand, float *d_tau,
+                                         float *d_keys, double *h_scale_mu);
+
 typedef struct b200nn_dev_csr {
   int64_t n_rows;      /* rows (== columns for the symmetric SNN block)             */
   int64_t nnz;

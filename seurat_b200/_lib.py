@@ -25,7 +25,7 @@ SYMBOLS = [
     "b200nn_knn", "b200nn_snn_count", "b200nn_snn_fill",
     "b200nn_nn_graph_count", "b200nn_nn_graph_fill",
     "b200nn_find_neighbors_count", "b200nn_find_neighbors_fill",
-    "b200nn_dev_knn", "b200nn_dev_graphs", "b200nn_dev_result", "b200nn_dev_copy_result",
+    "b200nn_dev_knn", "b200nn_dev_knn_candidates", "b200nn_dev_graphs", "b200nn_dev_result", "b200nn_dev_copy_result",
 ]
 
 
@@ -89,6 +89,7 @@ def load() -> C.CDLL:
                                                   C.POINTER(i64), C.POINTER(i64), C.POINTER(Stats)]
         L.b200nn_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b200nn_dev_knn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
+        L.b200nn_dev_knn_candidates.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp, vp]
         L.b200nn_dev_graphs.argtypes = [vp, vp, i64, i32, dbl, i32, i64, i64, C.POINTER(i64), C.POINTER(i64),
                                         C.POINTER(Stats)]
         L.b200nn_dev_result.argtypes = [vp, i32, C.POINTER(DevCsr)]
@@ -233,6 +234,11 @@ class Context:
         check(self._L.b200nn_dev_knn(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, k, _ptr(d_idx0),
                                      _ptr(d_dist), C.byref(o), C.byref(st)))
         return st.as_dict()
+
+    def dev_knn_candidates(self, d_ref, nr: int, d_qry, nq: int, d: int, n_cand: int, d_cand, d_tau,
+                           d_keys, scale_mu: np.ndarray | None = None) -> None:
+        check(self._L.b200nn_dev_knn_candidates(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, n_cand,
+                                                _ptr(d_cand), _ptr(d_tau), _ptr(d_keys), _ptr(scale_mu)))
 
     def dev_graphs(self, d_idx0, n: int, k: int, prune: float, compute_snn: bool, row_begin: int,
                    row_end: int) -> dict:

@@ -253,6 +253,17 @@ int b200nn_dev_knn(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const doubl
   return rc;
 }
 
+int b200nn_dev_knn_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                              int64_t nq, int32_t d, int32_t n_cand, int32_t *d_cand, float *d_tau,
+                              float *d_keys, double *h_scale_mu) {
+  RC_TRY(check_ctx(ctx));
+  if (!d_ref || nr <= 0 || nq <= 0 || d <= 0 || d > 61 || n_cand < 8 || n_cand > 56 || (n_cand & 7)) {
+    b200nn_set_error("knn_candidates: invalid argument (d <= 61, n_cand a multiple of 8 in [8, 56])");
+    return B200NN_ERR_INVALID;
+  }
+  return knn_tc_debug(ctx, d_ref, nr, d_qry, nq, d, n_cand, d_keys, d_cand, d_tau, h_scale_mu);
+}
+
 int b200nn_dev_graphs(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n, int32_t k, double prune,
                       int32_t compute_snn, int64_t row_begin, int64_t row_end,
                       int64_t *nnz_nn_out, int64_t *nnz_snn_out, b200nn_stats *stats) {

@@ -165,6 +165,10 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
                   int64_t nq, int d, int k, int n_cand, int32_t *d_idx0, double *d_dist,
                   b200nn_stats *stats);
 
+int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
+                 int d, int kp, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
+                 double *h_scale_mu);
+
 // snn.cu
 int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k, int64_t n,
                   double prune, bool want_nn_graph, bool compute_snn, int64_t row_begin,

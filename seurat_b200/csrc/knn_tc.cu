@@ -1,11 +1,932 @@
-// knn_tc.cu -- tcgen05 candidate generation + FP64 re-rank (placeholder until
-// the tensor path lands; the dispatcher falls back to the FP64 exact scan).
+// knn_tc.cu -- exact kNN with tensor-core candidate generation (sm_100a).
+//
+// Replaces RANN::nn2 (call site /root/reference/R/clustering.R:1664-1667) for
+// d <= 61 and k <= 40.  Three stages, all on the device:
+//
+//  P  prep      every point is centred (mean of a strided sample), scaled by a
+//               power of two s so that |y|^2 <= 2^15, and rounded to FP16:
+//               yh = fp16(s (x - mu)).  Queries become rows [yh, 1, 1, 1, 0..]
+//               of the A operand, reference points rows
+//               [-2 yh, h1, h2, h3, 0..] of the B operand where h1+h2+h3 is
+//               the FP16 triple split of |yh|^2.  One 64-wide K block.
+//  K1 candidates  persistent warp-specialised kernel.  TMA streams 128-row B
+//               tiles (SWIZZLE_128B) through a 4-stage mbarrier ring;
+//               one thread issues tcgen05.mma (M=128, N=128, K=16 x KSTEPS,
+//               FP16 in, FP32 accumulate in TMEM) for the CTA's two resident
+//               query tiles; the accumulator IS the selection key
+//               key(q,r) = |yh_r|^2 - 2 yh_q.yh_r  (= |yh_q - yh_r|^2 - |yh_q|^2).
+//               Eight epilogue warps (one thread per query row) read it back
+//               with tcgen05.ld, reject 32-column chunks with a FMNMX3 min
+//               tree against the running k'-th best, and insert the rare
+//               survivors into a per-thread list in shared memory.  The
+//               nq x nr key matrix never leaves the SM.
+//  K2 re-rank   one warp per query: FP64 distances of the k' candidates in the
+//               reference arithmetic (sequential sum, no FMA), sorted by
+//               (d2, index); then the exactness certificate
+//                   s * d_k  <  sqrt(tau + |yh_q|^2 - eta) - e_q - E_max
+//               (tau: smallest rejected key bound, e: FP16 rounding residual
+//               norms, eta: bound on the FP32 accumulation error).  By the
+//               triangle inequality every non-candidate is then strictly
+//               farther than the k-th candidate, so the result equals the
+//               exhaustive FP64 search.  Rows that fail go to knn_exact.cu.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
 #include "internal.cuh"
 
-bool knn_tc_applicable(int64_t, int64_t, int, int) { return false; }
+namespace {
 
-int knn_tc_launch(b200nn_ctx *, const double *, int64_t, const double *, int64_t, int, int, int,
-                  int32_t *, double *, b200nn_stats *) {
-  b200nn_set_error("tensor-core kNN path not built");
-  return B200NN_ERR_INVALID;
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+constexpr int BM = 128;             // queries per query tile (= TMEM lanes)
+constexpr int QT = 2;               // query tiles resident per CTA
+constexpr int BN = 128;             // reference rows per B tile
+constexpr int BK = 64;              // K: one 128-byte swizzle row of FP16
+constexpr int STAGES = 4;           // B ring
+constexpr int EPI_WARPS = 8;        // 4 per query tile
+constexpr int CTRL_WARPS = 4;       // TMA, MMA, TMEM alloc, spare
+constexpr int NUM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr uint32_t TILE_BYTES = BM * BK * 2;  // 16 KB (A tile == B tile)
+constexpr int MAX_D = BK - 3;       // 61
+constexpr int MAX_KP = 56;          // shared-memory budget of the candidate lists
+constexpr double ETA_COEF = 64.0 * 5.9604644775390625e-08;  // 64 * 2^-24
+constexpr double NORM_TARGET = 32000.0;
+
+struct TcMisc {            // small device-resident state of one kNN call
+  double mu[BK];
+  double scale;            // s (a power of two)
+  double max_norm2;        // max |x - mu|^2 over reference and query points
+  double e_max;            // max FP16 rounding residual norm over the reference set (scaled units)
+  double rn2_max;          // max |yh_r|^2
+  double qn2_max;
+  int32_t n_fail;
+  int32_t hang;            // set when an mbarrier wait timed out
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must end in a trap (CUDA error), never in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, TcMisc *misc) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 6000000000LL) {  // ~3 s at 2 GHz: far beyond any legitimate wait
+      misc->hang = 1;
+      __threadfence();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for outstanding tcgen05.ld; the registers are in/out operands so that no use of the
+// loaded values can be scheduled above the wait
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]),
+                 "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]),
+                 "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) SBO >> 4 (8 rows * 128 B = 1024) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------
+// per-thread candidate list in shared memory (one list per query row)
+//   keys  : float [kp + 4][EPI_THREADS]   rows kp.. hold count, tau, maxpos
+//   ids   : int   [kp][EPI_THREADS]
+// ---------------------------------------------------------------------------
+constexpr uint32_t LROW = EPI_THREADS * 4;  // bytes between consecutive list slots of one thread
+
+// Unsorted list + tracked maximum.  Called for keys strictly below tau.
+__device__ __noinline__ void list_insert(uint32_t keys, uint32_t ids, int kp, float key, int id) {
+  const uint32_t st = keys + (uint32_t)kp * LROW;
+  int count = lds_s32(st);
+  int slot;
+  if (count < kp) {
+    slot = count;
+    count++;
+    sts_s32(st, count);
+    sts_f32(keys + (uint32_t)slot * LROW, key);
+    sts_s32(ids + (uint32_t)slot * LROW, id);
+    if (count < kp) return;
+  } else {
+    slot = lds_s32(st + 2 * LROW);
+    sts_f32(keys + (uint32_t)slot * LROW, key);
+    sts_s32(ids + (uint32_t)slot * LROW, id);
+  }
+  // list is full: recompute the maximum (the new threshold)
+  float m = -CUDART_INF_F;
+  int mp = 0;
+  for (int e = 0; e < kp; ++e) {
+    float v = lds_f32(keys + (uint32_t)e * LROW);
+    if (v > m) {
+      m = v;
+      mp = e;
+    }
+  }
+  sts_f32(st + LROW, m);
+  sts_s32(st + 2 * LROW, mp);
+}
+
+struct TcParams {
+  int64_t nq, nr;
+  int32_t n_items;     // ceil(nq / (QT * BM))
+  int32_t n_btiles;    // ceil(nr / BN)
+  int32_t ksteps;      // ceil((d + 3) / 16)
+  int32_t kp;          // candidates kept per query
+  int32_t *cand;       // [nq x kp]
+  float *tau;          // [nq]
+  float *dbg_keys;     // optional [QT*BM x BN]: keys of item 0 / B tile 0
+  TcMisc *misc;
+};
+
+// scan 8 statically-indexed values; insert the ones below tau
+#define TC_SCAN8(V, G)                                                             \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                  \
+    float kv = __uint_as_float(V[(G)*8 + j]);                                      \
+    if (kv < tau) {                                                                \
+      int id = col0 + (G)*8 + j;                                                   \
+      if (id < nr_i) {                                                             \
+        list_insert(keys, ids, kp, kv, id);                                        \
+        tau = lds_f32(keys + (uint32_t)(kp + 1) * LROW);                           \
+      }                                                                            \
+    }                                                                              \
+  }
+
+__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], float &tau, uint32_t keys,
+                                              uint32_t ids, int kp, int col0, int nr_i) {
+  float g0 = min3f(min3f(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2])),
+                   min3f(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5])),
+                   fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+  float g1 = min3f(min3f(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10])),
+                   min3f(__uint_as_float(v[11]), __uint_as_float(v[12]), __uint_as_float(v[13])),
+                   fminf(__uint_as_float(v[14]), __uint_as_float(v[15])));
+  float g2 = min3f(min3f(__uint_as_float(v[16]), __uint_as_float(v[17]), __uint_as_float(v[18])),
+                   min3f(__uint_as_float(v[19]), __uint_as_float(v[20]), __uint_as_float(v[21])),
+                   fminf(__uint_as_float(v[22]), __uint_as_float(v[23])));
+  float g3 = min3f(min3f(__uint_as_float(v[24]), __uint_as_float(v[25]), __uint_as_float(v[26])),
+                   min3f(__uint_as_float(v[27]), __uint_as_float(v[28]), __uint_as_float(v[29])),
+                   fminf(__uint_as_float(v[30]), __uint_as_float(v[31])));
+  float m = min3f(g0, g1, fminf(g2, g3));
+  if (m < tau) {
+    if (g0 < tau) { TC_SCAN8(v, 0) }
+    if (g1 < tau) { TC_SCAN8(v, 1) }
+    if (g2 < tau) { TC_SCAN8(v, 2) }
+    if (g3 < tau) { TC_SCAN8(v, 3) }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: candidate generation
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
+         TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;                                 // QT tiles
+  const uint32_t sB = sA + QT * TILE_BYTES;                 // STAGES tiles
+  const uint32_t sKeys = sB + STAGES * TILE_BYTES;          // (kp + 4) rows
+  const uint32_t sIds = sKeys + (uint32_t)(P.kp + 4) * LROW;
+  const uint32_t sBar = sIds + (uint32_t)P.kp * LROW;       // 8-byte aligned
+  const uint32_t bar_a_full = sBar + 0, bar_a_empty = sBar + 8;
+  const uint32_t bar_b_full = sBar + 16;                    // [STAGES]
+  const uint32_t bar_b_empty = bar_b_full + 8 * STAGES;     // [STAGES]
+  const uint32_t bar_t_full = bar_b_empty + 8 * STAGES;     // [2 acc][QT]
+  const uint32_t bar_t_empty = bar_t_full + 8 * 2 * QT;     // [2 acc][QT]
+  const uint32_t s_tmem = bar_t_empty + 8 * 2 * QT;         // uint32
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_empty, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_b_full + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2 * QT; ++i) {
+      mbar_init(bar_t_full + 8 * i, 1);
+      mbar_init(bar_t_empty + 8 * i, EPI_WARPS / QT);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_tmem),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0, bi = 0;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
+        mbar_wait(bar_a_empty, (it & 1) ^ 1, P.misc);
+        mbar_expect_tx(bar_a_full, QT * TILE_BYTES);
+        for (int t = 0; t < QT; ++t)
+          tma_load_2d(sA + t * TILE_BYTES, &map_q, 0, (item * QT + t) * BM, bar_a_full);
+        for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+          const uint32_t s = bi % STAGES, ph = (bi / STAGES) & 1;
+          mbar_wait(bar_b_empty + 8 * s, ph ^ 1, P.misc);
+          mbar_expect_tx(bar_b_full + 8 * s, TILE_BYTES);
+          tma_load_2d(sB + s * TILE_BYTES, &map_r, 0, j * BN, bar_b_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, bi = 0;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
+        mbar_wait(bar_a_full, it & 1, P.misc);
+        tc_fence_after();
+        for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+          const uint32_t s = bi % STAGES, ph = (bi / STAGES) & 1;
+          const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
+          mbar_wait(bar_b_full + 8 * s, ph, P.misc);
+          tc_fence_after();
+          const uint64_t db = make_desc_sw128(sB + s * TILE_BYTES);
+          for (int t = 0; t < QT; ++t) {
+            mbar_wait(bar_t_empty + 8 * (acc * QT + t), aph ^ 1, P.misc);
+            tc_fence_after();
+            const uint64_t da = make_desc_sw128(sA + t * TILE_BYTES);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + t) * BN);
+            for (int kk = 0; kk < P.ksteps; ++kk)
+              tc_mma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, kk > 0);
+            tc_commit(bar_t_full + 8 * (acc * QT + t));
+          }
+          tc_commit(bar_b_empty + 8 * s);  // the B stage may be refilled once these MMAs retire
+        }
+        tc_commit(bar_a_empty);
+      }
+    }
+  } else if (warp >= CTRL_WARPS) {
+    // ===================== epilogue: running top-k' per query row =====================
+    const int ew = warp - CTRL_WARPS;        // 0..7
+    const int t = ew / 4;                    // query tile of this warp
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;     // row inside the query tile
+    const int et = ew * 32 + lane;           // list column of this thread
+    const uint32_t keys = sKeys + (uint32_t)et * 4;
+    const uint32_t ids = sIds + (uint32_t)et * 4;
+    const int kp = P.kp;
+    const int nr_i = (int)P.nr;
+    uint32_t bi = 0;
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      sts_s32(keys + (uint32_t)kp * LROW, 0);
+      sts_f32(keys + (uint32_t)(kp + 1) * LROW, CUDART_INF_F);
+      sts_s32(keys + (uint32_t)(kp + 2) * LROW, 0);
+      float tau = CUDART_INF_F;
+      const int64_t gq = ((int64_t)item * QT + t) * BM + row;
+      for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+        const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
+        mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + t) * BN);
+        const int colbase = j * BN;
+        uint32_t va[32], vb[32];
+        tc_ld32(taddr + 0, va);
+        tc_wait_ld(va);
+        tc_ld32(taddr + 32, vb);
+        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + c] = __uint_as_float(va[c]);
+        }
+        process_chunk(va, tau, keys, ids, kp, colbase + 0, nr_i);
+        tc_wait_ld(vb);
+        tc_ld32(taddr + 64, va);
+        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + 32 + c] = __uint_as_float(vb[c]);
+        }
+        process_chunk(vb, tau, keys, ids, kp, colbase + 32, nr_i);
+        tc_wait_ld(va);
+        tc_ld32(taddr + 96, vb);
+        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + 64 + c] = __uint_as_float(va[c]);
+        }
+        process_chunk(va, tau, keys, ids, kp, colbase + 64, nr_i);
+        tc_wait_ld(vb);
+        // all four loads have landed in registers: hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
+        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + 96 + c] = __uint_as_float(vb[c]);
+        }
+        process_chunk(vb, tau, keys, ids, kp, colbase + 96, nr_i);
+      }
+      // flush this query's candidates
+      if (gq < P.nq) {
+        const int count = lds_s32(keys + (uint32_t)kp * LROW);
+        int32_t *dst = P.cand + gq * kp;
+        for (int e = 0; e < kp; ++e) dst[e] = e < count ? lds_s32(ids + (uint32_t)e * LROW) : -1;
+        P.tau[gq] = count == kp ? tau : CUDART_INF_F;
+      }
+    }
+  }
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// P: operand preparation
+// ---------------------------------------------------------------------------
+constexpr int MEAN_BLOCKS = 128;
+constexpr int MEAN_ROWS = 256;  // sampled rows per block
+
+__global__ void __launch_bounds__(64)
+k_mean_partial(const double *__restrict__ X, int64_t n, int d, double *__restrict__ partial) {
+  const int j = threadIdx.x;
+  const int64_t m = (int64_t)MEAN_BLOCKS * MEAN_ROWS;
+  const int64_t stride = n > m ? n / m : 1;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (j < d) {
+    for (int r = 0; r < MEAN_ROWS; r += 4) {
+      int64_t i0 = ((int64_t)blockIdx.x * MEAN_ROWS + r) * stride;
+      if (i0 < n) a0 += X[i0 * d + j];
+      if (i0 + stride < n) a1 += X[(i0 + stride) * d + j];
+      if (i0 + 2 * stride < n) a2 += X[(i0 + 2 * stride) * d + j];
+      if (i0 + 3 * stride < n) a3 += X[(i0 + 3 * stride) * d + j];
+    }
+    partial[blockIdx.x * BK + j] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+__global__ void __launch_bounds__(64)
+k_mean_final(const double *__restrict__ partial, int64_t n, int d, TcMisc *__restrict__ misc) {
+  const int j = threadIdx.x;
+  const int64_t m = (int64_t)MEAN_BLOCKS * MEAN_ROWS;
+  const int64_t stride = n > m ? n / m : 1;
+  int64_t cnt = 0;  // number of sampled rows that exist
+  for (int64_t r = 0; r < m; ++r) {
+    if (r * stride < n) cnt++; else break;
+  }
+  if (j < BK) {
+    double s = 0;
+    if (j < d)
+      for (int b = 0; b < MEAN_BLOCKS; ++b) s += partial[b * BK + j];
+    misc->mu[j] = (j < d && cnt > 0) ? s / (double)cnt : 0.0;
+  }
+  if (j == 0) {
+    misc->max_norm2 = 0.0;
+    misc->e_max = 0.0;
+    misc->rn2_max = 0.0;
+    misc->qn2_max = 0.0;
+    misc->n_fail = 0;
+    misc->hang = 0;
+  }
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+  // non-negative doubles order like their bit patterns
+  atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void __launch_bounds__(256)
+k_max_norm(const double *__restrict__ X, int64_t n, int d, TcMisc *__restrict__ misc) {
+  __shared__ double mu[BK];
+  if (threadIdx.x < BK) mu[threadIdx.x] = misc->mu[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double n2 = 0.0;
+  if (i < n) {
+    const double *x = X + i * d;
+    for (int j = 0; j < d; ++j) {
+      double y = x[j] - mu[j];
+      n2 += y * y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2 = fmax(n2, __shfl_xor_sync(0xffffffffu, n2, o));
+  if ((threadIdx.x & 31) == 0 && n2 > 0.0) atomic_max_nonneg(&misc->max_norm2, n2);
+}
+
+__global__ void k_pick_scale(TcMisc *misc) {
+  double m = misc->max_norm2;
+  double s = 1.0;
+  if (m > 0.0 && isfinite(m)) {
+    // largest power of two with s^2 * m <= NORM_TARGET
+    int e = (int)floor(0.5 * log2(NORM_TARGET / m));
+    if (e > 100) e = 100;
+    if (e < -100) e = -100;
+    s = ldexp(1.0, e);
+    while (s * s * m > NORM_TARGET) s *= 0.5;
+  }
+  misc->scale = s;
+}
+
+// one thread per point: FP16 operands rows + rounding residuals.
+// a_out: query operand [n x 64] (may be null), b_out: reference operand (may be null)
+__global__ void __launch_bounds__(128)
+k_convert(const double *__restrict__ X, int64_t n, int d, __half *__restrict__ a_out,
+          __half *__restrict__ b_out, double *__restrict__ q_n2, double *__restrict__ q_err,
+          TcMisc *__restrict__ misc) {
+  __shared__ double mu[BK];
+  if (threadIdx.x < BK) mu[threadIdx.x] = misc->mu[threadIdx.x];
+  __syncthreads();
+  const double s = misc->scale;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double n2 = 0.0, e2 = 0.0;
+  if (i < n) {
+    const double *x = X + i * d;
+    __half *a = a_out ? a_out + i * BK : nullptr;
+    __half *b = b_out ? b_out + i * BK : nullptr;
+    for (int j0 = 0; j0 < BK; j0 += 8) {
+      __align__(16) __half ha[8];
+      __align__(16) __half hb[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        __half h = __float2half_rn(0.f);
+        if (j < d) {
+          double y = s * (x[j] - mu[j]);
+          h = __double2half(y);
+          double hv = (double)__half2float(h);
+          double del = hv - y;
+          e2 += del * del;
+          n2 += hv * hv;
+        }
+        ha[jj] = h;
+        hb[jj] = __hmul(h, __float2half_rn(-2.0f));  // exact
+      }
+      if (j0 + 8 <= d) {
+        if (a) *reinterpret_cast<uint4 *>(a + j0) = *reinterpret_cast<uint4 *>(ha);
+        if (b) *reinterpret_cast<uint4 *>(b + j0) = *reinterpret_cast<uint4 *>(hb);
+      } else {
+        // the chunk holding columns d, d+1, d+2 (and possibly the one after it)
+        double rem = n2;  // complete only once j0 + 8 > d, which holds here
+        __half h1 = __double2half(rem);
+        double r1 = rem - (double)__half2float(h1);
+        __half h2 = __double2half(r1);
+        double r2 = r1 - (double)__half2float(h2);
+        __half h3 = __double2half(r2);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int j = j0 + jj;
+          if (j == d) { ha[jj] = __float2half_rn(1.f); hb[jj] = h1; }
+          else if (j == d + 1) { ha[jj] = __float2half_rn(1.f); hb[jj] = h2; }
+          else if (j == d + 2) { ha[jj] = __float2half_rn(1.f); hb[jj] = h3; }
+          else if (j > d + 2) { ha[jj] = __float2half_rn(0.f); hb[jj] = __float2half_rn(0.f); }
+        }
+        if (a) *reinterpret_cast<uint4 *>(a + j0) = *reinterpret_cast<uint4 *>(ha);
+        if (b) *reinterpret_cast<uint4 *>(b + j0) = *reinterpret_cast<uint4 *>(hb);
+      }
+    }
+    if (q_n2) q_n2[i] = n2;
+    if (q_err) q_err[i] = sqrt(e2);
+  }
+  // maxima over the block's points
+  double em = (i < n) ? sqrt(e2) : 0.0, nm = (i < n) ? n2 : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    em = fmax(em, __shfl_xor_sync(0xffffffffu, em, o));
+    nm = fmax(nm, __shfl_xor_sync(0xffffffffu, nm, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (b_out) {
+      if (em > 0.0) atomic_max_nonneg(&misc->e_max, em);
+      if (nm > 0.0) atomic_max_nonneg(&misc->rn2_max, nm);
+    }
+    if (a_out && nm > 0.0) atomic_max_nonneg(&misc->qn2_max, nm);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: FP64 re-rank + certificate.  One warp per query.
+// ---------------------------------------------------------------------------
+constexpr int RR_WARPS = 4;
+
+__global__ void __launch_bounds__(RR_WARPS * 32)
+k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t nq, int d, int k,
+         int kp, const int32_t *__restrict__ cand, const float *__restrict__ tau,
+         const double *__restrict__ q_n2, const double *__restrict__ q_err,
+         TcMisc *__restrict__ misc, int32_t *__restrict__ idx0, double *__restrict__ dist,
+         int32_t *__restrict__ fail_list) {
+  extern __shared__ __align__(16) unsigned char rr_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ds = d + 1;  // padded row stride
+  // per warp: rows[32][ds] doubles, q[d] doubles, key[64] u64, id[64] i32
+  const size_t per_warp = sizeof(double) * ((size_t)32 * ds + d) + 64 * 8 + 64 * 4;
+  unsigned char *wbase = rr_smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+  double *rows = reinterpret_cast<double *>(wbase);
+  double *qv = rows + 32 * ds;
+  unsigned long long *skey = reinterpret_cast<unsigned long long *>(qv + d);
+  int32_t *sid = reinterpret_cast<int32_t *>(skey + 64);
+
+  const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
+  if (q >= nq) return;
+  for (int j = lane; j < d; j += 32) qv[j] = qry[q * d + j];
+  for (int half = 0; half * 32 < kp; ++half) {
+    const int c = half * 32 + lane;
+    int id = c < kp ? cand[q * kp + c] : -1;
+    // cooperative, coalesced gather of the 32 candidate rows
+    for (int cc = 0; cc < 32; ++cc) {
+      int idc = __shfl_sync(0xffffffffu, id, cc);
+      if (idc >= 0)
+        for (int j = lane; j < d; j += 32) rows[cc * ds + j] = ref[(int64_t)idc * d + j];
+    }
+    __syncwarp();
+    double d2 = CUDART_INF;
+    if (id >= 0) {
+      d2 = 0.0;
+      const double *rr = rows + lane * ds;
+      for (int j = 0; j < d; ++j) {
+        double tt = __dsub_rn(qv[j], rr[j]);
+        d2 = __dadd_rn(d2, __dmul_rn(tt, tt));
+      }
+    }
+    skey[c] = (unsigned long long)__double_as_longlong(d2);  // d2 >= 0: bit order == value order
+    sid[c] = id >= 0 ? id : 0x7fffffff;
+    __syncwarp();
+  }
+  // pad to 64 and sort ascending by (d2, index)
+  for (int c = ((kp + 31) / 32) * 32 + lane; c < 64; c += 32) {
+    skey[c] = (unsigned long long)__double_as_longlong(CUDART_INF);
+    sid[c] = 0x7fffffff;
+  }
+  __syncwarp();
+  for (int kk = 2; kk <= 64; kk <<= 1) {
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      const int i = lane;  // 32 comparators per step
+      const int lo = ((i / jj) * 2 * jj) + (i % jj);
+      const int hi = lo + jj;
+      const bool up = ((lo & kk) == 0) || kk == 64;
+      unsigned long long ka = skey[lo], kb = skey[hi];
+      int ia = sid[lo], ib = sid[hi];
+      bool gt = ka > kb || (ka == kb && ia > ib);
+      if (gt == up) {
+        skey[lo] = kb; skey[hi] = ka;
+        sid[lo] = ib; sid[hi] = ia;
+      }
+      __syncwarp();
+    }
+  }
+  // certificate
+  const double s = misc->scale;
+  const double qn = q_n2[q], eq = q_err[q];
+  const double M = misc->rn2_max + 2.0 * sqrt(qn) * sqrt(misc->rn2_max) + 1.0;
+  const double eta = ETA_COEF * M + 1e-4;
+  const double tq = (double)tau[q];
+  const double dk2 = __longlong_as_double((long long)skey[k - 1]);
+  bool ok = false;
+  if (isfinite(tq) && isfinite(dk2)) {
+    double lb2 = tq + qn - eta;
+    double lb = (lb2 > 0.0 ? sqrt(lb2) : 0.0) - eq - misc->e_max;
+    ok = s * sqrt(dk2) * (1.0 + 1e-9) < lb * (1.0 - 1e-9);
+  }
+  for (int t = lane; t < k; t += 32) {
+    idx0[q * k + t] = sid[t];
+    dist[q * k + t] = sqrt(__longlong_as_double((long long)skey[t]));
+  }
+  if (!ok && lane == 0) {
+    int pos = atomicAdd(&misc->n_fail, 1);
+    fail_list[pos] = (int32_t)q;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_operand_map(CUtensorMap *map, const void *ptr, int64_t rows) {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    if (!p || qr != cudaDriverEntryPointSuccess) {
+      b200nn_set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return B200NN_ERR_CUDA;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)BK, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)BK * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    b200nn_set_error("cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return B200NN_ERR_CUDA;
+  }
+  return B200NN_OK;
+}
+
+int pick_kp(int k, int n_cand) {
+  int kp = n_cand > 0 ? n_cand : k + (k / 2 > 8 ? k / 2 : 8);
+  if (kp < k + 1) kp = k + 1;
+  kp = (kp + 7) & ~7;
+  return kp;
+}
+
+size_t tc_smem_bytes(int kp) {
+  return 1024 + (size_t)(QT + STAGES) * TILE_BYTES + (size_t)(2 * kp + 4) * LROW + 8 * (2 + 2 * STAGES + 4 * QT) + 16;
+}
+
+}  // namespace
+
+bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
+  if (d > MAX_D || d < 1) return false;
+  if (pick_kp(k, 0) > MAX_KP) return false;
+  if (nr < 2048 || nq < 1) return false;          // tiny problems: the exact scan is faster
+  if (nr >= 0x7fffffffLL - BN || nq >= 0x7fffffffLL - QT * BM) return false;
+  return true;
+}
+
+// candidate stage alone (also used by the debug / profiling entry point)
+int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                      int64_t nq, int d, int kp, int32_t **cand_out, float **tau_out,
+                      double **qn2_out, double **qerr_out, void **misc_out, float *d_dbg_keys,
+                      b200nn_stats *stats) {
+  cudaStream_t st = ctx->stream;
+  const bool self = (d_qry == d_ref);
+  TcMisc *misc;
+  double *partial, *q_n2, *q_err;
+  __half *r16, *q16;
+  int32_t *cand;
+  float *tau;
+  RC_TRY(ws_get(ctx, WS_TC_MISC, 1, &misc));
+  RC_TRY(ws_get(ctx, WS_SCAN_TMP, (size_t)MEAN_BLOCKS * BK, &partial));
+  RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr * BK, &r16));
+  RC_TRY(ws_get(ctx, WS_TC_QRY16, (size_t)nq * BK, &q16));
+  RC_TRY(ws_get(ctx, WS_TC_QRYERR, (size_t)nq * 2, &q_n2));
+  q_err = q_n2 + nq;
+  RC_TRY(ws_get(ctx, WS_TC_CAND, (size_t)nq * kp, &cand));
+  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq, &tau));
+
+  cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10];
+  CU_TRY(cudaEventRecord(e0, st));
+  k_mean_partial<<<MEAN_BLOCKS, 64, 0, st>>>(d_ref, nr, d, partial);
+  KERNEL_CHECK(ctx);
+  k_mean_final<<<1, 64, 0, st>>>(partial, nr, d, misc);
+  KERNEL_CHECK(ctx);
+  k_max_norm<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(d_ref, nr, d, misc);
+  KERNEL_CHECK(ctx);
+  if (!self) {
+    k_max_norm<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(d_qry, nq, d, misc);
+    KERNEL_CHECK(ctx);
+  }
+  k_pick_scale<<<1, 1, 0, st>>>(misc);
+  KERNEL_CHECK(ctx);
+  if (self) {
+    k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, q16, r16, q_n2, q_err, misc);
+    KERNEL_CHECK(ctx);
+  } else {
+    k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, nullptr, r16, nullptr, nullptr,
+                                                              misc);
+    KERNEL_CHECK(ctx);
+    k_convert<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(d_qry, nq, d, q16, nullptr, q_n2, q_err,
+                                                              misc);
+    KERNEL_CHECK(ctx);
+  }
+  CU_TRY(cudaEventRecord(e1, st));
+
+  CUtensorMap map_q, map_r;
+  RC_TRY(make_operand_map(&map_q, q16, nq));
+  RC_TRY(make_operand_map(&map_r, r16, nr));
+  TcParams P;
+  P.nq = nq;
+  P.nr = nr;
+  P.n_items = (int32_t)ceil_div64(nq, QT * BM);
+  P.n_btiles = (int32_t)ceil_div64(nr, BN);
+  P.ksteps = (d + 3 + 15) / 16;
+  P.kp = kp;
+  P.cand = cand;
+  P.tau = tau;
+  P.dbg_keys = d_dbg_keys;
+  P.misc = misc;
+  size_t smem = tc_smem_bytes(kp);
+  if (smem > 227 * 1024) {
+    b200nn_set_error("candidate list of %d entries does not fit shared memory", kp);
+    return B200NN_ERR_INVALID;
+  }
+  CU_TRY(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
+  k_knn_tc<<<grid, NUM_THREADS, smem, st>>>(map_q, map_r, P);
+  KERNEL_CHECK(ctx);
+  CU_TRY(cudaEventRecord(e2, st));
+  CU_TRY(cudaEventSynchronize(e2));
+  if (stats) {
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    stats->ms_prep += ms;
+    CU_TRY(cudaEventElapsedTime(&ms, e1, e2));
+    stats->ms_knn_cand += ms;
+  }
+  *cand_out = cand;
+  *tau_out = tau;
+  *qn2_out = q_n2;
+  *qerr_out = q_err;
+  *misc_out = misc;
+  return B200NN_OK;
+}
+
+int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
+                  int d, int k, int n_cand, int32_t *d_idx0, double *d_dist, b200nn_stats *stats) {
+  cudaStream_t st = ctx->stream;
+  int kp = pick_kp(k, n_cand);
+  if (kp > MAX_KP) kp = MAX_KP;
+  if (kp <= k) {
+    b200nn_set_error("k = %d leaves no room for a widened candidate set (max %d)", k, MAX_KP);
+    return B200NN_ERR_INVALID;
+  }
+  int32_t *cand;
+  float *tau;
+  double *q_n2, *q_err;
+  void *misc_v;
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, &cand, &tau, &q_n2, &q_err, &misc_v,
+                           nullptr, stats));
+  TcMisc *misc = static_cast<TcMisc *>(misc_v);
+  int32_t *flags;
+  RC_TRY(ws_get(ctx, WS_TC_FLAGS, (size_t)nq + 4, &flags));
+  int32_t *fail_list = flags + 1;  // flags[0] receives the count (knn_exact reads list[-1])
+
+  cudaEvent_t e0 = ctx->ev[11], e1 = ctx->ev[12], e2 = ctx->ev[13];
+  CU_TRY(cudaEventRecord(e0, st));
+  const int ds = d + 1;
+  size_t per_warp = sizeof(double) * ((size_t)32 * ds + d) + 64 * 8 + 64 * 4;
+  per_warp = (per_warp + 15) & ~(size_t)15;
+  size_t smem = per_warp * RR_WARPS;
+  CU_TRY(cudaFuncSetAttribute(k_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_rerank<<<(unsigned)ceil_div64(nq, RR_WARPS), RR_WARPS * 32, smem, st>>>(
+      d_ref, d_qry, nq, d, k, kp, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list);
+  KERNEL_CHECK(ctx);
+  CU_TRY(cudaEventRecord(e1, st));
+  TcMisc h;
+  CU_TRY(cudaMemcpyAsync(&h, misc, sizeof(TcMisc), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (h.hang) {
+    b200nn_set_error("tensor-core kNN kernel: mbarrier wait timed out (pipeline protocol error)");
+    return B200NN_ERR_CUDA;
+  }
+  if (h.n_fail > 0) {
+    CU_TRY(cudaMemcpyAsync(flags, &misc->n_fail, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    RC_TRY(knn_exact_launch(ctx, d_ref, nr, d_qry, nq, d, k, fail_list, h.n_fail, d_idx0, d_dist));
+  }
+  CU_TRY(cudaEventRecord(e2, st));
+  CU_TRY(cudaEventSynchronize(e2));
+  if (stats) {
+    float ms = 0;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    stats->ms_knn_rerank += ms;
+    CU_TRY(cudaEventElapsedTime(&ms, e1, e2));
+    stats->ms_knn_fallback += ms;
+    stats->n_uncertified = h.n_fail;
+  }
+  return B200NN_OK;
+}
+
+// diagnostic entry point: raw keys of (item 0, B tile 0) + candidates + prep state
+int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
+                 int d, int kp, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
+                 double *h_scale_mu /* [1 + 64] */) {
+  int32_t *cand;
+  float *tau;
+  double *q_n2, *q_err;
+  void *misc_v;
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, &cand, &tau, &q_n2,
+                           &q_err, &misc_v, d_keys_out, nullptr));
+  cudaStream_t st = ctx->stream;
+  if (d_cand_out)
+    CU_TRY(cudaMemcpyAsync(d_cand_out, cand, sizeof(int32_t) * (size_t)nq * kp,
+                           cudaMemcpyDeviceToDevice, st));
+  if (d_tau_out)
+    CU_TRY(cudaMemcpyAsync(d_tau_out, tau, sizeof(float) * (size_t)nq, cudaMemcpyDeviceToDevice, st));
+  TcMisc h;
+  CU_TRY(cudaMemcpyAsync(&h, misc_v, sizeof(TcMisc), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (h_scale_mu) {
+    h_scale_mu[0] = h.scale;
+    for (int j = 0; j < BK; ++j) h_scale_mu[1 + j] = h.mu[j];
+  }
+  if (h.hang) {
+    b200nn_set_error("tensor-core kNN kernel: mbarrier wait timed out");
+    return B200NN_ERR_CUDA;
+  }
+  return B200NN_OK;
 }

@@ -1,0 +1,116 @@
+"""GPU suite: the tensor-core kNN path (tcgen05 candidates + FP64 re-rank + certificate)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import seurat_b200 as sb
+from seurat_b200 import _lib
+from seurat_b200.synthetic import gaussian_mixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sb.Context(0)
+    yield c
+    c.close()
+
+
+def fp16_operands(X, scale, mu):
+    y = scale * (X - mu[None, :X.shape[1]])
+    yh = y.astype(np.float16).astype(np.float64)     # round-to-nearest-even, like __double2half
+    return y, yh
+
+
+@pytest.mark.parametrize("n,d", [(4096, 50), (3000, 30), (2500, 61), (5000, 7)])
+def test_raw_keys_match_fp16_model(ctx, n, d):
+    """accumulator == |yh_r|^2 - 2 yh_q.yh_r for the first 256 queries x 128 references:
+    validates TMA swizzle, UMMA descriptors, TMEM addressing and the norm-column trick"""
+    X, _ = gaussian_mixture(n, d, seed=d, n_centres=8)
+    ref = torch.from_numpy(X).cuda()
+    keys = torch.full((256, 128), float("nan"), dtype=torch.float32, device="cuda")
+    cand = torch.empty((n, 32), dtype=torch.int32, device="cuda")
+    tau = torch.empty(n, dtype=torch.float32, device="cuda")
+    sm = np.zeros(65)
+    torch.cuda.synchronize()
+    ctx.dev_knn_candidates(ref, n, ref, n, d, 32, cand, tau, keys, sm)
+    scale, mu = sm[0], sm[1:]
+    assert scale > 0 and np.log2(scale) == np.round(np.log2(scale))
+    y, yh = fp16_operands(X, scale, mu)
+    assert (yh ** 2).sum(1).max() <= 33000
+    want = (yh[:128] ** 2).sum(1)[None, :] - 2.0 * yh[:256] @ yh[:128].T
+    got = keys.cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    M = (yh ** 2).sum(1).max() * 3
+    err = np.abs(got - want).max()
+    print(f"n={n} d={d} scale={scale} max key err={err:.3e} (M 2^-24 = {M * 2**-24:.3e})")
+    assert err <= 16 * M * 2.0 ** -24, "FP32 accumulation error far above the certificate's model"
+    # candidates: every true neighbour of the FP16-rounded problem below tau is in the list
+    full = (yh ** 2).sum(1)[None, :] - 2.0 * yh[:64] @ yh.T
+    c = cand.cpu().numpy()[:64]
+    t = tau.cpu().numpy()[:64].astype(np.float64)
+    eta = 64 * M * 2.0 ** -24
+    for q in range(64):
+        must = np.nonzero(full[q] < t[q] - eta)[0]
+        assert set(must) <= set(c[q]), f"query {q}: a key below tau is missing from the candidates"
+        assert len(set(c[q])) == 32 and c[q].min() >= 0 and c[q].max() < n
+
+
+@pytest.mark.parametrize("n,d,k", [(20000, 50, 20), (9000, 30, 30), (4097, 50, 5), (2048, 10, 37), (33000, 2, 10)])
+def test_tensor_path_equals_oracle(ctx, n, d, k):
+    X, _ = gaussian_mixture(n, d, seed=n % 97, n_centres=16)
+    wi, wd = oracle.knn(X, k=k, method="kdtree" if d > 4 else "brute")
+    idx, dist, st = ctx.knn(X, None, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert st["ms_knn_cand"] > 0
+    assert (dist == wd).all()
+    assert (idx == wi).all()
+    print(f"n={n} d={d} k={k}: uncertified rows {st['n_uncertified']} / {n}")
+    assert st["n_uncertified"] < 0.05 * n, "the certificate should pass for almost every row"
+
+
+def test_tensor_path_query_ne_reference(ctx):
+    ref, c = gaussian_mixture(30000, 50, seed=3, n_centres=8)
+    qry, _ = gaussian_mixture(7001, 50, seed=4, centres=c)
+    qry[:10] += 40.0            # far outside the reference cloud
+    wi, wd = oracle.knn(ref, qry, 20, method="kdtree")
+    idx, dist, st = ctx.knn(ref, qry, 20, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert (idx == wi).all() and (dist == wd).all()
+
+
+def test_tensor_path_ties_and_duplicates(ctx):
+    """exact duplicates and lattice ties defeat the certificate; the FP64 fallback must resolve them"""
+    rng = np.random.default_rng(1)
+    base = rng.integers(0, 4, size=(3000, 6)).astype(np.float64)
+    X = np.vstack([base, base[:500]])
+    wi, wd = oracle.knn(X, k=10)
+    idx, dist, st = ctx.knn(X, None, 10, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert (dist == wd).all() and (idx == wi).all()
+    assert st["n_uncertified"] > 0
+    Z = np.ones((2500, 20)) * 3.25
+    idx, dist, st = ctx.knn(Z, None, 5, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert (idx == np.tile(np.arange(1, 6), (2500, 1))).all() and (dist == 0).all()
+
+
+def test_tensor_path_badly_scaled_data(ctx):
+    """huge offsets, tiny spreads and mixed magnitudes: results stay exact (certificate or fallback)"""
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(6000, 20))
+    X[:, 0] *= 1e4
+    X[:, 1] *= 1e-4
+    X += 1e6
+    wi, wd = oracle.knn(X, k=15, method="kdtree")
+    idx, dist, st = ctx.knn(X, None, 15, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert (dist == wd).all() and (idx == wi).all()
+    print("badly scaled: uncertified", st["n_uncertified"])
+
+
+def test_tensor_path_rejects_unsupported_shapes(ctx):
+    X = np.random.default_rng(0).normal(size=(3000, 70))
+    with pytest.raises(sb.B200Error):
+        ctx.knn(X, None, 10, _lib.ROW_MAJOR, _lib.KNN_TENSOR)      # d > 61
+    idx, dist, st = ctx.knn(X, None, 10, _lib.ROW_MAJOR, _lib.KNN_AUTO)   # auto falls back to the exact scan
+    assert st["ms_knn_cand"] == 0
+    wi, wd = oracle.knn(X, k=10)
+    assert (idx == wi).all() and (dist == wd).all()
