@@ -257,8 +257,8 @@ int b200nn_dev_knn_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, 
                               int64_t nq, int32_t d, int32_t n_cand, int32_t *d_cand, float *d_tau,
                               float *d_keys, double *h_scale_mu) {
   RC_TRY(check_ctx(ctx));
-  if (!d_ref || nr <= 0 || nq <= 0 || d <= 0 || d > 61 || n_cand < 8 || n_cand > 56 || (n_cand & 7)) {
-    b200nn_set_error("knn_candidates: invalid argument (d <= 61, n_cand a multiple of 8 in [8, 56])");
+  if (!d_ref || nr <= 0 || nq <= 0 || d <= 0 || d > 61 || n_cand < 8 || n_cand > 48 || (n_cand & 7)) {
+    b200nn_set_error("knn_candidates: invalid argument (d <= 61, n_cand a multiple of 8 in [8, 48])");
     return B200NN_ERR_INVALID;
   }
   return knn_tc_debug(ctx, d_ref, nr, d_qry, nq, d, n_cand, d_keys, d_cand, d_tau, h_scale_mu);

@@ -14,6 +14,8 @@
 // buffer and merged into its sorted top-k list by one warp after every tile.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "internal.cuh"
 
 namespace {
@@ -45,7 +47,9 @@ template <int QB>
 __global__ void __launch_bounds__(KX_THREADS)
 k_knn_exact(const double *__restrict__ ref, int64_t nr, const double *__restrict__ qry, int d, int k,
             const int32_t *__restrict__ qsel, const int32_t *__restrict__ n_sel_ptr,
-            int64_t n_items, int32_t *__restrict__ idx0, double *__restrict__ dist) {
+            int64_t n_items, int32_t *__restrict__ idx0, double *__restrict__ dist,
+            int64_t slice_len, int n_slices, int32_t *__restrict__ part_idx,
+            double *__restrict__ part_d2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *q_s = reinterpret_cast<double *>(smem_raw);
   double *r_s = q_s + QB * KX_DC;
@@ -84,8 +88,11 @@ k_knn_exact(const double *__restrict__ ref, int64_t nr, const double *__restrict
     }
   }
 
-  for (int64_t tile = 0; tile < nr; tile += KX_THREADS) {
-    const int rows_here = (int)((nr - tile) < KX_THREADS ? (nr - tile) : KX_THREADS);
+  // blockIdx.y selects a slice of the reference set (split scan of a few fallback rows)
+  const int64_t r_lo = (int64_t)blockIdx.y * slice_len;
+  const int64_t r_hi = (r_lo + slice_len) < nr ? (r_lo + slice_len) : nr;
+  for (int64_t tile = r_lo; tile < r_hi; tile += KX_THREADS) {
+    const int rows_here = (int)((r_hi - tile) < KX_THREADS ? (r_hi - tile) : KX_THREADS);
     double acc[QB];
 #pragma unroll
     for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.0;
@@ -182,6 +189,20 @@ k_knn_exact(const double *__restrict__ ref, int64_t nr, const double *__restrict
   }
   __syncthreads();
 
+  if (part_idx != nullptr) {
+    // split scan: this slice's sorted partial result (squared distances) for the merge kernel
+    for (int qi = 0; qi < QB; ++qi) {
+      if (qid[qi] < 0) continue;
+      const int64_t item = item0 + qi;
+      const int tn = top_n[qi];
+      const int64_t o = (item * n_slices + blockIdx.y) * k;
+      for (int t = tid; t < k; t += KX_THREADS) {
+        part_idx[o + t] = t < tn ? top_i[qi * k + t] : 0x7fffffff;
+        part_d2[o + t] = t < tn ? top_d[qi * k + t] : CUDART_INF;
+      }
+    }
+    return;
+  }
   for (int qi = 0; qi < QB; ++qi) {
     const int64_t q = qid[qi];
     if (q < 0) continue;
@@ -198,10 +219,63 @@ k_knn_exact(const double *__restrict__ ref, int64_t nr, const double *__restrict
   }
 }
 
+// merge the per-slice partial results of one fallback row: sort n_slices * k (d2, idx)
+// pairs ascending (ascending-comparator bitonic network, virtual +inf padding) and keep k
+__global__ void __launch_bounds__(256)
+k_merge_parts(const int32_t *__restrict__ qsel, int k, int n_slices,
+              const int32_t *__restrict__ part_idx, const double *__restrict__ part_d2,
+              int32_t *__restrict__ idx0, double *__restrict__ dist) {
+  extern __shared__ __align__(16) unsigned char ms_raw[];
+  const int m = n_slices * k;
+  unsigned long long *key = reinterpret_cast<unsigned long long *>(ms_raw);
+  int32_t *val = reinterpret_cast<int32_t *>(key + m);
+  const int64_t item = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int t = tid; t < m; t += nthr) {
+    key[t] = (unsigned long long)__double_as_longlong(part_d2[item * m + t]);  // d2 >= 0
+    val[t] = part_idx[item * m + t];
+  }
+  __syncthreads();
+  int P = 1;
+  while (P < m) P <<= 1;
+  const int half = P >> 1;
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int jj = kk >> 1, first = 1; jj > 0; jj >>= 1, first = 0) {
+      for (int t = tid; t < half; t += nthr) {
+        int lo, hi;
+        if (first) {
+          const int hk = kk >> 1, blk = t / hk, off = t - blk * hk;
+          lo = blk * kk + off;
+          hi = blk * kk + kk - 1 - off;
+        } else {
+          const int blk = t / jj, off = t - blk * jj;
+          lo = blk * 2 * jj + off;
+          hi = lo + jj;
+        }
+        if (hi < m) {
+          unsigned long long ka = key[lo], kb = key[hi];
+          int32_t ia = val[lo], ib = val[hi];
+          if (ka > kb || (ka == kb && ia > ib)) {
+            key[lo] = kb; key[hi] = ka;
+            val[lo] = ib; val[hi] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int64_t q = qsel[item];
+  for (int t = tid; t < k; t += nthr) {
+    idx0[q * k + t] = val[t];
+    dist[q * k + t] = sqrt(__longlong_as_double((long long)key[t]));
+  }
+}
+
 template <int QB>
 int launch_qb(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int d, int k,
               const int32_t *d_qsel, const int32_t *d_nsel, int64_t n_items, int32_t *d_idx0,
-              double *d_dist) {
+              double *d_dist, int n_slices = 1, int32_t *part_idx = nullptr,
+              double *part_d2 = nullptr) {
   size_t smem = kx_smem_bytes(QB, k);
   if (smem > 227 * 1024) {
     b200nn_set_error("k = %d is too large for the exact kNN kernel (shared memory %zu B)", k, smem);
@@ -211,8 +285,11 @@ int launch_qb(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_
                               (int)smem));
   int64_t blocks = ceil_div64(n_items, QB);
   if (blocks <= 0) return B200NN_OK;
-  k_knn_exact<QB><<<(unsigned)blocks, KX_THREADS, smem, ctx->stream>>>(
-      d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist);
+  const int64_t slice_len = n_slices > 1 ? ceil_div64(ceil_div64(nr, n_slices), KX_THREADS) * KX_THREADS : nr;
+  dim3 grid((unsigned)blocks, (unsigned)n_slices);
+  k_knn_exact<QB><<<grid, KX_THREADS, smem, ctx->stream>>>(d_ref, nr, d_qry, d, k, d_qsel, d_nsel,
+                                                          n_items, d_idx0, d_dist, slice_len,
+                                                          n_slices, part_idx, part_d2);
   KERNEL_CHECK(ctx);
   return B200NN_OK;
 }
@@ -222,16 +299,41 @@ int launch_qb(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_
 int knn_exact_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                      int64_t nq, int d, int k, const int32_t *d_qsel, int64_t n_sel,
                      int32_t *d_idx0, double *d_dist) {
-  // d_qsel != nullptr: process the rows listed in d_qsel; their count lives on
-  // the device right behind the list's capacity is unknown to the host, so the
-  // caller passes the device counter through d_qsel[-1] convention instead:
-  // the counter is the int32 just before the list.
+  // d_qsel != nullptr: scan only the n_sel query rows listed there; the int32 just before
+  // the list (d_qsel[-1]) holds the same count on the device.
   const int32_t *d_nsel = d_qsel ? d_qsel - 1 : nullptr;
   int64_t n_items = d_qsel ? n_sel : nq;
   if (n_items <= 0) return B200NN_OK;
-  if (kx_smem_bytes(16, k) <= 110 * 1024 && d_qsel == nullptr)
-    return launch_qb<16>(ctx, d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist);
-  if (kx_smem_bytes(4, k) <= 227 * 1024)
-    return launch_qb<4>(ctx, d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist);
-  return launch_qb<1>(ctx, d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist);
+  if (d_qsel == nullptr) {
+    if (kx_smem_bytes(16, k) <= 110 * 1024)
+      return launch_qb<16>(ctx, d_ref, nr, d_qry, d, k, nullptr, nullptr, n_items, d_idx0, d_dist);
+    if (kx_smem_bytes(4, k) <= 227 * 1024)
+      return launch_qb<4>(ctx, d_ref, nr, d_qry, d, k, nullptr, nullptr, n_items, d_idx0, d_dist);
+    return launch_qb<1>(ctx, d_ref, nr, d_qry, d, k, nullptr, nullptr, n_items, d_idx0, d_dist);
+  }
+  // A handful of rows against the whole reference set: split the scan over slices of the
+  // reference set so that the grid fills the machine, then merge the partial top-k lists.
+  const int64_t blocks4 = ceil_div64(n_items, 4);
+  int64_t want = ceil_div64((int64_t)ctx->sm_count * 4, blocks4);
+  int64_t cap = 8192 / k;
+  int64_t by_rows = ceil_div64(nr, 4 * KX_THREADS);
+  int n_slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, cap), std::min<int64_t>(by_rows, 512)));
+  if (n_slices <= 1 || kx_smem_bytes(4, k) > 227 * 1024) {
+    if (kx_smem_bytes(4, k) <= 227 * 1024)
+      return launch_qb<4>(ctx, d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist);
+    return launch_qb<1>(ctx, d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist);
+  }
+  int32_t *part_idx;
+  double *part_d2;
+  const size_t cnt = (size_t)n_items * n_slices * k;
+  RC_TRY(ws_get(ctx, WS_STAGE_B, cnt * 2, &part_d2));  // doubles, then the int32 block
+  part_idx = reinterpret_cast<int32_t *>(part_d2 + cnt);
+  RC_TRY((launch_qb<4>(ctx, d_ref, nr, d_qry, d, k, d_qsel, d_nsel, n_items, d_idx0, d_dist,
+                       n_slices, part_idx, part_d2)));
+  const size_t msmem = (size_t)n_slices * k * 12 + 16;
+  CU_TRY(cudaFuncSetAttribute(k_merge_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+  k_merge_parts<<<(unsigned)n_items, 256, msmem, ctx->stream>>>(d_qsel, k, n_slices, part_idx, part_d2,
+                                                               d_idx0, d_dist);
+  KERNEL_CHECK(ctx);
+  return B200NN_OK;
 }

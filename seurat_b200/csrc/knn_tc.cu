@@ -44,14 +44,13 @@ constexpr int BM = 128;             // queries per query tile (= TMEM lanes)
 constexpr int QT = 2;               // query tiles resident per CTA
 constexpr int BN = 128;             // reference rows per B tile
 constexpr int BK = 64;              // K: one 128-byte swizzle row of FP16
-constexpr int STAGES = 4;           // B ring
 constexpr int EPI_WARPS = 8;        // 4 per query tile
 constexpr int CTRL_WARPS = 4;       // TMA, MMA, TMEM alloc, spare
 constexpr int NUM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;  // 16 KB (A tile == B tile)
 constexpr int MAX_D = BK - 3;       // 61
-constexpr int MAX_KP = 56;          // shared-memory budget of the candidate lists
+constexpr int MAX_KP = 48;          // shared-memory budget of the candidate lists
 constexpr double ETA_COEF = 64.0 * 5.9604644775390625e-08;  // 64 * 2^-24
 constexpr double NORM_TARGET = 32000.0;
 
@@ -195,41 +194,73 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ---------------------------------------------------------------------------
-// per-thread candidate list in shared memory (one list per query row)
-//   keys  : float [kp + 4][EPI_THREADS]   rows kp.. hold count, tau, maxpos
-//   ids   : int   [kp][EPI_THREADS]
+// per-thread candidate state in shared memory (one epilogue thread == one query row)
+//   list : kp (key, id) pairs, unsorted, maximum tracked in registers (tau, maxpos)
+//   pend : PEND pairs appended by the filter, merged warp-synchronously
+// slot e of thread t lives at word e * EPI_THREADS + t  (conflict-free across a warp)
 // ---------------------------------------------------------------------------
-constexpr uint32_t LROW = EPI_THREADS * 4;  // bytes between consecutive list slots of one thread
+constexpr int PEND = 16;            // pending-hit buffer per thread
+constexpr int PEND_TRIGGER = 8;     // merge as soon as any lane holds more than this
+constexpr int LSTRIDE = EPI_THREADS;
 
-// Unsorted list + tracked maximum.  Called for keys strictly below tau.
-__device__ __noinline__ void list_insert(uint32_t keys, uint32_t ids, int kp, float key, int id) {
-  const uint32_t st = keys + (uint32_t)kp * LROW;
-  int count = lds_s32(st);
-  int slot;
-  if (count < kp) {
-    slot = count;
-    count++;
-    sts_s32(st, count);
-    sts_f32(keys + (uint32_t)slot * LROW, key);
-    sts_s32(ids + (uint32_t)slot * LROW, id);
-    if (count < kp) return;
-  } else {
-    slot = lds_s32(st + 2 * LROW);
-    sts_f32(keys + (uint32_t)slot * LROW, key);
-    sts_s32(ids + (uint32_t)slot * LROW, id);
-  }
-  // list is full: recompute the maximum (the new threshold)
+struct Sel {          // register-resident selection state of one query row
+  float tau;          // current k'-th best key (+inf until the list is full)
+  int cnt_list;       // entries in the list
+  int maxpos;         // slot holding tau
+  int cnt_pend;       // entries in the pending buffer
+  int last_id;        // largest reference row appended so far (scan order is monotone)
+};
+
+// recompute the maximum of the (full) list; 8 independent loads in flight
+__device__ __forceinline__ void list_rescan(const float *lk, int kp, float &tau, int &maxpos) {
   float m = -CUDART_INF_F;
   int mp = 0;
-  for (int e = 0; e < kp; ++e) {
-    float v = lds_f32(keys + (uint32_t)e * LROW);
-    if (v > m) {
-      m = v;
-      mp = e;
+  for (int e0 = 0; e0 < kp; e0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = lk[(e0 + u) * LSTRIDE];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (v[u] > m) {
+        m = v[u];
+        mp = e0 + u;
+      }
+  }
+  tau = m;
+  maxpos = mp;
+}
+
+// Warp-synchronous merge of every lane's pending hits into its list.
+// Deliberately not inlined: it is called from 17 sites and runs only ~100 times per
+// query tile; the hot filter loop must stay small enough for the instruction cache.
+__device__ __noinline__ Sel merge_pending(float *lk, int *li, const float *pk, const int *pi, int kp,
+                                          Sel S) {
+  int maxc = S.cnt_pend;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+  for (int e = 0; e < maxc; ++e) {
+    bool rescan = false;
+    if (e < S.cnt_pend) {
+      const float key = pk[e * LSTRIDE];
+      const int id = pi[e * LSTRIDE];
+      if (S.cnt_list < kp) {
+        lk[S.cnt_list * LSTRIDE] = key;
+        li[S.cnt_list * LSTRIDE] = id;
+        S.cnt_list++;
+        rescan = S.cnt_list == kp;
+      } else if (key < S.tau) {
+        lk[S.maxpos * LSTRIDE] = key;
+        li[S.maxpos * LSTRIDE] = id;
+        rescan = true;
+      }
+    }
+    if (__any_sync(0xffffffffu, rescan)) {
+      // idempotent for lanes that did not change their list
+      if (S.cnt_list == kp) list_rescan(lk, kp, S.tau, S.maxpos);
     }
   }
-  sts_f32(st + LROW, m);
-  sts_s32(st + 2 * LROW, mp);
+  S.cnt_pend = 0;
+  return S;
 }
 
 struct TcParams {
@@ -238,47 +269,68 @@ struct TcParams {
   int32_t n_btiles;    // ceil(nr / BN)
   int32_t ksteps;      // ceil((d + 3) / 16)
   int32_t kp;          // candidates kept per query
+  int32_t stages;      // B ring depth (<= MAX_STAGES)
   int32_t *cand;       // [nq x kp]
   float *tau;          // [nq]
   float *dbg_keys;     // optional [QT*BM x BN]: keys of item 0 / B tile 0
   TcMisc *misc;
 };
 
-// scan 8 statically-indexed values; insert the ones below tau
-#define TC_SCAN8(V, G)                                                             \
-  _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                  \
-    float kv = __uint_as_float(V[(G)*8 + j]);                                      \
-    if (kv < tau) {                                                                \
-      int id = col0 + (G)*8 + j;                                                   \
-      if (id < nr_i) {                                                             \
-        list_insert(keys, ids, kp, kv, id);                                        \
-        tau = lds_f32(keys + (uint32_t)(kp + 1) * LROW);                           \
+// append one key if it beats tau.  ids grow monotonically along the scan, so `last_id`
+// lets a chunk be re-scanned after a merge without appending anything twice.
+#define TC_TRY(V, C)                                                               \
+  {                                                                                \
+    const float kv = __uint_as_float(V[C]);                                        \
+    const int id = col0 + (C);                                                     \
+    if (kv < S.tau && id > S.last_id && id < nr_i) {                               \
+      if (S.cnt_pend < PEND) {                                                     \
+        pk[S.cnt_pend * LSTRIDE] = kv;                                             \
+        pi[S.cnt_pend * LSTRIDE] = id;                                             \
+        S.cnt_pend++;                                                              \
+        S.last_id = id;                                                            \
+      } else {                                                                     \
+        ovf = true;                                                                \
       }                                                                            \
     }                                                                              \
   }
 
-__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], float &tau, uint32_t keys,
-                                              uint32_t ids, int kp, int col0, int nr_i) {
-  float g0 = min3f(min3f(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2])),
-                   min3f(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5])),
-                   fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-  float g1 = min3f(min3f(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10])),
-                   min3f(__uint_as_float(v[11]), __uint_as_float(v[12]), __uint_as_float(v[13])),
-                   fminf(__uint_as_float(v[14]), __uint_as_float(v[15])));
-  float g2 = min3f(min3f(__uint_as_float(v[16]), __uint_as_float(v[17]), __uint_as_float(v[18])),
-                   min3f(__uint_as_float(v[19]), __uint_as_float(v[20]), __uint_as_float(v[21])),
-                   fminf(__uint_as_float(v[22]), __uint_as_float(v[23])));
-  float g3 = min3f(min3f(__uint_as_float(v[24]), __uint_as_float(v[25]), __uint_as_float(v[26])),
-                   min3f(__uint_as_float(v[27]), __uint_as_float(v[28]), __uint_as_float(v[29])),
-                   fminf(__uint_as_float(v[30]), __uint_as_float(v[31])));
-  float m = min3f(g0, g1, fminf(g2, g3));
-  if (m < tau) {
-    if (g0 < tau) { TC_SCAN8(v, 0) }
-    if (g1 < tau) { TC_SCAN8(v, 1) }
-    if (g2 < tau) { TC_SCAN8(v, 2) }
-    if (g3 < tau) { TC_SCAN8(v, 3) }
+#define TC_GROUP(V, G)                                                             \
+  if (gm[G] < S.tau) {                                                             \
+    if (sa[G] < S.tau) { TC_TRY(V, (G)*8 + 0) TC_TRY(V, (G)*8 + 1) TC_TRY(V, (G)*8 + 2) } \
+    if (sb[G] < S.tau) { TC_TRY(V, (G)*8 + 3) TC_TRY(V, (G)*8 + 4) TC_TRY(V, (G)*8 + 5) } \
+    if (sc[G] < S.tau) { TC_TRY(V, (G)*8 + 6) TC_TRY(V, (G)*8 + 7) }               \
   }
+
+// 32 keys of one query row: a FMNMX3 tree rejects the chunk for the whole warp in
+// ~21 instructions; otherwise the sub-group minima steer the scan to the few keys below tau.
+__device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, float *lk, int *li,
+                                              float *pk, int *pi, int kp, int col0, int nr_i) {
+  float sa[4], sb[4], sc[4], gm[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    sa[g] = min3f(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
+    sb[g] = min3f(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+    sc[g] = fminf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+    gm[g] = min3f(sa[g], sb[g], sc[g]);
+  }
+  const float m = min3f(gm[0], gm[1], fminf(gm[2], gm[3]));
+  if (!__any_sync(0xffffffffu, m < S.tau)) return;
+  // slow path (warp-uniform entry): some lane holds a key below its threshold
+  bool again;
+  do {
+    bool ovf = false;
+    if (m < S.tau) {
+      TC_GROUP(v, 0)
+      TC_GROUP(v, 1)
+      TC_GROUP(v, 2)
+      TC_GROUP(v, 3)
+    }
+    again = __any_sync(0xffffffffu, ovf);
+    if (again || __any_sync(0xffffffffu, S.cnt_pend > PEND_TRIGGER)) S = merge_pending(lk, li, pk, pi, kp, S);
+  } while (again);
 }
+
+constexpr int MAX_STAGES = 6;
 
 // ---------------------------------------------------------------------------
 // K1: candidate generation
@@ -287,25 +339,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
          TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;                                 // QT tiles
-  const uint32_t sB = sA + QT * TILE_BYTES;                 // STAGES tiles
-  const uint32_t sKeys = sB + STAGES * TILE_BYTES;          // (kp + 4) rows
-  const uint32_t sIds = sKeys + (uint32_t)(P.kp + 4) * LROW;
-  const uint32_t sBar = sIds + (uint32_t)P.kp * LROW;       // 8-byte aligned
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw_u32);
+  const int stages = P.stages;
+  const uint32_t sA = base;                                     // QT tiles
+  const uint32_t sB = sA + QT * TILE_BYTES;                     // `stages` tiles
+  const uint32_t off_lists = (QT + stages) * TILE_BYTES;
+  float *s_lk = reinterpret_cast<float *>(sm + off_lists);      // [kp][EPI_THREADS]
+  int *s_li = reinterpret_cast<int *>(s_lk + P.kp * LSTRIDE);   // [kp][EPI_THREADS]
+  float *s_pk = reinterpret_cast<float *>(s_li + P.kp * LSTRIDE);  // [PEND][EPI_THREADS]
+  int *s_pi = reinterpret_cast<int *>(s_pk + PEND * LSTRIDE);      // [PEND][EPI_THREADS]
+  const uint32_t sBar = base + off_lists + (uint32_t)(2 * P.kp + 2 * PEND) * LSTRIDE * 4;
   const uint32_t bar_a_full = sBar + 0, bar_a_empty = sBar + 8;
-  const uint32_t bar_b_full = sBar + 16;                    // [STAGES]
-  const uint32_t bar_b_empty = bar_b_full + 8 * STAGES;     // [STAGES]
-  const uint32_t bar_t_full = bar_b_empty + 8 * STAGES;     // [2 acc][QT]
-  const uint32_t bar_t_empty = bar_t_full + 8 * 2 * QT;     // [2 acc][QT]
-  const uint32_t s_tmem = bar_t_empty + 8 * 2 * QT;         // uint32
+  const uint32_t bar_b_full = sBar + 16;                        // [MAX_STAGES]
+  const uint32_t bar_b_empty = bar_b_full + 8 * MAX_STAGES;     // [MAX_STAGES]
+  const uint32_t bar_t_full = bar_b_empty + 8 * MAX_STAGES;     // [2 acc][QT]
+  const uint32_t bar_t_empty = bar_t_full + 8 * 2 * QT;         // [2 acc][QT]
+  const uint32_t s_tmem = bar_t_empty + 8 * 2 * QT;             // uint32
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
     mbar_init(bar_a_empty, 1);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(bar_b_full + 8 * s, 1);
       mbar_init(bar_b_empty + 8 * s, 1);
     }
@@ -330,29 +388,28 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0, bi = 0;
+      uint32_t it = 0, s = 0, ph = 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
         mbar_wait(bar_a_empty, (it & 1) ^ 1, P.misc);
         mbar_expect_tx(bar_a_full, QT * TILE_BYTES);
         for (int t = 0; t < QT; ++t)
           tma_load_2d(sA + t * TILE_BYTES, &map_q, 0, (item * QT + t) * BM, bar_a_full);
-        for (int j = 0; j < P.n_btiles; ++j, ++bi) {
-          const uint32_t s = bi % STAGES, ph = (bi / STAGES) & 1;
+        for (int j = 0; j < P.n_btiles; ++j) {
           mbar_wait(bar_b_empty + 8 * s, ph ^ 1, P.misc);
           mbar_expect_tx(bar_b_full + 8 * s, TILE_BYTES);
           tma_load_2d(sB + s * TILE_BYTES, &map_r, 0, j * BN, bar_b_full + 8 * s);
+          if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t it = 0, bi = 0;
+      uint32_t it = 0, bi = 0, s = 0, ph = 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
         mbar_wait(bar_a_full, it & 1, P.misc);
         tc_fence_after();
         for (int j = 0; j < P.n_btiles; ++j, ++bi) {
-          const uint32_t s = bi % STAGES, ph = (bi / STAGES) & 1;
           const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
           mbar_wait(bar_b_full + 8 * s, ph, P.misc);
           tc_fence_after();
@@ -367,6 +424,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
             tc_commit(bar_t_full + 8 * (acc * QT + t));
           }
           tc_commit(bar_b_empty + 8 * s);  // the B stage may be refilled once these MMAs retire
+          if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
         tc_commit(bar_a_empty);
       }
@@ -378,16 +436,20 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;     // row inside the query tile
     const int et = ew * 32 + lane;           // list column of this thread
-    const uint32_t keys = sKeys + (uint32_t)et * 4;
-    const uint32_t ids = sIds + (uint32_t)et * 4;
+    float *lk = s_lk + et;
+    int *li = s_li + et;
+    float *pk = s_pk + et;
+    int *pi = s_pi + et;
     const int kp = P.kp;
     const int nr_i = (int)P.nr;
     uint32_t bi = 0;
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      sts_s32(keys + (uint32_t)kp * LROW, 0);
-      sts_f32(keys + (uint32_t)(kp + 1) * LROW, CUDART_INF_F);
-      sts_s32(keys + (uint32_t)(kp + 2) * LROW, 0);
-      float tau = CUDART_INF_F;
+      Sel S;
+      S.tau = CUDART_INF_F;
+      S.cnt_list = 0;
+      S.maxpos = 0;
+      S.cnt_pend = 0;
+      S.last_id = -1;
       const int64_t gq = ((int64_t)item * QT + t) * BM + row;
       for (int j = 0; j < P.n_btiles; ++j, ++bi) {
         const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
@@ -395,47 +457,43 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + t) * BN);
         const int colbase = j * BN;
+        const bool dbg = P.dbg_keys != nullptr && item == 0 && j == 0;
+        float *dk = dbg ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
         uint32_t va[32], vb[32];
         tc_ld32(taddr + 0, va);
-        tc_wait_ld(va);
-        tc_ld32(taddr + 32, vb);
-        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          tc_wait_ld(va);
+          tc_ld32(taddr + 64 * h + 32, vb);
+          if (dbg) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + c] = __uint_as_float(va[c]);
-        }
-        process_chunk(va, tau, keys, ids, kp, colbase + 0, nr_i);
-        tc_wait_ld(vb);
-        tc_ld32(taddr + 64, va);
-        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
+            for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
+          }
+          process_chunk(va, S, lk, li, pk, pi, kp, colbase + 64 * h, nr_i);
+          tc_wait_ld(vb);
+          if (h == 0) {
+            tc_ld32(taddr + 64, va);
+          } else {
+            // all four loads have landed in registers: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
+          }
+          if (dbg) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + 32 + c] = __uint_as_float(vb[c]);
+            for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
+          }
+          process_chunk(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, nr_i);
         }
-        process_chunk(vb, tau, keys, ids, kp, colbase + 32, nr_i);
-        tc_wait_ld(va);
-        tc_ld32(taddr + 96, vb);
-        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + 64 + c] = __uint_as_float(va[c]);
-        }
-        process_chunk(va, tau, keys, ids, kp, colbase + 64, nr_i);
-        tc_wait_ld(vb);
-        // all four loads have landed in registers: hand the accumulator back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-        if (P.dbg_keys != nullptr && item == 0 && j == 0) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) P.dbg_keys[(size_t)(t * BM + row) * BN + 96 + c] = __uint_as_float(vb[c]);
-        }
-        process_chunk(vb, tau, keys, ids, kp, colbase + 96, nr_i);
       }
       // flush this query's candidates
+      S = merge_pending(lk, li, pk, pi, kp, S);
       if (gq < P.nq) {
-        const int count = lds_s32(keys + (uint32_t)kp * LROW);
         int32_t *dst = P.cand + gq * kp;
-        for (int e = 0; e < kp; ++e) dst[e] = e < count ? lds_s32(ids + (uint32_t)e * LROW) : -1;
-        P.tau[gq] = count == kp ? tau : CUDART_INF_F;
+        for (int e = 0; e < kp; ++e) dst[e] = e < S.cnt_list ? li[e * LSTRIDE] : -1;
+        P.tau[gq] = S.cnt_list == kp ? S.tau : CUDART_INF_F;
       }
+      __syncwarp();
     }
   }
   // teardown
@@ -744,8 +802,15 @@ int pick_kp(int k, int n_cand) {
   return kp;
 }
 
-size_t tc_smem_bytes(int kp) {
-  return 1024 + (size_t)(QT + STAGES) * TILE_BYTES + (size_t)(2 * kp + 4) * LROW + 8 * (2 + 2 * STAGES + 4 * QT) + 16;
+size_t tc_smem_bytes(int kp, int stages) {
+  return 1024 + (size_t)(QT + stages) * TILE_BYTES + (size_t)(2 * kp + 2 * PEND) * LSTRIDE * 4 +
+         8 * (2 + 2 * MAX_STAGES + 4 * QT) + 16;
+}
+
+int pick_stages(int kp) {
+  int st = MAX_STAGES;
+  while (st > 2 && tc_smem_bytes(kp, st) > 227 * 1024) --st;
+  return st;
 }
 
 }  // namespace
@@ -764,7 +829,7 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
                       double **qn2_out, double **qerr_out, void **misc_out, float *d_dbg_keys,
                       b200nn_stats *stats) {
   cudaStream_t st = ctx->stream;
-  const bool self = (d_qry == d_ref);
+  const bool self = (d_qry == d_ref) && (nq == nr);
   TcMisc *misc;
   double *partial, *q_n2, *q_err;
   __half *r16, *q16;
@@ -816,12 +881,13 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   P.n_btiles = (int32_t)ceil_div64(nr, BN);
   P.ksteps = (d + 3 + 15) / 16;
   P.kp = kp;
+  P.stages = pick_stages(kp);
   P.cand = cand;
   P.tau = tau;
   P.dbg_keys = d_dbg_keys;
   P.misc = misc;
-  size_t smem = tc_smem_bytes(kp);
-  if (smem > 227 * 1024) {
+  size_t smem = tc_smem_bytes(kp, P.stages);
+  if (smem > 227 * 1024 || P.stages < 3) {
     b200nn_set_error("candidate list of %d entries does not fit shared memory", kp);
     return B200NN_ERR_INVALID;
   }
