@@ -96,8 +96,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, TcMisc *misc) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 6000000000LL) {  // ~3 s at 2 GHz: far beyond any legitimate wait
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 6000000000LL) {  // ~3 s: beyond any real wait
       misc->hang = 1;
       __threadfence();
       __trap();
@@ -335,6 +336,7 @@ constexpr int MAX_STAGES = 6;
 // ---------------------------------------------------------------------------
 // K1: candidate generation
 // ---------------------------------------------------------------------------
+template <bool DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
          TcParams P) {
@@ -362,10 +364,10 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a_full, 1);
-    mbar_init(bar_a_empty, 1);
+    mbar_init(bar_a_empty, QT);          // one commit per MMA issuer
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_b_full + 8 * s, 1);
-      mbar_init(bar_b_empty + 8 * s, 1);
+      mbar_init(bar_b_empty + 8 * s, QT);  // a stage is free once both issuers' MMAs retired
     }
     for (int i = 0; i < 2 * QT; ++i) {
       mbar_init(bar_t_full + 8 * i, 1);
@@ -402,9 +404,13 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers: one thread per resident query tile ==============
+    // The two query tiles advance independently (each has its own pair of accumulator
+    // stages); a B stage is recycled when both issuers' MMAs on it have retired.
     if (lane == 0) {
+      const int t = warp == 1 ? 0 : 1;
+      const uint64_t da = make_desc_sw128(sA + t * TILE_BYTES);
       uint32_t it = 0, bi = 0, s = 0, ph = 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
         mbar_wait(bar_a_full, it & 1, P.misc);
@@ -412,18 +418,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         for (int j = 0; j < P.n_btiles; ++j, ++bi) {
           const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
           mbar_wait(bar_b_full + 8 * s, ph, P.misc);
+          mbar_wait(bar_t_empty + 8 * (acc * QT + t), aph ^ 1, P.misc);
           tc_fence_after();
           const uint64_t db = make_desc_sw128(sB + s * TILE_BYTES);
-          for (int t = 0; t < QT; ++t) {
-            mbar_wait(bar_t_empty + 8 * (acc * QT + t), aph ^ 1, P.misc);
-            tc_fence_after();
-            const uint64_t da = make_desc_sw128(sA + t * TILE_BYTES);
-            const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + t) * BN);
-            for (int kk = 0; kk < P.ksteps; ++kk)
-              tc_mma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, kk > 0);
-            tc_commit(bar_t_full + 8 * (acc * QT + t));
-          }
-          tc_commit(bar_b_empty + 8 * s);  // the B stage may be refilled once these MMAs retire
+          const uint32_t d_tmem = tmem_base + (uint32_t)((acc * QT + t) * BN);
+          for (int kk = 0; kk < P.ksteps; ++kk)
+            tc_mma_f16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), IDESC, kk > 0);
+          tc_commit(bar_t_full + 8 * (acc * QT + t));
+          tc_commit(bar_b_empty + 8 * s);
           if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
         tc_commit(bar_a_empty);
@@ -451,21 +453,25 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       S.cnt_pend = 0;
       S.last_id = -1;
       const int64_t gq = ((int64_t)item * QT + t) * BM + row;
-      for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+      uint32_t va[32], vb[32];
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      {  // prologue: first chunk of the first tile
         const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
         mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * QT + t) * BN);
+        tc_ld32(lane_addr + (uint32_t)((acc * QT + t) * BN), va);
+      }
+      for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+        const uint32_t acc = bi & 1;
+        const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
         const int colbase = j * BN;
-        const bool dbg = P.dbg_keys != nullptr && item == 0 && j == 0;
-        float *dk = dbg ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
-        uint32_t va[32], vb[32];
-        tc_ld32(taddr + 0, va);
+        float *dk = nullptr;
+        if (DBG) dk = (item == 0 && j == 0) ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           tc_wait_ld(va);
           tc_ld32(taddr + 64 * h + 32, vb);
-          if (dbg) {
+          if (DBG && dk) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
           }
@@ -474,12 +480,19 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           if (h == 0) {
             tc_ld32(taddr + 64, va);
           } else {
-            // all four loads have landed in registers: hand the accumulator back to the MMA warp
+            // all four loads of this tile have landed: hand the accumulator back, and start
+            // on the next tile (normally already computed) before scanning the last chunk
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
+            if (j + 1 < P.n_btiles) {
+              const uint32_t nb = bi + 1, nacc = nb & 1, naph = (nb >> 1) & 1;
+              mbar_wait(bar_t_full + 8 * (nacc * QT + t), naph, P.misc);
+              tc_fence_after();
+              tc_ld32(lane_addr + (uint32_t)((nacc * QT + t) * BN), va);
+            }
           }
-          if (dbg) {
+          if (DBG && dk) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
           }
@@ -891,9 +904,14 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     b200nn_set_error("candidate list of %d entries does not fit shared memory", kp);
     return B200NN_ERR_INVALID;
   }
-  CU_TRY(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
-  k_knn_tc<<<grid, NUM_THREADS, smem, st>>>(map_q, map_r, P);
+  if (d_dbg_keys) {
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<true><<<grid, NUM_THREADS, smem, st>>>(map_q, map_r, P);
+  } else {
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<false><<<grid, NUM_THREADS, smem, st>>>(map_q, map_r, P);
+  }
   KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));
