@@ -71,7 +71,8 @@ typedef struct b200nn_opts {
   int32_t layout;      /* B200NN_COL_MAJOR (default, R) or B200NN_ROW_MAJOR          */
   int32_t knn_algo;    /* B200NN_KNN_*                                               */
   int32_t n_cand;      /* widened candidate count k' of the tensor path, 0 = auto    */
-  int32_t reserved;
+  int32_t reserved;    /* bits 0-1: tensor-path scan mode, 0 = auto, 1 = exhaustive
+                          (every reference tile), 2 = grouped (tile-pruned)           */
 } b200nn_opts;
 
 typedef struct b200nn_stats {
@@ -187,11 +188,13 @@ B200NN_API int b200nn_dev_graphs(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t
  * d_keys [256 x 128] float raw accumulator keys of the first 256 queries against
  * the first 128 reference rows.  h_scale_mu (host, 65 doubles, may be NULL)
  * receives the power-of-two scale and the centring vector of the prep stage.
+ * scan_mode: 0 = auto, 1 = exhaustive scan, 2 = grouped (tile-pruned) search;
+ * d_keys forces the exhaustive scan.
  */
 B200NN_API int b200nn_dev_knn_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr,
                                          const double *d_qry, int64_t nq, int32_t d,
-                                         int32_t n_cand, int32_t *d_cand, float *d_tau,
-                                         float *d_keys, double *h_scale_mu);
+                                         int32_t n_cand, int32_t scan_mode, int32_t *d_cand,
+                                         float *d_tau, float *d_keys, double *h_scale_mu);
 
 typedef struct b200nn_dev_csr {
   int64_t n_rows;      /* rows (== columns for the symmetric SNN block)             */

@@ -89,7 +89,7 @@ def load() -> C.CDLL:
                                                   C.POINTER(i64), C.POINTER(i64), C.POINTER(Stats)]
         L.b200nn_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b200nn_dev_knn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
-        L.b200nn_dev_knn_candidates.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp, vp]
+        L.b200nn_dev_knn_candidates.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp]
         L.b200nn_dev_graphs.argtypes = [vp, vp, i64, i32, dbl, i32, i64, i64, C.POINTER(i64), C.POINTER(i64),
                                         C.POINTER(Stats)]
         L.b200nn_dev_result.argtypes = [vp, i32, C.POINTER(DevCsr)]
@@ -146,14 +146,14 @@ class Context:
         return int(self._L.b200nn_ctx_stream(self._h) or 0)
 
     # ---- host-buffer calls ------------------------------------------------
-    def knn(self, ref, qry, k: int, layout: int, algo: int = KNN_AUTO, n_cand: int = 0):
+    def knn(self, ref, qry, k: int, layout: int, algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0):
         """ref/qry: float64 arrays [n, d] stored in `layout`.  Returns (idx, dist, stats)."""
         nr, d = ref.shape
         nq = nr if qry is None else qry.shape[0]
         order = "C" if layout == ROW_MAJOR else "F"
         idx = np.empty((nq, k), dtype=np.int32, order=order)
         dist = np.empty((nq, k), dtype=np.float64, order=order)
-        o = Opts(layout, algo, n_cand, 0)
+        o = Opts(layout, algo, n_cand, scan_mode)
         st = Stats()
         check(self._L.b200nn_knn(self._h, _ptr(ref), nr, _ptr(qry), nq, d, k, _ptr(idx), _ptr(dist),
                                  C.byref(o), C.byref(st)))
@@ -228,17 +228,18 @@ class Context:
 
     # ---- device-buffer calls (pointers or torch CUDA tensors) --------------
     def dev_knn(self, d_ref, nr: int, d_qry, nq: int, d: int, k: int, d_idx0, d_dist,
-                algo: int = KNN_AUTO, n_cand: int = 0) -> dict:
-        o = Opts(ROW_MAJOR, algo, n_cand, 0)
+                algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0) -> dict:
+        o = Opts(ROW_MAJOR, algo, n_cand, scan_mode)
         st = Stats()
         check(self._L.b200nn_dev_knn(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, k, _ptr(d_idx0),
                                      _ptr(d_dist), C.byref(o), C.byref(st)))
         return st.as_dict()
 
     def dev_knn_candidates(self, d_ref, nr: int, d_qry, nq: int, d: int, n_cand: int, d_cand, d_tau,
-                           d_keys, scale_mu: np.ndarray | None = None) -> None:
+                           d_keys, scale_mu: np.ndarray | None = None, scan_mode: int = 0) -> None:
         check(self._L.b200nn_dev_knn_candidates(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, n_cand,
-                                                _ptr(d_cand), _ptr(d_tau), _ptr(d_keys), _ptr(scale_mu)))
+                                                scan_mode, _ptr(d_cand), _ptr(d_tau), _ptr(d_keys),
+                                                _ptr(scale_mu)))
 
     def dev_graphs(self, d_idx0, n: int, k: int, prune: float, compute_snn: bool, row_begin: int,
                    row_end: int) -> dict:

@@ -150,6 +150,7 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
   int algo = o.knn_algo;
   if (algo == B200NN_KNN_AUTO)
     algo = knn_tc_applicable(nr, nq, d, k) ? B200NN_KNN_TENSOR : B200NN_KNN_EXACT;
+  knn_tc_set_mode(o.reserved & 3);
   if (algo == B200NN_KNN_TENSOR) {
     if (!knn_tc_applicable(nr, nq, d, k)) {
       b200nn_set_error("tensor-core kNN path does not cover nr=%lld d=%d k=%d", (long long)nr, d, k);
@@ -254,13 +255,14 @@ int b200nn_dev_knn(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const doubl
 }
 
 int b200nn_dev_knn_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
-                              int64_t nq, int32_t d, int32_t n_cand, int32_t *d_cand, float *d_tau,
-                              float *d_keys, double *h_scale_mu) {
+                              int64_t nq, int32_t d, int32_t n_cand, int32_t scan_mode,
+                              int32_t *d_cand, float *d_tau, float *d_keys, double *h_scale_mu) {
   RC_TRY(check_ctx(ctx));
   if (!d_ref || nr <= 0 || nq <= 0 || d <= 0 || d > 61 || n_cand < 8 || n_cand > 48 || (n_cand & 7)) {
     b200nn_set_error("knn_candidates: invalid argument (d <= 61, n_cand a multiple of 8 in [8, 48])");
     return B200NN_ERR_INVALID;
   }
+  knn_tc_set_mode(scan_mode & 3);
   return knn_tc_debug(ctx, d_ref, nr, d_qry, nq, d, n_cand, d_keys, d_cand, d_tau, h_scale_mu);
 }
 

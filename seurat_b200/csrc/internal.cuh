@@ -81,6 +81,12 @@ enum WsSlot {
   WS_TC_CANDKEY,   // candidate keys (fp32, nq * k')
   WS_TC_FLAGS,     // per-query certificate flags / fallback list
   WS_TC_MISC,
+  WS_TC_Y16R,      // FP16 rows of the reference set in original order (grouped search)
+  WS_TC_Y16Q,
+  WS_TC_SPLIT,     // FP16 triple split of |yh|^2 per reference row
+  WS_TC_IBUF,      // group ids, permutations, offsets, list counts
+  WS_TC_FBUF,      // centroids, radii, item balls
+  WS_TC_TILES,     // per-item tile lists
   WS_NUM
 };
 
@@ -160,6 +166,7 @@ int knn_exact_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const dou
                      int32_t *d_idx0, double *d_dist);
 
 // knn_tc.cu : tcgen05 candidate generation + FP64 re-rank + certificate
+void knn_tc_set_mode(int mode);
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k);
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                   int64_t nq, int d, int k, int n_cand, int32_t *d_idx0, double *d_dist,

@@ -32,6 +32,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "internal.cuh"
 
@@ -81,6 +83,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// (a suspend-time hint on try_wait was measured: it frees issue slots but its wake-up
+// latency slows the exhaustive scan by 10%, and the spin loops were not the bottleneck)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -95,13 +99,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // bounded wait: a protocol bug must end in a trap (CUDA error), never in a hung GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, TcMisc *misc) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 6000000000LL) {  // ~3 s: beyond any real wait
-      misc->hang = 1;
-      __threadfence();
-      __trap();
+    if ((++spins & 0xffu) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 8000000000LL) {  // ~4 s: beyond any legitimate wait
+        misc->hang = 1;
+        __threadfence();
+        __trap();
+      }
     }
   }
 }
@@ -275,7 +282,26 @@ struct TcParams {
   float *tau;          // [nq]
   float *dbg_keys;     // optional [QT*BM x BN]: keys of item 0 / B tile 0
   TcMisc *misc;
+  // grouped (tile-pruned) search: item i visits the list_cnt[i] tiles stored at
+  // tiles[i * list_stride ...]; null for the exhaustive scan
+  const int32_t *list_cnt;
+  int64_t list_stride;
+  const int32_t *tiles;
+  const int32_t *rperm;  // sorted reference position -> original row (-1: padding)
+  const int32_t *qperm;  // sorted query position -> original row
+  const double *q_n2;    // |yh_q|^2 by original query row (pass 1 only)
+  float *item_T;         // pass 1: per-item max over rows of (tau + |yh_q|^2), via atomicMax
+  int32_t pass1;         // 1: only item_T is produced
+  const int32_t *order;  // items by decreasing list length (null: identity)
 };
+
+// Item visited by CTA `b` in its round `i`: positions are dealt out in a snake so that the
+// longest lists (order[] is sorted by decreasing length) spread evenly over the CTAs.
+__device__ __forceinline__ int item_at(const TcParams &P, int i, int b, int grid) {
+  const int pos = i * grid + ((i & 1) ? grid - 1 - b : b);
+  if (pos >= P.n_items) return -1;
+  return P.order ? P.order[pos] : pos;
+}
 
 // append one key if it beats tau.  ids grow monotonically along the scan, so `last_id`
 // lets a chunk be re-scanned after a merge without appending anything twice.
@@ -332,6 +358,7 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, f
 }
 
 constexpr int MAX_STAGES = 6;
+constexpr int RING = 16;            // tile-id ring (power of two > stages + accumulator stages)
 
 // ---------------------------------------------------------------------------
 // K1: candidate generation
@@ -359,6 +386,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   const uint32_t bar_t_full = bar_b_empty + 8 * MAX_STAGES;     // [2 acc][QT]
   const uint32_t bar_t_empty = bar_t_full + 8 * 2 * QT;         // [2 acc][QT]
   const uint32_t s_tmem = bar_t_empty + 8 * 2 * QT;             // uint32
+  // ring of tile ids (producer -> epilogue), indexed by the running B-tile counter
+  volatile int32_t *s_ring = reinterpret_cast<volatile int32_t *>(sm + (s_tmem - base) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -390,18 +419,38 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0, s = 0, ph = 0;
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
+      uint32_t it = 0, s = 0, ph = 0, bi = 0;
+      for (int rnd = 0; rnd * (int)gridDim.x < P.n_items; ++rnd) {
+        const int item = item_at(P, rnd, blockIdx.x, gridDim.x);
+        if (item < 0) continue;
         mbar_wait(bar_a_empty, (it & 1) ^ 1, P.misc);
         mbar_expect_tx(bar_a_full, QT * TILE_BYTES);
         for (int t = 0; t < QT; ++t)
           tma_load_2d(sA + t * TILE_BYTES, &map_q, 0, (item * QT + t) * BM, bar_a_full);
-        for (int j = 0; j < P.n_btiles; ++j) {
+        const int64_t l0 = (int64_t)item * P.list_stride;
+        const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
+        // tile ids are fetched four at a time, one batch ahead of their use (list_stride % 4 == 0)
+        const int4 *tl = reinterpret_cast<const int4 *>(P.tiles ? P.tiles + l0 : nullptr);
+        int4 cur = make_int4(0, 0, 0, 0), nxt4 = make_int4(0, 0, 0, 0);
+        if (P.tiles && nt > 0) cur = tl[0];
+        if (P.tiles && nt > 4) nxt4 = tl[1];
+        for (int jj = 0; jj < nt; ++jj, ++bi) {
+          int j = jj;
+          if (P.tiles) {
+            const int u = jj & 3;
+            j = u == 0 ? cur.x : u == 1 ? cur.y : u == 2 ? cur.z : cur.w;
+            if (u == 3) {
+              cur = nxt4;
+              if (jj + 5 < nt) nxt4 = tl[(jj + 5) >> 2];
+            }
+          }
           mbar_wait(bar_b_empty + 8 * s, ph ^ 1, P.misc);
+          s_ring[bi & (RING - 1)] = j;  // ordered before the epilogue's read by the barrier chain
           mbar_expect_tx(bar_b_full + 8 * s, TILE_BYTES);
           tma_load_2d(sB + s * TILE_BYTES, &map_r, 0, j * BN, bar_b_full + 8 * s);
           if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
+        ++it;
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -412,10 +461,13 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       const int t = warp == 1 ? 0 : 1;
       const uint64_t da = make_desc_sw128(sA + t * TILE_BYTES);
       uint32_t it = 0, bi = 0, s = 0, ph = 0;
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x, ++it) {
+      for (int rnd = 0; rnd * (int)gridDim.x < P.n_items; ++rnd) {
+        const int item = item_at(P, rnd, blockIdx.x, gridDim.x);
+        if (item < 0) continue;
         mbar_wait(bar_a_full, it & 1, P.misc);
         tc_fence_after();
-        for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+        const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
+        for (int j = 0; j < nt; ++j, ++bi) {
           const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
           mbar_wait(bar_b_full + 8 * s, ph, P.misc);
           mbar_wait(bar_t_empty + 8 * (acc * QT + t), aph ^ 1, P.misc);
@@ -429,6 +481,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
         }
         tc_commit(bar_a_empty);
+        ++it;
       }
     }
   } else if (warp >= CTRL_WARPS) {
@@ -445,7 +498,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     const int kp = P.kp;
     const int nr_i = (int)P.nr;
     uint32_t bi = 0;
-    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+    for (int rnd = 0; rnd * (int)gridDim.x < P.n_items; ++rnd) {
+      const int item = item_at(P, rnd, blockIdx.x, gridDim.x);
+      if (item < 0) continue;
       Sel S;
       S.tau = CUDART_INF_F;
       S.cnt_list = 0;
@@ -453,18 +508,19 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       S.cnt_pend = 0;
       S.last_id = -1;
       const int64_t gq = ((int64_t)item * QT + t) * BM + row;
+      const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
       uint32_t va[32], vb[32];
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      {  // prologue: first chunk of the first tile
+      if (nt > 0) {  // prologue: first chunk of the first tile
         const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
         mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
         tc_fence_after();
         tc_ld32(lane_addr + (uint32_t)((acc * QT + t) * BN), va);
       }
-      for (int j = 0; j < P.n_btiles; ++j, ++bi) {
+      for (int j = 0; j < nt; ++j, ++bi) {
         const uint32_t acc = bi & 1;
         const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
-        const int colbase = j * BN;
+        const int colbase = s_ring[bi & (RING - 1)] * BN;
         float *dk = nullptr;
         if (DBG) dk = (item == 0 && j == 0) ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
 #pragma unroll 1
@@ -485,7 +541,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-            if (j + 1 < P.n_btiles) {
+            if (j + 1 < nt) {
               const uint32_t nb = bi + 1, nacc = nb & 1, naph = (nb >> 1) & 1;
               mbar_wait(bar_t_full + 8 * (nacc * QT + t), naph, P.misc);
               tc_fence_after();
@@ -501,10 +557,23 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
       // flush this query's candidates
       S = merge_pending(lk, li, pk, pi, kp, S);
-      if (gq < P.nq) {
-        int32_t *dst = P.cand + gq * kp;
-        for (int e = 0; e < kp; ++e) dst[e] = e < S.cnt_list ? li[e * LSTRIDE] : -1;
-        P.tau[gq] = S.cnt_list == kp ? S.tau : CUDART_INF_F;
+      const int64_t oq = gq < P.nq ? (P.qperm ? (int64_t)P.qperm[gq] : gq) : -1;  // original query row
+      if (oq >= 0) {
+        const float tq = S.cnt_list == kp ? S.tau : CUDART_INF_F;
+        if (P.pass1) {
+          // upper bound of tau + |yh_q|^2 (an approximate squared distance, >= 0 up to rounding)
+          float T = tq + (float)P.q_n2[oq];
+          T = T > 0.f ? T * 1.0001f + 1e-3f : 1e-3f;
+          atomicMax(reinterpret_cast<int *>(P.item_T + item), __float_as_int(T));
+        } else {
+          int32_t *dst = P.cand + oq * kp;
+          for (int e = 0; e < kp; ++e) {
+            int id = e < S.cnt_list ? li[e * LSTRIDE] : -1;
+            if (id >= 0 && P.rperm) id = P.rperm[id];
+            dst[e] = id;
+          }
+          P.tau[oq] = tq;
+        }
       }
       __syncwarp();
     }
@@ -610,7 +679,7 @@ __global__ void k_pick_scale(TcMisc *misc) {
 __global__ void __launch_bounds__(128)
 k_convert(const double *__restrict__ X, int64_t n, int d, __half *__restrict__ a_out,
           __half *__restrict__ b_out, double *__restrict__ q_n2, double *__restrict__ q_err,
-          TcMisc *__restrict__ misc) {
+          TcMisc *__restrict__ misc, uint2 *__restrict__ split_out, int is_ref) {
   __shared__ double mu[BK];
   if (threadIdx.x < BK) mu[threadIdx.x] = misc->mu[threadIdx.x];
   __syncthreads();
@@ -664,6 +733,17 @@ k_convert(const double *__restrict__ X, int64_t n, int d, __half *__restrict__ a
     }
     if (q_n2) q_n2[i] = n2;
     if (q_err) q_err[i] = sqrt(e2);
+    if (split_out) {
+      __half h1 = __double2half(n2);
+      double r1 = n2 - (double)__half2float(h1);
+      __half h2 = __double2half(r1);
+      double r2 = r1 - (double)__half2float(h2);
+      __half h3 = __double2half(r2);
+      uint2 pk;
+      pk.x = (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h2) << 16);
+      pk.y = (uint32_t)__half_as_ushort(h3);
+      split_out[i] = pk;
+    }
   }
   // maxima over the block's points
   double em = (i < n) ? sqrt(e2) : 0.0, nm = (i < n) ? n2 : 0.0;
@@ -673,12 +753,407 @@ k_convert(const double *__restrict__ X, int64_t n, int d, __half *__restrict__ a
     nm = fmax(nm, __shfl_xor_sync(0xffffffffu, nm, o));
   }
   if ((threadIdx.x & 31) == 0) {
-    if (b_out) {
+    if (b_out || is_ref) {
       if (em > 0.0) atomic_max_nonneg(&misc->e_max, em);
       if (nm > 0.0) atomic_max_nonneg(&misc->rn2_max, nm);
     }
     if (a_out && nm > 0.0) atomic_max_nonneg(&misc->qn2_max, nm);
   }
+}
+
+// ---------------------------------------------------------------------------
+// G: grouping for the tile-pruned search.  Reference points are partitioned by a
+// coarse k-means (any partition is valid; quality only affects how much can be
+// skipped), stored group by group (groups padded to whole B tiles with rows whose
+// key is +inf), and every work item (256 consecutive sorted queries) visits only
+// the groups whose ball can intersect its own:
+//     skip g  <=>  (|c_item - c_g| - rho_item - rho_g)^2  >  T_item
+// where T_item bounds tau + |yh_q|^2 for every row of the item (from pass 1 over the
+// item's nearest group).  By the triangle inequality every point of a skipped group
+// has a key above the row's final tau, exactly what the re-rank certificate assumes
+// of a non-candidate, so the result stays exact.
+// ---------------------------------------------------------------------------
+constexpr int KM_SAMPLE = 32768;
+constexpr int KM_ITERS = 6;
+constexpr int KM_CH = 32;  // centroids staged per shared-memory chunk
+
+__device__ __forceinline__ void load_y_row(const __half *__restrict__ y16, int64_t i, int d, float (&y)[BK]) {
+  const uint4 *src = reinterpret_cast<const uint4 *>(y16 + i * BK);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 v = src[c];
+    const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 f = __half22float2(h[u]);
+      y[c * 8 + 2 * u] = (c * 8 + 2 * u) < d ? f.x : 0.f;
+      y[c * 8 + 2 * u + 1] = (c * 8 + 2 * u + 1) < d ? f.y : 0.f;
+    }
+  }
+}
+
+__global__ void k_km_init(const __half *__restrict__ y16, int64_t n, int d, int G, float *__restrict__ cent,
+                          float *__restrict__ cnorm) {
+  const int g = blockIdx.x, j = threadIdx.x;  // 64 threads
+  const int64_t i = (int64_t)g * (n / G) + (n / G) / 2;
+  float v = j < d ? __half2float(y16[i * BK + j]) : 0.f;
+  cent[g * BK + j] = v;
+  float s = v * v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float part[2];
+  if ((j & 31) == 0) part[j >> 5] = s;
+  __syncthreads();
+  if (j == 0) cnorm[g] = part[0] + part[1];
+}
+
+// nearest centroid of rows i = r * stride (r < m); optional k-means accumulation
+__global__ void __launch_bounds__(128)
+k_km_assign(const __half *__restrict__ y16, int64_t m, int64_t stride, int d, int G,
+            const float *__restrict__ cent, const float *__restrict__ cnorm, int32_t *__restrict__ gid,
+            int32_t *__restrict__ counts, float *__restrict__ sums) {
+  __shared__ __align__(16) float cs[KM_CH * BK];
+  __shared__ float cn[KM_CH];
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = r < m;
+  float y[BK];
+  if (act) load_y_row(y16, r * stride, d, y);
+  else {
+#pragma unroll
+    for (int j = 0; j < BK; ++j) y[j] = 0.f;
+  }
+  float best = CUDART_INF_F;
+  int bg = 0;
+  for (int g0 = 0; g0 < G; g0 += KM_CH) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < KM_CH * BK; e += blockDim.x) {
+      int g = g0 + e / BK;
+      cs[e] = g < G ? cent[(size_t)g * BK + (e % BK)] : 0.f;
+    }
+    if (threadIdx.x < KM_CH) cn[threadIdx.x] = (g0 + threadIdx.x) < G ? cnorm[g0 + threadIdx.x] : CUDART_INF_F;
+    __syncthreads();
+    for (int c = 0; c < KM_CH; ++c) {
+      const float4 *cv = reinterpret_cast<const float4 *>(cs + c * BK);
+      float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < BK / 4; q4 += 2) {
+        float4 a = cv[q4], b = cv[q4 + 1];
+        dot0 = fmaf(y[q4 * 4 + 0], a.x, dot0);
+        dot0 = fmaf(y[q4 * 4 + 1], a.y, dot0);
+        dot0 = fmaf(y[q4 * 4 + 2], a.z, dot0);
+        dot0 = fmaf(y[q4 * 4 + 3], a.w, dot0);
+        dot1 = fmaf(y[q4 * 4 + 4], b.x, dot1);
+        dot1 = fmaf(y[q4 * 4 + 5], b.y, dot1);
+        dot1 = fmaf(y[q4 * 4 + 6], b.z, dot1);
+        dot1 = fmaf(y[q4 * 4 + 7], b.w, dot1);
+      }
+      const float sc = cn[c] - 2.f * (dot0 + dot1);
+      if (sc < best) {
+        best = sc;
+        bg = g0 + c;
+      }
+    }
+  }
+  if (act) {
+    if (gid) gid[r] = bg;
+    if (counts) atomicAdd(&counts[bg], 1);
+    if (sums) {
+#pragma unroll
+      for (int j = 0; j < BK; ++j)
+        if (j < d) atomicAdd(&sums[(size_t)bg * BK + j], y[j]);
+    }
+  }
+}
+
+__global__ void k_km_update(float *__restrict__ sums, int32_t *__restrict__ counts, int d,
+                            float *__restrict__ cent, float *__restrict__ cnorm) {
+  const int g = blockIdx.x, j = threadIdx.x;  // 64 threads
+  const int c = counts[g];
+  float v = cent[g * BK + j];
+  if (c > 0) v = j < d ? sums[(size_t)g * BK + j] / (float)c : 0.f;
+  cent[g * BK + j] = v;
+  sums[(size_t)g * BK + j] = 0.f;
+  float s = v * v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float part[2];
+  if ((j & 31) == 0) part[j >> 5] = s;
+  __syncthreads();
+  if (j == 0) {
+    cnorm[g] = part[0] + part[1];
+    counts[g] = 0;
+  }
+}
+
+// padded reference offsets (multiples of BN) and query offsets (multiples of an item); zeroes the cursors
+__global__ void k_group_offsets(const int32_t *__restrict__ rcount, const int32_t *__restrict__ qcount, int G,
+                                int32_t *__restrict__ goff, int32_t *__restrict__ qoff,
+                                int32_t *__restrict__ rcursor, int32_t *__restrict__ qcursor) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int ro = 0, qo = 0;
+  for (int g = 0; g < G; ++g) {
+    goff[g] = ro;
+    qoff[g] = qo;
+    ro += ((rcount[g] + BN - 1) / BN) * BN;
+    qo += ((qcount[g] + QT * BM - 1) / (QT * BM)) * (QT * BM);  // items never straddle two groups
+    rcursor[g] = 0;
+    qcursor[g] = 0;
+  }
+  goff[G] = ro;
+  qoff[G] = qo;
+}
+
+__global__ void k_group_scatter(const int32_t *__restrict__ gid, int64_t n, const int32_t *__restrict__ off,
+                                int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = gid[i];
+  const int pos = off[g] + atomicAdd(&cursor[g], 1);
+  perm[pos] = (int32_t)i;
+}
+
+// B operand rows in sorted, padded order; padding rows get key = +inf
+__global__ void __launch_bounds__(256)
+k_gather_ref(const __half *__restrict__ y16, const uint2 *__restrict__ split, const int32_t *__restrict__ rperm,
+             int64_t nr_pad, int d, __half *__restrict__ r16) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = e >> 3;
+  const int c = (int)(e & 7);
+  if (p >= nr_pad) return;
+  const int i = rperm[p];
+  __align__(16) __half out[8];
+  if (i < 0) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) out[jj] = (c * 8 + jj) == d ? __ushort_as_half(0x7c00) : __float2half_rn(0.f);
+  } else {
+    uint4 v = *reinterpret_cast<const uint4 *>(y16 + (int64_t)i * BK + c * 8);
+    const __half *h = reinterpret_cast<const __half *>(&v);
+    const uint2 sp = split[i];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = c * 8 + jj;
+      __half o;
+      if (j < d) o = __hmul(h[jj], __float2half_rn(-2.0f));
+      else if (j == d) o = __ushort_as_half((unsigned short)(sp.x & 0xffff));
+      else if (j == d + 1) o = __ushort_as_half((unsigned short)(sp.x >> 16));
+      else if (j == d + 2) o = __ushort_as_half((unsigned short)(sp.y & 0xffff));
+      else o = __float2half_rn(0.f);
+      out[jj] = o;
+    }
+  }
+  *reinterpret_cast<uint4 *>(r16 + p * BK + c * 8) = *reinterpret_cast<uint4 *>(out);
+}
+
+// A operand rows in sorted order (plain row gather)
+__global__ void __launch_bounds__(256)
+k_gather_qry(const __half *__restrict__ y16, const int32_t *__restrict__ qperm, int64_t nq,
+             __half *__restrict__ q16) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = e >> 3;
+  const int c = (int)(e & 7);
+  if (p >= nq) return;
+  const int64_t i = qperm[p];
+  uint4 v = make_uint4(0, 0, 0, 0);  // padding rows are all zero and never flushed
+  if (i >= 0) v = *reinterpret_cast<const uint4 *>(y16 + i * BK + c * 8);
+  *reinterpret_cast<uint4 *>(q16 + p * BK + c * 8) = v;
+}
+
+// radius of every group around its centroid (rounded up)
+__global__ void __launch_bounds__(128)
+k_group_radius(const __half *__restrict__ y16, const int32_t *__restrict__ rperm, const int32_t *__restrict__ goff,
+               int d, const float *__restrict__ cent, float *__restrict__ grad) {
+  __shared__ float cs[BK];
+  __shared__ float red[4];
+  const int g = blockIdx.x;
+  if (threadIdx.x < BK) cs[threadIdx.x] = cent[(size_t)g * BK + threadIdx.x];
+  __syncthreads();
+  float mx = 0.f;
+  for (int p = goff[g] + threadIdx.x; p < goff[g + 1]; p += blockDim.x) {
+    const int i = rperm[p];
+    if (i < 0) continue;
+    float y[BK];
+    load_y_row(y16, i, d, y);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < BK; ++j) {
+      float t = y[j] - cs[j];
+      s = fmaf(t, t, s);
+    }
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    grad[g] = sqrtf(m) * 1.0001f + 1e-4f;
+  }
+}
+
+// centroid and radius of every work item (QT*BM consecutive sorted queries)
+__global__ void __launch_bounds__(64)
+k_item_stats(const __half *__restrict__ q16, const int32_t *__restrict__ qperm, int64_t nq, int d,
+             float *__restrict__ item_c, float *__restrict__ item_rad) {
+  __shared__ float cs[BK];
+  __shared__ float red[2];
+  __shared__ int s_rows;
+  const int item = blockIdx.x, j = threadIdx.x;
+  const int64_t r0 = (int64_t)item * QT * BM;
+  if (j == 0) s_rows = 0;
+  __syncthreads();
+  {  // valid rows form a prefix of the item (the group's queries, then padding)
+    int c = 0;
+    for (int r = j; r < QT * BM; r += 64)
+      if (r0 + r < nq && qperm[r0 + r] >= 0) c++;
+    atomicAdd(&s_rows, c);
+  }
+  __syncthreads();
+  const int rows = s_rows;
+  float s = 0.f;
+  if (j < d)
+    for (int r = 0; r < rows; ++r) s += __half2float(q16[(r0 + r) * BK + j]);
+  cs[j] = (j < d && rows > 0) ? s / (float)rows : 0.f;
+  item_c[(size_t)item * BK + j] = cs[j];
+  __syncthreads();
+  float mx = 0.f;
+  for (int r = j; r < rows; r += 64) {
+    float y[BK];
+    load_y_row(q16, r0 + r, d, y);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < BK; ++c) {
+      float t = y[c] - cs[c];
+      q = fmaf(t, t, q);
+    }
+    mx = fmaxf(mx, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((j & 31) == 0) red[j >> 5] = mx;
+  __syncthreads();
+  if (j == 0) item_rad[item] = rows > 0 ? sqrtf(fmaxf(red[0], red[1])) * 1.0001f + 1e-4f : -1.f;
+}
+
+// tile list of every item.  pass 1: the tiles of the nearest group (to establish T_item);
+// pass 2: every group whose ball may hold a key below the item's bound, plus the pass-1 group.
+constexpr int LIST_THREADS = 256;
+constexpr int PASS1_TILES = 8;
+__global__ void __launch_bounds__(LIST_THREADS)
+k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_rad,
+              const float *__restrict__ item_T, int G, const float *__restrict__ cent,
+              const float *__restrict__ grad, const int32_t *__restrict__ goff, int pass1,
+              int64_t list_stride, int32_t *__restrict__ tiles, int32_t *__restrict__ list_cnt) {
+  __shared__ float cs[BK];
+  __shared__ float s_min[LIST_THREADS / 32];
+  __shared__ int s_scan[LIST_THREADS / 32];
+  __shared__ float s_dmin;
+  const int item = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (item_rad[item] < 0.f) {  // padding-only item
+    if (tid == 0) list_cnt[item] = 0;
+    return;
+  }
+  if (tid < BK) cs[tid] = item_c[(size_t)item * BK + tid];
+  __syncthreads();
+  constexpr int GPT = 4;  // groups per thread (G <= 1024)
+  float dist[GPT];
+  float dmin = CUDART_INF_F;
+#pragma unroll
+  for (int u = 0; u < GPT; ++u) {
+    const int g = tid * GPT + u;
+    dist[u] = CUDART_INF_F;
+    if (g < G && goff[g + 1] > goff[g]) {
+      const float4 *cv = reinterpret_cast<const float4 *>(cent + (size_t)g * BK);
+      float s = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < BK / 4; ++q4) {
+        float4 a = cv[q4];
+        float t0 = a.x - cs[q4 * 4], t1 = a.y - cs[q4 * 4 + 1], t2 = a.z - cs[q4 * 4 + 2], t3 = a.w - cs[q4 * 4 + 3];
+        s = fmaf(t0, t0, s);
+        s = fmaf(t1, t1, s);
+        s = fmaf(t2, t2, s);
+        s = fmaf(t3, t3, s);
+      }
+      dist[u] = sqrtf(s);
+      dmin = fminf(dmin, dist[u]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+  if (lane == 0) s_min[w] = dmin;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_min[0];
+    for (int i = 1; i < LIST_THREADS / 32; ++i) m = fminf(m, s_min[i]);
+    s_dmin = m;
+  }
+  __syncthreads();
+  dmin = s_dmin;
+  const float T = pass1 ? 0.f : item_T[item];
+  const float ri = item_rad[item];
+  int ntile[GPT], mine = 0;
+#pragma unroll
+  for (int u = 0; u < GPT; ++u) {
+    const int g = tid * GPT + u;
+    ntile[u] = 0;
+    if (dist[u] < CUDART_INF_F) {
+      bool keep = dist[u] <= dmin;  // the nearest group is always visited (pass 1 == subset of pass 2)
+      if (!pass1 && !keep) {
+        float lb = dist[u] * 0.99999f - ri - grad[g];
+        keep = !(lb > 0.f && lb * lb > T);  // also keeps everything when T is +inf / NaN
+      }
+      if (keep) ntile[u] = (goff[g + 1] - goff[g]) / BN;
+      // pass 1 only needs an upper bound of tau: a few tiles of the own group suffice
+      if (pass1 && ntile[u] > PASS1_TILES) ntile[u] = PASS1_TILES;
+    }
+    mine += ntile[u];
+  }
+  // block exclusive scan of `mine`
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_scan[w] = inc;
+  __syncthreads();
+  int woff = 0, total = 0;
+  for (int i = 0; i < LIST_THREADS / 32; ++i) {
+    if (i < w) woff += s_scan[i];
+    total += s_scan[i];
+  }
+  int pos = woff + inc - mine;
+  int32_t *dst = tiles + (int64_t)item * list_stride;
+#pragma unroll
+  for (int u = 0; u < GPT; ++u) {
+    const int g = tid * GPT + u;
+    if (ntile[u] > 0) {
+      const int t0 = goff[g] / BN;
+      for (int t = 0; t < ntile[u]; ++t) dst[pos + t] = t0 + t;
+      pos += ntile[u];
+    }
+  }
+  if (tid == 0) list_cnt[item] = total;
+}
+
+// items ordered by decreasing list length (counting sort; one block)
+__global__ void __launch_bounds__(1024)
+k_order_items(const int32_t *__restrict__ list_cnt, int n_items, int max_cnt, int32_t *__restrict__ bins,
+              int32_t *__restrict__ order) {
+  for (int b = threadIdx.x; b <= max_cnt; b += blockDim.x) bins[b] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) atomicAdd(&bins[list_cnt[i]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {  // descending exclusive scan
+    int run = 0;
+    for (int b = max_cnt; b >= 0; --b) {
+      int c = bins[b];
+      bins[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_items; i += blockDim.x) order[atomicAdd(&bins[list_cnt[i]], 1)] = i;
 }
 
 // ---------------------------------------------------------------------------
@@ -817,7 +1292,7 @@ int pick_kp(int k, int n_cand) {
 
 size_t tc_smem_bytes(int kp, int stages) {
   return 1024 + (size_t)(QT + stages) * TILE_BYTES + (size_t)(2 * kp + 2 * PEND) * LSTRIDE * 4 +
-         8 * (2 + 2 * MAX_STAGES + 4 * QT) + 16;
+         8 * (2 + 2 * MAX_STAGES + 4 * QT) + 32 + 4 * RING;
 }
 
 int pick_stages(int kp) {
@@ -828,6 +1303,11 @@ int pick_stages(int kp) {
 
 }  // namespace
 
+// 0 = auto (grouped for large reference sets), 1 = exhaustive scan, 2 = grouped; set through
+// b200nn_opts.reserved (bits 0-1) for benchmarking the two variants against each other
+static thread_local int g_tc_mode = 0;
+void knn_tc_set_mode(int mode) { g_tc_mode = mode; }
+
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
   if (d > MAX_D || d < 1) return false;
   if (pick_kp(k, 0) > MAX_KP) return false;
@@ -836,13 +1316,84 @@ bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
   return true;
 }
 
-// candidate stage alone (also used by the debug / profiling entry point)
+// launch helper for the candidate kernel
+static int launch_tc(b200nn_ctx *ctx, const CUtensorMap &map_q, const CUtensorMap &map_r, const TcParams &P,
+                     bool dbg) {
+  size_t smem = tc_smem_bytes(P.kp, P.stages);
+  if (smem > 227 * 1024 || P.stages < 3) {
+    b200nn_set_error("candidate list of %d entries does not fit shared memory", P.kp);
+    return B200NN_ERR_INVALID;
+  }
+  int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
+  if (grid <= 0) return B200NN_OK;
+  if (dbg) {
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<true><<<grid, NUM_THREADS, smem, ctx->stream>>>(map_q, map_r, P);
+  } else {
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<false><<<grid, NUM_THREADS, smem, ctx->stream>>>(map_q, map_r, P);
+  }
+  KERNEL_CHECK(ctx);
+  return B200NN_OK;
+}
+
+// B200NN_DEBUG=1: print the tile-list statistics of the grouped search to stderr
+static int debug_list_stats(b200nn_ctx *ctx, const char *what, const int32_t *d_cnt, int n_items,
+                            const float *dbg_T = nullptr, const float *dbg_R = nullptr) {
+  static const bool on = getenv("B200NN_DEBUG") != nullptr;
+  if (!on) return B200NN_OK;
+  std::vector<int32_t> h((size_t)n_items);
+  CU_TRY(cudaMemcpyAsync(h.data(), d_cnt, sizeof(int32_t) * (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  long long sum = 0;
+  int mx = 0, mn = 1 << 30;
+  std::vector<long long> per_cta((size_t)ctx->sm_count, 0);
+  for (int i = 0; i < n_items; ++i) {
+    sum += h[i];
+    mx = h[i] > mx ? h[i] : mx;
+    mn = h[i] < mn ? h[i] : mn;
+    per_cta[(size_t)(i % ctx->sm_count)] += h[i];
+  }
+  long long cmax = 0;
+  for (long long v : per_cta) cmax = v > cmax ? v : cmax;
+  int big = 0;
+  for (int i = 0; i < n_items; ++i) big += h[i] > 2 * (sum / n_items + 1);
+  fprintf(stderr, "[b200nn] %s: %d items, tiles/item min %d mean %.1f max %d, total %lld, busiest CTA %lld (ideal %.0f), "
+          "%d items above twice the mean\n",
+          what, n_items, mn, (double)sum / n_items, mx, sum, cmax, (double)sum / ctx->sm_count, big);
+  if (dbg_T) {
+    std::vector<float> T((size_t)n_items), R((size_t)n_items);
+    CU_TRY(cudaMemcpy(T.data(), dbg_T, sizeof(float) * (size_t)n_items, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(R.data(), dbg_R, sizeof(float) * (size_t)n_items, cudaMemcpyDeviceToHost));
+    int shown = 0;
+    for (int i = 0; i < n_items && shown < 12; ++i)
+      if (h[i] > 2 * (sum / n_items + 1)) {
+        fprintf(stderr, "   item %d: %d tiles, T = %g, radius = %g\n", i, h[i], T[i], R[i]);
+        shown++;
+      }
+    double tm = 0; int tc = 0;
+    for (int i = 0; i < n_items; ++i) if (h[i] > 0 && h[i] <= 2 * (sum / n_items + 1)) { tm += T[i]; tc++; }
+    fprintf(stderr, "   typical T = %g\n", tc ? tm / tc : 0.0);
+  }
+  return B200NN_OK;
+}
+
+static int pick_groups(int64_t nr) {
+  int64_t want = nr / 4096;
+  int G = 16;
+  while (G < want && G < 1024) G <<= 1;
+  return G;
+}
+
+// candidate stage alone (also used by the debug / profiling entry point).
+// mode: 0 = auto, 1 = exhaustive scan of every tile, 2 = grouped (tile-pruned)
 int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
-                      int64_t nq, int d, int kp, int32_t **cand_out, float **tau_out,
+                      int64_t nq, int d, int kp, int mode, int32_t **cand_out, float **tau_out,
                       double **qn2_out, double **qerr_out, void **misc_out, float *d_dbg_keys,
                       b200nn_stats *stats) {
   cudaStream_t st = ctx->stream;
   const bool self = (d_qry == d_ref) && (nq == nr);
+  const bool grouped = mode == 2 || (mode == 0 && nr >= 32768 && d_dbg_keys == nullptr);
   TcMisc *misc;
   double *partial, *q_n2, *q_err;
   __half *r16, *q16;
@@ -850,7 +1401,6 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   float *tau;
   RC_TRY(ws_get(ctx, WS_TC_MISC, 1, &misc));
   RC_TRY(ws_get(ctx, WS_SCAN_TMP, (size_t)MEAN_BLOCKS * BK, &partial));
-  RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr * BK, &r16));
   RC_TRY(ws_get(ctx, WS_TC_QRY16, (size_t)nq * BK, &q16));
   RC_TRY(ws_get(ctx, WS_TC_QRYERR, (size_t)nq * 2, &q_n2));
   q_err = q_n2 + nq;
@@ -871,27 +1421,12 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   }
   k_pick_scale<<<1, 1, 0, st>>>(misc);
   KERNEL_CHECK(ctx);
-  if (self) {
-    k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, q16, r16, q_n2, q_err, misc);
-    KERNEL_CHECK(ctx);
-  } else {
-    k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, nullptr, r16, nullptr, nullptr,
-                                                              misc);
-    KERNEL_CHECK(ctx);
-    k_convert<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(d_qry, nq, d, q16, nullptr, q_n2, q_err,
-                                                              misc);
-    KERNEL_CHECK(ctx);
-  }
-  CU_TRY(cudaEventRecord(e1, st));
 
-  CUtensorMap map_q, map_r;
-  RC_TRY(make_operand_map(&map_q, q16, nq));
-  RC_TRY(make_operand_map(&map_r, r16, nr));
   TcParams P;
+  memset(&P, 0, sizeof(P));
   P.nq = nq;
   P.nr = nr;
   P.n_items = (int32_t)ceil_div64(nq, QT * BM);
-  P.n_btiles = (int32_t)ceil_div64(nr, BN);
   P.ksteps = (d + 3 + 15) / 16;
   P.kp = kp;
   P.stages = pick_stages(kp);
@@ -899,20 +1434,151 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   P.tau = tau;
   P.dbg_keys = d_dbg_keys;
   P.misc = misc;
-  size_t smem = tc_smem_bytes(kp, P.stages);
-  if (smem > 227 * 1024 || P.stages < 3) {
-    b200nn_set_error("candidate list of %d entries does not fit shared memory", kp);
-    return B200NN_ERR_INVALID;
-  }
-  int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
-  if (d_dbg_keys) {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<true><<<grid, NUM_THREADS, smem, st>>>(map_q, map_r, P);
+  P.q_n2 = q_n2;
+  CUtensorMap map_q, map_r;
+
+  if (!grouped) {
+    RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr * BK, &r16));
+    if (self) {
+      k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, q16, r16, q_n2, q_err, misc,
+                                                                nullptr, 1);
+      KERNEL_CHECK(ctx);
+    } else {
+      k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, nullptr, r16, nullptr,
+                                                                nullptr, misc, nullptr, 1);
+      KERNEL_CHECK(ctx);
+      k_convert<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(d_qry, nq, d, q16, nullptr, q_n2, q_err,
+                                                                misc, nullptr, 0);
+      KERNEL_CHECK(ctx);
+    }
+    CU_TRY(cudaEventRecord(e1, st));
+    RC_TRY(make_operand_map(&map_q, q16, nq));
+    RC_TRY(make_operand_map(&map_r, r16, nr));
+    P.n_btiles = (int32_t)ceil_div64(nr, BN);
+    RC_TRY(launch_tc(ctx, map_q, map_r, P, d_dbg_keys != nullptr));
   } else {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<false><<<grid, NUM_THREADS, smem, st>>>(map_q, map_r, P);
+    // ---- grouped search ------------------------------------------------------------
+    const int G = pick_groups(nr);
+    const int64_t nr_pad = ((nr + BN - 1) / BN + G) * BN;  // upper bound of the padded length
+    const int64_t n_tiles_max = nr_pad / BN;
+    const int64_t nq_pad = ((nq + QT * BM - 1) / (QT * BM) + G) * (QT * BM);
+    const int64_t list_stride = (n_tiles_max + 3) & ~(int64_t)3;
+    P.n_items = (int32_t)(nq_pad / (QT * BM));
+    RC_TRY(ws_get(ctx, WS_TC_QRY16, (size_t)nq_pad * BK, &q16));
+    // scratch: FP16 rows in original order (A format) for both sets, splits, group ids
+    __half *yr16, *yq16;
+    uint2 *split;
+    int32_t *gid_r, *gid_q, *rperm, *qperm, *ibuf;
+    float *fbuf;
+    RC_TRY(ws_get(ctx, WS_TC_Y16R, (size_t)nr * BK, &yr16));
+    RC_TRY(ws_get(ctx, WS_TC_SPLIT, (size_t)nr, &split));
+    RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr_pad * BK, &r16));
+    // int scratch: gid_r[nr] gid_q[nq] rperm[nr_pad] qperm[nq] + 8 small arrays of (G+1)
+    RC_TRY(ws_get(ctx, WS_TC_IBUF,
+                  (size_t)nr + nq + nr_pad + nq_pad + 8 * (size_t)(G + 1) + 2 * (size_t)P.n_items +
+                      (size_t)list_stride + 64,
+                  &ibuf));
+    gid_r = ibuf;
+    gid_q = gid_r + nr;
+    rperm = gid_q + nq;
+    qperm = rperm + nr_pad;
+    int32_t *rcount = qperm + nq_pad, *qcount = rcount + (G + 1), *goff = qcount + (G + 1),
+            *qoff = goff + (G + 1), *rcursor = qoff + (G + 1), *qcursor = rcursor + (G + 1),
+            *kcount = qcursor + (G + 1), *list_cnt = kcount + (G + 1) * 2, *order = list_cnt + P.n_items,
+            *bins = order + P.n_items;
+    // float scratch: cent[G*64] cnorm[G] sums[G*64] grad[G] item_c[nI*64] item_rad[nI] item_T[nI]
+    const size_t nI = (size_t)P.n_items;
+    RC_TRY(ws_get(ctx, WS_TC_FBUF, (size_t)G * BK * 2 + 2 * (size_t)G + nI * BK + 2 * nI + 64, &fbuf));
+    float *cent = fbuf, *sums = cent + (size_t)G * BK, *cnorm = sums + (size_t)G * BK, *grad = cnorm + G,
+          *item_c = grad + G, *item_rad = item_c + nI * BK, *item_T = item_rad + nI;
+    int32_t *tiles;
+    RC_TRY(ws_get(ctx, WS_TC_TILES, nI * (size_t)list_stride, &tiles));
+
+    // 1. FP16 rows (original order), residuals, norms
+    k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, yr16, nullptr, self ? q_n2 : nullptr,
+                                                              self ? q_err : nullptr, misc, split, 1);
+    KERNEL_CHECK(ctx);
+    if (self) {
+      yq16 = yr16;
+    } else {
+      RC_TRY(ws_get(ctx, WS_TC_Y16Q, (size_t)nq * BK, &yq16));
+      k_convert<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(d_qry, nq, d, yq16, nullptr, q_n2, q_err, misc,
+                                                                nullptr, 0);
+      KERNEL_CHECK(ctx);
+    }
+    // 2. coarse k-means on a strided sample of the reference rows
+    const int64_t m = nr < KM_SAMPLE ? nr : KM_SAMPLE;
+    const int64_t stride = nr / m;
+    CU_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)G * BK, st));
+    CU_TRY(cudaMemsetAsync(rcount, 0, sizeof(int32_t) * 8 * (size_t)(G + 1), st));
+    k_km_init<<<G, 64, 0, st>>>(yr16, m * stride, d, G, cent, cnorm);
+    KERNEL_CHECK(ctx);
+    for (int itn = 0; itn < KM_ITERS; ++itn) {
+      k_km_assign<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(yr16, m, stride, d, G, cent, cnorm, nullptr,
+                                                                 kcount, sums);
+      KERNEL_CHECK(ctx);
+      k_km_update<<<G, 64, 0, st>>>(sums, kcount, d, cent, cnorm);
+      KERNEL_CHECK(ctx);
+    }
+    // 3. assign every reference / query row, sort by group
+    k_km_assign<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, nr, 1, d, G, cent, cnorm, gid_r, rcount,
+                                                                nullptr);
+    KERNEL_CHECK(ctx);
+    if (self) {
+      CU_TRY(cudaMemcpyAsync(qcount, rcount, sizeof(int32_t) * G, cudaMemcpyDeviceToDevice, st));
+      gid_q = gid_r;
+    } else {
+      k_km_assign<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(yq16, nq, 1, d, G, cent, cnorm, gid_q, qcount,
+                                                                  nullptr);
+      KERNEL_CHECK(ctx);
+    }
+    k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor);
+    KERNEL_CHECK(ctx);
+    CU_TRY(cudaMemsetAsync(rperm, 0xff, sizeof(int32_t) * (size_t)(nr_pad + nq_pad), st));  // rperm and qperm
+    k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, goff, rcursor, rperm);
+    KERNEL_CHECK(ctx);
+    k_group_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, nq, qoff, qcursor, qperm);
+    KERNEL_CHECK(ctx);
+    // 4. operands in sorted order
+    k_gather_ref<<<(unsigned)ceil_div64(nr_pad * 8, 256), 256, 0, st>>>(yr16, split, rperm, nr_pad, d, r16);
+    KERNEL_CHECK(ctx);
+    k_gather_qry<<<(unsigned)ceil_div64(nq_pad * 8, 256), 256, 0, st>>>(yq16, qperm, nq_pad, q16);
+    KERNEL_CHECK(ctx);
+    // 5. balls
+    k_group_radius<<<G, 128, 0, st>>>(yr16, rperm, goff, d, cent, grad);
+    KERNEL_CHECK(ctx);
+    k_item_stats<<<P.n_items, 64, 0, st>>>(q16, qperm, nq_pad, d, item_c, item_rad);
+    KERNEL_CHECK(ctx);
+    CU_TRY(cudaMemsetAsync(item_T, 0, sizeof(float) * nI, st));
+    CU_TRY(cudaEventRecord(e1, st));
+    // 6. pass 1: nearest group only -> T_item;  pass 2: pruned lists
+    RC_TRY(make_operand_map(&map_q, q16, nq_pad));
+    RC_TRY(make_operand_map(&map_r, r16, nr_pad));  // rows past the last group are never listed
+    P.nq = nq_pad;
+    P.nr = nr_pad;
+    P.n_btiles = (int32_t)n_tiles_max;
+    P.list_cnt = list_cnt;
+    P.list_stride = list_stride;
+    P.tiles = tiles;
+    P.rperm = rperm;
+    P.qperm = qperm;
+    P.item_T = item_T;
+    k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, 1,
+                                                      P.list_stride, tiles, list_cnt);
+    KERNEL_CHECK(ctx);
+    P.pass1 = 1;
+    RC_TRY(debug_list_stats(ctx, "pass 1", list_cnt, P.n_items));
+    RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
+    k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, 0,
+                                                      P.list_stride, tiles, list_cnt);
+    KERNEL_CHECK(ctx);
+    P.pass1 = 0;
+    k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order);
+    KERNEL_CHECK(ctx);
+    P.order = order;
+    RC_TRY(debug_list_stats(ctx, "pass 2", list_cnt, P.n_items, item_T, item_rad));
+    RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
   }
-  KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));
   if (stats) {
@@ -943,8 +1609,8 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   float *tau;
   double *q_n2, *q_err;
   void *misc_v;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, &cand, &tau, &q_n2, &q_err, &misc_v,
-                           nullptr, stats));
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, g_tc_mode, &cand, &tau, &q_n2, &q_err,
+                           &misc_v, nullptr, stats));
   TcMisc *misc = static_cast<TcMisc *>(misc_v);
   int32_t *flags;
   RC_TRY(ws_get(ctx, WS_TC_FLAGS, (size_t)nq + 4, &flags));
@@ -993,8 +1659,8 @@ int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
   float *tau;
   double *q_n2, *q_err;
   void *misc_v;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, &cand, &tau, &q_n2,
-                           &q_err, &misc_v, d_keys_out, nullptr));
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, d_keys_out ? 1 : g_tc_mode,
+                           &cand, &tau, &q_n2, &q_err, &misc_v, d_keys_out, nullptr));
   cudaStream_t st = ctx->stream;
   if (d_cand_out)
     CU_TRY(cudaMemcpyAsync(d_cand_out, cand, sizeof(int32_t) * (size_t)nq * kp,

@@ -35,7 +35,7 @@ def test_raw_keys_match_fp16_model(ctx, n, d):
     tau = torch.empty(n, dtype=torch.float32, device="cuda")
     sm = np.zeros(65)
     torch.cuda.synchronize()
-    ctx.dev_knn_candidates(ref, n, ref, n, d, 32, cand, tau, keys, sm)
+    ctx.dev_knn_candidates(ref, n, ref, n, d, 32, cand, tau, keys, sm, 1)
     scale, mu = sm[0], sm[1:]
     assert scale > 0 and np.log2(scale) == np.round(np.log2(scale))
     y, yh = fp16_operands(X, scale, mu)
@@ -58,11 +58,14 @@ def test_raw_keys_match_fp16_model(ctx, n, d):
         assert len(set(c[q])) == 32 and c[q].min() >= 0 and c[q].max() < n
 
 
-@pytest.mark.parametrize("n,d,k", [(20000, 50, 20), (9000, 30, 30), (4097, 50, 5), (2048, 10, 32), (33000, 2, 10)])
-def test_tensor_path_equals_oracle(ctx, n, d, k):
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,d,k", [(20000, 50, 20), (9000, 30, 30), (4097, 50, 5), (2048, 10, 32), (33000, 2, 10),
+                                   (70000, 50, 20)])
+def test_tensor_path_equals_oracle(ctx, n, d, k, mode):
+    """mode 1: exhaustive scan of every reference tile; mode 2: grouped, tile-pruned search"""
     X, _ = gaussian_mixture(n, d, seed=n % 97, n_centres=16)
     wi, wd = oracle.knn(X, k=k, method="kdtree" if d > 4 else "brute")
-    idx, dist, st = ctx.knn(X, None, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    idx, dist, st = ctx.knn(X, None, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, mode)
     assert st["ms_knn_cand"] > 0
     assert (dist == wd).all()
     assert (idx == wi).all()
@@ -75,8 +78,9 @@ def test_tensor_path_query_ne_reference(ctx):
     qry, _ = gaussian_mixture(7001, 50, seed=4, centres=c)
     qry[:10] += 40.0            # far outside the reference cloud
     wi, wd = oracle.knn(ref, qry, 20, method="kdtree")
-    idx, dist, st = ctx.knn(ref, qry, 20, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
-    assert (idx == wi).all() and (dist == wd).all()
+    for mode in (1, 2):
+        idx, dist, st = ctx.knn(ref, qry, 20, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, mode)
+        assert (idx == wi).all() and (dist == wd).all(), f"scan mode {mode}"
 
 
 def test_tensor_path_ties_and_duplicates(ctx):
@@ -85,9 +89,10 @@ def test_tensor_path_ties_and_duplicates(ctx):
     base = rng.integers(0, 4, size=(3000, 6)).astype(np.float64)
     X = np.vstack([base, base[:500]])
     wi, wd = oracle.knn(X, k=10)
-    idx, dist, st = ctx.knn(X, None, 10, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
-    assert (dist == wd).all() and (idx == wi).all()
-    assert st["n_uncertified"] > 0
+    for mode in (1, 2):
+        idx, dist, st = ctx.knn(X, None, 10, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, mode)
+        assert (dist == wd).all() and (idx == wi).all(), f"scan mode {mode}"
+        assert st["n_uncertified"] > 0
     Z = np.ones((2500, 20)) * 3.25
     idx, dist, st = ctx.knn(Z, None, 5, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
     assert (idx == np.tile(np.arange(1, 6), (2500, 1))).all() and (dist == 0).all()
@@ -101,9 +106,10 @@ def test_tensor_path_badly_scaled_data(ctx):
     X[:, 1] *= 1e-4
     X += 1e6
     wi, wd = oracle.knn(X, k=15, method="kdtree")
-    idx, dist, st = ctx.knn(X, None, 15, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
-    assert (dist == wd).all() and (idx == wi).all()
-    print("badly scaled: uncertified", st["n_uncertified"])
+    for mode in (1, 2):
+        idx, dist, st = ctx.knn(X, None, 15, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, mode)
+        assert (dist == wd).all() and (idx == wi).all(), f"scan mode {mode}"
+        print("badly scaled: mode", mode, "uncertified", st["n_uncertified"])
 
 
 def test_tensor_path_rejects_unsupported_shapes(ctx):

@@ -25,6 +25,7 @@ ap.add_argument("--d", type=int, default=50)
 ap.add_argument("--kp", type=int, default=32)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 exhaustive, 2 grouped")
 ap.add_argument("--sort", default="none", choices=["none", "cluster", "pc1"])
 a = ap.parse_args()
 
@@ -50,7 +51,7 @@ tau = torch.empty(a.nq, dtype=torch.float32, device="cuda")
 torch.cuda.synchronize()
 for r in range(a.reps):
     t0 = time.perf_counter()
-    ctx.dev_knn_candidates(ref, a.nr, qry, a.nq, a.d, a.kp, cand, tau, None, None)
+    ctx.dev_knn_candidates(ref, a.nr, qry, a.nq, a.d, a.kp, cand, tau, None, None, a.mode)
     dt = time.perf_counter() - t0
     print(f"rep {r}: {dt * 1e3:.2f} ms  ({a.nq * a.nr / dt / 1e12:.3f} T candidates/s, "
           f"{2 * a.nq * a.nr * a.d / dt / 1e12:.1f} algorithmic TFLOP/s)")
