@@ -105,7 +105,7 @@ struct DevInfo {
   int64_t sum_bound;
   int64_t nnz_nn;
   int64_t nnz_snn;
-  int32_t class_count[4];    // rows per work class
+  int32_t class_count[8];    // rows per work class (5 used)
   int32_t n_uncertified;
   int32_t n_long;            // columns too long for the warp-level sort
 };

@@ -315,6 +315,42 @@ __device__ __forceinline__ void hash_insert(Word *tab, uint32_t mask, int log_t,
   }
 }
 
+// Atomic-free insert for a table owned by ONE warp.  Requires that the (up to 32) keys
+// inserted by one call are pairwise distinct -- true for the entries of one reverse list
+// unless the input lists a neighbour twice (the caller then uses the atomic variant).
+// An empty slot is claimed with a plain store and a read-back (one of the racing lanes
+// wins, the others probe on); an existing key is bumped with a plain read-modify-write,
+// which no other lane can touch.  Shared-memory atomics (ATOMS.CAS) were the bottleneck
+// of this stage: ~9 SM-cycles per insert against ~1 for plain LDS/STS traffic.
+template <typename Word>
+__device__ __forceinline__ void hash_insert_warp(Word *tab, uint32_t mask, int log_t, int cbits,
+                                                 uint32_t j, bool active) {
+  const Word EMPTY = WordTraits<Word>::EMPTY;
+  uint32_t h = (j * 2654435761u) >> (32 - log_t);
+  const Word fresh = ((Word)j << cbits) | (Word)1;
+  volatile Word *vt = tab;
+  bool todo = active;
+  do {
+    // phase 1: every lane walks its own probe sequence with plain loads (cheap, divergent)
+    Word cur = EMPTY;
+    if (todo) {
+      while (true) {
+        cur = vt[h];
+        if (cur == EMPTY || (uint32_t)(cur >> cbits) == j) break;
+        h = (h + 1) & mask;
+      }
+    }
+    // phase 2 (warp-uniform): bump an existing key, or claim the empty slot
+    const bool claim = todo && cur == EMPTY;
+    if (todo && !claim) vt[h] = cur + 1;
+    if (claim) vt[h] = fresh;
+    __syncwarp();
+    // a lane whose claim was overwritten by another lane's (different) key probes on
+    todo = claim && vt[h] != fresh;
+    __syncwarp();
+  } while (__any_sync(0xffffffffu, todo));
+}
+
 // G threads cooperate on one row.  LOG_T > 0: table of 2^LOG_T words in shared
 // memory (+ a survivor buffer of half that size when G > 32);  LOG_T == 0: table
 // in HBM, survivors written straight to their slot in `tmp` and sorted there.
@@ -412,6 +448,118 @@ __global__ void __launch_bounds__(G *RPB) k_snn_rows(SnnParams P) {
   }
 }
 
+// Warp-per-row variant for the common classes (table <= 8192 words).  Compared with the
+// cooperative kernel above it needs no barriers, fetches the k list descriptors with one
+// load per lane, and keeps four list loads in flight per lane before inserting.
+template <typename Word, int LOG_T, int WARPS, bool ATOMIC>
+__global__ void __launch_bounds__(WARPS * 32) k_snn_rows_warp(SnnParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Word EMPTY = WordTraits<Word>::EMPTY;
+  constexpr uint32_t T = 1u << LOG_T;
+  constexpr uint32_t mask = T - 1;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Word *tab = reinterpret_cast<Word *>(smem_raw) + (size_t)w * T;
+  const Word cmask = (((Word)1) << P.cbits) - 1;
+  const int n_warps = gridDim.x * WARPS;
+  for (int r = blockIdx.x * WARPS + w; r < P.n_rows_class; r += n_warps) {
+    const int row_l = P.row_list[r];
+    const int64_t row = P.row_begin + row_l;
+    // 1. clear (16-byte stores)
+    {
+      constexpr int VEC = 16 / sizeof(Word);
+      uint4 e4;
+      e4.x = e4.y = e4.z = e4.w = 0xffffffffu;
+      uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+      for (uint32_t s = lane; s < T / VEC; s += 32) t4[s] = e4;
+    }
+    __syncwarp();
+    // 2. count every candidate of the k reverse lists
+    const int32_t *nbr = P.idx0 + row * P.k;
+    for (int p0 = 0; p0 < P.k; p0 += 32) {
+      int64_t beg = 0;
+      int len = 0;
+      if (p0 + lane < P.k) {
+        const int32_t c = nbr[p0 + lane];
+        beg = P.colptr[c];
+        len = (int)(P.colptr[c + 1] - beg);
+      }
+      const int np = (P.k - p0) < 32 ? (P.k - p0) : 32;
+      for (int p = 0; p < np; ++p) {
+        const int64_t b = __shfl_sync(0xffffffffu, beg, p);
+        const int l = __shfl_sync(0xffffffffu, len, p);
+        const int32_t *src = P.rev + b;
+        for (int t = lane; ATOMIC && t < l; t += 128) {
+          // up to four independent loads in flight, then the (serialising) inserts
+          const int32_t v0 = src[t];
+          const int32_t v1 = (t + 32 < l) ? src[t + 32] : -1;
+          const int32_t v2 = (t + 64 < l) ? src[t + 64] : -1;
+          const int32_t v3 = (t + 96 < l) ? src[t + 96] : -1;
+          if (ATOMIC) {
+            hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v0);
+            if (v1 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v1);
+            if (v2 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v2);
+            if (v3 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v3);
+          }
+        }
+        if (!ATOMIC) {
+          // warp-synchronous variant: the loop bound must be warp-uniform
+          for (int t0 = 0; t0 < l; t0 += 128) {
+            const int t = t0 + lane;
+            const int32_t v0 = (t < l) ? src[t] : -1;
+            const int32_t v1 = (t + 32 < l) ? src[t + 32] : -1;
+            const int32_t v2 = (t + 64 < l) ? src[t + 64] : -1;
+            const int32_t v3 = (t + 96 < l) ? src[t + 96] : -1;
+            hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v0, v0 >= 0);
+            if (t0 + 32 < l) hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v1, v1 >= 0);
+            if (t0 + 64 < l) hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v2, v2 >= 0);
+            if (t0 + 96 < l) hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v3, v3 >= 0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // 3. keep the entries that pass the prune cut-off (in-place compaction)
+    int m = 0;
+    for (uint32_t base = 0; base < T; base += 32) {
+      Word wv = tab[base + lane];
+      bool kp = (wv != EMPTY) && P.keep[(uint32_t)(wv & cmask)];
+      unsigned bal = __ballot_sync(0xffffffffu, kp);
+      if (bal) {  // warp-uniform
+        __syncwarp();
+        if (kp) tab[m + __popc(bal & ((1u << lane) - 1))] = wv;
+        m += __popc(bal);
+      }
+    }
+    __syncwarp();
+    // 4. ascending column order, 5. emit
+    bitonic_sort_asc(tab, m, lane, 32, [] { __syncwarp(); });
+    Word *dst = reinterpret_cast<Word *>(P.tmp) + P.tmp_off[row_l];
+    for (int t = lane; t < m; t += 32) dst[t] = tab[t];
+    if (lane == 0) P.row_nnz[row_l] = m;
+    __syncwarp();
+  }
+}
+
+template <typename Word, int LOG_T, int WARPS>
+int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atomic) {
+  if (P.n_rows_class <= 0) return B200NN_OK;
+  size_t smem = ((size_t)1 << LOG_T) * sizeof(Word) * WARPS;
+  int64_t want = ceil_div64(P.n_rows_class, WARPS);
+  int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
+  int blocks = (int)std::min<int64_t>(want, cap);
+  if (atomic) {
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_warp<Word, LOG_T, WARPS, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_snn_rows_warp<Word, LOG_T, WARPS, true><<<blocks, WARPS * 32, smem, ctx->stream>>>(P);
+  } else {
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_warp<Word, LOG_T, WARPS, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_snn_rows_warp<Word, LOG_T, WARPS, false><<<blocks, WARPS * 32, smem, ctx->stream>>>(P);
+  }
+  KERNEL_CHECK(ctx);
+  return B200NN_OK;
+}
+
 // expanded work, survivor bound and work class of every row
 struct RowWorkParams {
   const int32_t *idx0;
@@ -421,9 +569,9 @@ struct RowWorkParams {
   int32_t k;
   int32_t s_min;   // smallest kept count (0: nothing is ever kept)
   int64_t n;
-  int32_t class_lim[3];
+  int32_t class_lim[4];
   int32_t *row_bound;
-  int32_t *class_list;  // 4 x n_rows
+  int32_t *class_list;  // 5 x n_rows
   DevInfo *info;
 };
 
@@ -446,10 +594,10 @@ __global__ void __launch_bounds__(256) k_row_work(RowWorkParams P) {
   }
   if (act) P.row_bound[rl] = (int32_t)bound;
   int cls = -1;
-  if (act) cls = e <= P.class_lim[0] ? 0 : e <= P.class_lim[1] ? 1 : e <= P.class_lim[2] ? 2 : 3;
+  if (act) cls = e <= P.class_lim[0] ? 0 : e <= P.class_lim[1] ? 1 : e <= P.class_lim[2] ? 2 : e <= P.class_lim[3] ? 3 : 4;
   // warp-aggregated append to the class lists
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 5; ++q) {
     unsigned bal = __ballot_sync(0xffffffffu, cls == q);
     if (bal) {
       int base = 0;
@@ -508,40 +656,46 @@ int launch_class(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm) {
   return B200NN_OK;
 }
 
+// table sizes (log2 words) of the three warp-per-row classes and the block-per-row class
 struct WordCfg32 {
   typedef uint32_t Word;
-  static constexpr int L0 = 11, L1 = 13, L2 = 15;
+  static constexpr int L0 = 11, L1 = 12, L2 = 13, L3 = 15;
 };
 struct WordCfg64 {
   typedef uint64_t Word;
-  static constexpr int L0 = 10, L1 = 12, L2 = 14;
+  static constexpr int L0 = 10, L1 = 11, L2 = 12, L3 = 14;
 };
+// a table of T words takes rows with at most 0.8 T expanded candidates (distinct keys <= that)
+static inline int32_t class_limit(int log_t) { return (int32_t)(((int64_t)1 << log_t) * 4 / 5); }
 
 constexpr int HUGE_BLOCKS_PER_SM = 1;
 
 template <typename Cfg>
 int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int32_t n_rows,
-                    const int32_t class_count[4], int max_row_e) {
+                    const int32_t *class_count, int max_row_e, bool has_dups) {
   typedef typename Cfg::Word Word;
   P.row_list = class_list + 0 * (int64_t)n_rows;
   P.n_rows_class = class_count[0];
-  RC_TRY((launch_class<Word, Cfg::L0, 32, 8>(ctx, P, 3)));
+  RC_TRY((launch_class_warp<Word, Cfg::L0, 8>(ctx, P, 3, has_dups)));
   P.row_list = class_list + 1 * (int64_t)n_rows;
   P.n_rows_class = class_count[1];
-  RC_TRY((launch_class<Word, Cfg::L1, 128, 2>(ctx, P, 2)));
+  RC_TRY((launch_class_warp<Word, Cfg::L1, 4>(ctx, P, 3, has_dups)));
   P.row_list = class_list + 2 * (int64_t)n_rows;
   P.n_rows_class = class_count[2];
-  RC_TRY((launch_class<Word, Cfg::L2, 256, 1>(ctx, P, 1)));
-  if (class_count[3] > 0) {
+  RC_TRY((launch_class_warp<Word, Cfg::L2, 2>(ctx, P, 3, has_dups)));
+  P.row_list = class_list + 3 * (int64_t)n_rows;
+  P.n_rows_class = class_count[3];
+  RC_TRY((launch_class<Word, Cfg::L3, 256, 1>(ctx, P, 1)));
+  if (class_count[4] > 0) {
     int log_t = 1;
     while (((int64_t)1 << log_t) < 2 * (int64_t)max_row_e) ++log_t;
-    int64_t blocks = std::min<int64_t>(class_count[3], (int64_t)ctx->sm_count * HUGE_BLOCKS_PER_SM);
+    int64_t blocks = std::min<int64_t>(class_count[4], (int64_t)ctx->sm_count * HUGE_BLOCKS_PER_SM);
     Word *tables;
     RC_TRY(ws_get(ctx, WS_HUGE_TABLE, (size_t)blocks << log_t, &tables));
     P.huge_tables = tables;
     P.huge_log_t = log_t;
-    P.row_list = class_list + 3 * (int64_t)n_rows;
-    P.n_rows_class = class_count[3];
+    P.row_list = class_list + 4 * (int64_t)n_rows;
+    P.n_rows_class = class_count[4];
     RC_TRY((launch_class<Word, 0, 256, 1>(ctx, P, HUGE_BLOCKS_PER_SM)));
   }
   return B200NN_OK;
@@ -665,7 +819,8 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     const int64_t rows = row_end - row_begin;
     if (rows >= 0x7fffffffLL) return B200NN_ERR_INVALID;
     // count range: without duplicates |N(i) ∩ N(j)| <= k; with duplicates <= k^2
-    int64_t smax = hi.has_dups ? (int64_t)k * k : (int64_t)k;
+    const bool has_dups = hi.has_dups != 0;
+    int64_t smax = has_dups ? (int64_t)k * k : (int64_t)k;
     if (smax > (1 << 20)) {
       b200nn_set_error("k = %d with duplicated neighbours exceeds the supported count range", k);
       return B200NN_ERR_INVALID;
@@ -701,7 +856,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     int32_t *row_bound, *class_list, *row_nnz;
     int64_t *tmp_off, *snn_p;
     RC_TRY(ws_get(ctx, WS_ROW_BOUND, (size_t)rows + 1, &row_bound));
-    RC_TRY(ws_get(ctx, WS_CLASS_LIST, (size_t)rows * 4 + 4, &class_list));
+    RC_TRY(ws_get(ctx, WS_CLASS_LIST, (size_t)rows * 5 + 8, &class_list));
     RC_TRY(ws_get(ctx, WS_ROW_NNZ, (size_t)rows + 1, &row_nnz));
     RC_TRY(ws_get(ctx, WS_TMP_OFF, (size_t)rows + 1, &tmp_off));
     RC_TRY(ws_get(ctx, WS_SNN_P, (size_t)rows + 1, &snn_p));
@@ -714,12 +869,11 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     rw.k = k;
     rw.s_min = s_min;
     rw.n = n;
-    const int L0 = use32 ? WordCfg32::L0 : WordCfg64::L0;
-    const int L1 = use32 ? WordCfg32::L1 : WordCfg64::L1;
-    const int L2 = use32 ? WordCfg32::L2 : WordCfg64::L2;
-    rw.class_lim[0] = (1 << L0) / 2;
-    rw.class_lim[1] = (1 << L1) / 2;
-    rw.class_lim[2] = (1 << L2) / 2;
+    rw.class_lim[0] = class_limit(use32 ? WordCfg32::L0 : WordCfg64::L0);
+    rw.class_lim[1] = class_limit(use32 ? WordCfg32::L1 : WordCfg64::L1);
+    rw.class_lim[2] = class_limit(use32 ? WordCfg32::L2 : WordCfg64::L2);
+    // the block-per-row kernel keeps survivors in a buffer of T/2 words: E <= T/2 there
+    rw.class_lim[3] = (1 << (use32 ? WordCfg32::L3 : WordCfg64::L3)) / 2;
     rw.row_bound = row_bound;
     rw.class_list = class_list;
     rw.info = d_info;
@@ -752,10 +906,10 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     P.huge_log_t = 0;
     if (use32)
       RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, hi.class_count,
-                                        hi.max_row_e));
+                                        hi.max_row_e, has_dups));
     else
       RC_TRY(run_snn_classes<WordCfg64>(ctx, P, class_list, (int32_t)rows, hi.class_count,
-                                        hi.max_row_e));
+                                        hi.max_row_e, has_dups));
     RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
     // sync #3: nnz
     int64_t nnz = 0;
