@@ -72,6 +72,7 @@ enum WsSlot {
   WS_HUGE_TABLE,   // global-memory hash tables of the "huge row" path
   WS_OUT_P32,      // int32 copies of p for dgCMatrix
   WS_LONG_LIST,    // columns handled by the block-level sort
+  WS_OVF_LIST,     // rows that overflowed the filtered SNN kernel's exact table
   // tensor-core kNN path
   WS_TC_REF16,     // fp16 operand matrix of the reference set (K-padded, augmented)
   WS_TC_QRY16,     // fp16 operand matrix of the queries
@@ -108,6 +109,8 @@ struct DevInfo {
   int32_t class_count[8];    // rows per work class (5 used)
   int32_t n_uncertified;
   int32_t n_long;            // columns too long for the warp-level sort
+  int32_t n_ovf;             // rows the filtered SNN kernel handed to the big-table kernel
+  int32_t pad_;
 };
 
 struct CsrResult {

@@ -560,6 +560,182 @@ int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atom
   return B200NN_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Filtered warp-per-row kernel (prune cut-off needs an overlap of s_min >= 2).
+// Only ~2% of the ~1000 distinct candidates of a row survive the cut-off, so exact
+// hashing of every candidate occurrence is wasted work.  Pass A counts occurrences in
+// a direct-mapped array of byte counters (no keys, no probing; colliding keys only
+// ever over-count).  Pass B walks the lists again and sends to the exact hash table
+// only the occurrences whose counter reached s_min -- true survivors plus a few
+// collision victims (~10% of the occurrences), compacted into dense batches first.
+// The exact table is small; a row that would overflow it is handed to the big-table
+// kernel instead.  Counts, cut-off and output are exactly those of the plain kernel.
+// ---------------------------------------------------------------------------
+constexpr int F_CW_LOG = 13;                   // 8192 byte counters per row
+constexpr int F_TX_LOG = 10;                   // exact table: 1024 words
+constexpr int F_SLOTS = 800;                   // distinct keys allowed in it
+constexpr int F_SLOT_CAP = 832;
+constexpr int F_WARPS = 8;
+constexpr int F_BYTES = (1 << F_CW_LOG) + (1 << F_TX_LOG) * 4 + F_SLOT_CAP * 2 + 64 * 4;
+
+__device__ __forceinline__ uint32_t hash_cnt(uint32_t j) { return (j * 0x9E3779B1u) >> (32 - F_CW_LOG); }
+
+// exact insert of one batch (<= 32 occurrences, repeats of a key allowed)
+__device__ __forceinline__ void filt_insert_batch(uint32_t *tab, uint16_t *slots, int &nslots, int cbits,
+                                                  uint32_t j, bool active, int lane) {
+  constexpr uint32_t mask = (1u << F_TX_LOG) - 1;
+  const unsigned same = __match_any_sync(0xffffffffu, active ? j : (0x80000000u | (uint32_t)lane));
+  const bool leader = active && (__ffs(same) - 1) == lane;
+  const uint32_t inc = (uint32_t)__popc(same);
+  uint32_t h = (j * 2654435761u) >> (32 - F_TX_LOG);
+  const uint32_t fresh = (j << cbits) | inc;
+  volatile uint32_t *vt = tab;
+  bool todo = leader;
+  do {
+    uint32_t cur = 0xffffffffu;
+    if (todo) {
+      while (true) {
+        cur = vt[h];
+        if (cur == 0xffffffffu || (cur >> cbits) == j) break;
+        h = (h + 1) & mask;
+      }
+    }
+    const bool claim = todo && cur == 0xffffffffu;
+    if (todo && !claim) vt[h] = cur + inc;
+    if (claim) vt[h] = fresh;
+    __syncwarp();
+    const bool won = claim && vt[h] == fresh;
+    todo = claim && !won;
+    const unsigned wb = __ballot_sync(0xffffffffu, won);
+    if (won) {
+      const int pos = nslots + __popc(wb & ((1u << lane) - 1));
+      if (pos < F_SLOT_CAP) slots[pos] = (uint16_t)h;
+    }
+    nslots += __popc(wb);
+    __syncwarp();
+  } while (__any_sync(0xffffffffu, todo));
+}
+
+__global__ void __launch_bounds__(F_WARPS * 32)
+k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem_raw + (size_t)w * F_BYTES;
+  uint8_t *cnt = base;
+  uint32_t *tab = reinterpret_cast<uint32_t *>(base + (1 << F_CW_LOG));
+  uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
+  uint32_t *pend = reinterpret_cast<uint32_t *>(slots + F_SLOT_CAP);
+  const uint32_t cmask = (1u << P.cbits) - 1;
+  for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+  const int n_warps = gridDim.x * F_WARPS;
+  for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
+    const int row_l = P.row_list[r];
+    const int64_t row = P.row_begin + row_l;
+    {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
+      for (int s = lane; s < (1 << F_CW_LOG) / 16; s += 32) c4[s] = z;
+    }
+    __syncwarp();
+    const int32_t *nbr = P.idx0 + row * P.k;
+    int nslots = 0, npend = 0;
+    bool ovf = false;
+    for (int pass = 0; pass < 2 && !ovf; ++pass) {
+      for (int p0 = 0; p0 < P.k && !ovf; p0 += 32) {
+        int64_t beg = 0;
+        int len = 0;
+        if (p0 + lane < P.k) {
+          const int32_t c = nbr[p0 + lane];
+          beg = P.colptr[c];
+          len = (int)(P.colptr[c + 1] - beg);
+        }
+        const int np = (P.k - p0) < 32 ? (P.k - p0) : 32;
+        for (int p = 0; p < np && !ovf; ++p) {
+          const int64_t b = __shfl_sync(0xffffffffu, beg, p);
+          const int l = __shfl_sync(0xffffffffu, len, p);
+          const int32_t *src = P.rev + b;
+          for (int t0 = 0; t0 < l; t0 += 128) {
+            int32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (t0 + 32 * u + lane < l) ? src[t0 + 32 * u + lane] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (t0 + 32 * u >= l) break;  // warp-uniform
+              const bool act = v[u] >= 0;
+              const uint32_t hc = hash_cnt((uint32_t)v[u]);
+              if (pass == 0) {
+                // occurrences of one list are distinct rows, but two of them may share a counter
+                const unsigned same = __match_any_sync(0xffffffffu, act ? hc : (0x80000000u | (uint32_t)lane));
+                if (act && (__ffs(same) - 1) == lane) {
+                  const int c = (int)cnt[hc] + __popc(same);
+                  cnt[hc] = (uint8_t)(c > 255 ? 255 : c);
+                }
+                __syncwarp();
+              } else {
+                const bool pass_f = act && (int)cnt[hc] >= s_min;
+                const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
+                if (bal) {
+                  if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
+                  npend += __popc(bal);
+                  __syncwarp();
+                  if (npend >= 32) {
+                    filt_insert_batch(tab, slots, nslots, P.cbits, pend[lane], true, lane);
+                    const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
+                    __syncwarp();
+                    if (32 + lane < npend) pend[lane] = mv;
+                    npend -= 32;
+                    __syncwarp();
+                    if (nslots > F_SLOTS) ovf = true;
+                  }
+                }
+              }
+            }
+            if (ovf) break;
+          }
+        }
+      }
+    }
+    if (!ovf && npend > 0) {
+      filt_insert_batch(tab, slots, nslots, P.cbits, lane < npend ? pend[lane] : 0, lane < npend, lane);
+      if (nslots > F_SLOTS) ovf = true;
+    }
+    __syncwarp();
+    if (ovf) {
+      // hand the row to the big-table kernel; leave the table clean
+      for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+      if (lane == 0) {
+        P.row_nnz[row_l] = 0;
+        ovf_list[atomicAdd(&info->n_ovf, 1)] = row_l;
+      }
+      __syncwarp();
+      continue;
+    }
+    // survivors: exact counts against the cut-off, compacted into the (now free) counter area
+    uint32_t *out = reinterpret_cast<uint32_t *>(cnt);
+    int m = 0;
+    for (int t0 = 0; t0 < nslots; t0 += 32) {
+      const int t = t0 + lane;
+      uint32_t wv = 0;
+      bool kp = false;
+      if (t < nslots) {
+        const int sl = slots[t];
+        wv = tab[sl];
+        tab[sl] = 0xffffffffu;
+        kp = P.keep[wv & cmask] != 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, kp);
+      if (kp) out[m + __popc(bal & ((1u << lane) - 1))] = wv;
+      m += __popc(bal);
+    }
+    __syncwarp();
+    bitonic_sort_asc(out, m, lane, 32, [] { __syncwarp(); });
+    uint32_t *dst = reinterpret_cast<uint32_t *>(P.tmp) + P.tmp_off[row_l];
+    for (int t = lane; t < m; t += 32) dst[t] = out[t];
+    if (lane == 0) P.row_nnz[row_l] = m;
+    __syncwarp();
+  }
+}
+
 // expanded work, survivor bound and work class of every row
 struct RowWorkParams {
   const int32_t *idx0;
@@ -672,17 +848,34 @@ constexpr int HUGE_BLOCKS_PER_SM = 1;
 
 template <typename Cfg>
 int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int32_t n_rows,
-                    const int32_t *class_count, int max_row_e, bool has_dups) {
+                    const int32_t *class_count, int max_row_e, bool has_dups, int filter_s_min,
+                    int32_t *ovf_list, DevInfo *d_info) {
   typedef typename Cfg::Word Word;
-  P.row_list = class_list + 0 * (int64_t)n_rows;
-  P.n_rows_class = class_count[0];
-  RC_TRY((launch_class_warp<Word, Cfg::L0, 8>(ctx, P, 3, has_dups)));
-  P.row_list = class_list + 1 * (int64_t)n_rows;
-  P.n_rows_class = class_count[1];
-  RC_TRY((launch_class_warp<Word, Cfg::L1, 4>(ctx, P, 3, has_dups)));
-  P.row_list = class_list + 2 * (int64_t)n_rows;
-  P.n_rows_class = class_count[2];
-  RC_TRY((launch_class_warp<Word, Cfg::L2, 2>(ctx, P, 3, has_dups)));
+  if (filter_s_min >= 2) {
+    // classes 0-2 through the filtered kernel; overflowing rows are re-run below
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                F_BYTES * F_WARPS));
+    for (int c = 0; c < 3; ++c) {
+      P.row_list = class_list + c * (int64_t)n_rows;
+      P.n_rows_class = class_count[c];
+      if (P.n_rows_class <= 0) continue;
+      int64_t want = ceil_div64(P.n_rows_class, F_WARPS);
+      int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
+      k_snn_rows_filter<<<blocks, F_WARPS * 32, F_BYTES * F_WARPS, ctx->stream>>>(P, filter_s_min, ovf_list,
+                                                                                  d_info);
+      KERNEL_CHECK(ctx);
+    }
+  } else {
+    P.row_list = class_list + 0 * (int64_t)n_rows;
+    P.n_rows_class = class_count[0];
+    RC_TRY((launch_class_warp<Word, Cfg::L0, 8>(ctx, P, 3, has_dups)));
+    P.row_list = class_list + 1 * (int64_t)n_rows;
+    P.n_rows_class = class_count[1];
+    RC_TRY((launch_class_warp<Word, Cfg::L1, 4>(ctx, P, 3, has_dups)));
+    P.row_list = class_list + 2 * (int64_t)n_rows;
+    P.n_rows_class = class_count[2];
+    RC_TRY((launch_class_warp<Word, Cfg::L2, 2>(ctx, P, 3, has_dups)));
+  }
   P.row_list = class_list + 3 * (int64_t)n_rows;
   P.n_rows_class = class_count[3];
   RC_TRY((launch_class<Word, Cfg::L3, 256, 1>(ctx, P, 1)));
@@ -697,6 +890,17 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     P.row_list = class_list + 4 * (int64_t)n_rows;
     P.n_rows_class = class_count[4];
     RC_TRY((launch_class<Word, 0, 256, 1>(ctx, P, HUGE_BLOCKS_PER_SM)));
+  }
+  if (filter_s_min >= 2) {
+    // rows whose exact table overflowed in the filtered kernel (E <= 0.8 * 2^L2 <= 2^L3 / 2)
+    int32_t n_ovf = 0;
+    CU_TRY(cudaMemcpyAsync(&n_ovf, &d_info->n_ovf, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (n_ovf > 0) {
+      P.row_list = ovf_list;
+      P.n_rows_class = n_ovf;
+      RC_TRY((launch_class<Word, Cfg::L3, 256, 1>(ctx, P, 1)));
+    }
   }
   return B200NN_OK;
 }
@@ -904,12 +1108,17 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     P.row_nnz = row_nnz;
     P.huge_tables = nullptr;
     P.huge_log_t = 0;
+    int32_t *ovf_list;
+    RC_TRY(ws_get(ctx, WS_OVF_LIST, (size_t)rows + 1, &ovf_list));
+    // the filtered kernel needs 32-bit words, no duplicated neighbours, byte-sized counts
+    // and a cut-off that actually removes single overlaps
+    const int filter_s_min = (use32 && !has_dups && k <= 255 && s_min >= 2 && s_min <= 255) ? s_min : 0;
     if (use32)
       RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, hi.class_count,
-                                        hi.max_row_e, has_dups));
+                                        hi.max_row_e, has_dups, filter_s_min, ovf_list, d_info));
     else
       RC_TRY(run_snn_classes<WordCfg64>(ctx, P, class_list, (int32_t)rows, hi.class_count,
-                                        hi.max_row_e, has_dups));
+                                        hi.max_row_e, has_dups, 0, ovf_list, d_info));
     RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
     // sync #3: nnz
     int64_t nnz = 0;
