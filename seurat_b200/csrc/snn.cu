@@ -571,14 +571,14 @@ int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atom
 // The exact table is small; a row that would overflow it is handed to the big-table
 // kernel instead.  Counts, cut-off and output are exactly those of the plain kernel.
 // ---------------------------------------------------------------------------
-constexpr int F_CW_LOG = 13;                   // 8192 byte counters per row
 constexpr int F_TX_LOG = 10;                   // exact table: 1024 words
 constexpr int F_SLOTS = 800;                   // distinct keys allowed in it
 constexpr int F_SLOT_CAP = 832;
 constexpr int F_WARPS = 8;
-constexpr int F_BYTES = (1 << F_CW_LOG) + (1 << F_TX_LOG) * 4 + F_SLOT_CAP * 2 + 64 * 4;
+constexpr int filt_bytes(int cw_log) { return (1 << cw_log) + (1 << F_TX_LOG) * 4 + F_SLOT_CAP * 2 + 64 * 4; }
 
-__device__ __forceinline__ uint32_t hash_cnt(uint32_t j) { return (j * 0x9E3779B1u) >> (32 - F_CW_LOG); }
+template <int CW_LOG>
+__device__ __forceinline__ uint32_t hash_cnt(uint32_t j) { return (j * 0x9E3779B1u) >> (32 - CW_LOG); }
 
 // exact insert of one batch (<= 32 occurrences, repeats of a key allowed)
 __device__ __forceinline__ void filt_insert_batch(uint32_t *tab, uint16_t *slots, int &nslots, int cbits,
@@ -616,8 +616,12 @@ __device__ __forceinline__ void filt_insert_batch(uint32_t *tab, uint16_t *slots
   } while (__any_sync(0xffffffffu, todo));
 }
 
+template <int CW_LOG>  // log2 of the number of byte counters per row
 __global__ void __launch_bounds__(F_WARPS * 32)
 k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+  constexpr int F_BYTES = filt_bytes(CW_LOG);
+  constexpr int F_CW_LOG = CW_LOG;
+  static_assert((1 << CW_LOG) >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + (size_t)w * F_BYTES;
@@ -658,21 +662,32 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
             int32_t v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = (t0 + 32 * u + lane < l) ? src[t0 + 32 * u + lane] : -1;
+            uint32_t hc[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (t0 + 32 * u >= l) break;  // warp-uniform
-              const bool act = v[u] >= 0;
-              const uint32_t hc = hash_cnt((uint32_t)v[u]);
-              if (pass == 0) {
-                // occurrences of one list are distinct rows, but two of them may share a counter
-                const unsigned same = __match_any_sync(0xffffffffu, act ? hc : (0x80000000u | (uint32_t)lane));
-                if (act && (__ffs(same) - 1) == lane) {
-                  const int c = (int)cnt[hc] + __popc(same);
-                  cnt[hc] = (uint8_t)(c > 255 ? 255 : c);
+            for (int u = 0; u < 4; ++u) hc[u] = hash_cnt<CW_LOG>((uint32_t)v[u]);
+            if (pass == 0) {
+              // occurrences of one list are distinct rows, but two of them may share a counter:
+              // MATCH finds the lanes with equal counter index; all four are issued before use
+              unsigned same[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                same[u] = (t0 + 32 * u < l)
+                              ? __match_any_sync(0xffffffffu, v[u] >= 0 ? hc[u] : (0x80000000u | (uint32_t)lane))
+                              : 0u;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (t0 + 32 * u >= l) break;  // warp-uniform
+                if (v[u] >= 0 && (__ffs(same[u]) - 1) == lane) {
+                  const int c = (int)cnt[hc[u]] + __popc(same[u]);
+                  cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
                 }
                 __syncwarp();
-              } else {
-                const bool pass_f = act && (int)cnt[hc] >= s_min;
+              }
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (t0 + 32 * u >= l) break;  // warp-uniform
+                const bool pass_f = v[u] >= 0 && (int)cnt[hc[u]] >= s_min;
                 const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
                 if (bal) {
                   if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
@@ -853,16 +868,24 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
   typedef typename Cfg::Word Word;
   if (filter_s_min >= 2) {
     // classes 0-2 through the filtered kernel; overflowing rows are re-run below
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                F_BYTES * F_WARPS));
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                filt_bytes(12) * F_WARPS));
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                filt_bytes(13) * F_WARPS));
     for (int c = 0; c < 3; ++c) {
       P.row_list = class_list + c * (int64_t)n_rows;
       P.n_rows_class = class_count[c];
       if (P.n_rows_class <= 0) continue;
       int64_t want = ceil_div64(P.n_rows_class, F_WARPS);
-      int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
-      k_snn_rows_filter<<<blocks, F_WARPS * 32, F_BYTES * F_WARPS, ctx->stream>>>(P, filter_s_min, ovf_list,
-                                                                                  d_info);
+      if (c == 0) {  // few distinct candidates: 4096 counters suffice
+        int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
+        k_snn_rows_filter<12><<<blocks, F_WARPS * 32, filt_bytes(12) * F_WARPS, ctx->stream>>>(
+            P, filter_s_min, ovf_list, d_info);
+      } else {
+        int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
+        k_snn_rows_filter<13><<<blocks, F_WARPS * 32, filt_bytes(13) * F_WARPS, ctx->stream>>>(
+            P, filter_s_min, ovf_list, d_info);
+      }
       KERNEL_CHECK(ctx);
     }
   } else {
