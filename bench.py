@@ -166,6 +166,15 @@ def run_reference_arm(args, cfg):
     print(json.dumps(line))
 
 
+def traffic_from_profiles(kernel: str):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), else None"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
 def workload_config(cfg, gpus):
     return {"workload": f"synthetic Gaussian mixture {cfg['n']} cells x {cfg['d']} PCs, k={cfg['k']}, prune.SNN=1/15 "
                         f"(SURVEY 8d seed {cfg['seed']})",
@@ -184,6 +193,8 @@ def main():
     ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
     ap.add_argument("--n", type=int, default=0, help="override the number of cells (debugging)")
     ap.add_argument("--knn-algo", type=int, default=0, help="0 auto, 1 exact FP64 scan, 2 tensor-core")
+    ap.add_argument("--scan-mode", type=int, default=0,
+                    help="tensor path: 0 auto (grouped, tile-pruned), 1 exhaustive scan of every tile, 2 grouped")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-knn-sample", type=int, default=2000)
     ap.add_argument("--cpu-snn-rows", type=int, default=100_000)
@@ -216,7 +227,7 @@ def main():
 
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
     X, _ = gaussian_mixture(n, d, cfg["seed"])           # identical on every rank (seeded)
-    be = sdist.CudaBackend(local, knn_algo=args.knn_algo)
+    be = sdist.CudaBackend(local, knn_algo=args.knn_algo, scan_mode=args.scan_mode)
     ctx = be.ctx
     ref = torch.from_numpy(X).to(dev)
     torch.cuda.synchronize()
@@ -237,6 +248,9 @@ def main():
         idx0, dd = be.knn_shard(ref, b, e, k)
         s1 = dict(be.last_stats)
         idx_full = sdist.all_gather_index(idx0, n) if world > 1 else idx0
+        if world > 1:
+            # the library runs on its own stream: the all-gather (NCCL stream) must have landed
+            torch.cuda.current_stream().synchronize()
         g = be.ctx.dev_graphs(idx_full, n, k, PRUNE, True, b, e)
         if record:
             for key in ("knn_cand", "knn_rerank", "knn_fallback"):
@@ -285,9 +299,10 @@ def main():
                "nn_p": pin(n + 1, torch.int32), "nn_i": pin(nnz_nn, torch.int32), "nn_x": pin(nnz_nn, torch.float64),
                "snn_p": pin(n + 1, torch.int32), "snn_i": pin(slack, torch.int32), "snn_x": pin(slack, torch.float64)}
         times = []
-        for s in range(1 + args.e2e_steps):
+        for s in range(1 + max(1, args.e2e_steps)):
             t0 = time.perf_counter()
-            r = ctx.find_neighbors(Xh, k, PRUNE, True, _lib.ROW_MAJOR, args.knn_algo, 0, True, out)
+            r = ctx.find_neighbors(Xh, k, PRUNE, True, _lib.ROW_MAJOR, args.knn_algo, 0, True, out,
+                                   scan_mode=args.scan_mode)
             t1 = time.perf_counter()
             if s > 0:
                 times.append(t1 - t0)
@@ -300,7 +315,7 @@ def main():
         # every rank: H2D of the replicated embedding + its query shard's results back
         Xp = torch.from_numpy(X).pin_memory()
         times = []
-        for s in range(1 + args.e2e_steps):
+        for s in range(1 + max(1, args.e2e_steps)):
             barrier()
             t0 = time.perf_counter()
             refe = Xp.to(dev, non_blocking=True)
@@ -331,13 +346,28 @@ def main():
     knn_ms = st["knn_cand"] if st["knn_cand"] > 0 else st["knn_fallback"]
     flops = 2.0 * nq_local * n * d
     tensor_peak = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": "knn_tc_candidates (tcgen05)" if st["knn_cand"] > 0 else "k_knn_exact (FP64 scan, no tensor cores)",
+    ks = last["knn"]
+    tv, tt = ks.get("knn_tiles_visited", 0), ks.get("knn_tiles_total", 0)
+    roofline = {"kernel": "k_knn_tc (tcgen05 candidates, both passes + list building)" if st["knn_cand"] > 0
+                else "k_knn_exact (FP64 scan, no tensor cores)",
                 "bound": "tensor", "achieved": flops / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else None,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": None, "traffic": traffic_from_profiles("k_knn_tc"),
                 "peak_source": peaks["source"] + " bf16 sustained", "algorithmic_flops_per_launch": flops,
                 "ms_per_launch": knn_ms}
     if roofline["achieved"]:
         roofline["frac"] = roofline["achieved"] / tensor_peak
+    if tt:
+        # the grouped search skips (item, tile) pairs that provably hold no neighbour, so the
+        # ALGORITHMIC rate can exceed the tensor peak; the executed rate cannot
+        exec_flops = 2.0 * tv * 256 * 128 * 64
+        roofline.update({
+            "tiles_visited": tv, "tiles_total": tt, "tiles_visited_frac": tv / tt,
+            "executed_mma_tflops": exec_flops / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else None,
+            "candidates_per_s_executed": tv * 256 * 128 / (knn_ms * 1e-3) if knn_ms > 0 else None,
+            "note": ("frac uses the algorithmic 2*nq*nr*d FLOPs of SURVEY 8d; the grouped search visits only "
+                     "tiles_visited_frac of the key tiles (bound-based skipping, result certified exact). "
+                     "The exhaustive scan (--scan-mode 1) is limited by the TMEM read path at 16 keys/clk/SM, "
+                     "see DESIGN.md section 4")})
     g = last["graphs"]
     rows_local = e - b
     snn_bytes = 4.0 * n * k + (4.0 * (n + 1) + 12.0 * g["nnz_nn"]) + (4.0 * (rows_local + 1) + 12.0 * g["nnz_snn"])
@@ -345,7 +375,8 @@ def main():
     roofline_snn = {"kernel": "K3 transpose + K4 SNN rows (stage total)", "bound": "hbm",
                     "achieved": snn_bytes / (snn_ms * 1e-3) / 1e9 if snn_ms > 0 else None, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "algorithmic_bytes": snn_bytes, "ms": snn_ms,
-                    "expanded_bytes": 4.0 * g.get("snn_expanded", 0), "traffic": None}
+                    "expanded_bytes": 4.0 * g.get("snn_expanded", 0),
+                    "traffic": traffic_from_profiles("k_snn_rows_filter")}
     if roofline_snn["achieved"]:
         roofline_snn["frac"] = roofline_snn["achieved"] / peaks["hbm_gbs"]
 

@@ -90,6 +90,8 @@ typedef struct b200nn_stats {
   int64_t snn_expanded;   /* sum over rows of expanded candidates (sum_c indeg^2)    */
   int64_t max_indegree;   /* longest reverse-neighbour list                          */
   int64_t gpu_launches;   /* kernels launched by this call                           */
+  int64_t knn_tiles_visited; /* (work item, reference tile) pairs the tensor kernel scanned  */
+  int64_t knn_tiles_total;   /* ... out of this many (equal for the exhaustive scan)         */
 } b200nn_stats;
 
 /* ---- context ---------------------------------------------------------- */

@@ -47,7 +47,7 @@ class Stats(C.Structure):
                  "ms_nn_graph", "ms_snn", "ms_d2h")] + \
                [(n, C.c_int64) for n in
                 ("n_uncertified", "nnz_nn", "nnz_snn", "snn_expanded", "max_indegree",
-                 "gpu_launches")]
+                 "gpu_launches", "knn_tiles_visited", "knn_tiles_total")]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -187,7 +187,7 @@ class Context:
 
     def find_neighbors(self, data, k: int, prune: float, compute_snn: bool, layout: int,
                        algo: int = KNN_AUTO, n_cand: int = 0, want_knn: bool = True,
-                       out: dict | None = None):
+                       out: dict | None = None, scan_mode: int = 0):
         """Fused kNN + nn Graph (+ SNN) on host buffers.  `out` may carry
         preallocated (pinned) result arrays keyed idx/dist/nn_p/nn_i/nn_x/snn_p/snn_i/snn_x."""
         n, d = data.shape
@@ -201,7 +201,7 @@ class Context:
                 idx = np.empty((n, k), dtype=np.int32, order=order)
             if dist is None:
                 dist = np.empty((n, k), dtype=np.float64, order=order)
-        o = Opts(layout, algo, n_cand, 0)
+        o = Opts(layout, algo, n_cand, scan_mode)
         st = Stats()
         nnz_nn, nnz_snn = C.c_int64(0), C.c_int64(0)
         check(self._L.b200nn_find_neighbors_count(self._h, _ptr(data), n, d, k, float(prune),

@@ -65,6 +65,8 @@ struct TcMisc {            // small device-resident state of one kNN call
   double qn2_max;
   int32_t n_fail;
   int32_t hang;            // set when an mbarrier wait timed out
+  long long tiles_visited; // (item, tile) pairs of the last candidate launch
+  long long tiles_total;
 };
 
 // ---------------------------------------------------------------------------
@@ -633,6 +635,8 @@ k_mean_final(const double *__restrict__ partial, int64_t n, int d, TcMisc *__res
     misc->qn2_max = 0.0;
     misc->n_fail = 0;
     misc->hang = 0;
+    misc->tiles_visited = 0;
+    misc->tiles_total = 0;
   }
 }
 
@@ -1136,24 +1140,60 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
   if (tid == 0) list_cnt[item] = total;
 }
 
-// items ordered by decreasing list length (counting sort; one block)
+// items ordered by decreasing list length (counting sort; one block of 1024 threads)
 __global__ void __launch_bounds__(1024)
 k_order_items(const int32_t *__restrict__ list_cnt, int n_items, int max_cnt, int32_t *__restrict__ bins,
-              int32_t *__restrict__ order) {
-  for (int b = threadIdx.x; b <= max_cnt; b += blockDim.x) bins[b] = 0;
+              int32_t *__restrict__ order, TcMisc *__restrict__ misc) {
+  __shared__ int s_part[1024];
+  __shared__ long long s_vis[32];
+  const int tid = threadIdx.x;
+  for (int b = tid; b <= max_cnt; b += blockDim.x) bins[b] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n_items; i += blockDim.x) atomicAdd(&bins[list_cnt[i]], 1);
+  for (int i = tid; i < n_items; i += blockDim.x) atomicAdd(&bins[list_cnt[i]], 1);
   __syncthreads();
-  if (threadIdx.x == 0) {  // descending exclusive scan
+  // descending exclusive scan over bins: thread t owns a contiguous chunk, highest bins first
+  const int per = (max_cnt + 1 + 1023) / 1024;
+  const int hi = max_cnt - tid * per;            // first (largest) bin of this thread
+  int local = 0;
+  long long vis = 0;
+  for (int u = 0; u < per; ++u) {
+    const int b = hi - u;
+    if (b >= 0) {
+      local += bins[b];
+      vis += (long long)b * bins[b];
+    }
+  }
+  s_part[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
     int run = 0;
-    for (int b = max_cnt; b >= 0; --b) {
-      int c = bins[b];
+    for (int t = 0; t < 1024; ++t) {
+      int c = s_part[t];
+      s_part[t] = run;
+      run += c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(0xffffffffu, vis, o);
+  if ((tid & 31) == 0) s_vis[tid >> 5] = vis;
+  __syncthreads();
+  int run = s_part[tid];
+  for (int u = 0; u < per; ++u) {
+    const int b = hi - u;
+    if (b >= 0) {
+      const int c = bins[b];
       bins[b] = run;
       run += c;
     }
   }
+  if (tid == 0) {
+    long long v = 0;
+    for (int w = 0; w < 32; ++w) v += s_vis[w];
+    misc->tiles_visited = v;
+    misc->tiles_total = (long long)n_items * max_cnt;
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_items; i += blockDim.x) order[atomicAdd(&bins[list_cnt[i]], 1)] = i;
+  for (int i = tid; i < n_items; i += blockDim.x) order[atomicAdd(&bins[list_cnt[i]], 1)] = i;
 }
 
 // ---------------------------------------------------------------------------
@@ -1573,7 +1613,7 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
                                                       P.list_stride, tiles, list_cnt);
     KERNEL_CHECK(ctx);
     P.pass1 = 0;
-    k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order);
+    k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc);
     KERNEL_CHECK(ctx);
     P.order = order;
     RC_TRY(debug_list_stats(ctx, "pass 2", list_cnt, P.n_items, item_T, item_rad));
@@ -1647,6 +1687,9 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
     CU_TRY(cudaEventElapsedTime(&ms, e1, e2));
     stats->ms_knn_fallback += ms;
     stats->n_uncertified = h.n_fail;
+    const long long all = (long long)ceil_div64(nq, QT * BM) * ceil_div64(nr, BN);
+    stats->knn_tiles_visited = h.tiles_total ? h.tiles_visited : all;
+    stats->knn_tiles_total = all;
   }
   return B200NN_OK;
 }

@@ -31,10 +31,10 @@ def shard_bounds(n: int, world: int) -> list[tuple[int, int]]:
 class CudaBackend:
     """Compute stages on this rank's GPU through libb200nn's device-buffer entry points."""
 
-    def __init__(self, device: int, knn_algo: int = _lib.KNN_AUTO, n_cand: int = 0):
+    def __init__(self, device: int, knn_algo: int = _lib.KNN_AUTO, n_cand: int = 0, scan_mode: int = 0):
         self.device = torch.device("cuda", device)
         self.ctx = _lib.Context(device)
-        self.knn_algo, self.n_cand = knn_algo, n_cand
+        self.knn_algo, self.n_cand, self.scan_mode = knn_algo, n_cand, scan_mode
         self.last_stats: dict = {}
 
     def knn_shard(self, ref: torch.Tensor, q_begin: int, q_end: int, k: int, qry: torch.Tensor | None = None):
@@ -47,7 +47,8 @@ class CudaBackend:
         if rows > 0:
             q = src[q_begin:q_end]
             torch.cuda.current_stream(self.device).synchronize()
-            self.last_stats = self.ctx.dev_knn(ref, nr, q, rows, d, k, idx0, dst, self.knn_algo, self.n_cand)
+            self.last_stats = self.ctx.dev_knn(ref, nr, q, rows, d, k, idx0, dst, self.knn_algo, self.n_cand,
+                                               self.scan_mode)
         return idx0, dst
 
     def graph_rows(self, idx0_full: torch.Tensor, k: int, prune: float, compute_snn: bool,

@@ -1,0 +1,38 @@
+# b200nn.R -- R side of the drop-in (not run in the build container: no R there).
+#
+# Adds one arm to NNHelper's switch (R/clustering.R:1660-1677) and routes ComputeSNN
+# (R/RcppExports.R:96-98) through the GPU library when options(Seurat.nn.backend = "b200").
+# FindNeighbors.default / .Seurat keep their signatures and return values
+# (list(nn = Graph, snn = Graph) or a Neighbor), see R/clustering.R:582-685, 790-898.
+
+b200_nn2 <- function(data, query = data, k, ...) {
+  self <- identical(query, data)
+  storage.mode(data) <- "double"
+  if (!self) storage.mode(query) <- "double"
+  .Call("b200_nn2", data, if (self) NULL else query, as.integer(k), PACKAGE = "b200nn")
+}
+
+# In NNHelper (R/clustering.R:1660):
+#   "b200" = {
+#     args <- args[intersect(x = names(x = args), y = names(x = formals(fun = b200_nn2)))]
+#     do.call(what = 'b200_nn2', args = args)
+#   },
+# and nn.method = "rann" is redirected there when the backend option is set:
+#   if (method == "rann" && identical(getOption("Seurat.nn.backend"), "b200")) method <- "b200"
+
+ComputeSNN <- function(nn_ranked, prune) {
+  if (identical(getOption("Seurat.nn.backend"), "b200")) {
+    return(.Call("b200_ComputeSNN", nn_ranked, as.double(prune), PACKAGE = "b200nn"))
+  }
+  .Call('_Seurat_ComputeSNN', PACKAGE = 'Seurat', nn_ranked, prune)
+}
+
+# Optional fused path inside FindNeighbors.default, replacing R/clustering.R:633-682 when
+# query is NULL, return.neighbor is FALSE, nn.method is "rann"/"b200" and nn.eps == 0:
+#   g <- .Call("b200_FindNeighbors", object, as.integer(k.param), as.double(prune.SNN),
+#              isTRUE(compute.SNN), PACKAGE = "b200nn")
+#   for (nm in names(g)) { dimnames(g[[nm]]) <- list(rownames(object), rownames(object))
+#                          g[[nm]] <- as.Graph(g[[nm]]) }
+#   return(g)
+
+.onUnload <- function(libpath) .Call("b200_release", PACKAGE = "b200nn")

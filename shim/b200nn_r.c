@@ -1,0 +1,170 @@
+/*
+ * b200nn_r.c -- the `.Call` shim between R and libb200nn.so.
+ *
+ * NOT compiled in the build container (no R headers there); it is the binding a
+ * Seurat maintainer adds under src/ next to RcppExports.cpp.  It only marshals:
+ * every computation happens behind the C ABI of include/b200nn.h, which is what
+ * the test-suite exercises (through ctypes).
+ *
+ * Entry points and what they replace in the reference:
+ *   b200_nn2(data, query, k)        RANN::nn2(data, query, k, searchtype = "standard",
+ *                                   eps = 0) as reached from NNHelper,
+ *                                   R/clustering.R:1664-1667  -> list(nn.idx, nn.dists)
+ *   b200_ComputeSNN(nn_ranked, prune)  .Call('_Seurat_ComputeSNN', ...),
+ *                                   R/RcppExports.R:96-98, src/RcppExports.cpp:313-323
+ *                                   -> dgCMatrix (no dimnames; the caller sets them)
+ *   b200_FindNeighbors(data, k, prune, compute_snn)  the body of FindNeighbors.default,
+ *                                   R/clustering.R:633-682, with the index kept on the GPU
+ *                                   -> list(nn = dgCMatrix, snn = dgCMatrix)
+ * Registration follows src/RcppExports.cpp:407-445 (R_CallMethodDef table,
+ * R_registerRoutines, R_useDynamicSymbols(dll, FALSE)).
+ *
+ * Rules honoured: R owns every input and output vector (allocated here with
+ * Rf_allocVector and PROTECTed); the library never keeps an R pointer after a call;
+ * the C ABI never long-jumps, so the return code is checked after all transient state
+ * is released and only then turned into Rf_error().
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdint.h>
+
+#include "b200nn.h"
+
+static b200nn_ctx *g_ctx = NULL;
+
+static b200nn_ctx *get_ctx(void) {
+  if (g_ctx == NULL) {
+    const char *dev = getenv("B200NN_DEVICE");
+    if (b200nn_ctx_create(dev ? atoi(dev) : 0, &g_ctx) != B200NN_OK) Rf_error("%s", b200nn_last_error());
+  }
+  return g_ctx;
+}
+
+static SEXP make_dgCMatrix(int n, int64_t nnz, SEXP p, SEXP i, SEXP x) {
+  SEXP cls = PROTECT(R_do_MAKE_CLASS("dgCMatrix"));
+  SEXP m = PROTECT(R_do_new_object(cls));
+  SEXP dim = PROTECT(Rf_allocVector(INTSXP, 2));
+  INTEGER(dim)[0] = n;
+  INTEGER(dim)[1] = n;
+  R_do_slot_assign(m, Rf_install("Dim"), dim);
+  R_do_slot_assign(m, Rf_install("p"), p);
+  R_do_slot_assign(m, Rf_install("i"), i);
+  R_do_slot_assign(m, Rf_install("x"), x);
+  UNPROTECT(3);
+  (void)nnz;
+  return m;
+}
+
+/* RANN::nn2 drop-in: data, query are double matrices (column-major); query may be R_NilValue */
+SEXP b200_nn2(SEXP data, SEXP query, SEXP k_) {
+  if (!Rf_isReal(data) || !Rf_isMatrix(data)) Rf_error("data must be a numeric matrix");
+  const int nr = Rf_nrows(data), d = Rf_ncols(data), k = Rf_asInteger(k_);
+  const int self = Rf_isNull(query);
+  const int nq = self ? nr : Rf_nrows(query);
+  if (!self && Rf_ncols(query) != d) Rf_error("Query and data tables must have same dimensions");
+  if (k > nr) Rf_error("Cannot find more nearest neighbours than there are points");
+  SEXP idx = PROTECT(Rf_allocMatrix(INTSXP, nq, k));
+  SEXP dist = PROTECT(Rf_allocMatrix(REALSXP, nq, k));
+  b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
+  int rc = b200nn_knn(get_ctx(), REAL(data), nr, self ? NULL : REAL(query), nq, d, k, INTEGER(idx),
+                      REAL(dist), &o, NULL);
+  if (rc != B200NN_OK) {
+    UNPROTECT(2);
+    Rf_error("%s", b200nn_last_error());
+  }
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP nms = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_VECTOR_ELT(res, 0, idx);
+  SET_VECTOR_ELT(res, 1, dist);
+  SET_STRING_ELT(nms, 0, Rf_mkChar("nn.idx"));
+  SET_STRING_ELT(nms, 1, Rf_mkChar("nn.dists"));
+  Rf_setAttrib(res, R_NamesSymbol, nms);
+  UNPROTECT(4);
+  return res;
+}
+
+/* ComputeSNN drop-in: nn_ranked integer or double matrix (1-based), prune double */
+SEXP b200_ComputeSNN(SEXP nn_ranked, SEXP prune_) {
+  SEXP nn = PROTECT(Rf_coerceVector(nn_ranked, INTSXP)); /* Rcpp coerces to double; values are whole */
+  SEXP dims = Rf_getAttrib(nn_ranked, R_DimSymbol);
+  if (Rf_isNull(dims)) {
+    UNPROTECT(1);
+    Rf_error("nn_ranked must be a matrix");
+  }
+  const int n = INTEGER(dims)[0], k = INTEGER(dims)[1];
+  int64_t nnz = 0;
+  b200nn_opts o = {B200NN_COL_MAJOR, 0, 0, 0};
+  int rc = b200nn_snn_count(get_ctx(), INTEGER(nn), n, k, Rf_asReal(prune_), &o, &nnz, NULL);
+  if (rc != B200NN_OK) {
+    UNPROTECT(1);
+    Rf_error("%s", b200nn_last_error());
+  }
+  SEXP p = PROTECT(Rf_allocVector(INTSXP, n + 1));
+  SEXP i = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz));
+  SEXP x = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz));
+  rc = b200nn_snn_fill(get_ctx(), INTEGER(p), INTEGER(i), REAL(x));
+  if (rc != B200NN_OK) {
+    UNPROTECT(4);
+    Rf_error("%s", b200nn_last_error());
+  }
+  SEXP m = make_dgCMatrix(n, nnz, p, i, x);
+  UNPROTECT(4);
+  return m;
+}
+
+/* fused FindNeighbors.default body for query == object */
+SEXP b200_FindNeighbors(SEXP data, SEXP k_, SEXP prune_, SEXP compute_snn_) {
+  if (!Rf_isReal(data) || !Rf_isMatrix(data)) Rf_error("object must be a numeric matrix");
+  const int n = Rf_nrows(data), d = Rf_ncols(data), k = Rf_asInteger(k_);
+  const int snn = Rf_asLogical(compute_snn_);
+  int64_t nnz_nn = 0, nnz_snn = 0;
+  b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
+  int rc = b200nn_find_neighbors_count(get_ctx(), REAL(data), n, d, k, Rf_asReal(prune_), snn, NULL, NULL, &o,
+                                       &nnz_nn, &nnz_snn, NULL);
+  if (rc != B200NN_OK) Rf_error("%s", b200nn_last_error());
+  R_CheckUserInterrupt();
+  SEXP np = PROTECT(Rf_allocVector(INTSXP, n + 1));
+  SEXP ni = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz_nn));
+  SEXP nx = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz_nn));
+  SEXP sp = PROTECT(Rf_allocVector(INTSXP, snn ? n + 1 : 0));
+  SEXP si = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz_snn));
+  SEXP sx = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz_snn));
+  rc = b200nn_find_neighbors_fill(get_ctx(), INTEGER(np), INTEGER(ni), REAL(nx), snn ? INTEGER(sp) : NULL,
+                                  snn ? INTEGER(si) : NULL, snn ? REAL(sx) : NULL);
+  if (rc != B200NN_OK) {
+    UNPROTECT(6);
+    Rf_error("%s", b200nn_last_error());
+  }
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, snn ? 2 : 1));
+  SEXP nms = PROTECT(Rf_allocVector(STRSXP, snn ? 2 : 1));
+  SET_VECTOR_ELT(res, 0, make_dgCMatrix(n, nnz_nn, np, ni, nx));
+  SET_STRING_ELT(nms, 0, Rf_mkChar("nn"));
+  if (snn) {
+    SET_VECTOR_ELT(res, 1, make_dgCMatrix(n, nnz_snn, sp, si, sx));
+    SET_STRING_ELT(nms, 1, Rf_mkChar("snn"));
+  }
+  Rf_setAttrib(res, R_NamesSymbol, nms);
+  UNPROTECT(8);
+  return res;
+}
+
+SEXP b200_release(void) {
+  if (g_ctx) {
+    b200nn_ctx_destroy(g_ctx);
+    g_ctx = NULL;
+  }
+  return R_NilValue;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"b200_nn2", (DL_FUNC)&b200_nn2, 3},
+    {"b200_ComputeSNN", (DL_FUNC)&b200_ComputeSNN, 2},
+    {"b200_FindNeighbors", (DL_FUNC)&b200_FindNeighbors, 4},
+    {"b200_release", (DL_FUNC)&b200_release, 0},
+    {NULL, NULL, 0}};
+
+void R_init_b200nn(DllInfo *dll) {
+  R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
