@@ -314,7 +314,7 @@ int knn_exact_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const dou
   // A handful of rows against the whole reference set: split the scan over slices of the
   // reference set so that the grid fills the machine, then merge the partial top-k lists.
   const int64_t blocks4 = ceil_div64(n_items, 4);
-  int64_t want = ceil_div64((int64_t)ctx->sm_count * 4, blocks4);
+  int64_t want = ceil_div64((int64_t)ctx->sm_count * 16, blocks4);
   int64_t cap = 8192 / k;
   int64_t by_rows = ceil_div64(nr, 4 * KX_THREADS);
   int n_slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, cap), std::min<int64_t>(by_rows, 512)));

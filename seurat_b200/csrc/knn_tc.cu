@@ -295,6 +295,7 @@ struct TcParams {
   float *item_T;         // pass 1: per-item max over rows of (tau + |yh_q|^2), via atomicMax
   int32_t pass1;         // 1: only item_T is produced
   const int32_t *order;  // items by decreasing list length (null: identity)
+  const float *tau_init; // pass 2: per-row threshold found by pass 1 (null: start from +inf)
 };
 
 // Item visited by CTA `b` in its round `i`: positions are dealt out in a snake so that the
@@ -510,6 +511,13 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       S.cnt_pend = 0;
       S.last_id = -1;
       const int64_t gq = ((int64_t)item * QT + t) * BM + row;
+      const int64_t oq = gq < P.nq ? (P.qperm ? (int64_t)P.qperm[gq] : gq) : -1;  // original query row
+      if (P.tau_init && oq >= 0) {
+        // pass 2 starts from pass 1's threshold: the pass-1 tiles are visited again, so at least
+        // k' keys lie strictly below the next float above it and the list still fills
+        const float t1 = P.tau_init[oq];
+        if (t1 < CUDART_INF_F) S.tau = nextafterf(t1, CUDART_INF_F);
+      }
       const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
       uint32_t va[32], vb[32];
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -559,10 +567,10 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
       // flush this query's candidates
       S = merge_pending(lk, li, pk, pi, kp, S);
-      const int64_t oq = gq < P.nq ? (P.qperm ? (int64_t)P.qperm[gq] : gq) : -1;  // original query row
       if (oq >= 0) {
         const float tq = S.cnt_list == kp ? S.tau : CUDART_INF_F;
         if (P.pass1) {
+          P.tau[oq] = tq;
           // upper bound of tau + |yh_q|^2 (an approximate squared distance, >= 0 up to rounding)
           float T = tq + (float)P.q_n2[oq];
           T = T > 0.f ? T * 1.0001f + 1e-3f : 1e-3f;
@@ -618,10 +626,8 @@ k_mean_final(const double *__restrict__ partial, int64_t n, int d, TcMisc *__res
   const int j = threadIdx.x;
   const int64_t m = (int64_t)MEAN_BLOCKS * MEAN_ROWS;
   const int64_t stride = n > m ? n / m : 1;
-  int64_t cnt = 0;  // number of sampled rows that exist
-  for (int64_t r = 0; r < m; ++r) {
-    if (r * stride < n) cnt++; else break;
-  }
+  int64_t cnt = (n + stride - 1) / stride;  // number of sampled rows that exist
+  if (cnt > m) cnt = m;
   if (j < BK) {
     double s = 0;
     if (j < d)
@@ -1613,6 +1619,7 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
                                                       P.list_stride, tiles, list_cnt);
     KERNEL_CHECK(ctx);
     P.pass1 = 0;
+    P.tau_init = tau;  // written by pass 1, read at the start of every pass-2 row
     k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc);
     KERNEL_CHECK(ctx);
     P.order = order;

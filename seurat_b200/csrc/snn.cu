@@ -645,6 +645,10 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
     int nslots = 0, npend = 0;
     bool ovf = false;
     for (int pass = 0; pass < 2 && !ovf; ++pass) {
+      if (pass == 1) {  // the table doubled as claim scratch during pass 0
+        for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+        __syncwarp();
+      }
       for (int p0 = 0; p0 < P.k && !ovf; p0 += 32) {
         int64_t beg = 0;
         int len = 0;
@@ -666,20 +670,31 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
 #pragma unroll
             for (int u = 0; u < 4; ++u) hc[u] = hash_cnt<CW_LOG>((uint32_t)v[u]);
             if (pass == 0) {
-              // occurrences of one list are distinct rows, but two of them may share a counter:
-              // MATCH finds the lanes with equal counter index; all four are issued before use
-              unsigned same[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                same[u] = (t0 + 32 * u < l)
-                              ? __match_any_sync(0xffffffffu, v[u] >= 0 ? hc[u] : (0x80000000u | (uint32_t)lane))
-                              : 0u;
+              // The occurrences of one list are distinct rows, but two of them may share a
+              // counter.  Conflicts are rare (~6 % of the batches), and MATCH.ANY on 32 distinct
+              // values costs hundreds of cycles, so they are detected with a claim byte first
+              // (the exact table is still empty in this pass and serves as scratch): every lane
+              // stores its id, and a lane that reads back another id shares its slot.
+              uint8_t *claim = reinterpret_cast<uint8_t *>(tab);
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 if (t0 + 32 * u >= l) break;  // warp-uniform
-                if (v[u] >= 0 && (__ffs(same[u]) - 1) == lane) {
-                  const int c = (int)cnt[hc[u]] + __popc(same[u]);
-                  cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
+                const bool act = v[u] >= 0;
+                const uint32_t ci = hc[u] & ((1u << (F_TX_LOG + 2)) - 1);
+                if (act) claim[ci] = (uint8_t)lane;
+                __syncwarp();
+                const bool lost = act && claim[ci] != (uint8_t)lane;
+                if (!__any_sync(0xffffffffu, lost)) {
+                  if (act) {
+                    const int c = (int)cnt[hc[u]] + 1;
+                    cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
+                  }
+                } else {
+                  const unsigned same = __match_any_sync(0xffffffffu, act ? hc[u] : (0x80000000u | (uint32_t)lane));
+                  if (act && (__ffs(same) - 1) == lane) {
+                    const int c = (int)cnt[hc[u]] + __popc(same);
+                    cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
+                  }
                 }
                 __syncwarp();
               }
