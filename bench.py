@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--knn-algo", type=int, default=0, help="0 auto, 1 exact FP64 scan, 2 tensor-core")
     ap.add_argument("--scan-mode", type=int, default=0,
                     help="tensor path: 0 auto (grouped, tile-pruned), 1 exhaustive scan of every tile, 2 grouped")
+    ap.add_argument("--n-cand", type=int, default=0, help="candidates kept per query by the tensor path (0 = auto)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-knn-sample", type=int, default=2000)
     ap.add_argument("--cpu-snn-rows", type=int, default=100_000)
@@ -227,7 +228,7 @@ def main():
 
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
     X, _ = gaussian_mixture(n, d, cfg["seed"])           # identical on every rank (seeded)
-    be = sdist.CudaBackend(local, knn_algo=args.knn_algo, scan_mode=args.scan_mode)
+    be = sdist.CudaBackend(local, knn_algo=args.knn_algo, n_cand=args.n_cand, scan_mode=args.scan_mode)
     ctx = be.ctx
     ref = torch.from_numpy(X).to(dev)
     torch.cuda.synchronize()
@@ -301,7 +302,7 @@ def main():
         times = []
         for s in range(1 + max(1, args.e2e_steps)):
             t0 = time.perf_counter()
-            r = ctx.find_neighbors(Xh, k, PRUNE, True, _lib.ROW_MAJOR, args.knn_algo, 0, True, out,
+            r = ctx.find_neighbors(Xh, k, PRUNE, True, _lib.ROW_MAJOR, args.knn_algo, args.n_cand, True, out,
                                    scan_mode=args.scan_mode)
             t1 = time.perf_counter()
             if s > 0:

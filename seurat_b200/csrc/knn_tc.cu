@@ -1212,7 +1212,7 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
          int kp, const int32_t *__restrict__ cand, const float *__restrict__ tau,
          const double *__restrict__ q_n2, const double *__restrict__ q_err,
          TcMisc *__restrict__ misc, int32_t *__restrict__ idx0, double *__restrict__ dist,
-         int32_t *__restrict__ fail_list) {
+         int32_t *__restrict__ fail_list, const int32_t *__restrict__ visit, int64_t n_visit) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ds = d + 1;  // padded row stride
@@ -1224,8 +1224,12 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   unsigned long long *skey = reinterpret_cast<unsigned long long *>(qv + d);
   int32_t *sid = reinterpret_cast<int32_t *>(skey + 64);
 
-  const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
-  if (q >= nq) return;
+  // queries are visited in the group-sorted order of the candidate stage when available:
+  // neighbouring warps then gather overlapping candidate rows (L2 hits instead of HBM)
+  const int64_t pos = (int64_t)blockIdx.x * RR_WARPS + warp;
+  if (pos >= n_visit) return;
+  const int64_t q = visit ? (int64_t)visit[pos] : pos;
+  if (q < 0 || q >= nq) return;
   for (int j = lane; j < d; j += 32) qv[j] = qry[q * d + j];
   for (int half = 0; half * 32 < kp; ++half) {
     const int c = half * 32 + lane;
@@ -1352,6 +1356,10 @@ int pick_stages(int kp) {
 // 0 = auto (grouped for large reference sets), 1 = exhaustive scan, 2 = grouped; set through
 // b200nn_opts.reserved (bits 0-1) for benchmarking the two variants against each other
 static thread_local int g_tc_mode = 0;
+// visiting order (sorted query position -> original row, -1 = padding) left by the last
+// grouped candidate stage for the re-rank kernel
+static thread_local const int32_t *g_visit = nullptr;
+static thread_local int64_t g_n_visit = 0;
 void knn_tc_set_mode(int mode) { g_tc_mode = mode; }
 
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
@@ -1440,6 +1448,8 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   cudaStream_t st = ctx->stream;
   const bool self = (d_qry == d_ref) && (nq == nr);
   const bool grouped = mode == 2 || (mode == 0 && nr >= 32768 && d_dbg_keys == nullptr);
+  g_visit = nullptr;
+  g_n_visit = 0;
   TcMisc *misc;
   double *partial, *q_n2, *q_err;
   __half *r16, *q16;
@@ -1618,6 +1628,8 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, 0,
                                                       P.list_stride, tiles, list_cnt);
     KERNEL_CHECK(ctx);
+    g_visit = qperm;
+    g_n_visit = nq_pad;
     P.pass1 = 0;
     P.tau_init = tau;  // written by pass 1, read at the start of every pass-2 row
     k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc);
@@ -1670,8 +1682,9 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   per_warp = (per_warp + 15) & ~(size_t)15;
   size_t smem = per_warp * RR_WARPS;
   CU_TRY(cudaFuncSetAttribute(k_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_rerank<<<(unsigned)ceil_div64(nq, RR_WARPS), RR_WARPS * 32, smem, st>>>(
-      d_ref, d_qry, nq, d, k, kp, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list);
+  const int64_t n_visit = g_visit ? g_n_visit : nq;
+  k_rerank<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
+      d_ref, d_qry, nq, d, k, kp, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, g_visit, n_visit);
   KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e1, st));
   TcMisc h;

@@ -658,70 +658,90 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
           len = (int)(P.colptr[c + 1] - beg);
         }
         const int np = (P.k - p0) < 32 ? (P.k - p0) : 32;
-        for (int p = 0; p < np && !ovf; ++p) {
-          const int64_t b = __shfl_sync(0xffffffffu, beg, p);
-          const int l = __shfl_sync(0xffffffffu, len, p);
-          const int32_t *src = P.rev + b;
-          for (int t0 = 0; t0 < l; t0 += 128) {
-            int32_t v[4];
+        // walk (list, 128-element block) pairs; the next block's loads are issued before the
+        // current block is processed, so the L2/HBM latency of the gathers is overlapped
+        int pl = 0, t0 = 0;
+        int64_t b = __shfl_sync(0xffffffffu, beg, 0);
+        int l = __shfl_sync(0xffffffffu, len, 0);
+        int32_t v[4], nv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (t0 + 32 * u + lane < l) ? src[t0 + 32 * u + lane] : -1;
-            uint32_t hc[4];
+        for (int u = 0; u < 4; ++u) v[u] = (32 * u + lane < l) ? P.rev[b + 32 * u + lane] : -1;
+        while (pl < np && !ovf) {
+          int pn = pl, tn = t0 + 128;
+          int64_t bn = b;
+          int ln = l;
+          if (tn >= l) {
+            pn = pl + 1;
+            tn = 0;
+            if (pn < np) {
+              bn = __shfl_sync(0xffffffffu, beg, pn);
+              ln = __shfl_sync(0xffffffffu, len, pn);
+            }
+          }
+          if (pn < np) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) hc[u] = hash_cnt<CW_LOG>((uint32_t)v[u]);
-            if (pass == 0) {
-              // The occurrences of one list are distinct rows, but two of them may share a
-              // counter.  Conflicts are rare (~6 % of the batches), and MATCH.ANY on 32 distinct
-              // values costs hundreds of cycles, so they are detected with a claim byte first
-              // (the exact table is still empty in this pass and serves as scratch): every lane
-              // stores its id, and a lane that reads back another id shares its slot.
-              uint8_t *claim = reinterpret_cast<uint8_t *>(tab);
+            for (int u = 0; u < 4; ++u) nv[u] = (tn + 32 * u + lane < ln) ? P.rev[bn + tn + 32 * u + lane] : -1;
+          }
+          uint32_t hc[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (t0 + 32 * u >= l) break;  // warp-uniform
-                const bool act = v[u] >= 0;
-                const uint32_t ci = hc[u] & ((1u << (F_TX_LOG + 2)) - 1);
-                if (act) claim[ci] = (uint8_t)lane;
-                __syncwarp();
-                const bool lost = act && claim[ci] != (uint8_t)lane;
-                if (!__any_sync(0xffffffffu, lost)) {
-                  if (act) {
-                    const int c = (int)cnt[hc[u]] + 1;
-                    cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
-                  }
-                } else {
-                  const unsigned same = __match_any_sync(0xffffffffu, act ? hc[u] : (0x80000000u | (uint32_t)lane));
-                  if (act && (__ffs(same) - 1) == lane) {
-                    const int c = (int)cnt[hc[u]] + __popc(same);
-                    cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
-                  }
+          for (int u = 0; u < 4; ++u) hc[u] = hash_cnt<CW_LOG>((uint32_t)v[u]);
+          if (pass == 0) {
+            // The occurrences of one list are distinct rows, but two of them may share a
+            // counter.  Conflicts are rare (~6 % of the batches), and MATCH.ANY on 32 distinct
+            // values costs hundreds of cycles, so they are detected with a claim byte first
+            // (the exact table is still empty in this pass and serves as scratch): every lane
+            // stores its id, and a lane that reads back another id shares its slot.
+            uint8_t *claim = reinterpret_cast<uint8_t *>(tab);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (t0 + 32 * u >= l) break;  // warp-uniform
+              const bool act = v[u] >= 0;
+              const uint32_t ci = hc[u] & ((1u << (F_TX_LOG + 2)) - 1);
+              if (act) claim[ci] = (uint8_t)lane;
+              __syncwarp();
+              const bool lost = act && claim[ci] != (uint8_t)lane;
+              if (!__any_sync(0xffffffffu, lost)) {
+                if (act) {
+                  const int c = (int)cnt[hc[u]] + 1;
+                  cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
                 }
-                __syncwarp();
+              } else {
+                const unsigned same = __match_any_sync(0xffffffffu, act ? hc[u] : (0x80000000u | (uint32_t)lane));
+                if (act && (__ffs(same) - 1) == lane) {
+                  const int c = (int)cnt[hc[u]] + __popc(same);
+                  cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
+                }
               }
-            } else {
+              __syncwarp();
+            }
+          } else {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (t0 + 32 * u >= l) break;  // warp-uniform
-                const bool pass_f = v[u] >= 0 && (int)cnt[hc[u]] >= s_min;
-                const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
-                if (bal) {
-                  if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
-                  npend += __popc(bal);
+            for (int u = 0; u < 4; ++u) {
+              if (t0 + 32 * u >= l) break;  // warp-uniform
+              const bool pass_f = v[u] >= 0 && (int)cnt[hc[u]] >= s_min;
+              const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
+              if (bal) {
+                if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
+                npend += __popc(bal);
+                __syncwarp();
+                if (npend >= 32) {
+                  filt_insert_batch(tab, slots, nslots, P.cbits, pend[lane], true, lane);
+                  const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
                   __syncwarp();
-                  if (npend >= 32) {
-                    filt_insert_batch(tab, slots, nslots, P.cbits, pend[lane], true, lane);
-                    const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
-                    __syncwarp();
-                    if (32 + lane < npend) pend[lane] = mv;
-                    npend -= 32;
-                    __syncwarp();
-                    if (nslots > F_SLOTS) ovf = true;
-                  }
+                  if (32 + lane < npend) pend[lane] = mv;
+                  npend -= 32;
+                  __syncwarp();
+                  if (nslots > F_SLOTS) ovf = true;
                 }
               }
             }
-            if (ovf) break;
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = nv[u];
+          pl = pn;
+          t0 = tn;
+          b = bn;
+          l = ln;
         }
       }
     }
