@@ -56,7 +56,6 @@ enum WsSlot {
   WS_NN_P,         // nn Graph CSC: p (int64, n+1)
   WS_NN_I,         //               i (int32)
   WS_NN_X,         //               x (fp64)
-  WS_ROW_E,        // expanded candidates per row (int32)
   WS_ROW_BOUND,    // survivor bound per row (int32)
   WS_TMP_OFF,      // exclusive scan of bounds (int64)
   WS_TMP,          // packed survivors (uint32 or uint64 words)
@@ -76,10 +75,9 @@ enum WsSlot {
   // tensor-core kNN path
   WS_TC_REF16,     // fp16 operand matrix of the reference set (K-padded, augmented)
   WS_TC_QRY16,     // fp16 operand matrix of the queries
-  WS_TC_REFERR,    // per-point fp16 rounding residual norms
   WS_TC_QRYERR,
   WS_TC_CAND,      // candidate indices (int32, nq * k')
-  WS_TC_CANDKEY,   // candidate keys (fp32, nq * k')
+  WS_TC_CANDKEY,   // selection threshold tau per query (fp32, nq)
   WS_TC_FLAGS,     // per-query certificate flags / fallback list
   WS_TC_MISC,
   WS_TC_Y16R,      // FP16 rows of the reference set in original order (grouped search)
