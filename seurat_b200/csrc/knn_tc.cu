@@ -51,10 +51,13 @@ constexpr int BM = 128;             // queries per query tile (= TMEM lanes)
 constexpr int QT = 2;               // query tiles resident per CTA
 constexpr int BN = 128;             // reference rows per B tile
 constexpr int BK = 64;              // K: one 128-byte swizzle row of FP16
-constexpr int EPI_WARPS = 8;        // 4 per query tile
-constexpr int CTRL_WARPS = 4;       // TMA, MMA, TMEM alloc, spare
-constexpr int NUM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int CTRL_WARPS = 4;       // TMA, MMA, TMEM alloc, second MMA issuer
+// The epilogue runs 8 * SPLIT warps: SPLIT warps share a (query tile, TMEM lane quarter) and
+// each scans BN / SPLIT columns of every tile into its own candidate list.  SPLIT = 2 doubles
+// the warps per scheduler (the selection code is latency-bound, not issue-bound) at the price
+// of two k'-lists per query row, which fits shared memory for k <= 20.
+constexpr int epi_warps(int split) { return 8 * split; }
+constexpr int num_threads(int split) { return (CTRL_WARPS + epi_warps(split)) * 32; }
 constexpr uint32_t TILE_BYTES = BM * BK * 2;  // 16 KB (A tile == B tile)
 constexpr int MAX_D = BK - 3;       // 61
 constexpr int MAX_KP = 48;          // shared-memory budget of the candidate lists
@@ -194,12 +197,11 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)
 // ---------------------------------------------------------------------------
 // per-thread candidate state in shared memory (one epilogue thread == one query row)
 //   list : kp (key, id) pairs, unsorted, maximum tracked in registers (tau, maxpos)
-//   pend : PEND pairs appended by the filter, merged warp-synchronously
-// slot e of thread t lives at word e * EPI_THREADS + t  (conflict-free across a warp)
+//   pend : `pend` pairs appended by the filter, merged warp-synchronously
+// slot e of thread t lives at word e * ls + t, ls = number of epilogue threads (conflict-free)
 // ---------------------------------------------------------------------------
-constexpr int PEND = 16;            // pending-hit buffer per thread
-constexpr int PEND_TRIGGER = 8;     // merge as soon as any lane holds more than this
-constexpr int LSTRIDE = EPI_THREADS;
+constexpr int pend_size(int split) { return split == 1 ? 16 : 8; }   // pending-hit buffer per thread
+constexpr int pend_trigger(int split) { return split == 1 ? 8 : 4; }  // merge when a lane holds more
 
 struct Sel {          // register-resident selection state of one query row
   float tau;          // current k'-th best key (+inf until the list is full)
@@ -210,13 +212,13 @@ struct Sel {          // register-resident selection state of one query row
 };
 
 // recompute the maximum of the (full) list; 8 independent loads in flight
-__device__ __forceinline__ void list_rescan(const float *lk, int kp, float &tau, int &maxpos) {
+__device__ __forceinline__ void list_rescan(const float *lk, int kp, int ls, float &tau, int &maxpos) {
   float m = -CUDART_INF_F;
   int mp = 0;
   for (int e0 = 0; e0 < kp; e0 += 8) {
     float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = lk[(e0 + u) * LSTRIDE];
+    for (int u = 0; u < 8; ++u) v[u] = lk[(e0 + u) * ls];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
       if (v[u] > m) {
@@ -232,29 +234,29 @@ __device__ __forceinline__ void list_rescan(const float *lk, int kp, float &tau,
 // Deliberately not inlined: it is called from 17 sites and runs only ~100 times per
 // query tile; the hot filter loop must stay small enough for the instruction cache.
 __device__ __noinline__ Sel merge_pending(float *lk, int *li, const float *pk, const int *pi, int kp,
-                                          Sel S) {
+                                          int ls, Sel S) {
   int maxc = S.cnt_pend;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
   for (int e = 0; e < maxc; ++e) {
     bool rescan = false;
     if (e < S.cnt_pend) {
-      const float key = pk[e * LSTRIDE];
-      const int id = pi[e * LSTRIDE];
+      const float key = pk[e * ls];
+      const int id = pi[e * ls];
       if (S.cnt_list < kp) {
-        lk[S.cnt_list * LSTRIDE] = key;
-        li[S.cnt_list * LSTRIDE] = id;
+        lk[S.cnt_list * ls] = key;
+        li[S.cnt_list * ls] = id;
         S.cnt_list++;
         rescan = S.cnt_list == kp;
       } else if (key < S.tau) {
-        lk[S.maxpos * LSTRIDE] = key;
-        li[S.maxpos * LSTRIDE] = id;
+        lk[S.maxpos * ls] = key;
+        li[S.maxpos * ls] = id;
         rescan = true;
       }
     }
     if (__any_sync(0xffffffffu, rescan)) {
       // idempotent for lanes that did not change their list
-      if (S.cnt_list == kp) list_rescan(lk, kp, S.tau, S.maxpos);
+      if (S.cnt_list == kp) list_rescan(lk, kp, ls, S.tau, S.maxpos);
     }
   }
   S.cnt_pend = 0;
@@ -284,6 +286,7 @@ struct TcParams {
   int32_t pass1;         // 1: only item_T is produced
   const int32_t *order;  // items by decreasing list length (null: identity)
   const float *tau_init; // pass 2: per-row threshold found by pass 1 (null: start from +inf)
+  int32_t split;         // epilogue warps per (query tile, lane quarter): 1 or 2
 };
 
 // Item visited by CTA `b` in its round `i`: positions are dealt out in a snake so that the
@@ -301,9 +304,9 @@ __device__ __forceinline__ int item_at(const TcParams &P, int i, int b, int grid
     const float kv = __uint_as_float(V[C]);                                        \
     const int id = col0 + (C);                                                     \
     if (kv < S.tau && id > S.last_id && id < nr_i) {                               \
-      if (S.cnt_pend < PEND) {                                                     \
-        pk[S.cnt_pend * LSTRIDE] = kv;                                             \
-        pi[S.cnt_pend * LSTRIDE] = id;                                             \
+      if (S.cnt_pend < PENDN) {                                                    \
+        pk[S.cnt_pend * LS] = kv;                                                  \
+        pi[S.cnt_pend * LS] = id;                                                  \
         S.cnt_pend++;                                                              \
         S.last_id = id;                                                            \
       } else {                                                                     \
@@ -321,6 +324,7 @@ __device__ __forceinline__ int item_at(const TcParams &P, int i, int b, int grid
 
 // 32 keys of one query row: a FMNMX3 tree rejects the chunk for the whole warp in
 // ~21 instructions; otherwise the sub-group minima steer the scan to the few keys below tau.
+template <int LS, int PENDN, int TRIG>
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, float *lk, int *li,
                                               float *pk, int *pi, int kp, int col0, int nr_i) {
   float sa[4], sb[4], sc[4], gm[4];
@@ -344,7 +348,7 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, f
       TC_GROUP(v, 3)
     }
     again = __any_sync(0xffffffffu, ovf);
-    if (again || __any_sync(0xffffffffu, S.cnt_pend > PEND_TRIGGER)) S = merge_pending(lk, li, pk, pi, kp, S);
+    if (again || __any_sync(0xffffffffu, S.cnt_pend > TRIG)) S = merge_pending(lk, li, pk, pi, kp, LS, S);
   } while (again);
 }
 
@@ -354,10 +358,14 @@ constexpr int RING = 16;            // tile-id ring (power of two > stages + acc
 // ---------------------------------------------------------------------------
 // K1: candidate generation
 // ---------------------------------------------------------------------------
-template <bool DBG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool DBG, int SPLIT>
+__global__ void __launch_bounds__(num_threads(SPLIT), 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
          TcParams P) {
+  constexpr int EPI_WARPS = epi_warps(SPLIT);
+  constexpr int LSTRIDE = EPI_WARPS * 32;
+  constexpr int PEND = pend_size(SPLIT);
+  constexpr int TRIG = pend_trigger(SPLIT);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -391,7 +399,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     }
     for (int i = 0; i < 2 * QT; ++i) {
       mbar_init(bar_t_full + 8 * i, 1);
-      mbar_init(bar_t_empty + 8 * i, EPI_WARPS / QT);
+      mbar_init(bar_t_empty + 8 * i, EPI_WARPS / QT);  // one arrival per epilogue warp of the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -476,12 +484,14 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
     }
   } else if (warp >= CTRL_WARPS) {
-    // ===================== epilogue: running top-k' per query row =====================
-    const int ew = warp - CTRL_WARPS;        // 0..7
-    const int t = ew / 4;                    // query tile of this warp
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    // ===================== epilogue: running top-k' per (query row, column share) =========
+    const int ew = warp - CTRL_WARPS;        // 0 .. 8 * SPLIT - 1
+    const int t = ew / (4 * SPLIT);          // query tile of this warp
+    const int hh = (ew / 4) % SPLIT;         // column share of this warp
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access (== ew & 3)
     const int row = quarter * 32 + lane;     // row inside the query tile
     const int et = ew * 32 + lane;           // list column of this thread
+    constexpr int COLS = BN / SPLIT;         // columns of a tile scanned by this thread
     float *lk = s_lk + et;
     int *li = s_li + et;
     float *pk = s_pk + et;
@@ -503,74 +513,97 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       if (P.tau_init && oq >= 0) {
         // pass 2 starts from pass 1's threshold: the pass-1 tiles are visited again, so at least
         // k' keys lie strictly below the next float above it and the list still fills
-        const float t1 = P.tau_init[oq];
+        const float t1 = P.tau_init[oq * SPLIT + hh];
         if (t1 < CUDART_INF_F) S.tau = nextafterf(t1, CUDART_INF_F);
       }
       const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
-      uint32_t va[32], vb[32];
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      if (nt > 0) {  // prologue: first chunk of the first tile
-        const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
-        mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
-        tc_fence_after();
-        tc_ld32(lane_addr + (uint32_t)((acc * QT + t) * BN), va);
-      }
-      for (int j = 0; j < nt; ++j, ++bi) {
-        const uint32_t acc = bi & 1;
-        const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
-        const int colbase = s_ring[bi & (RING - 1)] * BN;
-        float *dk = nullptr;
-        if (DBG) dk = (item == 0 && j == 0) ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(hh * COLS);
+      if constexpr (SPLIT == 1) {
+        uint32_t va[32], vb[32];
+        if (nt > 0) {  // prologue: first chunk of the first tile
+          const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
+          mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
+          tc_fence_after();
+          tc_ld32(lane_addr + (uint32_t)((acc * QT + t) * BN), va);
+        }
+        for (int j = 0; j < nt; ++j, ++bi) {
+          const uint32_t acc = bi & 1;
+          const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
+          const int colbase = s_ring[bi & (RING - 1)] * BN;
+          float *dk = nullptr;
+          if (DBG) dk = (item == 0 && j == 0) ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          tc_wait_ld(va);
-          tc_ld32(taddr + 64 * h + 32, vb);
-          if (DBG && dk) {
+          for (int h = 0; h < 2; ++h) {
+            tc_wait_ld(va);
+            tc_ld32(taddr + 64 * h + 32, vb);
+            if (DBG && dk) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
-          }
-          process_chunk(va, S, lk, li, pk, pi, kp, colbase + 64 * h, nr_i);
-          tc_wait_ld(vb);
-          if (h == 0) {
-            tc_ld32(taddr + 64, va);
-          } else {
-            // all four loads of this tile have landed: hand the accumulator back, and start
-            // on the next tile (normally already computed) before scanning the last chunk
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-            if (j + 1 < nt) {
-              const uint32_t nb = bi + 1, nacc = nb & 1, naph = (nb >> 1) & 1;
-              mbar_wait(bar_t_full + 8 * (nacc * QT + t), naph, P.misc);
-              tc_fence_after();
-              tc_ld32(lane_addr + (uint32_t)((nacc * QT + t) * BN), va);
+              for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
             }
-          }
-          if (DBG && dk) {
+            process_chunk<LSTRIDE, PEND, TRIG>(va, S, lk, li, pk, pi, kp, colbase + 64 * h, nr_i);
+            tc_wait_ld(vb);
+            if (h == 0) {
+              tc_ld32(taddr + 64, va);
+            } else {
+              // all four loads of this tile have landed: hand the accumulator back, and start
+              // on the next tile (normally already computed) before scanning the last chunk
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
+              if (j + 1 < nt) {
+                const uint32_t nb = bi + 1, nacc = nb & 1, naph = (nb >> 1) & 1;
+                mbar_wait(bar_t_full + 8 * (nacc * QT + t), naph, P.misc);
+                tc_fence_after();
+                tc_ld32(lane_addr + (uint32_t)((nacc * QT + t) * BN), va);
+              }
+            }
+            if (DBG && dk) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
+              for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
+            }
+            process_chunk<LSTRIDE, PEND, TRIG>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, nr_i);
           }
-          process_chunk(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, nr_i);
+        }
+      } else {
+        // two chunks per tile and thread, single register buffer: with four epilogue warps per
+        // scheduler the TMEM load latency is covered by the other warps
+        uint32_t v[32];
+        for (int j = 0; j < nt; ++j, ++bi) {
+          const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
+          const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
+          mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
+          tc_fence_after();
+          const int colbase = s_ring[bi & (RING - 1)] * BN + hh * COLS;
+          tc_ld32(taddr, v);
+          tc_wait_ld(v);
+          process_chunk<LSTRIDE, PEND, TRIG>(v, S, lk, li, pk, pi, kp, colbase, nr_i);
+          tc_ld32(taddr + 32, v);
+          tc_wait_ld(v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
+          process_chunk<LSTRIDE, PEND, TRIG>(v, S, lk, li, pk, pi, kp, colbase + 32, nr_i);
         }
       }
-      // flush this query's candidates
-      S = merge_pending(lk, li, pk, pi, kp, S);
+      // flush this thread's candidates
+      S = merge_pending(lk, li, pk, pi, kp, LSTRIDE, S);
       if (oq >= 0) {
         const float tq = S.cnt_list == kp ? S.tau : CUDART_INF_F;
         if (P.pass1) {
-          P.tau[oq] = tq;
-          // upper bound of tau + |yh_q|^2 (an approximate squared distance, >= 0 up to rounding)
+          P.tau[oq * SPLIT + hh] = tq;
+          // upper bound of tau + |yh_q|^2 (an approximate squared distance, >= 0 up to rounding);
+          // the maximum over the column shares bounds the row's final threshold as well
           float T = tq + (float)P.q_n2[oq];
           T = T > 0.f ? T * 1.0001f + 1e-3f : 1e-3f;
           atomicMax(reinterpret_cast<int *>(P.item_T + item), __float_as_int(T));
         } else {
-          int32_t *dst = P.cand + oq * kp;
+          int32_t *dst = P.cand + (oq * SPLIT + hh) * kp;
           for (int e = 0; e < kp; ++e) {
             int id = e < S.cnt_list ? li[e * LSTRIDE] : -1;
             if (id >= 0 && P.rperm) id = P.rperm[id];
             dst[e] = id;
           }
-          P.tau[oq] = tq;
+          P.tau[oq * SPLIT + hh] = tq;
         }
       }
       __syncwarp();
@@ -1197,7 +1230,7 @@ constexpr int RR_WARPS = 4;
 
 __global__ void __launch_bounds__(RR_WARPS * 32)
 k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t nq, int d, int k,
-         int kp, const int32_t *__restrict__ cand, const float *__restrict__ tau,
+         int kp, int split, const int32_t *__restrict__ cand, const float *__restrict__ tau,
          const double *__restrict__ q_n2, const double *__restrict__ q_err,
          TcMisc *__restrict__ misc, int32_t *__restrict__ idx0, double *__restrict__ dist,
          int32_t *__restrict__ fail_list, const int32_t *__restrict__ visit, int64_t n_visit) {
@@ -1269,7 +1302,9 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   const double qn = q_n2[q], eq = q_err[q];
   const double M = misc->rn2_max + 2.0 * sqrt(qn) * sqrt(misc->rn2_max) + 1.0;
   const double eta = ETA_COEF * M + 1e-4;
-  const double tq = (double)tau[q];
+  // every non-candidate has a key >= the threshold of the list that rejected it
+  double tq = (double)tau[q * split];
+  for (int h = 1; h < split; ++h) tq = fmin(tq, (double)tau[q * split + h]);
   const double dk2 = __longlong_as_double((long long)skey[k - 1]);
   bool ok = false;
   if (isfinite(tq) && isfinite(dk2)) {
@@ -1328,14 +1363,15 @@ int pick_kp(int k, int n_cand) {
   return kp;
 }
 
-size_t tc_smem_bytes(int kp, int stages) {
-  return 1024 + (size_t)(QT + stages) * TILE_BYTES + (size_t)(2 * kp + 2 * PEND) * LSTRIDE * 4 +
+size_t tc_smem_bytes(int kp, int stages, int split) {
+  return 1024 + (size_t)(QT + stages) * TILE_BYTES +
+         (size_t)(2 * kp + 2 * pend_size(split)) * epi_warps(split) * 32 * 4 +
          8 * (2 + 2 * MAX_STAGES + 4 * QT) + 32 + 4 * RING;
 }
 
-int pick_stages(int kp) {
+int pick_stages(int kp, int split) {
   int st = MAX_STAGES;
-  while (st > 2 && tc_smem_bytes(kp, st) > 227 * 1024) --st;
+  while (st > 2 && tc_smem_bytes(kp, st, split) > 227 * 1024) --st;
   return st;
 }
 
@@ -1361,7 +1397,7 @@ bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
 // launch helper for the candidate kernel
 static int launch_tc(b200nn_ctx *ctx, const CUtensorMap &map_q, const CUtensorMap &map_r, const TcParams &P,
                      bool dbg) {
-  size_t smem = tc_smem_bytes(P.kp, P.stages);
+  size_t smem = tc_smem_bytes(P.kp, P.stages, P.split);
   if (smem > 227 * 1024 || P.stages < 3) {
     b200nn_set_error("candidate list of %d entries does not fit shared memory", P.kp);
     return B200NN_ERR_INVALID;
@@ -1369,11 +1405,14 @@ static int launch_tc(b200nn_ctx *ctx, const CUtensorMap &map_q, const CUtensorMa
   int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
   if (grid <= 0) return B200NN_OK;
   if (dbg) {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<true><<<grid, NUM_THREADS, smem, ctx->stream>>>(map_q, map_r, P);
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<true, 1><<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
+  } else if (P.split == 2) {
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<false, 2><<<grid, num_threads(2), smem, ctx->stream>>>(map_q, map_r, P);
   } else {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<false><<<grid, NUM_THREADS, smem, ctx->stream>>>(map_q, map_r, P);
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<false, 1><<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
   }
   KERNEL_CHECK(ctx);
   return B200NN_OK;
@@ -1430,7 +1469,7 @@ static int pick_groups(int64_t nr) {
 // candidate stage alone (also used by the debug / profiling entry point).
 // mode: 0 = auto, 1 = exhaustive scan of every tile, 2 = grouped (tile-pruned)
 int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
-                      int64_t nq, int d, int kp, int mode, int32_t **cand_out, float **tau_out,
+                      int64_t nq, int d, int kp, int split, int mode, int32_t **cand_out, float **tau_out,
                       double **qn2_out, double **qerr_out, void **misc_out, float *d_dbg_keys,
                       b200nn_stats *stats) {
   cudaStream_t st = ctx->stream;
@@ -1448,8 +1487,9 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   RC_TRY(ws_get(ctx, WS_TC_QRY16, (size_t)nq * BK, &q16));
   RC_TRY(ws_get(ctx, WS_TC_QRYERR, (size_t)nq * 2, &q_n2));
   q_err = q_n2 + nq;
-  RC_TRY(ws_get(ctx, WS_TC_CAND, (size_t)nq * kp, &cand));
-  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq, &tau));
+  if (d_dbg_keys) split = 1;
+  RC_TRY(ws_get(ctx, WS_TC_CAND, (size_t)nq * kp * split, &cand));
+  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq * split, &tau));
 
   cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10];
   CU_TRY(cudaEventRecord(e0, st));
@@ -1473,7 +1513,8 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   P.n_items = (int32_t)ceil_div64(nq, QT * BM);
   P.ksteps = (d + 3 + 15) / 16;
   P.kp = kp;
-  P.stages = pick_stages(kp);
+  P.split = split;
+  P.stages = pick_stages(kp, split);
   P.cand = cand;
   P.tau = tau;
   P.dbg_keys = d_dbg_keys;
@@ -1652,11 +1693,19 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
     b200nn_set_error("k = %d leaves no room for a widened candidate set (max %d)", k, MAX_KP);
     return B200NN_ERR_INVALID;
   }
+  // Experimental (B200NN_SPLIT=2, k <= 20): two epilogue warps share a row set, each keeping its
+  // own list of 24 (>= k + 4) candidates from its half of the columns; the re-rank sees the
+  // union (48 candidates).  Measured at 1M cells: candidate stage 46 -> 44 ms, re-rank 7 -> 10 ms,
+  // i.e. no net gain (register spills at 96 regs/thread, smaller pending buffers), so the
+  // default stays one warp per row set.
+  static const int env_split = getenv("B200NN_SPLIT") ? atoi(getenv("B200NN_SPLIT")) : 0;
+  int split = (env_split == 2 && k <= 20 && n_cand == 0) ? 2 : 1;
+  if (split == 2) kp = 24;
   int32_t *cand;
   float *tau;
   double *q_n2, *q_err;
   void *misc_v;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, g_tc_mode, &cand, &tau, &q_n2, &q_err,
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, split, g_tc_mode, &cand, &tau, &q_n2, &q_err,
                            &misc_v, nullptr, stats));
   TcMisc *misc = static_cast<TcMisc *>(misc_v);
   int32_t *flags;
@@ -1672,7 +1721,8 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   CU_TRY(cudaFuncSetAttribute(k_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_visit = g_visit ? g_n_visit : nq;
   k_rerank<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
-      d_ref, d_qry, nq, d, k, kp, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, g_visit, n_visit);
+      d_ref, d_qry, nq, d, k, kp * split, split, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, g_visit,
+      n_visit);
   KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e1, st));
   TcMisc h;
@@ -1710,7 +1760,7 @@ int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
   float *tau;
   double *q_n2, *q_err;
   void *misc_v;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, d_keys_out ? 1 : g_tc_mode,
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, 1, d_keys_out ? 1 : g_tc_mode,
                            &cand, &tau, &q_n2, &q_err, &misc_v, d_keys_out, nullptr));
   cudaStream_t st = ctx->stream;
   if (d_cand_out)

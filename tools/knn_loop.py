@@ -1,0 +1,12 @@
+import os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import seurat_b200 as sb
+from seurat_b200.synthetic import gaussian_mixture
+X,_ = gaussian_mixture(1_000_000, 50, 1)
+ctx = sb.Context(0)
+ref = torch.from_numpy(X).cuda()
+idx0 = torch.empty((1_000_000, 20), dtype=torch.int32, device="cuda"); dist = torch.empty((1_000_000, 20), dtype=torch.float64, device="cuda")
+torch.cuda.synchronize()
+for r in range(8):
+    t0=time.perf_counter(); st = ctx.dev_knn(ref, 1_000_000, None, 1_000_000, 50, 20, idx0, dist); dt=time.perf_counter()-t0
+    print(f"{dt*1e3:.1f} ms cand {st['ms_knn_cand']:.1f} rerank {st['ms_knn_rerank']:.1f} fallback {st['ms_knn_fallback']:.1f} uncert {st['n_uncertified']} tiles {st['knn_tiles_visited']}")
