@@ -574,7 +574,6 @@ int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atom
 constexpr int F_TX_LOG = 10;                   // exact table: 1024 words
 constexpr int F_SLOTS = 800;                   // distinct keys allowed in it
 constexpr int F_SLOT_CAP = 832;
-constexpr int F_WARPS = 8;
 constexpr int filt_bytes(int cw_log) { return (1 << cw_log) + (1 << F_TX_LOG) * 4 + F_SLOT_CAP * 2 + 64 * 4; }
 
 template <int CW_LOG>
@@ -616,7 +615,7 @@ __device__ __forceinline__ void filt_insert_batch(uint32_t *tab, uint16_t *slots
   } while (__any_sync(0xffffffffu, todo));
 }
 
-template <int CW_LOG>  // log2 of the number of byte counters per row
+template <int CW_LOG, int F_WARPS>  // log2 of the byte counters per row; warps (rows) per CTA
 __global__ void __launch_bounds__(F_WARPS * 32)
 k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
   constexpr int F_BYTES = filt_bytes(CW_LOG);
@@ -903,22 +902,23 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
   typedef typename Cfg::Word Word;
   if (filter_s_min >= 2) {
     // classes 0-2 through the filtered kernel; overflowing rows are re-run below
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                filt_bytes(12) * F_WARPS));
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                filt_bytes(13) * F_WARPS));
+    // 8 rows per CTA, 2 CTAs per SM (more, smaller CTAs and 4096 counters for class 1 measured no faster)
+    constexpr int W12 = 8, W13 = 8;
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<12, W12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                filt_bytes(12) * W12));
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<13, W13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                filt_bytes(13) * W13));
     for (int c = 0; c < 3; ++c) {
       P.row_list = class_list + c * (int64_t)n_rows;
       P.n_rows_class = class_count[c];
       if (P.n_rows_class <= 0) continue;
-      int64_t want = ceil_div64(P.n_rows_class, F_WARPS);
-      if (c == 0) {  // few distinct candidates: 4096 counters suffice
-        int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
-        k_snn_rows_filter<12><<<blocks, F_WARPS * 32, filt_bytes(12) * F_WARPS, ctx->stream>>>(
+      if (c == 0) {
+        int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, W12), (int64_t)ctx->sm_count * 2);
+        k_snn_rows_filter<12, W12><<<blocks, W12 * 32, filt_bytes(12) * W12, ctx->stream>>>(
             P, filter_s_min, ovf_list, d_info);
       } else {
-        int blocks = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 2);
-        k_snn_rows_filter<13><<<blocks, F_WARPS * 32, filt_bytes(13) * F_WARPS, ctx->stream>>>(
+        int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, W13), (int64_t)ctx->sm_count * 2);
+        k_snn_rows_filter<13, W13><<<blocks, W13 * 32, filt_bytes(13) * W13, ctx->stream>>>(
             P, filter_s_min, ovf_list, d_info);
       }
       KERNEL_CHECK(ctx);

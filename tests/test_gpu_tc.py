@@ -120,3 +120,56 @@ def test_tensor_path_rejects_unsupported_shapes(ctx):
     assert st["ms_knn_cand"] == 0
     wi, wd = oracle.knn(X, k=10)
     assert (idx == wi).all() and (dist == wd).all()
+
+
+@pytest.mark.parametrize("kind", ["uniform", "unbalanced", "duplicates", "line"])
+def test_grouped_search_on_awkward_data(ctx, kind):
+    """the tile-pruned search must stay exact when grouping is useless or lopsided"""
+    rng = np.random.default_rng(5)
+    n, d, k = 40000, 12, 10
+    if kind == "uniform":            # no cluster structure at all: nothing can be skipped
+        X = rng.uniform(-1, 1, size=(n, d))
+    elif kind == "unbalanced":       # one huge blob, a few tiny far-away ones (some groups nearly empty)
+        X = rng.normal(size=(n, d))
+        X[:50] += 200.0
+        X[50:60] -= 300.0
+    elif kind == "duplicates":       # every point three times: ties at every rank boundary
+        base = rng.normal(size=(n // 4, d))
+        X = np.vstack([base, base, base, rng.normal(size=(n - 3 * (n // 4), d))])
+    else:                            # points on a line: extreme anisotropy
+        t = rng.uniform(0, 1000, size=n)
+        X = np.outer(t, np.ones(d)) + 1e-3 * rng.normal(size=(n, d))
+    wi, wd = oracle.knn(X, k=k, method="kdtree" if kind != "duplicates" else "brute")
+    idx, dist, st = ctx.knn(X, None, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, 2)
+    assert (dist == wd).all(), kind
+    assert (idx == wi).all(), kind
+    print(kind, "uncertified", st["n_uncertified"], "tiles visited", st["knn_tiles_visited"], "of", st["knn_tiles_total"])
+
+
+def test_grouped_search_few_queries_many_references(ctx):
+    ref, c = gaussian_mixture(50000, 20, seed=8, n_centres=6)
+    qry, _ = gaussian_mixture(37, 20, seed=9, centres=c)
+    wi, wd = oracle.knn(ref, qry, 12, method="kdtree")
+    idx, dist, st = ctx.knn(ref, qry, 12, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, 2)
+    assert (idx == wi).all() and (dist == wd).all()
+
+
+def test_split_epilogue_variant(ctx, monkeypatch):
+    """the experimental two-warps-per-row-set epilogue (B200NN_SPLIT=2) gives the same answer"""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, oracle, seurat_b200 as sb
+        from seurat_b200 import _lib
+        from seurat_b200.synthetic import gaussian_mixture
+        X, _ = gaussian_mixture(40000, 50, seed=21, n_centres=8)
+        wi, wd = oracle.knn(X, k=20, method="kdtree")
+        ctx = sb.Context(0)
+        for mode in (1, 2):
+            idx, dist, st = ctx.knn(X, None, 20, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, mode)
+            assert (idx == wi).all() and (dist == wd).all(), mode
+        print("ok")
+    """)
+    env = dict(os.environ, B200NN_SPLIT="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
