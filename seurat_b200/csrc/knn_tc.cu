@@ -934,13 +934,26 @@ __global__ void k_group_offsets(const int32_t *__restrict__ rcount, const int32_
   qoff[G] = qo;
 }
 
-__global__ void k_group_scatter(const int32_t *__restrict__ gid, int64_t n, const int32_t *__restrict__ off,
-                                int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+// scatter of row ids into their group's range; cursors are bumped once per (block, group)
+// from a shared-memory histogram instead of once per row (G <= 1024)
+__global__ void __launch_bounds__(256)
+k_group_scatter(const int32_t *__restrict__ gid, int64_t n, int G, const int32_t *__restrict__ off,
+                int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+  __shared__ int s_cnt[1024];
+  __shared__ int s_base[1024];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) s_cnt[g] = 0;
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int g = gid[i];
-  const int pos = off[g] + atomicAdd(&cursor[g], 1);
-  perm[pos] = (int32_t)i;
+  int g = -1, local = 0;
+  if (i < n) {
+    g = gid[i];
+    local = atomicAdd(&s_cnt[g], 1);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < G; q += blockDim.x)
+    if (s_cnt[q] > 0) s_base[q] = atomicAdd(&cursor[q], s_cnt[q]);
+  __syncthreads();
+  if (i < n) perm[off[g] + s_base[g] + local] = (int32_t)i;
 }
 
 // B operand rows in sorted, padded order; padding rows get key = +inf
@@ -993,13 +1006,15 @@ k_gather_qry(const __half *__restrict__ y16, const int32_t *__restrict__ qperm, 
 __global__ void __launch_bounds__(128)
 k_group_radius(const __half *__restrict__ y16, const int32_t *__restrict__ rperm, const int32_t *__restrict__ goff,
                int d, const float *__restrict__ cent, float *__restrict__ grad) {
+  // grid (G, RAD_SLICES): every block covers a strided share of the group's rows and folds
+  // its maximum into grad[g] (pre-set to the rounding slack) with an integer atomicMax
   __shared__ float cs[BK];
   __shared__ float red[4];
   const int g = blockIdx.x;
   if (threadIdx.x < BK) cs[threadIdx.x] = cent[(size_t)g * BK + threadIdx.x];
   __syncthreads();
   float mx = 0.f;
-  for (int p = goff[g] + threadIdx.x; p < goff[g + 1]; p += blockDim.x) {
+  for (int p = goff[g] + blockIdx.y * blockDim.x + threadIdx.x; p < goff[g + 1]; p += blockDim.x * gridDim.y) {
     const int i = rperm[p];
     if (i < 0) continue;
     float y[BK];
@@ -1018,7 +1033,7 @@ k_group_radius(const __half *__restrict__ y16, const int32_t *__restrict__ rperm
   __syncthreads();
   if (threadIdx.x == 0) {
     float m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    grad[g] = sqrtf(m) * 1.0001f + 1e-4f;
+    atomicMax(reinterpret_cast<int *>(grad + g), __float_as_int(sqrtf(m) * 1.0001f + 1e-4f));  // positive floats
   }
 }
 
@@ -1620,9 +1635,9 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor);
     KERNEL_CHECK(ctx);
     CU_TRY(cudaMemsetAsync(rperm, 0xff, sizeof(int32_t) * (size_t)(nr_pad + nq_pad), st));  // rperm and qperm
-    k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, goff, rcursor, rperm);
+    k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, G, goff, rcursor, rperm);
     KERNEL_CHECK(ctx);
-    k_group_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, nq, qoff, qcursor, qperm);
+    k_group_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, nq, G, qoff, qcursor, qperm);
     KERNEL_CHECK(ctx);
     // 4. operands in sorted order
     k_gather_ref<<<(unsigned)ceil_div64(nr_pad * 8, 256), 256, 0, st>>>(yr16, split, rperm, nr_pad, d, r16);
@@ -1630,7 +1645,8 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     k_gather_qry<<<(unsigned)ceil_div64(nq_pad * 8, 256), 256, 0, st>>>(yq16, qperm, nq_pad, q16);
     KERNEL_CHECK(ctx);
     // 5. balls
-    k_group_radius<<<G, 128, 0, st>>>(yr16, rperm, goff, d, cent, grad);
+    CU_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)G, st));
+    k_group_radius<<<dim3(G, 8), 128, 0, st>>>(yr16, rperm, goff, d, cent, grad);
     KERNEL_CHECK(ctx);
     k_item_stats<<<P.n_items, 64, 0, st>>>(q16, qperm, nq_pad, d, item_c, item_rad);
     KERNEL_CHECK(ctx);
