@@ -201,7 +201,10 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)
 // slot e of thread t lives at word e * ls + t, ls = number of epilogue threads (conflict-free)
 // ---------------------------------------------------------------------------
 constexpr int pend_size(int split) { return split == 1 ? 16 : 8; }   // pending-hit buffer per thread
-constexpr int pend_trigger(int split) { return split == 1 ? 8 : 4; }  // merge when a lane holds more
+#ifndef B200NN_TRIG
+#define B200NN_TRIG 8
+#endif
+constexpr int pend_trigger(int split) { return split == 1 ? B200NN_TRIG : 4; }  // merge when a lane holds more
 
 struct Sel {          // register-resident selection state of one query row
   float tau;          // current k'-th best key (+inf until the list is full)
@@ -297,29 +300,26 @@ __device__ __forceinline__ int item_at(const TcParams &P, int i, int b, int grid
   return P.order ? P.order[pos] : pos;
 }
 
-// append one key if it beats tau.  ids grow monotonically along the scan, so `last_id`
-// lets a chunk be re-scanned after a merge without appending anything twice.
-#define TC_TRY(V, C)                                                               \
-  {                                                                                \
-    const float kv = __uint_as_float(V[C]);                                        \
-    const int id = col0 + (C);                                                     \
-    if (kv < S.tau && id > S.last_id && id < nr_i) {                               \
-      if (S.cnt_pend < PENDN) {                                                    \
-        pk[S.cnt_pend * LS] = kv;                                                  \
-        pi[S.cnt_pend * LS] = id;                                                  \
-        S.cnt_pend++;                                                              \
-        S.last_id = id;                                                            \
-      } else {                                                                     \
-        ovf = true;                                                                \
-      }                                                                            \
-    }                                                                              \
-  }
-
+// Scan of one 8-key group without inner branches: every key is stored to the next free
+// pending slot and the slot is kept only if the key beats tau (one spare slot makes the
+// store always legal).  ids grow monotonically along the scan, so `last_id` lets a chunk be
+// re-scanned after a merge without appending anything twice; a hit that finds the buffer
+// full sets `ovf` and is picked up by that re-scan.
 #define TC_GROUP(V, G)                                                             \
   if (gm[G] < S.tau) {                                                             \
-    if (sa[G] < S.tau) { TC_TRY(V, (G)*8 + 0) TC_TRY(V, (G)*8 + 1) TC_TRY(V, (G)*8 + 2) } \
-    if (sb[G] < S.tau) { TC_TRY(V, (G)*8 + 3) TC_TRY(V, (G)*8 + 4) TC_TRY(V, (G)*8 + 5) } \
-    if (sc[G] < S.tau) { TC_TRY(V, (G)*8 + 6) TC_TRY(V, (G)*8 + 7) }               \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                \
+      const float kv = __uint_as_float(V[(G)*8 + j]);                              \
+      const int id = col0 + (G)*8 + j;                                             \
+      const bool hit = kv < S.tau && id > S.last_id && id < nr_i;                  \
+      const bool room = S.cnt_pend < PENDN;                                        \
+      pk[S.cnt_pend * LS] = kv;                                                    \
+      pi[S.cnt_pend * LS] = id;                                                    \
+      ovf |= hit && !room;                                                         \
+      if (hit && room) {                                                           \
+        S.cnt_pend++;                                                              \
+        S.last_id = id;                                                            \
+      }                                                                            \
+    }                                                                              \
   }
 
 // 32 keys of one query row: a FMNMX3 tree rejects the chunk for the whole warp in
@@ -376,9 +376,9 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   const uint32_t off_lists = (QT + stages) * TILE_BYTES;
   float *s_lk = reinterpret_cast<float *>(sm + off_lists);      // [kp][EPI_THREADS]
   int *s_li = reinterpret_cast<int *>(s_lk + P.kp * LSTRIDE);   // [kp][EPI_THREADS]
-  float *s_pk = reinterpret_cast<float *>(s_li + P.kp * LSTRIDE);  // [PEND][EPI_THREADS]
-  int *s_pi = reinterpret_cast<int *>(s_pk + PEND * LSTRIDE);      // [PEND][EPI_THREADS]
-  const uint32_t sBar = base + off_lists + (uint32_t)(2 * P.kp + 2 * PEND) * LSTRIDE * 4;
+  float *s_pk = reinterpret_cast<float *>(s_li + P.kp * LSTRIDE);  // [PEND + 1][EPI_THREADS] (one spare slot)
+  int *s_pi = reinterpret_cast<int *>(s_pk + (PEND + 1) * LSTRIDE);  // [PEND + 1][EPI_THREADS]
+  const uint32_t sBar = base + off_lists + (uint32_t)(2 * P.kp + 2 * (PEND + 1)) * LSTRIDE * 4;
   const uint32_t bar_a_full = sBar + 0, bar_a_empty = sBar + 8;
   const uint32_t bar_b_full = sBar + 16;                        // [MAX_STAGES]
   const uint32_t bar_b_empty = bar_b_full + 8 * MAX_STAGES;     // [MAX_STAGES]
@@ -1380,7 +1380,7 @@ int pick_kp(int k, int n_cand) {
 
 size_t tc_smem_bytes(int kp, int stages, int split) {
   return 1024 + (size_t)(QT + stages) * TILE_BYTES +
-         (size_t)(2 * kp + 2 * pend_size(split)) * epi_warps(split) * 32 * 4 +
+         (size_t)(2 * kp + 2 * (pend_size(split) + 1)) * epi_warps(split) * 32 * 4 +
          8 * (2 + 2 * MAX_STAGES + 4 * QT) + 32 + 4 * RING;
 }
 
