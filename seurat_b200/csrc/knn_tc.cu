@@ -201,17 +201,13 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)
 // slot e of thread t lives at word e * ls + t, ls = number of epilogue threads (conflict-free)
 // ---------------------------------------------------------------------------
 constexpr int pend_size(int split) { return split == 1 ? 16 : 8; }   // pending-hit buffer per thread
-#ifndef B200NN_TRIG
-#define B200NN_TRIG 8
-#endif
-constexpr int pend_trigger(int split) { return split == 1 ? B200NN_TRIG : 4; }  // merge when a lane holds more
+constexpr int GROUP_KEYS = 8;  // keys scanned between two capacity checks of the pending buffer
 
 struct Sel {          // register-resident selection state of one query row
   float tau;          // current k'-th best key (+inf until the list is full)
   int cnt_list;       // entries in the list
   int maxpos;         // slot holding tau
   int cnt_pend;       // entries in the pending buffer
-  int last_id;        // largest reference row appended so far (scan order is monotone)
 };
 
 // recompute the maximum of the (full) list; 8 independent loads in flight
@@ -301,55 +297,45 @@ __device__ __forceinline__ int item_at(const TcParams &P, int i, int b, int grid
 }
 
 // Scan of one 8-key group without inner branches: every key is stored to the next free
-// pending slot and the slot is kept only if the key beats tau (one spare slot makes the
-// store always legal).  ids grow monotonically along the scan, so `last_id` lets a chunk be
-// re-scanned after a merge without appending anything twice; a hit that finds the buffer
-// full sets `ovf` and is picked up by that re-scan.
-#define TC_GROUP(V, G)                                                             \
-  if (gm[G] < S.tau) {                                                             \
-    _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                \
-      const float kv = __uint_as_float(V[(G)*8 + j]);                              \
-      const int id = col0 + (G)*8 + j;                                             \
-      const bool hit = kv < S.tau && id > S.last_id && id < nr_i;                  \
-      const bool room = S.cnt_pend < PENDN;                                        \
-      pk[S.cnt_pend * LS] = kv;                                                    \
-      pi[S.cnt_pend * LS] = id;                                                    \
-      ovf |= hit && !room;                                                         \
-      if (hit && room) {                                                           \
-        S.cnt_pend++;                                                              \
-        S.last_id = id;                                                            \
-      }                                                                            \
-    }                                                                              \
+// pending slot and the slot is kept only if the key beats tau.  Before a group is scanned
+// the warp makes sure that every lane has room for all of its keys (one warp-wide vote),
+// so the scan needs neither bounds nor overflow handling.  Padding rows of the reference
+// operand carry key = +inf and never pass the test.
+#define TC_GROUP(V, G)                                                                     \
+  if (__any_sync(0xffffffffu, gm[G] < S.tau)) {                                            \
+    if (__any_sync(0xffffffffu, S.cnt_pend > PENDN - GROUP_KEYS))                          \
+      S = merge_pending(lk, li, pk, pi, kp, LS, S);                                        \
+    if (gm[G] < S.tau) {                                                                   \
+      _Pragma("unroll") for (int j = 0; j < GROUP_KEYS; ++j) {                             \
+        const float kv = __uint_as_float(V[(G)*GROUP_KEYS + j]);                           \
+        pk[S.cnt_pend * LS] = kv;                                                          \
+        pi[S.cnt_pend * LS] = col0 + (G)*GROUP_KEYS + j;                                   \
+        S.cnt_pend += kv < S.tau ? 1 : 0;                                                  \
+      }                                                                                    \
+    }                                                                                      \
   }
 
 // 32 keys of one query row: a FMNMX3 tree rejects the chunk for the whole warp in
-// ~21 instructions; otherwise the sub-group minima steer the scan to the few keys below tau.
-template <int LS, int PENDN, int TRIG>
+// ~21 instructions; otherwise the group minima steer the scan to the groups holding hits.
+template <int LS, int PENDN>
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, float *lk, int *li,
-                                              float *pk, int *pi, int kp, int col0, int nr_i) {
-  float sa[4], sb[4], sc[4], gm[4];
+                                              float *pk, int *pi, int kp, int col0) {
+  static_assert(PENDN >= GROUP_KEYS, "pending buffer smaller than one group");
+  float gm[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    sa[g] = min3f(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
-    sb[g] = min3f(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-    sc[g] = fminf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-    gm[g] = min3f(sa[g], sb[g], sc[g]);
+    const float a = min3f(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]), __uint_as_float(v[g * 8 + 2]));
+    const float b = min3f(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+    const float c = fminf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+    gm[g] = min3f(a, b, c);
   }
   const float m = min3f(gm[0], gm[1], fminf(gm[2], gm[3]));
   if (!__any_sync(0xffffffffu, m < S.tau)) return;
   // slow path (warp-uniform entry): some lane holds a key below its threshold
-  bool again;
-  do {
-    bool ovf = false;
-    if (m < S.tau) {
-      TC_GROUP(v, 0)
-      TC_GROUP(v, 1)
-      TC_GROUP(v, 2)
-      TC_GROUP(v, 3)
-    }
-    again = __any_sync(0xffffffffu, ovf);
-    if (again || __any_sync(0xffffffffu, S.cnt_pend > TRIG)) S = merge_pending(lk, li, pk, pi, kp, LS, S);
-  } while (again);
+  TC_GROUP(v, 0)
+  TC_GROUP(v, 1)
+  TC_GROUP(v, 2)
+  TC_GROUP(v, 3)
 }
 
 constexpr int MAX_STAGES = 6;
@@ -365,7 +351,6 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
   constexpr int EPI_WARPS = epi_warps(SPLIT);
   constexpr int LSTRIDE = EPI_WARPS * 32;
   constexpr int PEND = pend_size(SPLIT);
-  constexpr int TRIG = pend_trigger(SPLIT);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -497,7 +482,6 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
     float *pk = s_pk + et;
     int *pi = s_pi + et;
     const int kp = P.kp;
-    const int nr_i = (int)P.nr;
     uint32_t bi = 0;
     for (int rnd = 0; rnd * (int)gridDim.x < P.n_items; ++rnd) {
       const int item = item_at(P, rnd, blockIdx.x, gridDim.x);
@@ -507,7 +491,6 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       S.cnt_list = 0;
       S.maxpos = 0;
       S.cnt_pend = 0;
-      S.last_id = -1;
       const int64_t gq = ((int64_t)item * QT + t) * BM + row;
       const int64_t oq = gq < P.nq ? (P.qperm ? (int64_t)P.qperm[gq] : gq) : -1;  // original query row
       if (P.tau_init && oq >= 0) {
@@ -540,7 +523,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 #pragma unroll
               for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
             }
-            process_chunk<LSTRIDE, PEND, TRIG>(va, S, lk, li, pk, pi, kp, colbase + 64 * h, nr_i);
+            process_chunk<LSTRIDE, PEND>(va, S, lk, li, pk, pi, kp, colbase + 64 * h);
             tc_wait_ld(vb);
             if (h == 0) {
               tc_ld32(taddr + 64, va);
@@ -561,7 +544,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 #pragma unroll
               for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
             }
-            process_chunk<LSTRIDE, PEND, TRIG>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, nr_i);
+            process_chunk<LSTRIDE, PEND>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32);
           }
         }
       } else {
@@ -576,13 +559,13 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           const int colbase = s_ring[bi & (RING - 1)] * BN + hh * COLS;
           tc_ld32(taddr, v);
           tc_wait_ld(v);
-          process_chunk<LSTRIDE, PEND, TRIG>(v, S, lk, li, pk, pi, kp, colbase, nr_i);
+          process_chunk<LSTRIDE, PEND>(v, S, lk, li, pk, pi, kp, colbase);
           tc_ld32(taddr + 32, v);
           tc_wait_ld(v);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-          process_chunk<LSTRIDE, PEND, TRIG>(v, S, lk, li, pk, pi, kp, colbase + 32, nr_i);
+          process_chunk<LSTRIDE, PEND>(v, S, lk, li, pk, pi, kp, colbase + 32);
         }
       }
       // flush this thread's candidates
@@ -956,6 +939,15 @@ k_group_scatter(const int32_t *__restrict__ gid, int64_t n, int G, const int32_t
   if (i < n) perm[off[g] + s_base[g] + local] = (int32_t)i;
 }
 
+// padding rows [n, n_pad) of an ungrouped reference operand: key = +inf for every query
+__global__ void __launch_bounds__(128)
+k_pad_ref(__half *__restrict__ r16, int64_t n, int64_t n_pad, int d) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = n + e / BK;
+  const int j = (int)(e % BK);
+  if (p < n_pad) r16[p * BK + j] = j == d ? __ushort_as_half(0x7c00) : __float2half_rn(0.f);
+}
+
 // B operand rows in sorted, padded order; padding rows get key = +inf
 __global__ void __launch_bounds__(256)
 k_gather_ref(const __half *__restrict__ y16, const uint2 *__restrict__ split, const int32_t *__restrict__ rperm,
@@ -1094,6 +1086,8 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
   __shared__ float s_min[LIST_THREADS / 32];
   __shared__ int s_scan[LIST_THREADS / 32];
   __shared__ float s_dmin;
+  __shared__ float s_gd[LIST_THREADS * 4];
+  __shared__ int s_gn[LIST_THREADS * 4];
   const int item = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (item_rad[item] < 0.f) {  // padding-only item
     if (tid == 0) list_cnt[item] = 0;
@@ -1168,15 +1162,47 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
     if (i < w) woff += s_scan[i];
     total += s_scan[i];
   }
-  int pos = woff + inc - mine;
   int32_t *dst = tiles + (int64_t)item * list_stride;
+  if (pass1) {
+    int pos = woff + inc - mine;
 #pragma unroll
-  for (int u = 0; u < GPT; ++u) {
-    const int g = tid * GPT + u;
-    if (ntile[u] > 0) {
-      const int t0 = goff[g] / BN;
-      for (int t = 0; t < ntile[u]; ++t) dst[pos + t] = t0 + t;
+    for (int u = 0; u < GPT; ++u) {
+      const int g = tid * GPT + u;
+      if (ntile[u] > 0) {
+        const int t0 = goff[g] / BN;
+        for (int t = 0; t < ntile[u]; ++t) dst[pos + t] = t0 + t;
+      }
       pos += ntile[u];
+    }
+  } else {
+    // pass 2 visits the kept groups by increasing centre distance: the thresholds drop to
+    // their final values within the first few tiles and later tiles yield almost no hits
+    // (the set of visited tiles, hence the result, does not depend on the order)
+#pragma unroll
+    for (int u = 0; u < GPT; ++u) {
+      s_gd[tid * GPT + u] = ntile[u] > 0 ? dist[u] : CUDART_INF_F;
+      s_gn[tid * GPT + u] = ntile[u];
+    }
+    __syncthreads();
+    int before[GPT];
+#pragma unroll
+    for (int u = 0; u < GPT; ++u) before[u] = 0;
+    for (int o = 0; o < G; ++o) {
+      const float od = s_gd[o];
+      const int on = s_gn[o];
+#pragma unroll
+      for (int u = 0; u < GPT; ++u) {
+        const int g = tid * GPT + u;
+        if (od < dist[u] || (od == dist[u] && o < g)) before[u] += on;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GPT; ++u) {
+      const int g = tid * GPT + u;
+      if (ntile[u] > 0) {
+        const int t0 = goff[g] / BN;
+        for (int t = 0; t < ntile[u]; ++t) dst[before[u] + t] = t0 + t;
+      }
     }
   }
   if (tid == 0) list_cnt[item] = total;
@@ -1538,7 +1564,12 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   CUtensorMap map_q, map_r;
 
   if (!grouped) {
-    RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr * BK, &r16));
+    const int64_t nr_pad = ceil_div64(nr, BN) * BN;  // whole tiles; the tail rows never qualify
+    RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr_pad * BK, &r16));
+    if (nr_pad > nr) {
+      k_pad_ref<<<(unsigned)ceil_div64((nr_pad - nr) * BK, 128), 128, 0, st>>>(r16, nr, nr_pad, d);
+      KERNEL_CHECK(ctx);
+    }
     if (self) {
       k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, q16, r16, q_n2, q_err, misc,
                                                                 nullptr, 1);
@@ -1553,8 +1584,8 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     }
     CU_TRY(cudaEventRecord(e1, st));
     RC_TRY(make_operand_map(&map_q, q16, nq));
-    RC_TRY(make_operand_map(&map_r, r16, nr));
-    P.n_btiles = (int32_t)ceil_div64(nr, BN);
+    RC_TRY(make_operand_map(&map_r, r16, nr_pad));
+    P.n_btiles = (int32_t)(nr_pad / BN);
     RC_TRY(launch_tc(ctx, map_q, map_r, P, d_dbg_keys != nullptr));
   } else {
     // ---- grouped search ------------------------------------------------------------
