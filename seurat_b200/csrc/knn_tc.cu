@@ -1269,6 +1269,23 @@ k_order_items(const int32_t *__restrict__ list_cnt, int n_items, int max_cnt, in
 // ---------------------------------------------------------------------------
 constexpr int RR_WARPS = 4;
 
+// shared-memory row stride (doubles) of the gathered candidate rows.  Even d: rows are moved
+// and read 16 bytes at a time, and a stride of an odd number of 16-byte units keeps the
+// per-lane row reads conflict-free; odd d: 8-byte accesses with an odd stride.
+__host__ __device__ inline int rr_stride(int d) { return (d & 1) ? d + 2 : ((d & 3) == 2 ? d : d + 2); }
+__host__ __device__ inline size_t rr_per_warp(int d) {
+  size_t b = sizeof(double) * ((size_t)32 * rr_stride(d) + ((d + 1) & ~1)) + 64 * 8 + 64 * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void cp_async8(void *s, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *s, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+
+template <bool VEC>  // VEC: d even and both matrices 16-byte aligned
 __global__ void __launch_bounds__(RR_WARPS * 32)
 k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t nq, int d, int k,
          int kp, int split, const int32_t *__restrict__ cand, const float *__restrict__ tau,
@@ -1277,13 +1294,12 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
          int32_t *__restrict__ fail_list, const int32_t *__restrict__ visit, int64_t n_visit) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ds = d + 1;  // padded row stride
+  const int ds = rr_stride(d);
   // per warp: rows[32][ds] doubles, q[d] doubles, key[64] u64, id[64] i32
-  const size_t per_warp = sizeof(double) * ((size_t)32 * ds + d) + 64 * 8 + 64 * 4;
-  unsigned char *wbase = rr_smem + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+  unsigned char *wbase = rr_smem + (size_t)warp * rr_per_warp(d);
   double *rows = reinterpret_cast<double *>(wbase);
   double *qv = rows + 32 * ds;
-  unsigned long long *skey = reinterpret_cast<unsigned long long *>(qv + d);
+  unsigned long long *skey = reinterpret_cast<unsigned long long *>(qv + ((d + 1) & ~1));
   int32_t *sid = reinterpret_cast<int32_t *>(skey + 64);
 
   // queries are visited in the group-sorted order of the candidate stage when available:
@@ -1292,51 +1308,77 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   if (pos >= n_visit) return;
   const int64_t q = visit ? (int64_t)visit[pos] : pos;
   if (q < 0 || q >= nq) return;
-  for (int j = lane; j < d; j += 32) qv[j] = qry[q * d + j];
+  if (VEC) {
+    if (lane < (d >> 1)) cp_async16(qv + 2 * lane, qry + q * d + 2 * lane);
+    for (int j = 64 + 2 * lane; j < d; j += 64) cp_async16(qv + j, qry + q * d + j);
+  } else {
+    for (int j = lane; j < d; j += 32) cp_async8(qv + j, qry + q * d + j);
+  }
   for (int half = 0; half * 32 < kp; ++half) {
     const int c = half * 32 + lane;
-    int id = c < kp ? cand[q * kp + c] : -1;
-    // cooperative, coalesced gather of the 32 candidate rows
+    const int id = c < kp ? cand[q * kp + c] : -1;
+    // cooperative, coalesced gather of the 32 candidate rows by asynchronous copies: every row
+    // is in flight at once (one L2 round trip per query instead of one per candidate)
+#pragma unroll 4
     for (int cc = 0; cc < 32; ++cc) {
-      int idc = __shfl_sync(0xffffffffu, id, cc);
-      if (idc >= 0)
-        for (int j = lane; j < d; j += 32) rows[cc * ds + j] = ref[(int64_t)idc * d + j];
+      const int idc = __shfl_sync(0xffffffffu, id, cc);
+      if (idc >= 0) {
+        const double *src = ref + (int64_t)idc * d;
+        double *dst = rows + cc * ds;
+        if (VEC) {
+          if (lane < (d >> 1)) cp_async16(dst + 2 * lane, src + 2 * lane);
+          for (int j = 64 + 2 * lane; j < d; j += 64) cp_async16(dst + j, src + j);
+        } else {
+          for (int j = lane; j < d; j += 32) cp_async8(dst + j, src + j);
+        }
+      }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
+    // the reference's arithmetic: differences squared and summed in column order, no FMA
     double d2 = CUDART_INF;
     if (id >= 0) {
       d2 = 0.0;
       const double *rr = rows + lane * ds;
-      for (int j = 0; j < d; ++j) {
-        double tt = __dsub_rn(qv[j], rr[j]);
-        d2 = __dadd_rn(d2, __dmul_rn(tt, tt));
+      if (VEC) {
+        for (int j = 0; j < d; j += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(qv + j);
+          const double2 b = *reinterpret_cast<const double2 *>(rr + j);
+          const double t0 = __dsub_rn(a.x, b.x), t1 = __dsub_rn(a.y, b.y);
+          d2 = __dadd_rn(d2, __dmul_rn(t0, t0));
+          d2 = __dadd_rn(d2, __dmul_rn(t1, t1));
+        }
+      } else {
+        for (int j = 0; j < d; ++j) {
+          const double tt = __dsub_rn(qv[j], rr[j]);
+          d2 = __dadd_rn(d2, __dmul_rn(tt, tt));
+        }
       }
     }
     skey[c] = (unsigned long long)__double_as_longlong(d2);  // d2 >= 0: bit order == value order
     sid[c] = id >= 0 ? id : 0x7fffffff;
     __syncwarp();
   }
-  // pad to 64 and sort ascending by (d2, index)
-  for (int c = ((kp + 31) / 32) * 32 + lane; c < 64; c += 32) {
-    skey[c] = (unsigned long long)__double_as_longlong(CUDART_INF);
-    sid[c] = 0x7fffffff;
-  }
-  __syncwarp();
-  for (int kk = 2; kk <= 64; kk <<= 1) {
-    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-      const int i = lane;  // 32 comparators per step
-      const int lo = ((i / jj) * 2 * jj) + (i % jj);
-      const int hi = lo + jj;
-      const bool up = ((lo & kk) == 0) || kk == 64;
-      unsigned long long ka = skey[lo], kb = skey[hi];
-      int ia = sid[lo], ib = sid[hi];
-      bool gt = ka > kb || (ka == kb && ia > ib);
-      if (gt == up) {
-        skey[lo] = kb; skey[hi] = ka;
-        sid[lo] = ib; sid[hi] = ia;
-      }
-      __syncwarp();
+  // rank of every candidate under (d2, index); ranks below k are the result rows.  Missing
+  // candidates share the key (+inf, INT_MAX): they rank after every real one.
+  const int kp_r = ((kp + 31) / 32) * 32;
+  unsigned long long kth = (unsigned long long)__double_as_longlong(CUDART_INF);
+  for (int c = lane; c < kp_r; c += 32) {
+    const unsigned long long mk = skey[c];
+    const int mi = sid[c];
+    int rank = 0;
+#pragma unroll 8
+    for (int o = 0; o < kp_r; ++o) {
+      const unsigned long long ok = skey[o];
+      const int oi = sid[o];
+      rank += (ok < mk || (ok == mk && oi < mi)) ? 1 : 0;
     }
+    if (rank < k && mi != 0x7fffffff) {
+      idx0[q * k + rank] = mi;
+      dist[q * k + rank] = sqrt(__longlong_as_double((long long)mk));
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, rank == k - 1);
+    if (hit) kth = __shfl_sync(0xffffffffu, mk, __ffs(hit) - 1);
   }
   // certificate
   const double s = misc->scale;
@@ -1346,16 +1388,12 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   // every non-candidate has a key >= the threshold of the list that rejected it
   double tq = (double)tau[q * split];
   for (int h = 1; h < split; ++h) tq = fmin(tq, (double)tau[q * split + h]);
-  const double dk2 = __longlong_as_double((long long)skey[k - 1]);
+  const double dk2 = __longlong_as_double((long long)kth);
   bool ok = false;
   if (isfinite(tq) && isfinite(dk2)) {
     double lb2 = tq + qn - eta;
     double lb = (lb2 > 0.0 ? sqrt(lb2) : 0.0) - eq - misc->e_max;
     ok = s * sqrt(dk2) * (1.0 + 1e-9) < lb * (1.0 - 1e-9);
-  }
-  for (int t = lane; t < k; t += 32) {
-    idx0[q * k + t] = sid[t];
-    dist[q * k + t] = sqrt(__longlong_as_double((long long)skey[t]));
   }
   if (!ok && lane == 0) {
     int pos = atomicAdd(&misc->n_fail, 1);
@@ -1761,13 +1799,13 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
 
   cudaEvent_t e0 = ctx->ev[11], e1 = ctx->ev[12], e2 = ctx->ev[13];
   CU_TRY(cudaEventRecord(e0, st));
-  const int ds = d + 1;
-  size_t per_warp = sizeof(double) * ((size_t)32 * ds + d) + 64 * 8 + 64 * 4;
-  per_warp = (per_warp + 15) & ~(size_t)15;
-  size_t smem = per_warp * RR_WARPS;
-  CU_TRY(cudaFuncSetAttribute(k_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = rr_per_warp(d) * RR_WARPS;
   const int64_t n_visit = g_visit ? g_n_visit : nq;
-  k_rerank<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
+  const bool vec = (d % 2 == 0) && (reinterpret_cast<uintptr_t>(d_ref) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(d_qry) % 16 == 0);
+  auto kern = vec ? k_rerank<true> : k_rerank<false>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
       d_ref, d_qry, nq, d, k, kp * split, split, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, g_visit,
       n_visit);
   KERNEL_CHECK(ctx);
