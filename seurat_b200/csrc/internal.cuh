@@ -79,6 +79,7 @@ enum WsSlot {
   WS_TC_CAND,      // candidate indices (int32, nq * k')
   WS_TC_CANDKEY,   // selection threshold tau per query (fp32, nq)
   WS_TC_FLAGS,     // per-query certificate flags / fallback list
+  WS_TC_FAILTAU,   // upper bound of the k-th squared distance of every fallback row
   WS_TC_MISC,
   WS_TC_Y16R,      // FP16 rows of the reference set in original order (grouped search)
   WS_TC_Y16Q,
@@ -164,7 +165,30 @@ int narrow_i64_to_i32(b200nn_ctx *ctx, const int64_t *d_in, int32_t *d_out, int6
 // (count read from the device at launch-time upper bound n_sel).
 int knn_exact_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                      int64_t nq, int d, int k, const int32_t *d_qsel, int64_t n_sel,
-                     int32_t *d_idx0, double *d_dist);
+                     int32_t *d_idx0, double *d_dist,
+                     const double *d_tau0 = nullptr);
+
+// Reference rows clustered by the tensor-core search (all device pointers): groups of
+// scaled, FP16-rounded points yh with centre and radius, stored group by group in a padded
+// order (`rperm`: position -> original row, -1 for padding; group g owns positions
+// [goff[g], goff[g+1]), a multiple of 128).
+struct GroupedRefs {
+  int G;                 // groups
+  int ld;                // leading dimension of cent / yq16 (elements)
+  const float *cent;     // [G x ld] group centres
+  const float *grad;     // [G] radius (upper bound) of the group's points around its centre
+  const int32_t *goff;   // [G + 1]
+  const int32_t *rperm;
+  const uint16_t *yq16;  // [nq x ld] FP16 bits of the scaled query rows, original order
+  const double *q_err;   // [nq] |y_q - yh_q|
+  const double *scale;   // s: y = s * (x - mu)
+  const double *e_max;   // max over reference rows of |y_r - yh_r|
+};
+// knn_exact.cu : same result as knn_exact_launch for the listed rows, but only the groups
+// that can hold a point within the row's bound d_tau0 (squared, reference arithmetic) are scanned
+int knn_exact_grouped_launch(b200nn_ctx *ctx, const double *d_ref, const double *d_qry, int d, int k,
+                             const int32_t *d_qsel, int64_t n_sel, const double *d_tau0,
+                             const GroupedRefs &R, int32_t *d_idx0, double *d_dist);
 
 // knn_tc.cu : tcgen05 candidate generation + FP64 re-rank + certificate
 void knn_tc_set_mode(int mode);

@@ -1291,7 +1291,8 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
          int kp, int split, const int32_t *__restrict__ cand, const float *__restrict__ tau,
          const double *__restrict__ q_n2, const double *__restrict__ q_err,
          TcMisc *__restrict__ misc, int32_t *__restrict__ idx0, double *__restrict__ dist,
-         int32_t *__restrict__ fail_list, const int32_t *__restrict__ visit, int64_t n_visit) {
+         int32_t *__restrict__ fail_list, double *__restrict__ fail_tau,
+         const int32_t *__restrict__ visit, int64_t n_visit) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ds = rr_stride(d);
@@ -1398,6 +1399,9 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   if (!ok && lane == 0) {
     int pos = atomicAdd(&misc->n_fail, 1);
     fail_list[pos] = (int32_t)q;
+    // the k-th candidate is a real point: its squared distance (reference arithmetic) bounds
+    // the true k-th squared distance from above and lets the exhaustive scan skip nearly all rows
+    fail_tau[pos] = isfinite(dk2) ? dk2 : CUDART_INF;
   }
 }
 
@@ -1463,6 +1467,9 @@ static thread_local int g_tc_mode = 0;
 // grouped candidate stage for the re-rank kernel
 static thread_local const int32_t *g_visit = nullptr;
 static thread_local int64_t g_n_visit = 0;
+// grouping of the reference rows built by the last grouped search (for the fallback scan)
+static thread_local GroupedRefs g_groups;
+static thread_local bool g_have_groups = false;
 void knn_tc_set_mode(int mode) { g_tc_mode = mode; }
 
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
@@ -1556,6 +1563,7 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   const bool grouped = mode == 2 || (mode == 0 && nr >= 32768 && d_dbg_keys == nullptr);
   g_visit = nullptr;
   g_n_visit = 0;
+  g_have_groups = false;
   TcMisc *misc;
   double *partial, *q_n2, *q_err;
   __half *r16, *q16;
@@ -1744,6 +1752,17 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     KERNEL_CHECK(ctx);
     g_visit = qperm;
     g_n_visit = nq_pad;
+    g_groups.G = G;
+    g_groups.ld = BK;
+    g_groups.cent = cent;
+    g_groups.grad = grad;
+    g_groups.goff = goff;
+    g_groups.rperm = rperm;
+    g_groups.yq16 = reinterpret_cast<const uint16_t *>(yq16);
+    g_groups.q_err = q_err;
+    g_groups.scale = &misc->scale;
+    g_groups.e_max = &misc->e_max;
+    g_have_groups = true;
     P.pass1 = 0;
     P.tau_init = tau;  // written by pass 1, read at the start of every pass-2 row
     k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc);
@@ -1796,6 +1815,8 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   int32_t *flags;
   RC_TRY(ws_get(ctx, WS_TC_FLAGS, (size_t)nq + 4, &flags));
   int32_t *fail_list = flags + 1;  // flags[0] receives the count (knn_exact reads list[-1])
+  double *fail_tau;
+  RC_TRY(ws_get(ctx, WS_TC_FAILTAU, (size_t)nq, &fail_tau));
 
   cudaEvent_t e0 = ctx->ev[11], e1 = ctx->ev[12], e2 = ctx->ev[13];
   CU_TRY(cudaEventRecord(e0, st));
@@ -1806,8 +1827,8 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   auto kern = vec ? k_rerank<true> : k_rerank<false>;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
-      d_ref, d_qry, nq, d, k, kp * split, split, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, g_visit,
-      n_visit);
+      d_ref, d_qry, nq, d, k, kp * split, split, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, fail_tau,
+      g_visit, n_visit);
   KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e1, st));
   TcMisc h;
@@ -1819,7 +1840,11 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   }
   if (h.n_fail > 0) {
     CU_TRY(cudaMemcpyAsync(flags, &misc->n_fail, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    RC_TRY(knn_exact_launch(ctx, d_ref, nr, d_qry, nq, d, k, fail_list, h.n_fail, d_idx0, d_dist));
+    if (g_have_groups)
+      RC_TRY(knn_exact_grouped_launch(ctx, d_ref, d_qry, d, k, fail_list, h.n_fail, fail_tau, g_groups, d_idx0,
+                                      d_dist));
+    else
+      RC_TRY(knn_exact_launch(ctx, d_ref, nr, d_qry, nq, d, k, fail_list, h.n_fail, d_idx0, d_dist, fail_tau));
   }
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));

@@ -154,6 +154,24 @@ def test_grouped_search_few_queries_many_references(ctx):
     assert (idx == wi).all() and (dist == wd).all()
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_many_uncertified_rows_take_the_exact_fallback(ctx, mode):
+    """a candidate set only slightly wider than k leaves many rows uncertified: they are redone by the
+    FP64 scan (the group-pruned one after a grouped search) and the result is still the oracle's"""
+    X, _ = gaussian_mixture(60000, 30, seed=12, n_centres=10)
+    k = 20
+    wi, wd = oracle.knn(X, k=k, method="kdtree")
+    idx, dist, st = ctx.knn(X, None, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR, k + 1, mode)
+    assert st["n_uncertified"] > 100, st
+    assert (idx == wi).all() and (dist == wd).all()
+    # query != reference, few uncertified rows (the split-slice variant of the fallback)
+    Q, _ = gaussian_mixture(300, 30, seed=13, n_centres=10)
+    wi, wd = oracle.knn(X, Q, k, method="kdtree")
+    idx, dist, st = ctx.knn(X, Q, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR, k + 2, mode)
+    assert (idx == wi).all() and (dist == wd).all()
+    print("mode", mode, "uncertified of 300:", st["n_uncertified"])
+
+
 def test_split_epilogue_variant(ctx, monkeypatch):
     """the experimental two-warps-per-row-set epilogue (B200NN_SPLIT=2) gives the same answer"""
     import subprocess, sys, os, textwrap

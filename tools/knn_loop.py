@@ -7,6 +7,8 @@ ctx = sb.Context(0)
 ref = torch.from_numpy(X).cuda()
 idx0 = torch.empty((1_000_000, 20), dtype=torch.int32, device="cuda"); dist = torch.empty((1_000_000, 20), dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
-for r in range(8):
-    t0=time.perf_counter(); st = ctx.dev_knn(ref, 1_000_000, None, 1_000_000, 50, 20, idx0, dist); dt=time.perf_counter()-t0
+NC = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+for r in range(REPS):
+    t0=time.perf_counter(); st = ctx.dev_knn(ref, 1_000_000, None, 1_000_000, 50, 20, idx0, dist, 0, NC); dt=time.perf_counter()-t0
     print(f"{dt*1e3:.1f} ms cand {st['ms_knn_cand']:.1f} rerank {st['ms_knn_rerank']:.1f} fallback {st['ms_knn_fallback']:.1f} uncert {st['n_uncertified']} tiles {st['knn_tiles_visited']}")
