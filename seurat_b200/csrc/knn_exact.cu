@@ -268,7 +268,7 @@ k_knn_exact_grouped(const double *__restrict__ ref, const double *__restrict__ q
   int32_t *buf_i = top_i + k;
   int32_t *row_s = buf_i + KX_THREADS;
   int32_t *sel = row_s + KX_THREADS;
-  __shared__ int s_nsel, s_bufn, s_topn;
+  __shared__ int s_bufn, s_topn;
   __shared__ double s_tau;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,7 +281,6 @@ k_knn_exact_grouped(const double *__restrict__ ref, const double *__restrict__ q
     yq[tid] = tid < R.ld ? (double)__half2float(__ushort_as_half(R.yq16[q * R.ld + tid])) : 0.0;
   }
   if (tid == 0) {
-    s_nsel = 0;
     s_bufn = 0;
     s_topn = 0;
     s_tau = tau0;
@@ -290,7 +289,10 @@ k_knn_exact_grouped(const double *__restrict__ ref, const double *__restrict__ q
   // groups that may hold a row within sqrt(tau0)
   const double reach = (*R.scale) * sqrt(tau0) * (1.0 + 1e-9) + R.q_err[q] + (*R.e_max) + 1e-6;
   for (int g = tid; g < R.G; g += KX_THREADS) {
-    if (R.goff[g + 1] <= R.goff[g]) continue;
+    if (R.goff[g + 1] <= R.goff[g]) {
+      sel[g] = 0;
+      continue;
+    }
     const float *c = R.cent + (size_t)g * R.ld;
     double s2 = 0.0;
     for (int j = 0; j < d; ++j) {  // columns >= d of the operand rows are not coordinates
@@ -298,13 +300,13 @@ k_knn_exact_grouped(const double *__restrict__ ref, const double *__restrict__ q
       s2 = fma(t, t, s2);
     }
     const double lb = sqrt(s2) * (1.0 - 1e-6) - (double)R.grad[g];
-    if (!(lb > reach)) sel[atomicAdd(&s_nsel, 1)] = g;  // also keeps everything when tau0 is +inf / NaN
+    sel[g] = !(lb > reach);  // also keeps everything when tau0 is +inf / NaN
   }
   __syncthreads();
-  const int nsel = s_nsel;
+  // every slice of this row enumerates the selected tiles in the same (group) order
   int n = 0;
-  for (int li = 0; li < nsel; ++li) {
-    const int g = sel[li];
+  for (int g = 0; g < R.G; ++g) {
+    if (!sel[g]) continue;
     const int t0 = R.goff[g] / KX_THREADS, nt = (R.goff[g + 1] - R.goff[g]) / KX_THREADS;
     for (int t = 0; t < nt; ++t, ++n) {
       if (n % n_slices != (int)blockIdx.y) continue;
