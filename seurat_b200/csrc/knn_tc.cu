@@ -317,9 +317,12 @@ __device__ __forceinline__ int item_at(const TcParams &P, int i, int b, int grid
 
 // 32 keys of one query row: a FMNMX3 tree rejects the chunk for the whole warp in
 // ~21 instructions; otherwise the group minima steer the scan to the groups holding hits.
-template <int LS, int PENDN>
+// P1 && bucket (pass 1 of the grouped search, which only has to produce a threshold with at
+// least k' keys below it): the minimum of every 8-key group stands for the group, so at most
+// four values per chunk reach the pending buffer.
+template <int LS, int PENDN, bool P1>
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, float *lk, int *li,
-                                              float *pk, int *pi, int kp, int col0) {
+                                              float *pk, int *pi, int kp, int col0, bool bucket) {
   static_assert(PENDN >= GROUP_KEYS, "pending buffer smaller than one group");
   float gm[4];
 #pragma unroll
@@ -332,6 +335,16 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], Sel &S, f
   const float m = min3f(gm[0], gm[1], fminf(gm[2], gm[3]));
   if (!__any_sync(0xffffffffu, m < S.tau)) return;
   // slow path (warp-uniform entry): some lane holds a key below its threshold
+  if (P1 && bucket) {
+    if (__any_sync(0xffffffffu, S.cnt_pend > PENDN - 4)) S = merge_pending(lk, li, pk, pi, kp, LS, S);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      pk[S.cnt_pend * LS] = gm[g];
+      pi[S.cnt_pend * LS] = col0 + g * GROUP_KEYS;
+      S.cnt_pend += gm[g] < S.tau ? 1 : 0;
+    }
+    return;
+  }
   TC_GROUP(v, 0)
   TC_GROUP(v, 1)
   TC_GROUP(v, 2)
@@ -344,7 +357,7 @@ constexpr int RING = 16;            // tile-id ring (power of two > stages + acc
 // ---------------------------------------------------------------------------
 // K1: candidate generation
 // ---------------------------------------------------------------------------
-template <bool DBG, int SPLIT>
+template <bool DBG, int SPLIT, bool P1>
 __global__ void __launch_bounds__(num_threads(SPLIT), 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
          TcParams P) {
@@ -500,6 +513,8 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
         if (t1 < CUDART_INF_F) S.tau = nextafterf(t1, CUDART_INF_F);
       }
       const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
+      // >= 4 tiles of one group hold >= 3 tiles without padding = 48 >= MAX_KP eight-key buckets
+      const bool bucket = P1 && nt >= 4;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(hh * COLS);
       if constexpr (SPLIT == 1) {
         uint32_t va[32], vb[32];
@@ -523,7 +538,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 #pragma unroll
               for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
             }
-            process_chunk<LSTRIDE, PEND>(va, S, lk, li, pk, pi, kp, colbase + 64 * h);
+            process_chunk<LSTRIDE, PEND, P1>(va, S, lk, li, pk, pi, kp, colbase + 64 * h, bucket);
             tc_wait_ld(vb);
             if (h == 0) {
               tc_ld32(taddr + 64, va);
@@ -544,7 +559,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
 #pragma unroll
               for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
             }
-            process_chunk<LSTRIDE, PEND>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32);
+            process_chunk<LSTRIDE, PEND, P1>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, bucket);
           }
         }
       } else {
@@ -559,13 +574,13 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           const int colbase = s_ring[bi & (RING - 1)] * BN + hh * COLS;
           tc_ld32(taddr, v);
           tc_wait_ld(v);
-          process_chunk<LSTRIDE, PEND>(v, S, lk, li, pk, pi, kp, colbase);
+          process_chunk<LSTRIDE, PEND, P1>(v, S, lk, li, pk, pi, kp, colbase, bucket);
           tc_ld32(taddr + 32, v);
           tc_wait_ld(v);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-          process_chunk<LSTRIDE, PEND>(v, S, lk, li, pk, pi, kp, colbase + 32);
+          process_chunk<LSTRIDE, PEND, P1>(v, S, lk, li, pk, pi, kp, colbase + 32, bucket);
         }
       }
       // flush this thread's candidates
@@ -1491,14 +1506,15 @@ static int launch_tc(b200nn_ctx *ctx, const CUtensorMap &map_q, const CUtensorMa
   int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
   if (grid <= 0) return B200NN_OK;
   if (dbg) {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<true, 1><<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<true, 1, false><<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
   } else if (P.split == 2) {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<false, 2><<<grid, num_threads(2), smem, ctx->stream>>>(map_q, map_r, P);
+    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_tc<false, 2, false><<<grid, num_threads(2), smem, ctx->stream>>>(map_q, map_r, P);
   } else {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<false, 1><<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
+    auto kern = P.pass1 ? k_knn_tc<false, 1, true> : k_knn_tc<false, 1, false>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
   }
   KERNEL_CHECK(ctx);
   return B200NN_OK;
