@@ -642,11 +642,14 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
     __syncwarp();
     const int32_t *nbr = P.idx0 + row * P.k;
     int nslots = 0, npend = 0;
-    bool ovf = false;
+    bool ovf = false, sat = false;
     for (int pass = 0; pass < 2 && !ovf; ++pass) {
-      if (pass == 1) {  // the table doubled as claim scratch during pass 0
-        for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+      if (pass == 1) {
         __syncwarp();
+        if (__any_sync(0xffffffffu, sat)) {
+          ovf = true;
+          break;
+        }
       }
       for (int p0 = 0; p0 < P.k && !ovf; p0 += 32) {
         int64_t beg = 0;
@@ -685,33 +688,19 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
 #pragma unroll
           for (int u = 0; u < 4; ++u) hc[u] = hash_cnt<CW_LOG>((uint32_t)v[u]);
           if (pass == 0) {
-            // The occurrences of one list are distinct rows, but two of them may share a
-            // counter.  Conflicts are rare (~6 % of the batches), and MATCH.ANY on 32 distinct
-            // values costs hundreds of cycles, so they are detected with a claim byte first
-            // (the exact table is still empty in this pass and serves as scratch): every lane
-            // stores its id, and a lane that reads back another id shares its slot.
-            uint8_t *claim = reinterpret_cast<uint8_t *>(tab);
+            // four byte counters per 32-bit word, bumped with one shared-memory atomic each
+            // (colliding lanes are serialised by the hardware; no conflict detection, no
+            // warp synchronisation).  A counter about to wrap would under-count, so a row that
+            // ever sees 255 is handed to the big-table kernel instead.
+            uint32_t *cw = reinterpret_cast<uint32_t *>(cnt);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (t0 + 32 * u >= l) break;  // warp-uniform
-              const bool act = v[u] >= 0;
-              const uint32_t ci = hc[u] & ((1u << (F_TX_LOG + 2)) - 1);
-              if (act) claim[ci] = (uint8_t)lane;
-              __syncwarp();
-              const bool lost = act && claim[ci] != (uint8_t)lane;
-              if (!__any_sync(0xffffffffu, lost)) {
-                if (act) {
-                  const int c = (int)cnt[hc[u]] + 1;
-                  cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
-                }
-              } else {
-                const unsigned same = __match_any_sync(0xffffffffu, act ? hc[u] : (0x80000000u | (uint32_t)lane));
-                if (act && (__ffs(same) - 1) == lane) {
-                  const int c = (int)cnt[hc[u]] + __popc(same);
-                  cnt[hc[u]] = (uint8_t)(c > 255 ? 255 : c);
-                }
+              if (v[u] >= 0) {
+                const uint32_t sh = (hc[u] & 3u) * 8u;
+                const uint32_t old = atomicAdd(&cw[hc[u] >> 2], 1u << sh);
+                sat |= ((old >> sh) & 0xffu) == 0xffu;
               }
-              __syncwarp();
             }
           } else {
 #pragma unroll
