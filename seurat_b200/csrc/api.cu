@@ -77,30 +77,42 @@ int upload_nn_ranked(b200nn_ctx *ctx, const int32_t *h, int64_t rows, int k, int
 }
 
 // device row-major idx0 / dist [nq x k] -> host buffers in `layout`, idx 1-based
+// Layout conversion on the compute stream, then the device->host copies on the copy stream:
+// they run while later kernels of the compute stream execute.  download_knn_end waits for them.
+int download_knn_begin(b200nn_ctx *ctx, const int32_t *d_idx0, const double *d_dist, int64_t nq, int k,
+                       int layout, int32_t *h_idx, double *h_dist) {
+  size_t cnt = (size_t)nq * (size_t)k;
+  int32_t *oi = nullptr;
+  const double *od = d_dist;
+  if (h_idx) {
+    RC_TRY(ws_get(ctx, WS_OUT_IDX, cnt, &oi));
+    if (layout == B200NN_ROW_MAJOR)
+      RC_TRY(add_i32(ctx, d_idx0, oi, (int64_t)cnt, 1));
+    else  // row-major [nq x k] == column-major [k x nq]; transposing that gives col-major [nq x k]
+      RC_TRY(transpose_i32_add(ctx, d_idx0, oi, k, nq, 1));
+  }
+  if (h_dist && layout != B200NN_ROW_MAJOR) {
+    double *o;
+    RC_TRY(ws_get(ctx, WS_OUT_DIST, cnt, &o));
+    RC_TRY(transpose_f64(ctx, d_dist, o, k, nq));
+    od = o;
+  }
+  CU_TRY(cudaEventRecord(ctx->ev_copy, ctx->stream));
+  CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, oi, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  if (h_dist) CU_TRY(cudaMemcpyAsync(h_dist, od, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  return B200NN_OK;
+}
+
+int download_knn_end(b200nn_ctx *ctx) {
+  CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
+  return B200NN_OK;
+}
+
 int download_knn(b200nn_ctx *ctx, const int32_t *d_idx0, const double *d_dist, int64_t nq, int k,
                  int layout, int32_t *h_idx, double *h_dist) {
-  size_t cnt = (size_t)nq * (size_t)k;
-  if (h_idx) {
-    int32_t *o;
-    RC_TRY(ws_get(ctx, WS_OUT_IDX, cnt, &o));
-    if (layout == B200NN_ROW_MAJOR)
-      RC_TRY(add_i32(ctx, d_idx0, o, (int64_t)cnt, 1));
-    else  // row-major [nq x k] == column-major [k x nq]; transposing that gives col-major [nq x k]
-      RC_TRY(transpose_i32_add(ctx, d_idx0, o, k, nq, 1));
-    CU_TRY(cudaMemcpyAsync(h_idx, o, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  if (h_dist) {
-    const double *src = d_dist;
-    if (layout != B200NN_ROW_MAJOR) {
-      double *o;
-      RC_TRY(ws_get(ctx, WS_OUT_DIST, cnt, &o));
-      RC_TRY(transpose_f64(ctx, d_dist, o, k, nq));
-      src = o;
-    }
-    CU_TRY(cudaMemcpyAsync(h_dist, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  return B200NN_OK;
+  RC_TRY(download_knn_begin(ctx, d_idx0, d_dist, nq, k, layout, h_idx, h_dist));
+  return download_knn_end(ctx);
 }
 
 int download_csr(b200nn_ctx *ctx, const CsrResult &r, int32_t *p, int32_t *i, double *x) {
@@ -212,6 +224,8 @@ int b200nn_ctx_create(int device, b200nn_ctx **ctx_out) {
   }
   ctx->sm_count = prop.multiProcessorCount;
   CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
   for (auto &ev : ctx->ev) CU_TRY(cudaEventCreate(&ev));
   CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(DevInfo)));
   *ctx_out = ctx;
@@ -227,6 +241,8 @@ void b200nn_ctx_destroy(b200nn_ctx *ctx) {
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;
@@ -454,9 +470,16 @@ int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, 
   RC_TRY(ws_get(ctx, WS_IDX0, (size_t)n * k, &d_idx0));
   RC_TRY(ws_get(ctx, WS_DIST, (size_t)n * k, &d_dist));
   RC_TRY(knn_dispatch(ctx, d_ref, n, nullptr, n, d, k, o, d_idx0, d_dist, stats));
+  // the kNN result travels to the host while the graphs are computed
+  const bool want_knn = idx_out || dist_out;
+  if (want_knn) RC_TRY(download_knn_begin(ctx, d_idx0, d_dist, n, k, o.layout, idx_out, dist_out));
   b200nn_stats gs;
   memset(&gs, 0, sizeof(gs));
-  RC_TRY(graphs_launch(ctx, d_idx0, n, k, n, prune, true, compute_snn != 0, 0, n, &gs));
+  int grc = graphs_launch(ctx, d_idx0, n, k, n, prune, true, compute_snn != 0, 0, n, &gs);
+  if (grc != B200NN_OK) {
+    if (want_knn) cudaStreamSynchronize(ctx->copy_stream);  // never leave a copy into caller memory in flight
+    return grc;
+  }
   if (stats) {
     stats->ms_nn_graph = gs.ms_nn_graph;
     stats->ms_snn = gs.ms_snn;
@@ -465,10 +488,10 @@ int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, 
     stats->snn_expanded = gs.snn_expanded;
     stats->max_indegree = gs.max_indegree;
   }
-  if (idx_out || dist_out) {
+  if (want_knn) {
     RC_TRY(th.start());
-    RC_TRY(download_knn(ctx, d_idx0, d_dist, n, k, o.layout, idx_out, dist_out));
-    RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));
+    RC_TRY(download_knn_end(ctx));
+    RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));  // what is left of the copy after the graphs
   }
   if (compute_snn && ctx->snn.nnz >= 0x7fffffffLL) {
     b200nn_set_error("SNN graph has %lld entries, more than a dgCMatrix can hold",

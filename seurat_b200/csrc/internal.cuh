@@ -124,7 +124,9 @@ struct CsrResult {
 struct b200nn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // device->host copies that overlap later stages
   cudaEvent_t ev[16] = {};
+  cudaEvent_t ev_copy = nullptr;
   WsBuf ws[WS_NUM];
   DevInfo *h_info = nullptr;  // pinned
   int sm_count = 148;
