@@ -571,54 +571,61 @@ int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atom
 // The exact table is small; a row that would overflow it is handed to the big-table
 // kernel instead.  Counts, cut-off and output are exactly those of the plain kernel.
 // ---------------------------------------------------------------------------
-constexpr int F_TX_LOG = 10;                   // exact table: 1024 words
-constexpr int F_SLOTS = 800;                   // distinct keys allowed in it
-constexpr int F_SLOT_CAP = 832;
-constexpr int filt_bytes(int cw_log) { return (1 << cw_log) + (1 << F_TX_LOG) * 4 + F_SLOT_CAP * 2 + 64 * 4; }
+// exact table of 2^tx_log words; ~78 % of it may fill before the row is handed on
+constexpr int filt_slots(int tx_log) { return (1 << tx_log) * 25 / 32; }      // distinct keys allowed
+constexpr int filt_slot_cap(int tx_log) { return (1 << tx_log) * 26 / 32; }
+constexpr int filt_bytes(int cw_log, int tx_log) {
+  return (1 << cw_log) + (1 << tx_log) * 4 + filt_slot_cap(tx_log) * 2 + 64 * 4;
+}
 
 template <int CW_LOG>
 __device__ __forceinline__ uint32_t hash_cnt(uint32_t j) { return (j * 0x9E3779B1u) >> (32 - CW_LOG); }
 
-// exact insert of one batch (<= 32 occurrences, repeats of a key allowed)
+// exact insert of one batch (<= 32 occurrences, repeats of a key allowed).  A key that is
+// already in the table costs one probe and one shared-memory atomic add; only the first
+// occurrence of a key claims a slot with a compare-and-swap (~40 per row).  The claimed slots
+// are recorded so that the table is read out and cleaned without scanning it.
+template <int F_TX_LOG>
 __device__ __forceinline__ void filt_insert_batch(uint32_t *tab, uint16_t *slots, int &nslots, int cbits,
                                                   uint32_t j, bool active, int lane) {
   constexpr uint32_t mask = (1u << F_TX_LOG) - 1;
-  const unsigned same = __match_any_sync(0xffffffffu, active ? j : (0x80000000u | (uint32_t)lane));
-  const bool leader = active && (__ffs(same) - 1) == lane;
-  const uint32_t inc = (uint32_t)__popc(same);
+  constexpr int F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
   uint32_t h = (j * 2654435761u) >> (32 - F_TX_LOG);
-  const uint32_t fresh = (j << cbits) | inc;
+  const uint32_t fresh = (j << cbits) | 1u;
   volatile uint32_t *vt = tab;
-  bool todo = leader;
-  do {
-    uint32_t cur = 0xffffffffu;
-    if (todo) {
-      while (true) {
-        cur = vt[h];
-        if (cur == 0xffffffffu || (cur >> cbits) == j) break;
-        h = (h + 1) & mask;
+  bool won = false, todo = active;
+  while (todo) {
+    uint32_t cur = vt[h];
+    if (cur == 0xffffffffu) {
+      cur = atomicCAS(&tab[h], 0xffffffffu, fresh);
+      if (cur == 0xffffffffu) {
+        won = true;
+        break;
       }
     }
-    const bool claim = todo && cur == 0xffffffffu;
-    if (todo && !claim) vt[h] = cur + inc;
-    if (claim) vt[h] = fresh;
-    __syncwarp();
-    const bool won = claim && vt[h] == fresh;
-    todo = claim && !won;
-    const unsigned wb = __ballot_sync(0xffffffffu, won);
-    if (won) {
-      const int pos = nslots + __popc(wb & ((1u << lane) - 1));
-      if (pos < F_SLOT_CAP) slots[pos] = (uint16_t)h;
+    if ((cur >> cbits) == j) {
+      atomicAdd(&tab[h], 1u);
+      todo = false;
+    } else {
+      h = (h + 1) & mask;
     }
-    nslots += __popc(wb);
-    __syncwarp();
-  } while (__any_sync(0xffffffffu, todo));
+  }
+  __syncwarp();
+  const unsigned wb = __ballot_sync(0xffffffffu, won);
+  if (won) {
+    const int pos = nslots + __popc(wb & ((1u << lane) - 1));
+    if (pos < F_SLOT_CAP) slots[pos] = (uint16_t)h;
+  }
+  nslots += __popc(wb);
+  __syncwarp();
 }
 
-template <int CW_LOG, int F_WARPS>  // log2 of the byte counters per row; warps (rows) per CTA
+// log2 of the byte counters per row, log2 of the exact table's words, warps (rows) per CTA
+template <int CW_LOG, int F_TX_LOG, int F_WARPS>
 __global__ void __launch_bounds__(F_WARPS * 32)
 k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
-  constexpr int F_BYTES = filt_bytes(CW_LOG);
+  constexpr int F_BYTES = filt_bytes(CW_LOG, F_TX_LOG);
+  constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
   constexpr int F_CW_LOG = CW_LOG;
   static_assert((1 << CW_LOG) >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -713,7 +720,7 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
                 npend += __popc(bal);
                 __syncwarp();
                 if (npend >= 32) {
-                  filt_insert_batch(tab, slots, nslots, P.cbits, pend[lane], true, lane);
+                  filt_insert_batch<F_TX_LOG>(tab, slots, nslots, P.cbits, pend[lane], true, lane);
                   const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
                   __syncwarp();
                   if (32 + lane < npend) pend[lane] = mv;
@@ -734,7 +741,7 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
       }
     }
     if (!ovf && npend > 0) {
-      filt_insert_batch(tab, slots, nslots, P.cbits, lane < npend ? pend[lane] : 0, lane < npend, lane);
+      filt_insert_batch<F_TX_LOG>(tab, slots, nslots, P.cbits, lane < npend ? pend[lane] : 0, lane < npend, lane);
       if (nslots > F_SLOTS) ovf = true;
     }
     __syncwarp();
@@ -891,23 +898,24 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
   typedef typename Cfg::Word Word;
   if (filter_s_min >= 2) {
     // classes 0-2 through the filtered kernel; overflowing rows are re-run below
-    // 8 rows per CTA, 2 CTAs per SM (more, smaller CTAs and 4096 counters for class 1 measured no faster)
-    constexpr int W12 = 8, W13 = 8;
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<12, W12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                filt_bytes(12) * W12));
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<13, W13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                filt_bytes(13) * W13));
+    // class 0 rows (E <= 3.2 k) need only a 512-word exact table: 15 rows per CTA, 30 warps per SM;
+    // classes 1-2: 8 rows per CTA, 16 warps per SM (shared memory bound)
+    constexpr int W12 = 15, T12 = 9, W13 = 8, T13 = 10;
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<12, T12, W12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                filt_bytes(12, T12) * W12));
+    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<13, T13, W13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                filt_bytes(13, T13) * W13));
     for (int c = 0; c < 3; ++c) {
       P.row_list = class_list + c * (int64_t)n_rows;
       P.n_rows_class = class_count[c];
       if (P.n_rows_class <= 0) continue;
       if (c == 0) {
         int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, W12), (int64_t)ctx->sm_count * 2);
-        k_snn_rows_filter<12, W12><<<blocks, W12 * 32, filt_bytes(12) * W12, ctx->stream>>>(
+        k_snn_rows_filter<12, T12, W12><<<blocks, W12 * 32, filt_bytes(12, T12) * W12, ctx->stream>>>(
             P, filter_s_min, ovf_list, d_info);
       } else {
         int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, W13), (int64_t)ctx->sm_count * 2);
-        k_snn_rows_filter<13, W13><<<blocks, W13 * 32, filt_bytes(13) * W13, ctx->stream>>>(
+        k_snn_rows_filter<13, T13, W13><<<blocks, W13 * 32, filt_bytes(13, T13) * W13, ctx->stream>>>(
             P, filter_s_min, ovf_list, d_info);
       }
       KERNEL_CHECK(ctx);
