@@ -564,8 +564,8 @@ int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atom
 // Filtered warp-per-row kernel (prune cut-off needs an overlap of s_min >= 2).
 // Only ~2% of the ~1000 distinct candidates of a row survive the cut-off, so exact
 // hashing of every candidate occurrence is wasted work.  Pass A counts occurrences in
-// a direct-mapped array of byte counters (no keys, no probing; colliding keys only
-// ever over-count).  Pass B walks the lists again and sends to the exact hash table
+// a direct-mapped array of 4-bit counters that stop at s_min (no keys, no probing;
+// colliding keys only ever over-count).  Pass B walks the lists again and sends to the exact hash table
 // only the occurrences whose counter reached s_min -- true survivors plus a few
 // collision victims (~10% of the occurrences), compacted into dense batches first.
 // The exact table is small; a row that would overflow it is handed to the big-table
@@ -574,8 +574,10 @@ int launch_class_warp(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, bool atom
 // exact table of 2^tx_log words; ~78 % of it may fill before the row is handed on
 constexpr int filt_slots(int tx_log) { return (1 << tx_log) * 25 / 32; }      // distinct keys allowed
 constexpr int filt_slot_cap(int tx_log) { return (1 << tx_log) * 26 / 32; }
+// 2^cw_log four-bit counters (the cut-off only asks "count >= s_min", s_min <= F_SMIN_MAX)
+constexpr int F_SMIN_MAX = 12;
 constexpr int filt_bytes(int cw_log, int tx_log) {
-  return (1 << cw_log) + (1 << tx_log) * 4 + filt_slot_cap(tx_log) * 2 + 64 * 4;
+  return (1 << cw_log) / 2 + (1 << tx_log) * 4 + filt_slot_cap(tx_log) * 2 + 64 * 4;
 }
 
 template <int CW_LOG>
@@ -627,12 +629,12 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
   constexpr int F_BYTES = filt_bytes(CW_LOG, F_TX_LOG);
   constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
   constexpr int F_CW_LOG = CW_LOG;
-  static_assert((1 << CW_LOG) >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
+  static_assert((1 << CW_LOG) / 2 >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + (size_t)w * F_BYTES;
-  uint8_t *cnt = base;
-  uint32_t *tab = reinterpret_cast<uint32_t *>(base + (1 << F_CW_LOG));
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(base);  // eight 4-bit counters per word
+  uint32_t *tab = reinterpret_cast<uint32_t *>(base + (1 << F_CW_LOG) / 2);
   uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
   uint32_t *pend = reinterpret_cast<uint32_t *>(slots + F_SLOT_CAP);
   const uint32_t cmask = (1u << P.cbits) - 1;
@@ -644,7 +646,7 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
     {
       uint4 z = make_uint4(0, 0, 0, 0);
       uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
-      for (int s = lane; s < (1 << F_CW_LOG) / 16; s += 32) c4[s] = z;
+      for (int s = lane; s < (1 << F_CW_LOG) / 32; s += 32) c4[s] = z;
     }
     __syncwarp();
     const int32_t *nbr = P.idx0 + row * P.k;
@@ -695,25 +697,28 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
 #pragma unroll
           for (int u = 0; u < 4; ++u) hc[u] = hash_cnt<CW_LOG>((uint32_t)v[u]);
           if (pass == 0) {
-            // four byte counters per 32-bit word, bumped with one shared-memory atomic each
-            // (colliding lanes are serialised by the hardware; no conflict detection, no
-            // warp synchronisation).  A counter about to wrap would under-count, so a row that
-            // ever sees 255 is handed to the big-table kernel instead.
-            uint32_t *cw = reinterpret_cast<uint32_t *>(cnt);
+            // eight 4-bit counters per 32-bit word, bumped with one shared-memory atomic each
+            // (colliding lanes are serialised by the hardware; no conflict detection, no warp
+            // synchronisation).  A counter that already reached s_min is left alone, so only
+            // simultaneous bumps can push one past 15; the lane that wraps a counter sees it in
+            // the returned word and the row is handed to the big-table kernel instead.
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (t0 + 32 * u >= l) break;  // warp-uniform
               if (v[u] >= 0) {
-                const uint32_t sh = (hc[u] & 3u) * 8u;
-                const uint32_t old = atomicAdd(&cw[hc[u] >> 2], 1u << sh);
-                sat |= ((old >> sh) & 0xffu) == 0xffu;
+                const uint32_t sh = (hc[u] & 7u) * 4u;
+                volatile uint32_t *wp = cnt + (hc[u] >> 3);
+                if ((int)((*wp >> sh) & 15u) < s_min) {
+                  const uint32_t old = atomicAdd(cnt + (hc[u] >> 3), 1u << sh);
+                  sat |= ((old >> sh) & 15u) == 15u;
+                }
               }
             }
           } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (t0 + 32 * u >= l) break;  // warp-uniform
-              const bool pass_f = v[u] >= 0 && (int)cnt[hc[u]] >= s_min;
+              const bool pass_f = v[u] >= 0 && (int)((cnt[hc[u] >> 3] >> ((hc[u] & 7u) * 4u)) & 15u) >= s_min;
               const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
               if (bal) {
                 if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
@@ -900,24 +905,30 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     // classes 0-2 through the filtered kernel; overflowing rows are re-run below
     // class 0 rows (E <= 3.2 k) need only a 512-word exact table: 15 rows per CTA, 30 warps per SM;
     // classes 1-2: 8 rows per CTA, 16 warps per SM (shared memory bound)
-    constexpr int W12 = 15, T12 = 9, W13 = 8, T13 = 10;
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<12, T12, W12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                filt_bytes(12, T12) * W12));
-    CU_TRY(cudaFuncSetAttribute(k_snn_rows_filter<13, T13, W13>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                filt_bytes(13, T13) * W13));
+    // (log2 counters, log2 exact-table words, rows per CTA) per class; two CTAs per SM.  These
+    // kernels live on occupancy (dependent shared-memory round trips) and on few false
+    // positives in the counters; measured best: class 0 (E <= 1.6 k) 8 k counters, 30 warps/SM;
+    // class 1 (E <= 3.2 k) 16 k counters, 20 warps/SM; class 2 (E <= 6.5 k) 16 k counters, 16.
+    constexpr int WA = 15, WB = 10, WC = 8;
+    auto kA = k_snn_rows_filter<13, 9, WA>;
+    auto kB = k_snn_rows_filter<14, 9, WB>;
+    auto kC = k_snn_rows_filter<14, 10, WC>;
+    constexpr int bytesA = filt_bytes(13, 9) * WA, bytesB = filt_bytes(14, 9) * WB, bytesC = filt_bytes(14, 10) * WC;
+    CU_TRY(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesA));
+    CU_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesB));
+    CU_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesC));
     for (int c = 0; c < 3; ++c) {
       P.row_list = class_list + c * (int64_t)n_rows;
       P.n_rows_class = class_count[c];
       if (P.n_rows_class <= 0) continue;
-      if (c == 0) {
-        int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, W12), (int64_t)ctx->sm_count * 2);
-        k_snn_rows_filter<12, T12, W12><<<blocks, W12 * 32, filt_bytes(12, T12) * W12, ctx->stream>>>(
-            P, filter_s_min, ovf_list, d_info);
-      } else {
-        int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, W13), (int64_t)ctx->sm_count * 2);
-        k_snn_rows_filter<13, T13, W13><<<blocks, W13 * 32, filt_bytes(13, T13) * W13, ctx->stream>>>(
-            P, filter_s_min, ovf_list, d_info);
-      }
+      const int w = c == 0 ? WA : c == 1 ? WB : WC;
+      const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, w), (int64_t)ctx->sm_count * 2);
+      if (c == 0)
+        kA<<<blocks, WA * 32, bytesA, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
+      else if (c == 1)
+        kB<<<blocks, WB * 32, bytesB, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
+      else
+        kC<<<blocks, WC * 32, bytesC, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
       KERNEL_CHECK(ctx);
     }
   } else {
@@ -1167,7 +1178,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     RC_TRY(ws_get(ctx, WS_OVF_LIST, (size_t)rows + 1, &ovf_list));
     // the filtered kernel needs 32-bit words, no duplicated neighbours, byte-sized counts
     // and a cut-off that actually removes single overlaps
-    const int filter_s_min = (use32 && !has_dups && k <= 255 && s_min >= 2 && s_min <= 255) ? s_min : 0;
+    const int filter_s_min = (use32 && !has_dups && k <= 255 && s_min >= 2 && s_min <= F_SMIN_MAX) ? s_min : 0;
     if (use32)
       RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, hi.class_count,
                                         hi.max_row_e, has_dups, filter_s_min, ovf_list, d_info));
