@@ -367,7 +367,7 @@ def main():
             "candidates_per_s_executed": tv * 256 * 128 / (knn_ms * 1e-3) if knn_ms > 0 else None,
             "note": ("frac uses the algorithmic 2*nq*nr*d FLOPs of SURVEY 8d; the grouped search visits only "
                      "tiles_visited_frac of the key tiles (bound-based skipping, result certified exact). "
-                     "The exhaustive scan (--scan-mode 1) is limited by the epilogue (TMEM reads + selection) at 16-17 keys/clk/SM, "
+                     "The exhaustive scan (--scan-mode 1) is limited by the epilogue (TMEM reads + selection) at 19-20 keys/clk/SM, "
                      "see DESIGN.md section 4")})
     g = last["graphs"]
     rows_local = e - b
