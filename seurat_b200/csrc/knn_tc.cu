@@ -10,30 +10,33 @@
 //               [-2 yh, h1, h2, h3, 0..] of the B operand where h1+h2+h3 is
 //               the FP16 triple split of |yh|^2.  One 64-wide K block.
 //  K1 candidates  persistent warp-specialised kernel.  TMA streams 128-row B
-//               tiles (SWIZZLE_128B) through a 4-stage mbarrier ring;
-//               one thread issues tcgen05.mma (M=128, N=128, K=16 x KSTEPS,
-//               FP16 in, FP32 accumulate in TMEM) for the CTA's two resident
-//               query tiles; the accumulator IS the selection key
+//               tiles (SWIZZLE_128B) through a 5-6-stage mbarrier ring;
+//               one thread per resident query tile issues tcgen05.mma (M=128,
+//               N=128, K=16 x KSTEPS, FP16 in, FP32 accumulate in TMEM) for the
+//               CTA's two resident query tiles; the accumulator IS the selection key
 //               key(q,r) = |yh_r|^2 - 2 yh_q.yh_r  (= |yh_q - yh_r|^2 - |yh_q|^2).
 //               Eight epilogue warps (one thread per query row) read it back
 //               with tcgen05.ld, reject 32-column chunks with a FMNMX3 min
-//               tree against the running k'-th best, and insert the rare
-//               survivors into a per-thread list in shared memory.  The
+//               tree against the running k'-th best, scan the 8-key groups that
+//               hold a hit without inner branches into a pending buffer, and
+//               merge that into a per-thread list in shared memory.  The
 //               nq x nr key matrix never leaves the SM.
 //  G  grouping  (nr >= 32768) coarse k-means partition of the reference set; operands are
 //               stored group by group and each work item scans only the groups whose
 //               ball can hold a key below its threshold bound (see the section above the
 //               grouping kernels).  Results are unchanged; ~3 % of the key tiles are
 //               visited on the 32-cluster benchmark mixture.
-//  K2 re-rank   one warp per query: FP64 distances of the k' candidates in the
-//               reference arithmetic (sequential sum, no FMA), sorted by
-//               (d2, index); then the exactness certificate
+//  K2 re-rank   one warp per query: the k' candidate rows are gathered with
+//               asynchronous copies, FP64 distances in the reference arithmetic
+//               (sequential sum, no FMA), ranked by (d2, index); then the
+//               exactness certificate
 //                   s * d_k  <  sqrt(tau + |yh_q|^2 - eta) - e_q - E_max
 //               (tau: smallest rejected key bound, e: FP16 rounding residual
 //               norms, eta: bound on the FP32 accumulation error).  By the
 //               triangle inequality every non-candidate is then strictly
 //               farther than the k-th candidate, so the result equals the
-//               exhaustive FP64 search.  Rows that fail go to knn_exact.cu.
+//               exhaustive FP64 search.  Rows that fail go to knn_exact.cu (after a
+//               grouped search: to its group-pruned scan, bounded by d_k).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
