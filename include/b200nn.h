@@ -158,6 +158,27 @@ B200NN_API int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, 
 B200NN_API int b200nn_find_neighbors_fill(b200nn_ctx *ctx, int32_t *nn_p, int32_t *nn_i, double *nn_x,
                                int32_t *snn_p, int32_t *snn_i, double *snn_x);
 
+/* ---- resident reference set ("index") ----------------------------------- */
+/*
+ * The reference's other kNN callers (FindNN / FindWeights / MappingScore /
+ * ProjectUMAP, R/integration.R:4411-4531, :2469-2664, R/dimensional_reduction.R:366-377)
+ * query one reference embedding many times through NNHelper(..., cache.index =
+ * TRUE) / FindNeighbors(index = ), R/clustering.R:596-597, :1658-1690.  For the
+ * exact search the "index" is the reference embedding kept on the device: it is
+ * uploaded once and every later query skips that transfer.  The object belongs
+ * to the context it was created on and must be destroyed before it.
+ */
+typedef struct b200nn_index b200nn_index;
+B200NN_API int b200nn_index_create(b200nn_ctx *ctx, const double *ref, int64_t nr, int32_t d,
+                                   const b200nn_opts *opts, b200nn_index **index_out);
+B200NN_API void b200nn_index_destroy(b200nn_ctx *ctx, b200nn_index *index);
+B200NN_API int64_t b200nn_index_rows(const b200nn_index *index);
+B200NN_API int32_t b200nn_index_dims(const b200nn_index *index);
+/* same contract as b200nn_knn with the reference taken from the index; qry == NULL: self */
+B200NN_API int b200nn_index_knn(b200nn_ctx *ctx, const b200nn_index *index, const double *qry, int64_t nq,
+                                int32_t k, int32_t *idx_out, double *dist_out, const b200nn_opts *opts,
+                                b200nn_stats *stats);
+
 /* ---- device-buffer entry points ---------------------------------------- */
 /* All pointers are device pointers on the context's device.  Work is queued
  * on the context's stream; calls that return sizes synchronise internally. */

@@ -6,6 +6,7 @@ B200 is visible, every compute call raises :class:`B200Error`.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import threading
 
@@ -25,6 +26,7 @@ SYMBOLS = [
     "b200nn_knn", "b200nn_snn_count", "b200nn_snn_fill",
     "b200nn_nn_graph_count", "b200nn_nn_graph_fill",
     "b200nn_find_neighbors_count", "b200nn_find_neighbors_fill",
+    "b200nn_index_create", "b200nn_index_destroy", "b200nn_index_rows", "b200nn_index_dims", "b200nn_index_knn",
     "b200nn_dev_knn", "b200nn_dev_knn_candidates", "b200nn_dev_graphs", "b200nn_dev_result", "b200nn_dev_copy_result",
 ]
 
@@ -88,6 +90,14 @@ def load() -> C.CDLL:
         L.b200nn_find_neighbors_count.argtypes = [vp, vp, i64, i32, i32, dbl, i32, vp, vp, C.POINTER(Opts),
                                                   C.POINTER(i64), C.POINTER(i64), C.POINTER(Stats)]
         L.b200nn_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.b200nn_index_create.argtypes = [vp, vp, i64, i32, C.POINTER(Opts), C.POINTER(vp)]
+        L.b200nn_index_destroy.argtypes = [vp, vp]
+        L.b200nn_index_destroy.restype = None
+        L.b200nn_index_rows.argtypes = [vp]
+        L.b200nn_index_rows.restype = i64
+        L.b200nn_index_dims.argtypes = [vp]
+        L.b200nn_index_dims.restype = i32
+        L.b200nn_index_knn.argtypes = [vp, vp, vp, i64, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
         L.b200nn_dev_knn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
         L.b200nn_dev_knn_candidates.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp]
         L.b200nn_dev_graphs.argtypes = [vp, vp, i64, i32, dbl, i32, i64, i64, C.POINTER(i64), C.POINTER(i64),
@@ -126,9 +136,12 @@ class Context:
         L = load()
         check(L.b200nn_ctx_create(int(device), C.byref(self._h)))
         self._L = L
+        self._indexes = weakref.WeakSet()   # resident reference sets; they must go before the context
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
+            for ix in list(getattr(self, "_indexes", ())):
+                ix.close()
             self._L.b200nn_ctx_destroy(self._h)
             self._h = C.c_void_p(None)
 
@@ -144,6 +157,10 @@ class Context:
     @property
     def stream_ptr(self) -> int:
         return int(self._L.b200nn_ctx_stream(self._h) or 0)
+
+    def index(self, ref, layout: int) -> "Index":
+        """Keep the reference embedding `ref` [nr, d] on the device for repeated queries."""
+        return Index(self, ref, layout)
 
     # ---- host-buffer calls ------------------------------------------------
     def knn(self, ref, qry, k: int, layout: int, algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0):
@@ -263,6 +280,56 @@ class Context:
 
 
 _default_ctx: dict[int, Context] = {}
+
+
+class Index:
+    """Device-resident reference set (b200nn_index): what NNHelper(cache.index = TRUE) returns as
+    `alg.idx` and FindNeighbors(index = ) accepts -- R/clustering.R:596-597, :1686-1688."""
+
+    def __init__(self, ctx: Context, ref, layout: int):
+        ref = np.asarray(ref)
+        if ref.dtype != np.float64 or ref.ndim != 2:
+            raise TypeError("the reference embedding must be a float64 matrix")
+        self._ctx = ctx
+        self._h = C.c_void_p(None)
+        o = Opts(layout, KNN_AUTO, 0, 0)
+        check(ctx._L.b200nn_index_create(ctx._h, _ptr(ref), ref.shape[0], ref.shape[1], C.byref(o),
+                                         C.byref(self._h)))
+        self.layout = layout
+        ctx._indexes.add(self)
+
+    @property
+    def rows(self) -> int:
+        return int(self._ctx._L.b200nn_index_rows(self._h))
+
+    @property
+    def dims(self) -> int:
+        return int(self._ctx._L.b200nn_index_dims(self._h))
+
+    def knn(self, qry, k: int, algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0):
+        """qry: float64 [nq, d] in the index's layout, or None for the self query."""
+        if not self._h.value:
+            raise B200Error(7, "the index was destroyed")
+        nq = self.rows if qry is None else qry.shape[0]
+        order = "C" if self.layout == ROW_MAJOR else "F"
+        idx = np.empty((nq, k), dtype=np.int32, order=order)
+        dist = np.empty((nq, k), dtype=np.float64, order=order)
+        o = Opts(self.layout, algo, n_cand, scan_mode)
+        st = Stats()
+        check(self._ctx._L.b200nn_index_knn(self._ctx._h, self._h, _ptr(qry), nq, k, _ptr(idx), _ptr(dist),
+                                            C.byref(o), C.byref(st)))
+        return idx, dist, st.as_dict()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value and self._ctx._h.value:
+            self._ctx._L.b200nn_index_destroy(self._ctx._h, self._h)
+        self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def default_context(device: int = 0) -> Context:

@@ -376,6 +376,109 @@ int b200nn_knn(b200nn_ctx *ctx, const double *ref, int64_t nr, const double *qry
   return B200NN_OK;
 }
 
+// ---------------------------------------------------------------------------
+// resident reference set
+// ---------------------------------------------------------------------------
+struct b200nn_index {
+  b200nn_ctx *owner = nullptr;
+  double *d_ref = nullptr;  // [nr x d] row-major, own allocation (not a workspace slot)
+  int64_t nr = 0;
+  int32_t d = 0;
+};
+
+int b200nn_index_create(b200nn_ctx *ctx, const double *ref, int64_t nr, int32_t d, const b200nn_opts *opts,
+                        b200nn_index **index_out) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (!ref || nr <= 0 || d <= 0 || !index_out) {
+    b200nn_set_error("index_create: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  *index_out = nullptr;
+  b200nn_index *ix = new (std::nothrow) b200nn_index;
+  if (!ix) return B200NN_ERR_NOMEM;
+  const size_t bytes = (size_t)nr * (size_t)d * sizeof(double);
+  if (cudaMalloc(&ix->d_ref, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    delete ix;
+    b200nn_set_error("index_create: cannot allocate %zu bytes of device memory", bytes);
+    return B200NN_ERR_NOMEM;
+  }
+  int rc = B200NN_OK;
+  if (o.layout == B200NN_ROW_MAJOR) {
+    if (cudaMemcpyAsync(ix->d_ref, ref, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = B200NN_ERR_CUDA;
+  } else {
+    double *raw = nullptr;
+    rc = ws_get(ctx, WS_STAGE_A, (size_t)nr * d, &raw);
+    if (rc == B200NN_OK && cudaMemcpyAsync(raw, ref, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+      rc = B200NN_ERR_CUDA;
+    if (rc == B200NN_OK) rc = transpose_f64(ctx, raw, ix->d_ref, nr, d);
+  }
+  if (rc == B200NN_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = B200NN_ERR_CUDA;
+  if (rc != B200NN_OK) {
+    if (rc == B200NN_ERR_CUDA) b200nn_set_error("index_create: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(ix->d_ref);
+    delete ix;
+    return rc;
+  }
+  ix->owner = ctx;
+  ix->nr = nr;
+  ix->d = d;
+  *index_out = ix;
+  return B200NN_OK;
+}
+
+void b200nn_index_destroy(b200nn_ctx *ctx, b200nn_index *index) {
+  if (!index) return;
+  if (ctx && ctx == index->owner) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (index->d_ref) cudaFree(index->d_ref);
+  delete index;
+}
+
+int64_t b200nn_index_rows(const b200nn_index *index) { return index ? index->nr : 0; }
+int32_t b200nn_index_dims(const b200nn_index *index) { return index ? index->d : 0; }
+
+int b200nn_index_knn(b200nn_ctx *ctx, const b200nn_index *index, const double *qry, int64_t nq, int32_t k,
+                     int32_t *idx_out, double *dist_out, const b200nn_opts *opts, b200nn_stats *stats) {
+  RC_TRY(check_ctx(ctx));
+  b200nn_opts o = opts ? *opts : default_opts();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (!index || index->owner != ctx) {
+    b200nn_set_error("index_knn: the index does not belong to this context");
+    return B200NN_ERR_STATE;
+  }
+  if (k <= 0 || (!idx_out && !dist_out) || (qry && nq <= 0)) {
+    b200nn_set_error("index_knn: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  const int64_t nr = index->nr;
+  const int32_t d = index->d;
+  if ((int64_t)k > nr) {
+    b200nn_set_error("Cannot find more nearest neighbours than there are points");
+    return B200NN_ERR_K_TOO_LARGE;
+  }
+  if (!qry) nq = nr;
+  int64_t l0 = ctx->launches;
+  Timer th(ctx, 6);
+  RC_TRY(th.start());
+  double *d_qry = nullptr;
+  if (qry) RC_TRY(upload_matrix_f64(ctx, qry, nq, d, o.layout, WS_STAGE_B, WS_QRY64, &d_qry));
+  RC_TRY(th.stop(stats ? &stats->ms_h2d : nullptr));
+  int32_t *d_idx0;
+  double *d_dist;
+  RC_TRY(ws_get(ctx, WS_IDX0, (size_t)nq * k, &d_idx0));
+  RC_TRY(ws_get(ctx, WS_DIST, (size_t)nq * k, &d_dist));
+  RC_TRY(knn_dispatch(ctx, index->d_ref, nr, d_qry, nq, d, k, o, d_idx0, d_dist, stats));
+  RC_TRY(th.start());
+  RC_TRY(download_knn(ctx, d_idx0, d_dist, nq, k, o.layout, idx_out, dist_out));
+  RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));
+  if (stats) stats->gpu_launches = ctx->launches - l0;
+  return B200NN_OK;
+}
+
 int b200nn_snn_count(b200nn_ctx *ctx, const int32_t *nn_ranked, int64_t n, int32_t k, double prune,
                      const b200nn_opts *opts, int64_t *nnz_out, b200nn_stats *stats) {
   RC_TRY(check_ctx(ctx));

@@ -173,37 +173,59 @@ def _check_finite(a: np.ndarray, what: str) -> None:
 
 
 def _nn2(data: np.ndarray, query: np.ndarray | None, k: int, ctx: _lib.Context, algo: int,
-         n_cand: int, stats_out: dict | None):
-    """Drop-in for ``RANN::nn2(data, query, k, searchtype="standard", eps=0)``."""
-    if k > data.shape[0]:
+         n_cand: int, stats_out: dict | None, cache_index: bool = False, index: "_lib.Index | None" = None):
+    """Drop-in for ``RANN::nn2(data, query, k, searchtype="standard", eps=0)``.
+
+    ``index`` (a resident reference set from an earlier ``cache_index=True`` call) replaces
+    ``data``; with ``cache_index`` the reference set is uploaded once, kept on the device and
+    returned under ``"idx"`` -- the exact-search counterpart of the annoy index the reference
+    caches (R/clustering.R:1686-1688)."""
+    nr = index.rows if index is not None else data.shape[0]
+    nd = index.dims if index is not None else data.shape[1]
+    if k > nr:
         raise ValueError("Cannot find more nearest neighbours than there are points")
-    _check_finite(data, "data")
+    if index is None:
+        _check_finite(data, "data")
     if query is not None:
         _check_finite(query, "query")
-        if query.shape[1] != data.shape[1]:
+        if query.shape[1] != nd:
             raise ValueError("Query and data tables must have same dimensions")
-        if _layout_of(query) != _layout_of(data):
-            query = np.asarray(query, order="C" if data.flags.c_contiguous else "F")
-    idx, dist, st = ctx.knn(data, query, int(k), _layout_of(data), algo, n_cand)
+        want_c = (index.layout == _lib.ROW_MAJOR) if index is not None else data.flags.c_contiguous
+        if query.flags.c_contiguous != want_c or not (query.flags.c_contiguous or query.flags.f_contiguous):
+            query = np.asarray(query, order="C" if want_c else "F")
+    if index is None and cache_index:
+        index = ctx.index(data, _layout_of(data))
+    if index is not None:
+        idx, dist, st = index.knn(query, int(k), algo, n_cand)
+    else:
+        idx, dist, st = ctx.knn(data, query, int(k), _layout_of(data), algo, n_cand)
     if stats_out is not None:
         stats_out.update(st)
-    return {"nn.idx": idx, "nn.dists": dist}
+    out = {"nn.idx": idx, "nn.dists": dist}
+    if cache_index:
+        out["idx"] = index
+    return out
 
 
 def NNHelper(data, query=None, k: int = 20, method: str = "rann", cache_index: bool = False,
              ctx: _lib.Context | None = None, knn_algo: int = _lib.KNN_AUTO, n_cand: int = 0,
-             stats_out: dict | None = None, **kwargs) -> Neighbor:
+             stats_out: dict | None = None, index=None, **kwargs) -> Neighbor:
     """R/clustering.R:1658-1690.  Only the exact ``"rann"`` arm is accelerated;
-    ``searchtype``/``eps`` other than the exact defaults are refused."""
+    ``searchtype``/``eps`` other than the exact defaults are refused.  ``cache_index`` /
+    ``index`` keep / reuse the reference embedding on the device (``Neighbor.alg_idx``)."""
     data = _as_embedding(data, "data")
     query_e = data if query is None else _as_embedding(query, "query")
     if method == "rann":
         if kwargs.get("eps", 0) not in (0, 0.0) or kwargs.get("searchtype", "standard") != "standard":
             raise NotImplementedError("the B200 path implements exact search only (eps = 0, "
                                       "searchtype = 'standard')")
-        ctx = ctx or _lib.default_context()
+        if index is not None and not isinstance(index, _lib.Index):
+            raise TypeError("index must be the alg_idx of a Neighbor computed with cache_index=True")
+        if index is not None and (index.rows != data.values.shape[0] or index.dims != data.values.shape[1]):
+            raise ValueError("the cached index does not match the dimensions of data")
+        ctx = ctx or (index._ctx if index is not None else _lib.default_context())
         results = _nn2(data.values, None if query is None or query_e is data else query_e.values, k,
-                       ctx, knn_algo, n_cand, stats_out)
+                       ctx, knn_algo, n_cand, stats_out, cache_index=cache_index is True, index=index)
     elif method in ("annoy", "hnsw"):
         raise NotImplementedError(f"nn.method = '{method}' is an approximate back end of the "
                                   "reference and outside the B200 path; use 'rann'")
@@ -285,7 +307,7 @@ def FindNeighbors(object, query=None, distance_matrix: bool = False, k_param: in
     if not distance_matrix:
         _message("Computing nearest neighbors" if return_neighbor
                  else "Computing nearest neighbor graph", verbose)
-        fused = (query is None and not return_neighbor and nn_method == "rann" and nn_eps == 0)
+        fused = (query is None and not return_neighbor and nn_method == "rann" and nn_eps == 0 and index is None)
         if fused:
             # kNN -> nn Graph -> SNN with the index resident on the device
             _check_finite(object.values, "data")

@@ -5,10 +5,22 @@
 # FindNeighbors.default / .Seurat keep their signatures and return values
 # (list(nn = Graph, snn = Graph) or a Neighbor), see R/clustering.R:582-685, 790-898.
 
-b200_nn2 <- function(data, query = data, k, ...) {
+# cache.index / index (R/clustering.R:596-597, 1686-1688): the "index" of the exact search is
+# the reference embedding kept on the GPU (an external pointer with a finaliser); NNHelper's
+# unchanged tail stores results$idx in the Neighbor's alg.idx slot.
+b200_nn2 <- function(data, query = data, k, cache.index = FALSE, index = NULL, ...) {
   self <- identical(query, data)
-  storage.mode(data) <- "double"
   if (!self) storage.mode(query) <- "double"
+  if (is.null(index) && isTRUE(cache.index)) {
+    storage.mode(data) <- "double"
+    index <- .Call("b200_index", data, PACKAGE = "b200nn")
+  }
+  if (!is.null(index)) {
+    res <- .Call("b200_index_nn2", index, if (self) NULL else query, as.integer(k), PACKAGE = "b200nn")
+    if (isTRUE(cache.index)) res$idx <- index
+    return(res)
+  }
+  storage.mode(data) <- "double"
   .Call("b200_nn2", data, if (self) NULL else query, as.integer(k), PACKAGE = "b200nn")
 }
 

@@ -16,6 +16,10 @@
  *   b200_FindNeighbors(data, k, prune, compute_snn)  the body of FindNeighbors.default,
  *                                   R/clustering.R:633-682, with the index kept on the GPU
  *                                   -> list(nn = dgCMatrix, snn = dgCMatrix)
+ *   b200_index(data) / b200_index_nn2(index, query, k)  the cache.index = TRUE / index =
+ *                                   arguments of NNHelper / FindNeighbors, R/clustering.R:596-597,
+ *                                   :1686-1688: the reference embedding stays on the GPU behind an
+ *                                   external pointer (finaliser pattern of src/valid_pointer.c:4-6)
  * Registration follows src/RcppExports.cpp:407-445 (R_CallMethodDef table,
  * R_registerRoutines, R_useDynamicSymbols(dll, FALSE)).
  *
@@ -149,6 +153,54 @@ SEXP b200_FindNeighbors(SEXP data, SEXP k_, SEXP prune_, SEXP compute_snn_) {
   return res;
 }
 
+/* resident reference set: external pointer with a finaliser */
+static void index_finalizer(SEXP ptr) {
+  b200nn_index *ix = (b200nn_index *)R_ExternalPtrAddr(ptr);
+  if (ix != NULL) {
+    b200nn_index_destroy(g_ctx, ix);
+    R_ClearExternalPtr(ptr);
+  }
+}
+
+SEXP b200_index(SEXP data) {
+  if (!Rf_isReal(data) || !Rf_isMatrix(data)) Rf_error("data must be a numeric matrix");
+  b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
+  b200nn_index *ix = NULL;
+  if (b200nn_index_create(get_ctx(), REAL(data), Rf_nrows(data), Rf_ncols(data), &o, &ix) != B200NN_OK)
+    Rf_error("%s", b200nn_last_error());
+  SEXP ptr = PROTECT(R_MakeExternalPtr(ix, Rf_install("b200nn_index"), R_NilValue));
+  R_RegisterCFinalizerEx(ptr, index_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* nn2 against a resident reference set; query may be R_NilValue (self) */
+SEXP b200_index_nn2(SEXP index, SEXP query, SEXP k_) {
+  b200nn_index *ix = (b200nn_index *)R_ExternalPtrAddr(index);
+  if (ix == NULL) Rf_error("the cached index is no longer valid");
+  const int nr = (int)b200nn_index_rows(ix), d = b200nn_index_dims(ix), k = Rf_asInteger(k_);
+  const int self = Rf_isNull(query);
+  const int nq = self ? nr : Rf_nrows(query);
+  if (!self && Rf_ncols(query) != d) Rf_error("Query and data tables must have same dimensions");
+  SEXP idx = PROTECT(Rf_allocMatrix(INTSXP, nq, k));
+  SEXP dist = PROTECT(Rf_allocMatrix(REALSXP, nq, k));
+  b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
+  int rc = b200nn_index_knn(get_ctx(), ix, self ? NULL : REAL(query), nq, k, INTEGER(idx), REAL(dist), &o, NULL);
+  if (rc != B200NN_OK) {
+    UNPROTECT(2);
+    Rf_error("%s", b200nn_last_error());
+  }
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP nms = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_VECTOR_ELT(res, 0, idx);
+  SET_VECTOR_ELT(res, 1, dist);
+  SET_STRING_ELT(nms, 0, Rf_mkChar("nn.idx"));
+  SET_STRING_ELT(nms, 1, Rf_mkChar("nn.dists"));
+  Rf_setAttrib(res, R_NamesSymbol, nms);
+  UNPROTECT(4);
+  return res;
+}
+
 SEXP b200_release(void) {
   if (g_ctx) {
     b200nn_ctx_destroy(g_ctx);
@@ -161,6 +213,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"b200_nn2", (DL_FUNC)&b200_nn2, 3},
     {"b200_ComputeSNN", (DL_FUNC)&b200_ComputeSNN, 2},
     {"b200_FindNeighbors", (DL_FUNC)&b200_FindNeighbors, 4},
+    {"b200_index", (DL_FUNC)&b200_index, 1},
+    {"b200_index_nn2", (DL_FUNC)&b200_index_nn2, 3},
     {"b200_release", (DL_FUNC)&b200_release, 0},
     {NULL, NULL, 0}};
 

@@ -329,3 +329,34 @@ def test_dev_entry_points_and_row_sharding(ctx):
         assert (p == P[b:e + 1] - P[b]).all()
         assert (i == I[P[b]:P[e]]).all() and (x == Xv[P[b]:P[e]]).all()
         assert_csr_equal(tuple(t.cpu().numpy() for t in g["nn"]), want["nn"], "nn graph (every rank holds it all)")
+
+
+@pytest.mark.parametrize("layout", ["C", "F"])
+def test_resident_index_repeated_queries(ctx, layout):
+    """NNHelper(cache_index=True) keeps the reference on the device; FindNeighbors(index=) / repeated
+    queries against it give exactly what a fresh call gives (R/clustering.R:596-597, :1686-1688)."""
+    ref, c = gaussian_mixture(6000, 20, seed=31, n_centres=5)
+    q1, _ = gaussian_mixture(700, 20, seed=32, centres=c)
+    q2, _ = gaussian_mixture(33, 20, seed=33, centres=c)
+    R = sb.Embedding(np.asarray(ref, order=layout), cell_names(6000))
+    first = sb.NNHelper(R, k=15, method="rann", cache_index=True, ctx=ctx)
+    assert isinstance(first.alg_idx, _lib.Index) and first.alg_idx.rows == 6000 and first.alg_idx.dims == 20
+    wi, wd = oracle.knn(ref, k=15, method="kdtree")
+    assert (first.nn_idx == wi).all() and (first.nn_dist == wd).all()
+    for q in (q1, q2):
+        Q = sb.Embedding(np.asarray(q, order=layout), cell_names(q.shape[0]))
+        nb = sb.FindNeighbors(R, query=Q, k_param=15, return_neighbor=True, index=first.alg_idx, verbose=False,
+                              ctx=ctx)
+        wi, wd = oracle.knn(ref, q, 15, method="kdtree")
+        assert (nb.nn_idx == wi).all() and (nb.nn_dist == wd).all()
+        assert nb.alg_idx is None and nb.cell_names == Q.rownames
+    # raw ABI: self query through the index, k too large, foreign context
+    idx, dist, st = first.alg_idx.knn(None, 15)
+    assert (idx == first.nn_idx).all() and st["ms_h2d"] < 1.0
+    with pytest.raises(sb.B200Error, match="Cannot find more nearest neighbours"):
+        first.alg_idx.knn(None, 6001)
+    with pytest.raises(ValueError, match="does not match"):
+        sb.NNHelper(sb.Embedding(ref[:100], cell_names(100)), k=5, index=first.alg_idx, ctx=ctx)
+    first.alg_idx.close()
+    with pytest.raises(sb.B200Error):
+        first.alg_idx.knn(None, 5)

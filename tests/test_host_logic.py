@@ -67,3 +67,9 @@ def test_shard_bounds():
             # every shard except the tail has the common (padded) length
             per = b[0][1] - b[0][0]
             assert all(e - s <= per for s, e in b)
+
+
+def test_index_argument_is_type_checked():
+    X = sb.Embedding(np.random.default_rng(0).normal(size=(30, 4)), [str(i) for i in range(30)])
+    with pytest.raises(TypeError, match="cache_index=True"):
+        sb.NNHelper(X, k=3, method="rann", index=object())
