@@ -71,8 +71,8 @@ typedef struct b200nn_opts {
   int32_t layout;      /* B200NN_COL_MAJOR (default, R) or B200NN_ROW_MAJOR          */
   int32_t knn_algo;    /* B200NN_KNN_*                                               */
   int32_t n_cand;      /* widened candidate count k' of the tensor path, 0 = auto    */
-  int32_t reserved;    /* bits 0-1: tensor-path scan mode, 0 = auto, 1 = exhaustive
-                          (every reference tile), 2 = grouped (tile-pruned)           */
+  int32_t scan_mode;   /* tensor path: 0 = auto, 1 = exhaustive (every reference tile),
+                          2 = grouped (tile-pruned); same result, for benchmarking   */
 } b200nn_opts;
 
 typedef struct b200nn_stats {

@@ -40,7 +40,7 @@ class B200Error(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("layout", C.c_int32), ("knn_algo", C.c_int32), ("n_cand", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("scan_mode", C.c_int32)]
 
 
 class Stats(C.Structure):

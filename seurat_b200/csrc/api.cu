@@ -162,13 +162,12 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
   int algo = o.knn_algo;
   if (algo == B200NN_KNN_AUTO)
     algo = knn_tc_applicable(nr, nq, d, k) ? B200NN_KNN_TENSOR : B200NN_KNN_EXACT;
-  knn_tc_set_mode(o.reserved & 3);
   if (algo == B200NN_KNN_TENSOR) {
     if (!knn_tc_applicable(nr, nq, d, k)) {
       b200nn_set_error("tensor-core kNN path does not cover nr=%lld d=%d k=%d", (long long)nr, d, k);
       return B200NN_ERR_INVALID;
     }
-    return knn_tc_launch(ctx, d_ref, nr, q, nq, d, k, o.n_cand, d_idx0, d_dist, stats);
+    return knn_tc_launch(ctx, d_ref, nr, q, nq, d, k, o.n_cand, o.scan_mode & 3, d_idx0, d_dist, stats);
   }
   Timer t(ctx, 4);
   RC_TRY(t.start());
@@ -278,8 +277,7 @@ int b200nn_dev_knn_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, 
     b200nn_set_error("knn_candidates: invalid argument (d <= 61, n_cand a multiple of 8 in [8, 48])");
     return B200NN_ERR_INVALID;
   }
-  knn_tc_set_mode(scan_mode & 3);
-  return knn_tc_debug(ctx, d_ref, nr, d_qry, nq, d, n_cand, d_keys, d_cand, d_tau, h_scale_mu);
+  return knn_tc_debug(ctx, d_ref, nr, d_qry, nq, d, n_cand, scan_mode & 3, d_keys, d_cand, d_tau, h_scale_mu);
 }
 
 int b200nn_dev_graphs(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n, int32_t k, double prune,

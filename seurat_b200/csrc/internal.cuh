@@ -193,14 +193,14 @@ int knn_exact_grouped_launch(b200nn_ctx *ctx, const double *d_ref, const double 
                              const GroupedRefs &R, int32_t *d_idx0, double *d_dist);
 
 // knn_tc.cu : tcgen05 candidate generation + FP64 re-rank + certificate
-void knn_tc_set_mode(int mode);
+// scan_mode: 0 = auto, 1 = exhaustive scan of every key tile, 2 = grouped (tile-pruned) search
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k);
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
-                  int64_t nq, int d, int k, int n_cand, int32_t *d_idx0, double *d_dist,
+                  int64_t nq, int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
                   b200nn_stats *stats);
 
 int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
-                 int d, int kp, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
+                 int d, int kp, int scan_mode, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
                  double *h_scale_mu);
 
 // snn.cu

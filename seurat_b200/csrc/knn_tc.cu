@@ -55,12 +55,8 @@ constexpr int QT = 2;               // query tiles resident per CTA
 constexpr int BN = 128;             // reference rows per B tile
 constexpr int BK = 64;              // K: one 128-byte swizzle row of FP16
 constexpr int CTRL_WARPS = 4;       // TMA, MMA, TMEM alloc, second MMA issuer
-// The epilogue runs 8 * SPLIT warps: SPLIT warps share a (query tile, TMEM lane quarter) and
-// each scans BN / SPLIT columns of every tile into its own candidate list.  SPLIT = 2 doubles
-// the warps per scheduler (the selection code is latency-bound, not issue-bound) at the price
-// of two k'-lists per query row, which fits shared memory for k <= 20.
-constexpr int epi_warps(int split) { return 8 * split; }
-constexpr int num_threads(int split) { return (CTRL_WARPS + epi_warps(split)) * 32; }
+constexpr int EPI_WARPS = 8;        // one thread per row of the two resident query tiles
+constexpr int NUM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;  // 16 KB (A tile == B tile)
 constexpr int MAX_D = BK - 3;       // 61
 constexpr int MAX_KP = 48;          // shared-memory budget of the candidate lists
@@ -203,7 +199,7 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)
 //   pend : `pend` pairs appended by the filter, merged warp-synchronously
 // slot e of thread t lives at word e * ls + t, ls = number of epilogue threads (conflict-free)
 // ---------------------------------------------------------------------------
-constexpr int pend_size(int split) { return split == 1 ? 16 : 8; }   // pending-hit buffer per thread
+constexpr int PEND = 16;        // pending-hit buffer per thread
 constexpr int GROUP_KEYS = 8;  // keys scanned between two capacity checks of the pending buffer
 
 struct Sel {          // register-resident selection state of one query row
@@ -288,7 +284,6 @@ struct TcParams {
   int32_t pass1;         // 1: only item_T is produced
   const int32_t *order;  // items by decreasing list length (null: identity)
   const float *tau_init; // pass 2: per-row threshold found by pass 1 (null: start from +inf)
-  int32_t split;         // epilogue warps per (query tile, lane quarter): 1 or 2
 };
 
 // Item visited by CTA `b` in its round `i`: positions are dealt out in a snake so that the
@@ -360,13 +355,11 @@ constexpr int RING = 16;            // tile-id ring (power of two > stages + acc
 // ---------------------------------------------------------------------------
 // K1: candidate generation
 // ---------------------------------------------------------------------------
-template <bool DBG, int SPLIT, bool P1>
-__global__ void __launch_bounds__(num_threads(SPLIT), 1)
+template <bool DBG, bool P1>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
          TcParams P) {
-  constexpr int EPI_WARPS = epi_warps(SPLIT);
   constexpr int LSTRIDE = EPI_WARPS * 32;
-  constexpr int PEND = pend_size(SPLIT);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -485,14 +478,12 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
     }
   } else if (warp >= CTRL_WARPS) {
-    // ===================== epilogue: running top-k' per (query row, column share) =========
-    const int ew = warp - CTRL_WARPS;        // 0 .. 8 * SPLIT - 1
-    const int t = ew / (4 * SPLIT);          // query tile of this warp
-    const int hh = (ew / 4) % SPLIT;         // column share of this warp
+    // ===================== epilogue: running top-k' per query row =========================
+    const int ew = warp - CTRL_WARPS;        // 0 .. 7
+    const int t = ew / 4;                    // query tile of this warp
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access (== ew & 3)
     const int row = quarter * 32 + lane;     // row inside the query tile
     const int et = ew * 32 + lane;           // list column of this thread
-    constexpr int COLS = BN / SPLIT;         // columns of a tile scanned by this thread
     float *lk = s_lk + et;
     int *li = s_li + et;
     float *pk = s_pk + et;
@@ -512,78 +503,56 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       if (P.tau_init && oq >= 0) {
         // pass 2 starts from pass 1's threshold: the pass-1 tiles are visited again, so at least
         // k' keys lie strictly below the next float above it and the list still fills
-        const float t1 = P.tau_init[oq * SPLIT + hh];
+        const float t1 = P.tau_init[oq];
         if (t1 < CUDART_INF_F) S.tau = nextafterf(t1, CUDART_INF_F);
       }
       const int nt = P.list_cnt ? P.list_cnt[item] : P.n_btiles;
       // >= 4 tiles of one group hold >= 3 tiles without padding = 48 >= MAX_KP eight-key buckets
       const bool bucket = P1 && nt >= 4;
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(hh * COLS);
-      if constexpr (SPLIT == 1) {
-        uint32_t va[32], vb[32];
-        if (nt > 0) {  // prologue: first chunk of the first tile
-          const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
-          mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
-          tc_fence_after();
-          tc_ld32(lane_addr + (uint32_t)((acc * QT + t) * BN), va);
-        }
-        for (int j = 0; j < nt; ++j, ++bi) {
-          const uint32_t acc = bi & 1;
-          const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
-          const int colbase = s_ring[bi & (RING - 1)] * BN;
-          float *dk = nullptr;
-          if (DBG) dk = (item == 0 && j == 0) ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      uint32_t va[32], vb[32];
+      if (nt > 0) {  // prologue: first chunk of the first tile
+        const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
+        mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
+        tc_fence_after();
+        tc_ld32(lane_addr + (uint32_t)((acc * QT + t) * BN), va);
+      }
+      for (int j = 0; j < nt; ++j, ++bi) {
+        const uint32_t acc = bi & 1;
+        const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
+        const int colbase = s_ring[bi & (RING - 1)] * BN;
+        float *dk = nullptr;
+        if (DBG) dk = (item == 0 && j == 0) ? P.dbg_keys + (size_t)(t * BM + row) * BN : nullptr;
 #pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            tc_wait_ld(va);
-            tc_ld32(taddr + 64 * h + 32, vb);
-            if (DBG && dk) {
+        for (int h = 0; h < 2; ++h) {
+          tc_wait_ld(va);
+          tc_ld32(taddr + 64 * h + 32, vb);
+          if (DBG && dk) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
-            }
-            process_chunk<LSTRIDE, PEND, P1>(va, S, lk, li, pk, pi, kp, colbase + 64 * h, bucket);
-            tc_wait_ld(vb);
-            if (h == 0) {
-              tc_ld32(taddr + 64, va);
-            } else {
-              // all four loads of this tile have landed: hand the accumulator back, and start
-              // on the next tile (normally already computed) before scanning the last chunk
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-              if (j + 1 < nt) {
-                const uint32_t nb = bi + 1, nacc = nb & 1, naph = (nb >> 1) & 1;
-                mbar_wait(bar_t_full + 8 * (nacc * QT + t), naph, P.misc);
-                tc_fence_after();
-                tc_ld32(lane_addr + (uint32_t)((nacc * QT + t) * BN), va);
-              }
-            }
-            if (DBG && dk) {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
-            }
-            process_chunk<LSTRIDE, PEND, P1>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, bucket);
+            for (int c = 0; c < 32; ++c) dk[64 * h + c] = __uint_as_float(va[c]);
           }
-        }
-      } else {
-        // two chunks per tile and thread, single register buffer: with four epilogue warps per
-        // scheduler the TMEM load latency is covered by the other warps
-        uint32_t v[32];
-        for (int j = 0; j < nt; ++j, ++bi) {
-          const uint32_t acc = bi & 1, aph = (bi >> 1) & 1;
-          const uint32_t taddr = lane_addr + (uint32_t)((acc * QT + t) * BN);
-          mbar_wait(bar_t_full + 8 * (acc * QT + t), aph, P.misc);
-          tc_fence_after();
-          const int colbase = s_ring[bi & (RING - 1)] * BN + hh * COLS;
-          tc_ld32(taddr, v);
-          tc_wait_ld(v);
-          process_chunk<LSTRIDE, PEND, P1>(v, S, lk, li, pk, pi, kp, colbase, bucket);
-          tc_ld32(taddr + 32, v);
-          tc_wait_ld(v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
-          process_chunk<LSTRIDE, PEND, P1>(v, S, lk, li, pk, pi, kp, colbase + 32, bucket);
+          process_chunk<LSTRIDE, PEND, P1>(va, S, lk, li, pk, pi, kp, colbase + 64 * h, bucket);
+          tc_wait_ld(vb);
+          if (h == 0) {
+            tc_ld32(taddr + 64, va);
+          } else {
+            // all four loads of this tile have landed: hand the accumulator back, and start
+            // on the next tile (normally already computed) before scanning the last chunk
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_t_empty + 8 * (acc * QT + t));
+            if (j + 1 < nt) {
+              const uint32_t nb = bi + 1, nacc = nb & 1, naph = (nb >> 1) & 1;
+              mbar_wait(bar_t_full + 8 * (nacc * QT + t), naph, P.misc);
+              tc_fence_after();
+              tc_ld32(lane_addr + (uint32_t)((nacc * QT + t) * BN), va);
+            }
+          }
+          if (DBG && dk) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) dk[64 * h + 32 + c] = __uint_as_float(vb[c]);
+          }
+          process_chunk<LSTRIDE, PEND, P1>(vb, S, lk, li, pk, pi, kp, colbase + 64 * h + 32, bucket);
         }
       }
       // flush this thread's candidates
@@ -591,20 +560,20 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       if (oq >= 0) {
         const float tq = S.cnt_list == kp ? S.tau : CUDART_INF_F;
         if (P.pass1) {
-          P.tau[oq * SPLIT + hh] = tq;
+          P.tau[oq] = tq;
           // upper bound of tau + |yh_q|^2 (an approximate squared distance, >= 0 up to rounding);
           // the maximum over the column shares bounds the row's final threshold as well
           float T = tq + (float)P.q_n2[oq];
           T = T > 0.f ? T * 1.0001f + 1e-3f : 1e-3f;
           atomicMax(reinterpret_cast<int *>(P.item_T + item), __float_as_int(T));
         } else {
-          int32_t *dst = P.cand + (oq * SPLIT + hh) * kp;
+          int32_t *dst = P.cand + oq * kp;
           for (int e = 0; e < kp; ++e) {
             int id = e < S.cnt_list ? li[e * LSTRIDE] : -1;
             if (id >= 0 && P.rperm) id = P.rperm[id];
             dst[e] = id;
           }
-          P.tau[oq * SPLIT + hh] = tq;
+          P.tau[oq] = tq;
         }
       }
       __syncwarp();
@@ -1306,7 +1275,7 @@ __device__ __forceinline__ void cp_async16(void *s, const void *g) {
 template <bool VEC>  // VEC: d even and both matrices 16-byte aligned
 __global__ void __launch_bounds__(RR_WARPS * 32)
 k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t nq, int d, int k,
-         int kp, int split, const int32_t *__restrict__ cand, const float *__restrict__ tau,
+         int kp, const int32_t *__restrict__ cand, const float *__restrict__ tau,
          const double *__restrict__ q_n2, const double *__restrict__ q_err,
          TcMisc *__restrict__ misc, int32_t *__restrict__ idx0, double *__restrict__ dist,
          int32_t *__restrict__ fail_list, double *__restrict__ fail_tau,
@@ -1405,8 +1374,7 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   const double M = misc->rn2_max + 2.0 * sqrt(qn) * sqrt(misc->rn2_max) + 1.0;
   const double eta = ETA_COEF * M + 1e-4;
   // every non-candidate has a key >= the threshold of the list that rejected it
-  double tq = (double)tau[q * split];
-  for (int h = 1; h < split; ++h) tq = fmin(tq, (double)tau[q * split + h]);
+  const double tq = (double)tau[q];
   const double dk2 = __longlong_as_double((long long)kth);
   bool ok = false;
   if (isfinite(tq) && isfinite(dk2)) {
@@ -1464,31 +1432,33 @@ int pick_kp(int k, int n_cand) {
   return kp;
 }
 
-size_t tc_smem_bytes(int kp, int stages, int split) {
+size_t tc_smem_bytes(int kp, int stages) {
   return 1024 + (size_t)(QT + stages) * TILE_BYTES +
-         (size_t)(2 * kp + 2 * (pend_size(split) + 1)) * epi_warps(split) * 32 * 4 +
+         (size_t)(2 * kp + 2 * (PEND + 1)) * EPI_WARPS * 32 * 4 +
          8 * (2 + 2 * MAX_STAGES + 4 * QT) + 32 + 4 * RING;
 }
 
-int pick_stages(int kp, int split) {
+int pick_stages(int kp) {
   int st = MAX_STAGES;
-  while (st > 2 && tc_smem_bytes(kp, st, split) > 227 * 1024) --st;
+  while (st > 2 && tc_smem_bytes(kp, st) > 227 * 1024) --st;
   return st;
 }
 
 }  // namespace
 
-// 0 = auto (grouped for large reference sets), 1 = exhaustive scan, 2 = grouped; set through
-// b200nn_opts.reserved (bits 0-1) for benchmarking the two variants against each other
-static thread_local int g_tc_mode = 0;
-// visiting order (sorted query position -> original row, -1 = padding) left by the last
-// grouped candidate stage for the re-rank kernel
-static thread_local const int32_t *g_visit = nullptr;
-static thread_local int64_t g_n_visit = 0;
-// grouping of the reference rows built by the last grouped search (for the fallback scan)
-static thread_local GroupedRefs g_groups;
-static thread_local bool g_have_groups = false;
-void knn_tc_set_mode(int mode) { g_tc_mode = mode; }
+// what the candidate stage hands to the re-rank / fallback stage (device pointers into the
+// context's workspace; valid until the next kNN call on the context)
+struct TcCandidates {
+  int32_t *cand = nullptr;     // [nq x kp] candidate rows (-1: none)
+  float *tau = nullptr;        // [nq] threshold below which every key is a candidate
+  double *q_n2 = nullptr;      // [nq] |yh_q|^2
+  double *q_err = nullptr;     // [nq] |y_q - yh_q|
+  TcMisc *misc = nullptr;
+  const int32_t *visit = nullptr;  // grouped search: queries in group-sorted order (-1: padding)
+  int64_t n_visit = 0;
+  bool have_groups = false;    // grouped search: the clustering of the reference rows
+  GroupedRefs groups;
+};
 
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
   if (d > MAX_D || d < 1) return false;
@@ -1501,24 +1471,16 @@ bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
 // launch helper for the candidate kernel
 static int launch_tc(b200nn_ctx *ctx, const CUtensorMap &map_q, const CUtensorMap &map_r, const TcParams &P,
                      bool dbg) {
-  size_t smem = tc_smem_bytes(P.kp, P.stages, P.split);
+  size_t smem = tc_smem_bytes(P.kp, P.stages);
   if (smem > 227 * 1024 || P.stages < 3) {
     b200nn_set_error("candidate list of %d entries does not fit shared memory", P.kp);
     return B200NN_ERR_INVALID;
   }
   int grid = P.n_items < ctx->sm_count ? P.n_items : ctx->sm_count;
   if (grid <= 0) return B200NN_OK;
-  if (dbg) {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<true, 1, false><<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
-  } else if (P.split == 2) {
-    CU_TRY(cudaFuncSetAttribute(k_knn_tc<false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_knn_tc<false, 2, false><<<grid, num_threads(2), smem, ctx->stream>>>(map_q, map_r, P);
-  } else {
-    auto kern = P.pass1 ? k_knn_tc<false, 1, true> : k_knn_tc<false, 1, false>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, num_threads(1), smem, ctx->stream>>>(map_q, map_r, P);
-  }
+  auto kern = dbg ? k_knn_tc<true, false> : P.pass1 ? k_knn_tc<false, true> : k_knn_tc<false, false>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, NUM_THREADS, smem, ctx->stream>>>(map_q, map_r, P);
   KERNEL_CHECK(ctx);
   return B200NN_OK;
 }
@@ -1573,16 +1535,13 @@ static int pick_groups(int64_t nr) {
 
 // candidate stage alone (also used by the debug / profiling entry point).
 // mode: 0 = auto, 1 = exhaustive scan of every tile, 2 = grouped (tile-pruned)
-int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
-                      int64_t nq, int d, int kp, int split, int mode, int32_t **cand_out, float **tau_out,
-                      double **qn2_out, double **qerr_out, void **misc_out, float *d_dbg_keys,
-                      b200nn_stats *stats) {
+static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
+                             int64_t nq, int d, int kp, int mode, TcCandidates *out,
+                             float *d_dbg_keys, b200nn_stats *stats) {
   cudaStream_t st = ctx->stream;
   const bool self = (d_qry == d_ref) && (nq == nr);
   const bool grouped = mode == 2 || (mode == 0 && nr >= 32768 && d_dbg_keys == nullptr);
-  g_visit = nullptr;
-  g_n_visit = 0;
-  g_have_groups = false;
+  *out = TcCandidates();
   TcMisc *misc;
   double *partial, *q_n2, *q_err;
   __half *r16, *q16;
@@ -1593,9 +1552,8 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   RC_TRY(ws_get(ctx, WS_TC_QRY16, (size_t)nq * BK, &q16));
   RC_TRY(ws_get(ctx, WS_TC_QRYERR, (size_t)nq * 2, &q_n2));
   q_err = q_n2 + nq;
-  if (d_dbg_keys) split = 1;
-  RC_TRY(ws_get(ctx, WS_TC_CAND, (size_t)nq * kp * split, &cand));
-  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq * split, &tau));
+  RC_TRY(ws_get(ctx, WS_TC_CAND, (size_t)nq * kp, &cand));
+  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq, &tau));
 
   cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10];
   CU_TRY(cudaEventRecord(e0, st));
@@ -1619,8 +1577,7 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
   P.n_items = (int32_t)ceil_div64(nq, QT * BM);
   P.ksteps = (d + 3 + 15) / 16;
   P.kp = kp;
-  P.split = split;
-  P.stages = pick_stages(kp, split);
+  P.stages = pick_stages(kp);
   P.cand = cand;
   P.tau = tau;
   P.dbg_keys = d_dbg_keys;
@@ -1769,19 +1726,19 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, 0,
                                                       P.list_stride, tiles, list_cnt);
     KERNEL_CHECK(ctx);
-    g_visit = qperm;
-    g_n_visit = nq_pad;
-    g_groups.G = G;
-    g_groups.ld = BK;
-    g_groups.cent = cent;
-    g_groups.grad = grad;
-    g_groups.goff = goff;
-    g_groups.rperm = rperm;
-    g_groups.yq16 = reinterpret_cast<const uint16_t *>(yq16);
-    g_groups.q_err = q_err;
-    g_groups.scale = &misc->scale;
-    g_groups.e_max = &misc->e_max;
-    g_have_groups = true;
+    out->visit = qperm;
+    out->n_visit = nq_pad;
+    out->groups.G = G;
+    out->groups.ld = BK;
+    out->groups.cent = cent;
+    out->groups.grad = grad;
+    out->groups.goff = goff;
+    out->groups.rperm = rperm;
+    out->groups.yq16 = reinterpret_cast<const uint16_t *>(yq16);
+    out->groups.q_err = q_err;
+    out->groups.scale = &misc->scale;
+    out->groups.e_max = &misc->e_max;
+    out->have_groups = true;
     P.pass1 = 0;
     P.tau_init = tau;  // written by pass 1, read at the start of every pass-2 row
     k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc);
@@ -1799,16 +1756,17 @@ int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const do
     CU_TRY(cudaEventElapsedTime(&ms, e1, e2));
     stats->ms_knn_cand += ms;
   }
-  *cand_out = cand;
-  *tau_out = tau;
-  *qn2_out = q_n2;
-  *qerr_out = q_err;
-  *misc_out = misc;
+  out->cand = cand;
+  out->tau = tau;
+  out->q_n2 = q_n2;
+  out->q_err = q_err;
+  out->misc = misc;
   return B200NN_OK;
 }
 
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
-                  int d, int k, int n_cand, int32_t *d_idx0, double *d_dist, b200nn_stats *stats) {
+                  int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
+                  b200nn_stats *stats) {
   cudaStream_t st = ctx->stream;
   int kp = pick_kp(k, n_cand);
   if (kp > MAX_KP) kp = MAX_KP;
@@ -1816,21 +1774,12 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
     b200nn_set_error("k = %d leaves no room for a widened candidate set (max %d)", k, MAX_KP);
     return B200NN_ERR_INVALID;
   }
-  // Experimental (B200NN_SPLIT=2, k <= 20): two epilogue warps share a row set, each keeping its
-  // own list of 24 (>= k + 4) candidates from its half of the columns; the re-rank sees the
-  // union (48 candidates).  Measured at 1M cells: candidate stage 46 -> 44 ms, re-rank 7 -> 10 ms,
-  // i.e. no net gain (register spills at 96 regs/thread, smaller pending buffers), so the
-  // default stays one warp per row set.
-  static const int env_split = getenv("B200NN_SPLIT") ? atoi(getenv("B200NN_SPLIT")) : 0;
-  int split = (env_split == 2 && k <= 20 && n_cand == 0) ? 2 : 1;
-  if (split == 2) kp = 24;
-  int32_t *cand;
-  float *tau;
-  double *q_n2, *q_err;
-  void *misc_v;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, split, g_tc_mode, &cand, &tau, &q_n2, &q_err,
-                           &misc_v, nullptr, stats));
-  TcMisc *misc = static_cast<TcMisc *>(misc_v);
+  TcCandidates C;
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, scan_mode, &C, nullptr, stats));
+  int32_t *cand = C.cand;
+  float *tau = C.tau;
+  double *q_n2 = C.q_n2, *q_err = C.q_err;
+  TcMisc *misc = C.misc;
   int32_t *flags;
   RC_TRY(ws_get(ctx, WS_TC_FLAGS, (size_t)nq + 4, &flags));
   int32_t *fail_list = flags + 1;  // flags[0] receives the count (knn_exact reads list[-1])
@@ -1840,14 +1789,14 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   cudaEvent_t e0 = ctx->ev[11], e1 = ctx->ev[12], e2 = ctx->ev[13];
   CU_TRY(cudaEventRecord(e0, st));
   const size_t smem = rr_per_warp(d) * RR_WARPS;
-  const int64_t n_visit = g_visit ? g_n_visit : nq;
+  const int64_t n_visit = C.visit ? C.n_visit : nq;
   const bool vec = (d % 2 == 0) && (reinterpret_cast<uintptr_t>(d_ref) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(d_qry) % 16 == 0);
   auto kern = vec ? k_rerank<true> : k_rerank<false>;
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
-      d_ref, d_qry, nq, d, k, kp * split, split, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, fail_tau,
-      g_visit, n_visit);
+      d_ref, d_qry, nq, d, k, kp, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, fail_tau,
+      C.visit, n_visit);
   KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e1, st));
   TcMisc h;
@@ -1859,8 +1808,8 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   }
   if (h.n_fail > 0) {
     CU_TRY(cudaMemcpyAsync(flags, &misc->n_fail, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    if (g_have_groups)
-      RC_TRY(knn_exact_grouped_launch(ctx, d_ref, d_qry, d, k, fail_list, h.n_fail, fail_tau, g_groups, d_idx0,
+    if (C.have_groups)
+      RC_TRY(knn_exact_grouped_launch(ctx, d_ref, d_qry, d, k, fail_list, h.n_fail, fail_tau, C.groups, d_idx0,
                                       d_dist));
     else
       RC_TRY(knn_exact_launch(ctx, d_ref, nr, d_qry, nq, d, k, fail_list, h.n_fail, d_idx0, d_dist, fail_tau));
@@ -1883,14 +1832,14 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
 
 // diagnostic entry point: raw keys of (item 0, B tile 0) + candidates + prep state
 int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
-                 int d, int kp, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
+                 int d, int kp, int scan_mode, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
                  double *h_scale_mu /* [1 + 64] */) {
-  int32_t *cand;
-  float *tau;
-  double *q_n2, *q_err;
-  void *misc_v;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, 1, d_keys_out ? 1 : g_tc_mode,
-                           &cand, &tau, &q_n2, &q_err, &misc_v, d_keys_out, nullptr));
+  TcCandidates C;
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, d_keys_out ? 1 : scan_mode, &C,
+                           d_keys_out, nullptr));
+  int32_t *cand = C.cand;
+  float *tau = C.tau;
+  void *misc_v = C.misc;
   cudaStream_t st = ctx->stream;
   if (d_cand_out)
     CU_TRY(cudaMemcpyAsync(d_cand_out, cand, sizeof(int32_t) * (size_t)nq * kp,

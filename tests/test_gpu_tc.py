@@ -170,24 +170,3 @@ def test_many_uncertified_rows_take_the_exact_fallback(ctx, mode):
     idx, dist, st = ctx.knn(X, Q, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR, k + 2, mode)
     assert (idx == wi).all() and (dist == wd).all()
     print("mode", mode, "uncertified of 300:", st["n_uncertified"])
-
-
-def test_split_epilogue_variant(ctx, monkeypatch):
-    """the experimental two-warps-per-row-set epilogue (B200NN_SPLIT=2) gives the same answer"""
-    import subprocess, sys, os, textwrap
-    code = textwrap.dedent("""
-        import numpy as np, oracle, seurat_b200 as sb
-        from seurat_b200 import _lib
-        from seurat_b200.synthetic import gaussian_mixture
-        X, _ = gaussian_mixture(40000, 50, seed=21, n_centres=8)
-        wi, wd = oracle.knn(X, k=20, method="kdtree")
-        ctx = sb.Context(0)
-        for mode in (1, 2):
-            idx, dist, st = ctx.knn(X, None, 20, _lib.ROW_MAJOR, _lib.KNN_TENSOR, 0, mode)
-            assert (idx == wi).all() and (dist == wd).all(), mode
-        print("ok")
-    """)
-    env = dict(os.environ, B200NN_SPLIT="2")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=280)
-    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
