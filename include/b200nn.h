@@ -148,11 +148,17 @@ B200NN_API int b200nn_nn_graph_fill(b200nn_ctx *ctx, int32_t *p, int32_t *i, dou
 /*
  * FindNeighbors.default for query == object: kNN, nn Graph and (optionally)
  * SNN with the index kept on the device between stages.  idx_out / dist_out
- * may be NULL when the caller only wants the graphs.
+ * may be NULL when the caller only wants the graphs.  nn_p_out [n + 1],
+ * nn_i_out [n * k], nn_x_out [n * k] are optional: the nn Graph never has more
+ * than n * k entries, so a caller may hand its buffers in already here; they are
+ * then filled while the SNN stage runs (page-locked buffers make that a true
+ * overlap) and _fill can be called with NULL for them.  The first *nnz_nn_out
+ * entries are valid.
  */
 B200NN_API int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, int32_t d,
                                 int32_t k, double prune, int32_t compute_snn,
                                 int32_t *idx_out, double *dist_out,
+                                int32_t *nn_p_out, int32_t *nn_i_out, double *nn_x_out,
                                 const b200nn_opts *opts, int64_t *nnz_nn_out,
                                 int64_t *nnz_snn_out, b200nn_stats *stats);
 B200NN_API int b200nn_find_neighbors_fill(b200nn_ctx *ctx, int32_t *nn_p, int32_t *nn_i, double *nn_x,

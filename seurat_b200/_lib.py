@@ -87,8 +87,8 @@ def load() -> C.CDLL:
         L.b200nn_snn_fill.argtypes = [vp, vp, vp, vp]
         L.b200nn_nn_graph_count.argtypes = [vp, vp, i64, i32, i64, C.POINTER(Opts), C.POINTER(i64), C.POINTER(Stats)]
         L.b200nn_nn_graph_fill.argtypes = [vp, vp, vp, vp]
-        L.b200nn_find_neighbors_count.argtypes = [vp, vp, i64, i32, i32, dbl, i32, vp, vp, C.POINTER(Opts),
-                                                  C.POINTER(i64), C.POINTER(i64), C.POINTER(Stats)]
+        L.b200nn_find_neighbors_count.argtypes = [vp, vp, i64, i32, i32, dbl, i32, vp, vp, vp, vp, vp,
+                                                  C.POINTER(Opts), C.POINTER(i64), C.POINTER(i64), C.POINTER(Stats)]
         L.b200nn_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b200nn_index_create.argtypes = [vp, vp, i64, i32, C.POINTER(Opts), C.POINTER(vp)]
         L.b200nn_index_destroy.argtypes = [vp, vp]
@@ -221,8 +221,19 @@ class Context:
         o = Opts(layout, algo, n_cand, scan_mode)
         st = Stats()
         nnz_nn, nnz_snn = C.c_int64(0), C.c_int64(0)
+        # nn Graph buffers handed in by the caller (capacity n * k) are filled during the count call,
+        # while the SNN stage runs
+        early = {}
+        for name, count, dt in (("nn_p", n + 1, np.int32), ("nn_i", n * k, np.int32), ("nn_x", n * k, np.float64)):
+            a = out.get(name)
+            if a is not None and a.size >= count and a.dtype == dt and a.flags.c_contiguous:
+                early[name] = a
+        if len(early) != 3:
+            early = {}
         check(self._L.b200nn_find_neighbors_count(self._h, _ptr(data), n, d, k, float(prune),
                                                   1 if compute_snn else 0, _ptr(idx), _ptr(dist),
+                                                  _ptr(early.get("nn_p")), _ptr(early.get("nn_i")),
+                                                  _ptr(early.get("nn_x")),
                                                   C.byref(o), C.byref(nnz_nn), C.byref(nnz_snn),
                                                   C.byref(st)))
 
@@ -232,14 +243,20 @@ class Context:
                 return a[:count] if a.size != count else a
             return np.empty(count, dtype=dtype)
 
-        nn_p, nn_i, nn_x = buf("nn_p", n + 1, np.int32), buf("nn_i", nnz_nn.value, np.int32), \
-            buf("nn_x", nnz_nn.value, np.float64)
+        if early:
+            nn_p, nn_i, nn_x = early["nn_p"][:n + 1], early["nn_i"][:nnz_nn.value], early["nn_x"][:nnz_nn.value]
+            fill_nn = (None, None, None)
+        else:
+            nn_p, nn_i, nn_x = buf("nn_p", n + 1, np.int32), buf("nn_i", nnz_nn.value, np.int32), \
+                buf("nn_x", nnz_nn.value, np.float64)
+            fill_nn = (nn_p, nn_i, nn_x)
         snn = (None, None, None)
         if compute_snn:
             snn = (buf("snn_p", n + 1, np.int32), buf("snn_i", nnz_snn.value, np.int32),
                    buf("snn_x", nnz_snn.value, np.float64))
-        check(self._L.b200nn_find_neighbors_fill(self._h, _ptr(nn_p), _ptr(nn_i), _ptr(nn_x),
-                                                 _ptr(snn[0]), _ptr(snn[1]), _ptr(snn[2])))
+        if fill_nn[0] is not None or compute_snn:
+            check(self._L.b200nn_find_neighbors_fill(self._h, _ptr(fill_nn[0]), _ptr(fill_nn[1]), _ptr(fill_nn[2]),
+                                                     _ptr(snn[0]), _ptr(snn[1]), _ptr(snn[2])))
         return {"idx": idx, "dist": dist, "nn": (nn_p, nn_i, nn_x), "snn": snn if compute_snn else None,
                 "stats": st.as_dict()}
 

@@ -546,8 +546,9 @@ int b200nn_nn_graph_fill(b200nn_ctx *ctx, int32_t *p, int32_t *i, double *x) {
 
 int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, int32_t d,
                                 int32_t k, double prune, int32_t compute_snn, int32_t *idx_out,
-                                double *dist_out, const b200nn_opts *opts, int64_t *nnz_nn_out,
-                                int64_t *nnz_snn_out, b200nn_stats *stats) {
+                                double *dist_out, int32_t *nn_p_out, int32_t *nn_i_out, double *nn_x_out,
+                                const b200nn_opts *opts, int64_t *nnz_nn_out, int64_t *nnz_snn_out,
+                                b200nn_stats *stats) {
   RC_TRY(check_ctx(ctx));
   b200nn_opts o = opts ? *opts : default_opts();
   if (stats) memset(stats, 0, sizeof(*stats));
@@ -576,9 +577,14 @@ int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, 
   if (want_knn) RC_TRY(download_knn_begin(ctx, d_idx0, d_dist, n, k, o.layout, idx_out, dist_out));
   b200nn_stats gs;
   memset(&gs, 0, sizeof(gs));
-  int grc = graphs_launch(ctx, d_idx0, n, k, n, prune, true, compute_snn != 0, 0, n, &gs);
+  NnGraphHostOut early;
+  early.p = nn_p_out;
+  early.i = nn_i_out;
+  early.x = nn_x_out;
+  const bool want_early = nn_p_out || nn_i_out || nn_x_out;
+  int grc = graphs_launch(ctx, d_idx0, n, k, n, prune, true, compute_snn != 0, 0, n, &gs, &early);
   if (grc != B200NN_OK) {
-    if (want_knn) cudaStreamSynchronize(ctx->copy_stream);  // never leave a copy into caller memory in flight
+    if (want_knn || want_early) cudaStreamSynchronize(ctx->copy_stream);  // no copy into caller memory stays in flight
     return grc;
   }
   if (stats) {
@@ -589,7 +595,7 @@ int b200nn_find_neighbors_count(b200nn_ctx *ctx, const double *data, int64_t n, 
     stats->snn_expanded = gs.snn_expanded;
     stats->max_indegree = gs.max_indegree;
   }
-  if (want_knn) {
+  if (want_knn || want_early) {
     RC_TRY(th.start());
     RC_TRY(download_knn_end(ctx));
     RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));  // what is left of the copy after the graphs

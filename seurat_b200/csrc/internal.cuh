@@ -204,6 +204,12 @@ int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
                  double *h_scale_mu);
 
 // snn.cu
+// optional host destination of the nn Graph (capacity n_rows * k entries): copied on the
+// context's copy stream as soon as the graph exists, i.e. while the SNN stage runs
+struct NnGraphHostOut {
+  int32_t *p = nullptr, *i = nullptr;
+  double *x = nullptr;
+};
 int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k, int64_t n,
                   double prune, bool want_nn_graph, bool compute_snn, int64_t row_begin,
-                  int64_t row_end, b200nn_stats *stats);
+                  int64_t row_end, b200nn_stats *stats, const NnGraphHostOut *early_nn = nullptr);

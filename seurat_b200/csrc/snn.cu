@@ -984,7 +984,7 @@ static inline double jaccard_of(double s, double k) { return s / (k + (k - s)); 
 
 int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k, int64_t n,
                   double prune, bool want_nn_graph, bool compute_snn, int64_t row_begin,
-                  int64_t row_end, b200nn_stats *stats) {
+                  int64_t row_end, b200nn_stats *stats, const NnGraphHostOut *early_nn) {
   cudaStream_t st = ctx->stream;
   ctx->nn_graph.valid = false;
   ctx->snn.valid = false;
@@ -1080,6 +1080,25 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     ctx->nn_graph.i = nn_i;
     ctx->nn_graph.x = nn_x;
     if (stats) stats->nnz_nn = nnz_nn;
+    if (early_nn && (early_nn->p || early_nn->i || early_nn->x)) {
+      // the caller's nn Graph buffers are known already: copy on the copy stream, behind the SNN stage
+      int32_t *p32 = nullptr;
+      if (early_nn->p) {
+        RC_TRY(ws_get(ctx, WS_OUT_P32, (size_t)n + 1, &p32));
+        RC_TRY(narrow_i64_to_i32(ctx, nn_p, p32, n + 1));
+      }
+      CU_TRY(cudaEventRecord(ctx->ev_copy, st));
+      CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+      if (early_nn->p)
+        CU_TRY(cudaMemcpyAsync(early_nn->p, p32, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+      if (early_nn->i && nnz_nn)
+        CU_TRY(cudaMemcpyAsync(early_nn->i, nn_i, sizeof(int32_t) * (size_t)nnz_nn, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+      if (early_nn->x && nnz_nn)
+        CU_TRY(cudaMemcpyAsync(early_nn->x, nn_x, sizeof(double) * (size_t)nnz_nn, cudaMemcpyDeviceToHost,
+                               ctx->copy_stream));
+    }
   }
   if (stats) stats->max_indegree = hi.max_indegree;
   CU_TRY(cudaEventRecord(e1, st));

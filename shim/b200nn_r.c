@@ -124,8 +124,8 @@ SEXP b200_FindNeighbors(SEXP data, SEXP k_, SEXP prune_, SEXP compute_snn_) {
   const int snn = Rf_asLogical(compute_snn_);
   int64_t nnz_nn = 0, nnz_snn = 0;
   b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
-  int rc = b200nn_find_neighbors_count(get_ctx(), REAL(data), n, d, k, Rf_asReal(prune_), snn, NULL, NULL, &o,
-                                       &nnz_nn, &nnz_snn, NULL);
+  int rc = b200nn_find_neighbors_count(get_ctx(), REAL(data), n, d, k, Rf_asReal(prune_), snn, NULL, NULL,
+                                       NULL, NULL, NULL, &o, &nnz_nn, &nnz_snn, NULL);
   if (rc != B200NN_OK) Rf_error("%s", b200nn_last_error());
   R_CheckUserInterrupt();
   SEXP np = PROTECT(Rf_allocVector(INTSXP, n + 1));

@@ -360,3 +360,21 @@ def test_resident_index_repeated_queries(ctx, layout):
     first.alg_idx.close()
     with pytest.raises(sb.B200Error):
         first.alg_idx.knn(None, 5)
+
+
+def test_find_neighbors_into_caller_buffers(ctx):
+    """nn Graph buffers handed to the count call are filled there (while the SNN stage runs);
+    the result equals the plain two-phase call"""
+    X, _ = gaussian_mixture(5000, 12, seed=41, n_centres=4)
+    n, k = 5000, 10
+    want = ctx.find_neighbors(X, k, 1 / 15, True, _lib.ROW_MAJOR)
+    out = {"idx": np.empty((n, k), np.int32), "dist": np.empty((n, k), np.float64),
+           "nn_p": np.empty(n + 1, np.int32), "nn_i": np.empty(n * k + 7, np.int32),
+           "nn_x": np.empty(n * k + 7, np.float64)}
+    got = ctx.find_neighbors(X, k, 1 / 15, True, _lib.ROW_MAJOR, out=out)
+    assert got["nn"][0].base is out["nn_p"] or got["nn"][0] is out["nn_p"]
+    for a, b in zip(want["nn"] + want["snn"] + (want["idx"], want["dist"]),
+                    got["nn"] + got["snn"] + (got["idx"], got["dist"])):
+        assert a.shape == b.shape and (a == b).all()
+    only_nn = ctx.find_neighbors(X, k, 1 / 15, False, _lib.ROW_MAJOR, out=out)
+    assert only_nn["snn"] is None and (only_nn["nn"][1] == want["nn"][1]).all()
