@@ -378,3 +378,33 @@ def test_find_neighbors_into_caller_buffers(ctx):
         assert a.shape == b.shape and (a == b).all()
     only_nn = ctx.find_neighbors(X, k, 1 / 15, False, _lib.ROW_MAJOR, out=out)
     assert only_nn["snn"] is None and (only_nn["nn"][1] == want["nn"][1]).all()
+
+
+@pytest.mark.parametrize("n,d,k", [(1, 3, 1), (2, 1, 2), (7, 1, 1), (33, 2, 33), (257, 5, 1), (3000, 61, 3), (2100, 1, 32)])
+def test_knn_degenerate_shapes(ctx, n, d, k):
+    """single points, one dimension, k = 1, k = n: both algorithms agree with the oracle"""
+    rng = np.random.default_rng(n * 131 + d)
+    X = rng.normal(size=(n, d))
+    wi, wd = oracle.knn(X, k=k)
+    for algo in ALGOS:
+        if algo == _lib.KNN_TENSOR and n < 2048:
+            continue
+        idx, dist, _ = ctx.knn(X, None, k, _lib.ROW_MAJOR, algo)
+        assert (idx == wi).all() and (dist == wd).all(), (n, d, k, algo)
+    q = rng.normal(size=(1, d))                     # a single query row
+    wi, wd = oracle.knn(X, q, k)
+    idx, dist, _ = ctx.knn(X, q, k, _lib.ROW_MAJOR)
+    assert (idx == wi).all() and (dist == wd).all()
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (2, 1), (5, 5), (40, 1)])
+def test_graphs_degenerate_shapes(ctx, n, k):
+    rng = np.random.default_rng(n + k)
+    nn = np.stack([rng.permutation(n)[:k] + 1 for _ in range(n)]).astype(np.int32)
+    for prune in (0.0, 1 / 15, 1.0):
+        want = oracle.compute_snn(nn, prune)
+        p, i, x, _ = ctx.compute_snn(nn, prune, _lib.ROW_MAJOR)
+        assert_csr_equal((p, i, x), want)
+    wp, wi_, wx = oracle.nn_graph(nn, n)
+    p, i, x, _ = ctx.nn_graph(nn, n, _lib.ROW_MAJOR)
+    assert_csr_equal((p, i, x), (wp, wi_, wx))
