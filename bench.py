@@ -316,6 +316,7 @@ def main():
         # every rank: H2D of the replicated embedding + its query shard's results back
         Xp = torch.from_numpy(X).pin_memory()
         times = []
+        pinned = {}
         for s in range(1 + max(1, args.e2e_steps)):
             barrier()
             t0 = time.perf_counter()
@@ -324,7 +325,13 @@ def main():
             idx0, dd = be.knn_shard(refe, b, e, k)
             idx_full = sdist.all_gather_index(idx0, n)
             g = be.graph_rows(idx_full, k, PRUNE, True, b, e)
-            host = [idx0.cpu(), dd.cpu()] + [tt.cpu() for tt in g["snn"]]
+            # results of this rank's shard go to page-locked host buffers (allocated once)
+            for name, src in (("idx", idx0), ("dist", dd), ("snn_p", g["snn"][0]), ("snn_i", g["snn"][1]),
+                              ("snn_x", g["snn"][2])):
+                flat = src.reshape(-1)
+                if name not in pinned or pinned[name].numel() < flat.numel():
+                    pinned[name] = torch.empty(int(flat.numel() * 1.05) + 1024, dtype=flat.dtype).pin_memory()
+                pinned[name][: flat.numel()].copy_(flat, non_blocking=True)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
