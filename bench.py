@@ -317,10 +317,14 @@ def main():
         Xp = torch.from_numpy(X).pin_memory()
         times = []
         pinned = {}
+        refe = torch.empty((n, d), dtype=torch.float64, device=dev)
         for s in range(1 + max(1, args.e2e_steps)):
             barrier()
             t0 = time.perf_counter()
-            refe = Xp.to(dev, non_blocking=True)
+            # rank 0 uploads the embedding once, the other ranks receive it over NVLink
+            if rank == 0:
+                refe.copy_(Xp, non_blocking=True)
+            dist.broadcast(refe, 0)
             torch.cuda.synchronize()
             idx0, dd = be.knn_shard(refe, b, e, k)
             idx_full = sdist.all_gather_index(idx0, n)
@@ -341,7 +345,8 @@ def main():
         nnz_local = int(g["snn"][1].numel())
         e2e = {"value": n / statistics.median(times), "unit": "cells/s", "h2d_bytes_per_step": n * d * 8,
                "d2h_bytes_per_step": (e - b) * k * 12 + 8 * (e - b + 1) + 12 * nnz_local,
-               "ms_per_step": 1e3 * statistics.median(times), "note": "bytes are per rank"}
+               "ms_per_step": 1e3 * statistics.median(times),
+               "note": "H2D once on rank 0 + NCCL broadcast of the embedding; D2H bytes are per rank"}
 
     if rank != 0:
         if world > 1:
