@@ -213,20 +213,30 @@ int b200nn_ctx_create(int device, b200nn_ctx **ctx_out) {
   b200nn_ctx *ctx = new (std::nothrow) b200nn_ctx();
   if (!ctx) return B200NN_ERR_NOMEM;
   ctx->device = device;
+  // from here on a failure releases what was created so far
+  cudaError_t ce = cudaSuccess;
   cudaDeviceProp prop;
-  CU_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) {
+  ce = cudaGetDeviceProperties(&prop, device);
+  if (ce == cudaSuccess && prop.major < 10) {
     b200nn_set_error("device %d is sm_%d%d; libb200nn is built for sm_100a (B200) only", device,
                      prop.major, prop.minor);
     delete ctx;
     return B200NN_ERR_CUDA;
   }
-  ctx->sm_count = prop.multiProcessorCount;
-  CU_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  CU_TRY(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
-  for (auto &ev : ctx->ev) CU_TRY(cudaEventCreate(&ev));
-  CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(DevInfo)));
+  if (ce == cudaSuccess) {
+    ctx->sm_count = prop.multiProcessorCount;
+    ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+  for (auto &ev : ctx->ev)
+    if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
+  if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(DevInfo));
+  if (ce != cudaSuccess) {
+    b200nn_set_error("ctx_create: %s", cudaGetErrorString(ce));
+    b200nn_ctx_destroy(ctx);
+    return B200NN_ERR_CUDA;
+  }
   *ctx_out = ctx;
   return B200NN_OK;
 }
