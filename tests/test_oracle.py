@@ -118,3 +118,18 @@ def test_l2norm():
     assert (out[3] == 0).all()
     nrm = np.sqrt((out ** 2).sum(axis=1))
     assert np.allclose(np.delete(nrm, 3), 1.0)
+
+
+def test_oracle_selftest_under_asan_ubsan():
+    """the checker is itself checked: every oracle entry point on small inputs under
+    AddressSanitizer + UBSan (leaks included), plus the SURVEY 8c vector from C"""
+    import os
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    b = subprocess.run(["make", "-C", root, "selftest_asan"], capture_output=True, text=True, timeout=300)
+    if b.returncode != 0 and "sanitize" in (b.stderr + b.stdout):
+        pytest.skip("compiler without sanitizer runtime")
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([os.path.join(root, "selftest_asan")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0 and "oracle selftest ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
