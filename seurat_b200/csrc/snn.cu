@@ -907,7 +907,7 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     // classes 1-2: 8 rows per CTA, 16 warps per SM (shared memory bound)
     // (log2 counters, log2 exact-table words, rows per CTA) per class; two CTAs per SM.  These
     // kernels live on occupancy (dependent shared-memory round trips) and on few false
-    // positives in the counters; measured best: class 0 (E <= 1.6 k) 8 k counters, 30 warps/SM;
+    // positives in the counters; measured best: class 0 (E <= 2.8 k) 8 k counters, 30 warps/SM;
     // class 1 (E <= 3.2 k) 16 k counters, 20 warps/SM; class 2 (E <= 6.5 k) 16 k counters, 16.
     constexpr int WA = 15, WB = 10, WC = 8;
     auto kA = k_snn_rows_filter<13, 9, WA>;
@@ -1158,7 +1158,13 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     rw.k = k;
     rw.s_min = s_min;
     rw.n = n;
-    rw.class_lim[0] = class_limit(use32 ? WordCfg32::L0 : WordCfg64::L0);
+    // the filtered kernel needs 32-bit words, no duplicated neighbours, byte-sized counts
+    // and a cut-off that actually removes single overlaps
+    const int filter_s_min = (use32 && !has_dups && k <= 255 && s_min >= 2 && s_min <= F_SMIN_MAX) ? s_min : 0;
+    // Class 0 is bounded by the 2^L0-word table of the plain warp kernel; the filtered kernel's
+    // tables are independent of it and its 30-warps-per-SM configuration is the fastest up to
+    // E ~ 2.8 k (measured: 1638 -> 13.2 ms, 2200 -> 12.8, 2800 -> 12.7, 3277 -> 12.8, 4000 -> 15.1)
+    rw.class_lim[0] = filter_s_min >= 2 ? 2800 : class_limit(use32 ? WordCfg32::L0 : WordCfg64::L0);
     rw.class_lim[1] = class_limit(use32 ? WordCfg32::L1 : WordCfg64::L1);
     rw.class_lim[2] = class_limit(use32 ? WordCfg32::L2 : WordCfg64::L2);
     // the block-per-row kernel keeps survivors in a buffer of T/2 words: E <= T/2 there
@@ -1195,9 +1201,6 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     P.huge_log_t = 0;
     int32_t *ovf_list;
     RC_TRY(ws_get(ctx, WS_OVF_LIST, (size_t)rows + 1, &ovf_list));
-    // the filtered kernel needs 32-bit words, no duplicated neighbours, byte-sized counts
-    // and a cut-off that actually removes single overlaps
-    const int filter_s_min = (use32 && !has_dups && k <= 255 && s_min >= 2 && s_min <= F_SMIN_MAX) ? s_min : 0;
     if (use32)
       RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, hi.class_count,
                                         hi.max_row_e, has_dups, filter_s_min, ovf_list, d_info));
