@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("B200NN_LIB", os.path.join(_HERE, "libb200nn.so"))  # override: A/B builds
+LIB_PATH = os.path.join(_HERE, "libb200nn.so")
 
 OK, ERR_INVALID, ERR_K_TOO_LARGE, ERR_CUDA, ERR_INDEX_RANGE, ERR_NNZ_OVERFLOW, ERR_NOMEM, ERR_STATE = range(8)
 COL_MAJOR, ROW_MAJOR = 0, 1
