@@ -1,20 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- FindNeighbors cells/sec (kNN + nn Graph + SNN) on synthetic PCA-like data.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C|B] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C|B|D] [--impl b200|reference]
 
 A "step" is one pass of the hot path over the whole embedding:
   value : inputs (FP64 embedding, row-major) already resident in HBM, results left in
           HBM (kNN index/distances, nn Graph CSC, SNN CSR); timed with CUDA events.
-  e2e   : the same through the host-buffer C ABI (b200nn_find_neighbors_count/_fill)
-          with pinned HOST buffers: H2D of the embedding and D2H of idx/dist/nn/snn
-          are inside the timed region.
-N > 1 (torchrun): query rows sharded over ranks, embedding replicated, one all-gather
-of the kNN index, each rank emits its SNN rows.  Total work is fixed -> "strong".
+  e2e   : the same through the host-buffer C ABI with pinned HOST buffers: H2D of the
+          embedding and D2H of idx/dist/nn/snn are inside the timed region.  One GPU:
+          b200nn_find_neighbors_count/_fill.  N GPUs: rank 0 drives all N devices through
+          the single-process multi-device entry points (b200nn_multi_*), which is what the
+          R shim binds; the other ranks stand by.
+N > 1 (torchrun): one rank per GPU, query cells sharded, embedding replicated, one exchange
+of the kNN index over NCCL, each rank emits the SNN rows of its shard.  Total work is fixed
+-> "strong".
 
---impl reference times the CPU restatement of the reference (oracle/: ANN-style
-kd-tree + Gustavson ComputeSNN, all host threads) on a bounded sample of the same
-workload; R, RANN and Eigen are not available so the real reference cannot run.
+Outside the timed region every run checks what it computed (`verify`): sampled kNN rows
+against the oracle's kd-tree over the full reference set and a block of SNN rows against the
+oracle's ComputeSNN restatement on the same index, on every rank.
+
+--impl reference times the CPU restatement of the reference (oracle/: ANN-style kd-tree +
+Gustavson ComputeSNN) on a bounded sample of the same workload, once; R, RANN and Eigen are
+not available on the box (profiles/r02_probe_box.txt), so the real reference cannot run.
 """
 from __future__ import annotations
 
@@ -32,7 +39,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from seurat_b200.synthetic import CONFIGS, gaussian_mixture  # noqa: E402
+from seurat_b200.synthetic import CONFIGS, gaussian_mixture, shaped_embedding  # noqa: E402
 
 METRIC = "FindNeighbors cells/sec (kNN+SNN)"
 PRUNE = 1.0 / 15.0
@@ -104,74 +111,101 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_baseline(X: np.ndarray, k: int, idx1_full: np.ndarray | None, knn_sample: int, snn_rows: int,
-                 threads: int) -> dict:
-    """ANN-style kd-tree kNN + Gustavson SNN (oracle/) on a bounded sample, extrapolated
-    linearly in the number of query rows / SNN rows (tree build and transpose are timed in full)."""
+def host_threads() -> int:
+    """all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(X: np.ndarray, k: int, idx1_full: np.ndarray | None, knn_sample: int, knn_sample_1core: int,
+                  snn_rows: int, threads: int) -> dict:
+    """The reference's path on the host cores, restated (oracle/): ANN-style kd-tree kNN (the algorithm
+    RANN::nn2 wraps) + Gustavson ComputeSNN, on a BOUNDED sample of the workload, extrapolated linearly
+    in the number of query / SNN rows (tree build and nn-Graph transpose timed in full).
+
+    Two figures: `cores` threads over query / output rows (generous: the reference is
+    single-threaded, src/Makevars has no OpenMP and ANN is serial) and the faithful 1-core figure."""
     import oracle
     n = X.shape[0]
     rng = np.random.default_rng(2024)
     qs = np.sort(rng.choice(n, size=min(knn_sample, n), replace=False))
     t = {}
-    idx_s, _ = oracle.knn(X, X[qs], k, method="kdtree", nthreads=threads, timings=t)
-    knn_total = t["build_s"] + t["search_s"] * (n / len(qs))
+    oracle.knn(X, X[qs], k, method="kdtree", nthreads=threads, timings=t)
+    build_s, search_all = t["build_s"], t["search_s"] * (n / len(qs))
+    q1 = qs[:: max(1, len(qs) // max(1, knn_sample_1core))][:knn_sample_1core]
+    t1 = {}
+    oracle.knn(X, X[q1], k, method="kdtree", nthreads=1, timings=t1)
+    search_1 = t1["search_s"] * (n / len(q1))
     if idx1_full is None:
-        # no GPU index available (reference arm): build a plausible full index cheaply is not
-        # possible on the CPU, so SNN is timed on the kd-tree result of a contiguous block instead
-        blk = min(n, max(snn_rows, len(qs)))
+        # reference arm: no GPU may run, so there is no full index; SNN is timed on the kd-tree kNN
+        # graph of a random tenth-sized block of the same data (the rows are i.i.d., so the block is
+        # a uniform subsample with the same in-degree statistics) and scaled by n / block
+        blk = min(n, max(snn_rows, 20000))
         sub = X[:blk]
         idx_blk, _ = oracle.knn(sub, sub, k, method="kdtree", nthreads=threads)
-        t2 = {}
+        r1 = max(1, blk // 5)
+        t2, t3 = {}, {}
         oracle.compute_snn_rows(idx_blk, PRUNE, 0, blk, nthreads=threads, timings=t2)
-        snn_total = (t2["transpose_s"] + t2["rows_s"]) * (n / blk)
-        snn_note = f"SNN on a {blk}-cell block's own kNN graph, scaled by n/{blk}"
+        oracle.compute_snn_rows(idx_blk, PRUNE, 0, r1, nthreads=1, timings=t3)
+        snn_all = (t2["transpose_s"] + t2["rows_s"]) * (n / blk)
+        snn_1 = t3["transpose_s"] * (n / blk) + t3["rows_s"] * (n / r1)
+        snn_note = f"SNN on the kNN graph of a {blk}-cell block of the same data, scaled by n/{blk}"
     else:
-        r0 = 0
-        r1 = min(n, snn_rows)
-        t2 = {}
-        oracle.compute_snn_rows(idx1_full, PRUNE, r0, r1, nthreads=threads, timings=t2)
-        snn_total = t2["transpose_s"] + t2["rows_s"] * (n / (r1 - r0))
-        snn_note = f"SNN rows 0..{r1} of the full index (transpose in full), scaled by n/{r1 - r0}"
-    total = knn_total + snn_total
-    return {"value": n / total, "unit": "cells/s", "cores": threads, "kind": "port",
-            "sample": (f"kd-tree build on all {n} cells ({t['build_s']:.1f}s) + search of {len(qs)} sampled queries "
-                       f"({t['search_s']:.1f}s) scaled by n/{len(qs)}; {snn_note}; oracle/ restatement, not R"),
-            "knn_s_extrapolated": knn_total, "snn_s_extrapolated": snn_total}
+        r_all = min(n, snn_rows)
+        r1 = max(1, r_all // 5)
+        t2, t3 = {}, {}
+        oracle.compute_snn_rows(idx1_full, PRUNE, 0, r_all, nthreads=threads, timings=t2)
+        oracle.compute_snn_rows(idx1_full, PRUNE, 0, r1, nthreads=1, timings=t3)
+        snn_all = t2["transpose_s"] + t2["rows_s"] * (n / r_all)
+        snn_1 = t3["transpose_s"] + t3["rows_s"] * (n / r1)
+        snn_note = f"SNN rows 0..{r_all} of the full index the GPU produced (transpose in full), scaled by n/{r_all}"
+    total_all = build_s + search_all + snn_all
+    total_1 = build_s + search_1 + snn_1
+    return {"value": n / total_all, "unit": "cells/s", "cores": threads, "kind": "port", "extrapolated": True,
+            "sample": (f"kd-tree build on all {n} cells ({build_s:.1f}s, serial) + search of {len(qs)} sampled queries "
+                       f"({t['search_s']:.1f}s on {threads} threads) scaled by n/{len(qs)}; {snn_note}; "
+                       f"oracle/ restatement of ANN + ComputeSNN, not R (no R on the box)"),
+            "knn_s_extrapolated": build_s + search_all, "snn_s_extrapolated": snn_all,
+            "one_core": {"value": n / total_1, "unit": "cells/s", "cores": 1,
+                         "sample": f"{len(q1)} sampled queries and {r1} SNN rows on one thread, same extrapolation",
+                         "knn_s_extrapolated": build_s + search_1, "snn_s_extrapolated": snn_1}}
 
 
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
     X, _ = gaussian_mixture(n, d, cfg["seed"])
-    threads = oracle.num_threads()
-    vals = []
-    for s in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        r = cpu_baseline(X, k, None, args.cpu_knn_sample, args.cpu_snn_rows, threads)
-        if s >= args.warmup:
-            vals.append((r, time.perf_counter() - t0))
-    r = vals[-1][0]
-    value = statistics.median(v[0]["value"] for v in vals)
+    threads = host_threads()
+    t0 = time.perf_counter()
+    r = cpu_reference(X, k, None, args.cpu_knn_sample, args.cpu_knn_sample_1core, args.cpu_snn_rows, threads)
+    took = time.perf_counter() - t0
+    value = r["value"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / value,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(cfg, args.gpus),
-            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": r["sample"]},
+            "cpu_baseline": {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample", "extrapolated", "one_core")},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "extrapolated from a bounded sample; each step took %.1fs of CPU time" % statistics.median(v[1] for v in vals)}
+            "note": ("the sample is deterministic, so it is measured once (%.1f s of CPU work) and not repeated "
+                     "warmup + steps times; ms_per_step is the extrapolated full-workload time" % took)}
     print(json.dumps(line))
 
 
-def traffic_from_profiles(kernel: str):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), else None"""
-    path = os.path.join(ROOT, "profiles", "traffic.json")
+def traffic_from_profiles(key: str, n_gpus: int):
+    """DRAM bytes per step (summed over the launches of the named stage) from the committed ncu
+    capture of the single-GPU bench command (profiles/r02_traffic.json); None when no capture
+    exists for this configuration (N > 1: ncu cannot wrap a multi-rank command)."""
+    if n_gpus != 1:
+        return None
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get(kernel)
+            return json.load(f).get(key)
     return None
 
 
@@ -179,15 +213,42 @@ def workload_config(cfg, gpus):
     return {"workload": f"synthetic Gaussian mixture {cfg['n']} cells x {cfg['d']} PCs, k={cfg['k']}, prune.SNN=1/15 "
                         f"(SURVEY 8d seed {cfg['seed']})",
             "n_cells": cfg["n"], "dims": cfg["d"], "k": cfg["k"], "prune": "1/15",
-            "parallelism": f"query-rows sharded x{gpus}, embedding replicated, kNN index all-gathered",
+            "parallelism": (f"kNN query cells sharded x{gpus} (whole groups of the tile-pruned search per GPU), embedding "
+                            f"replicated, kNN index combined once (sum all-reduce), SNN rows sharded contiguously"),
             "l2_flush": "inputs larger than L2 (embedding %.0f MB fp64)" % (cfg["n"] * cfg["d"] * 8 / 1e6)}
+
+
+def verify_rank(X, k, idx0_rows, dist_rows, b, e, snn_block, idx1_full, n_rows=400, snn_rows=4000):
+    """sampled kNN rows of this rank's range [b, e) vs the oracle (kd-tree over the full reference set) and
+    the first SNN rows of the range vs the oracle's ComputeSNN on the same index.  Outside the timed region.
+    idx0_rows / dist_rows hold rows [b, e); distance rows computed by another rank are NaN here (group-aligned
+    shares, N > 1) and are checked by the rank that computed them... every rank samples its own range."""
+    import oracle
+    out = {"knn_rows_checked": 0, "knn_rows_exact": 0, "dist_rows_checked": 0, "snn_rows_checked": 0,
+           "snn_rows_exact": None}
+    if e > b:
+        rows = np.sort(np.random.default_rng(b + 1).choice(e - b, size=min(n_rows, e - b), replace=False))
+        wi, wd = oracle.knn(X, X[b + rows], k, method="kdtree", nthreads=host_threads())
+        have_d = ~np.isnan(dist_rows[rows][:, 0])
+        ok = (idx0_rows[rows] + 1 == wi).all(axis=1) & ((dist_rows[rows] == wd).all(axis=1) | ~have_d)
+        out["knn_rows_checked"], out["knn_rows_exact"] = int(rows.size), int(ok.sum())
+        out["dist_rows_checked"] = int(have_d.sum())
+        if snn_block is not None:
+            r1 = min(e, b + snn_rows)
+            wp, wi2, wx = oracle.compute_snn_rows(idx1_full, PRUNE, b, r1, nthreads=host_threads())
+            p, i, x = snn_block
+            m = r1 - b
+            same = bool((p[:m + 1] - p[0] == wp).all() and (i[p[0]:p[m]] == wi2).all()
+                        and (x[p[0]:p[m]].view(np.int64) == wx.view(np.int64)).all())
+            out["snn_rows_checked"], out["snn_rows_exact"] = int(m), same
+    return out
 
 
 # --------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C", choices=sorted(CONFIGS))
@@ -196,10 +257,13 @@ def main():
     ap.add_argument("--scan-mode", type=int, default=0,
                     help="tensor path: 0 auto (grouped, tile-pruned), 1 exhaustive scan of every tile, 2 grouped")
     ap.add_argument("--n-cand", type=int, default=0, help="candidates kept per query by the tensor path (0 = auto)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-knn-sample", type=int, default=2000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-knn-sample", type=int, default=10_000)
+    ap.add_argument("--cpu-knn-sample-1core", type=int, default=800)
     ap.add_argument("--cpu-snn-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-extra-workload", action="store_true")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.n:
@@ -210,7 +274,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import seurat_b200 as sb
+    import seurat_b200 as sb  # noqa: F401
     from seurat_b200 import _lib
     from seurat_b200 import dist as sdist
 
@@ -240,60 +304,103 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    stage_ms = {"knn_cand": 0.0, "knn_rerank": 0.0, "knn_fallback": 0.0, "nn_graph": 0.0, "snn": 0.0}
+    stage_keys = ("prep", "knn_cand", "knn_pass2", "knn_rerank", "knn_fallback", "nn_graph", "snn")
+    stage_ms = {kk: 0.0 for kk in stage_keys}
+    stage_ms["exchange"] = 0.0
     launches = 0
     last = {}
 
-    def step(record: bool):
+    def step(record: bool, ref_t=ref):
         nonlocal launches, last
-        idx0, dd = be.knn_shard(ref, b, e, k)
-        s1 = dict(be.last_stats)
-        idx_full = sdist.all_gather_index(idx0, n) if world > 1 else idx0
         if world > 1:
-            # the library runs on its own stream: the all-gather (NCCL stream) must have landed
+            # group-aligned shares (b200nn_opts.shard_rank / shard_world): this rank's kNN rows are whole
+            # groups of the tile-pruned search; the zero-filled index buffers are summed over the ranks
+            idx_full, dd_full = be.knn_owned(ref_t, rank, world, k)
+            s1 = dict(be.last_stats)
+            t_x = time.perf_counter()
+            sdist.all_reduce_index(idx_full)
+            # the library runs on its own stream: the all-reduce (NCCL stream) must have landed
             torch.cuda.current_stream().synchronize()
+            t_x = (time.perf_counter() - t_x) * 1e3
+            idx0, dd = idx_full[b:e], dd_full[b:e]
+        else:
+            idx0, dd = be.knn_shard(ref_t, b, e, k)
+            s1 = dict(be.last_stats)
+            idx_full, t_x = idx0, 0.0
         g = be.ctx.dev_graphs(idx_full, n, k, PRUNE, True, b, e)
         if record:
-            for key in ("knn_cand", "knn_rerank", "knn_fallback"):
+            for key in ("prep", "knn_cand", "knn_pass2", "knn_rerank", "knn_fallback"):
                 stage_ms[key] += s1.get("ms_" + key, 0.0)
             stage_ms["nn_graph"] += g["ms_nn_graph"]
             stage_ms["snn"] += g["ms_snn"]
+            stage_ms["exchange"] += t_x
             launches += int(s1.get("gpu_launches", 0)) + int(g.get("gpu_launches", 0))
-        last = {"knn": s1, "graphs": g, "idx0": idx0}
+        last = {"knn": s1, "graphs": g, "idx0": idx0, "dist": dd, "idx_full": idx_full}
+
+    def timed_steps(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        # the library works on its own stream and synchronises before returning, so the host wall
+        # clock between the two barriers is the device-side duration; take the larger of both
+        my_ms = max(ev0.elapsed_time(ev1), wall_ms)
+        t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
 
     for _ in range(args.warmup):
         step(False)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(True)
-    ev1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_per_step = timed_steps(lambda: step(True), args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    ev_ms = ev0.elapsed_time(ev1)
-    # the library works on its own stream and synchronises before returning, so the host
-    # wall clock between the two barriers is the device-side duration; take the larger of both
-    my_ms = max(ev_ms, wall_ms)
-    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
     value = n / (ms_per_step / 1e3)
+    main_last = last
+
+    # ---- verification of what was just computed (outside the timed region, every rank) -------
+    verify = None
+    if not args.no_verify:
+        idx1_full = (main_last["idx_full"].cpu().numpy() + 1).astype(np.int32)
+        r = ctx.dev_result(1)
+        P_ = torch.empty(r.n_rows + 1, dtype=torch.int64, device=dev)
+        I_ = torch.empty(r.nnz, dtype=torch.int32, device=dev)
+        X_ = torch.empty(r.nnz, dtype=torch.float64, device=dev)
+        ctx.dev_copy_result(1, P_, I_, X_)
+        nb = min(e - b, 4000)
+        pn = P_[:nb + 1].cpu().numpy()
+        blk = (pn, I_[:int(pn[-1])].cpu().numpy(), X_[:int(pn[-1])].cpu().numpy())
+        v = verify_rank(X, k, main_last["idx0"].cpu().numpy(), main_last["dist"].cpu().numpy(), b, e, blk, idx1_full)
+        vt = torch.tensor([v["knn_rows_checked"], v["knn_rows_exact"], v["snn_rows_checked"],
+                           1 if v["snn_rows_exact"] in (True, None) else 0, v["dist_rows_checked"]],
+                          dtype=torch.int64, device=dev)
+        if world > 1:
+            allv = [torch.empty_like(vt) for _ in range(world)]
+            dist.all_gather(allv, vt)
+            vt = torch.stack(allv)
+        else:
+            vt = vt[None]
+        verify = {"knn_rows_checked": int(vt[:, 0].sum()), "knn_rows_exact": int(vt[:, 1].sum()),
+                  "dist_rows_checked": int(vt[:, 4].sum()),
+                  "snn_rows_checked": int(vt[:, 2].sum()), "snn_blocks_exact": bool(vt[:, 3].min() == 1),
+                  "ranks": world, "oracle": "oracle/ kd-tree over the full reference set; ComputeSNN restatement on the same index",
+                  "ok": bool(int(vt[:, 0].sum()) == int(vt[:, 1].sum()) and vt[:, 3].min() == 1)}
+        del P_, I_, X_
 
     # ---- end-to-end through the host-buffer C ABI (pinned host memory) --------------------
     e2e = None
     if world == 1:
         Xp = torch.from_numpy(X).pin_memory()
         Xh = Xp.numpy()
-        nnz_nn = last["graphs"]["nnz_nn"]
-        nnz_snn = last["graphs"]["nnz_snn"]
+        nnz_nn = main_last["graphs"]["nnz_nn"]
+        nnz_snn = main_last["graphs"]["nnz_snn"]
         slack = int(nnz_snn * 1.05) + 1024
         pin = lambda count, dt: torch.empty(count, dtype=dt).pin_memory().numpy()  # noqa: E731
         out = {"idx": pin(n * k, torch.int32).reshape(n, k), "dist": pin(n * k, torch.float64).reshape(n, k),
@@ -311,42 +418,30 @@ def main():
         d2h = n * k * 12 + 2 * 4 * (n + 1) + 12 * (nnz_nn + r["stats"]["nnz_snn"])
         e2e = {"value": n / statistics.median(times), "unit": "cells/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * statistics.median(times),
+               "api": "b200nn_find_neighbors_count/_fill (host buffers, page-locked)",
                "stage_ms": {kk: vv for kk, vv in r["stats"].items() if kk.startswith("ms_")}}
+        if not args.no_verify:
+            e2e["same_as_value_leg"] = bool((r["idx"] - 1 == main_last["idx0"].cpu().numpy()).all()
+                                            and r["stats"]["nnz_snn"] == nnz_snn)
+        del out
     else:
-        # every rank: H2D of the replicated embedding + its query shard's results back
-        Xp = torch.from_numpy(X).pin_memory()
-        times = []
-        pinned = {}
-        refe = torch.empty((n, d), dtype=torch.float64, device=dev)
-        for s in range(1 + max(1, args.e2e_steps)):
-            barrier()
-            t0 = time.perf_counter()
-            # rank 0 uploads the embedding once, the other ranks receive it over NVLink
-            if rank == 0:
-                refe.copy_(Xp, non_blocking=True)
-            dist.broadcast(refe, 0)
-            torch.cuda.synchronize()
-            idx0, dd = be.knn_shard(refe, b, e, k)
-            idx_full = sdist.all_gather_index(idx0, n)
-            g = be.graph_rows(idx_full, k, PRUNE, True, b, e)
-            # results of this rank's shard go to page-locked host buffers (allocated once)
-            for name, src in (("idx", idx0), ("dist", dd), ("snn_p", g["snn"][0]), ("snn_i", g["snn"][1]),
-                              ("snn_x", g["snn"][2])):
-                flat = src.reshape(-1)
-                if name not in pinned or pinned[name].numel() < flat.numel():
-                    pinned[name] = torch.empty(int(flat.numel() * 1.05) + 1024, dtype=flat.dtype).pin_memory()
-                pinned[name][: flat.numel()].copy_(flat, non_blocking=True)
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            if s > 0:
-                times.append(float(tt.item()))
-        nnz_local = int(g["snn"][1].numel())
-        e2e = {"value": n / statistics.median(times), "unit": "cells/s", "h2d_bytes_per_step": n * d * 8,
-               "d2h_bytes_per_step": (e - b) * k * 12 + 8 * (e - b + 1) + 12 * nnz_local,
-               "ms_per_step": 1e3 * statistics.median(times),
-               "note": "H2D once on rank 0 + NCCL broadcast of the embedding; D2H bytes are per rank"}
+        e2e = e2e_multi(args, cfg, X, rank, world, local, dev, barrier, main_last)
+
+    # ---- a second workload without the mixture's coarse cluster structure (1 GPU only) ------
+    other = None
+    if world == 1 and not args.no_extra_workload and args.config == "C":
+        other = []
+        Xo = shaped_embedding("pca_like", n, d)
+        refo = torch.from_numpy(Xo).to(dev)
+        for _ in range(2):
+            step(False, refo)
+        ms_o = timed_steps(lambda: step(False, refo), 3)
+        ko = last["knn"]
+        other.append({"workload": f"pca_like: decaying spectrum, 40 clusters of very different sizes, {n} x {d}, k={k}",
+                      "ms_per_step": ms_o, "value": n / (ms_o / 1e3), "unit": "cells/s",
+                      "tiles_visited_frac": ko.get("knn_tiles_visited", 0) / max(1, ko.get("knn_tiles_total", 1)),
+                      "n_uncertified": ko.get("n_uncertified"), "nnz_snn": last["graphs"]["nnz_snn"]})
+        del refo
 
     if rank != 0:
         if world > 1:
@@ -356,59 +451,112 @@ def main():
     # ---- roofline of the dominant kernel + the SNN stage --------------------------------
     st = {kk: vv / args.steps for kk, vv in stage_ms.items()}
     nq_local = e - b
-    knn_ms = st["knn_cand"] if st["knn_cand"] > 0 else st["knn_fallback"]
-    flops = 2.0 * nq_local * n * d
-    tensor_peak = peaks["bf16_tflops_sustained"]
-    ks = last["knn"]
-    tv, tt = ks.get("knn_tiles_visited", 0), ks.get("knn_tiles_total", 0)
-    roofline = {"kernel": "k_knn_tc (tcgen05 candidates, both passes + list building)" if st["knn_cand"] > 0
-                else "k_knn_exact (FP64 scan, no tensor cores)",
-                "bound": "tensor", "achieved": flops / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else None,
-                "peak": tensor_peak, "unit": "TFLOP/s", "frac": None, "traffic": traffic_from_profiles("k_knn_tc"),
-                "peak_source": peaks["source"] + " bf16 sustained", "algorithmic_flops_per_launch": flops,
-                "ms_per_launch": knn_ms}
-    if roofline["achieved"]:
-        roofline["frac"] = roofline["achieved"] / tensor_peak
-    if tt:
-        # the grouped search skips (item, tile) pairs that provably hold no neighbour, so the
-        # ALGORITHMIC rate can exceed the tensor peak; the executed rate cannot
-        exec_flops = 2.0 * tv * 256 * 128 * 64
-        roofline.update({
-            "tiles_visited": tv, "tiles_total": tt, "tiles_visited_frac": tv / tt,
-            "executed_mma_tflops": exec_flops / (knn_ms * 1e-3) / 1e12 if knn_ms > 0 else None,
-            "candidates_per_s_executed": tv * 256 * 128 / (knn_ms * 1e-3) if knn_ms > 0 else None,
-            "note": ("frac uses the algorithmic 2*nq*nr*d FLOPs of SURVEY 8d; the grouped search visits only "
-                     "tiles_visited_frac of the key tiles (bound-based skipping, result certified exact). "
-                     "The exhaustive scan (--scan-mode 1) is limited by the epilogue (TMEM reads + selection) at 19-20 keys/clk/SM, "
-                     "see DESIGN.md section 4")})
-    g = last["graphs"]
+    ks = main_last["knn"]
+    tensor_path = st["knn_cand"] > 0
+    sm_count, sm_hz = 148, (clocks or {}).get("sm_mhz") or 1965.0
+    if tensor_path:
+        tv, tt = ks.get("knn_tiles_visited", 0), ks.get("knn_tiles_total", 0)
+        k1_ms = st["knn_pass2"] if st["knn_pass2"] > 0 else st["knn_cand"]
+        exec_flops = 2.0 * tv * 256 * 128 * 64          # every visited (item, tile) pair issues M256 N128 K64
+        achieved = exec_flops / (k1_ms * 1e-3) / 1e12
+        keys_clk_sm = tv * 256 * 128 / (k1_ms * 1e-3) / (sm_count * sm_hz * 1e6)
+        roofline = {"kernel": "k_knn_tc (tcgen05; the pass-2 launch of the grouped search)", "bound": "tensor",
+                    "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " bf16 sustained",
+                    "traffic": traffic_from_profiles("k_knn_tc", world),
+                    "executed_flops_per_launch": exec_flops, "ms_per_launch": k1_ms,
+                    "tiles_visited": tv, "tiles_total": tt, "tiles_visited_frac": tv / tt if tt else None,
+                    "algorithmic_equiv_tflops": 2.0 * nq_local * n * d / (st["knn_cand"] * 1e-3) / 1e12,
+                    "keys_per_clk_per_sm": keys_clk_sm,
+                    "note": ("frac = executed MMA FLOPs / time / sustained bf16 peak.  The kernel is not MMA-bound: every key "
+                             "costs 4 B of TMEM->RF traffic plus the selection, and the exhaustive scan saturates at "
+                             "19-20 keys/clk/SM (TMEM read); algorithmic_equiv_tflops is SURVEY 8d's 2*nq*nr*d over the whole "
+                             "candidate stage and exceeds any peak because bound-based pruning skips "
+                             "1 - tiles_visited_frac of the key tiles")}
+    else:
+        flops = 3.0 * nq_local * n * d
+        roofline = {"kernel": "k_knn_exact (FP64 scan, no tensor cores)", "bound": "tensor",
+                    "achieved": flops / (st["knn_fallback"] * 1e-3) / 1e12 if st["knn_fallback"] > 0 else None,
+                    "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": None, "traffic": None}
+    g = main_last["graphs"]
     rows_local = e - b
     snn_bytes = 4.0 * n * k + (4.0 * (n + 1) + 12.0 * g["nnz_nn"]) + (4.0 * (rows_local + 1) + 12.0 * g["nnz_snn"])
     snn_ms = st["nn_graph"] + st["snn"]
-    roofline_snn = {"kernel": "K3 transpose + K4 SNN rows (stage total)", "bound": "hbm",
+    roofline_snn = {"kernel": "K3 transpose + K4 SNN rows (stage total, all launches)", "bound": "hbm",
                     "achieved": snn_bytes / (snn_ms * 1e-3) / 1e9 if snn_ms > 0 else None, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "algorithmic_bytes": snn_bytes, "ms": snn_ms,
-                    "expanded_bytes": 4.0 * g.get("snn_expanded", 0),
-                    "traffic": traffic_from_profiles("k_snn_rows_filter")}
+                    "expanded_occurrences": g.get("snn_expanded", 0),
+                    "occurrences_per_clk_per_sm": g.get("snn_expanded", 0) / (st["snn"] * 1e-3) / (sm_count * sm_hz * 1e6)
+                    if st["snn"] > 0 else None,
+                    "traffic": traffic_from_profiles("snn_stage", world),
+                    "traffic_source": "sum of dram bytes over every K3 + K4 launch of one step, committed ncu launch list "
+                                      "(profiles/r02_traffic.json); null when no capture exists for this N"}
     if roofline_snn["achieved"]:
         roofline_snn["frac"] = roofline_snn["achieved"] / peaks["hbm_gbs"]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        import oracle
-        idx1 = (last["idx0"].cpu().numpy() + 1).astype(np.int32)
-        cpu = cpu_baseline(X, k, idx1, args.cpu_knn_sample, args.cpu_snn_rows, oracle.num_threads())
+        idx1 = (main_last["idx0"].cpu().numpy() + 1).astype(np.int32)
+        cpu = cpu_reference(X, k, idx1, args.cpu_knn_sample, args.cpu_knn_sample_1core, args.cpu_snn_rows,
+                            host_threads())
 
     line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f16 tensor candidates + f64 re-rank" if st["knn_cand"] > 0 else "f64",
+            "vs_baseline": None, "dtype": "f16 tensor candidates + f64 re-rank" if tensor_path else "f64",
             "data": "synthetic", "config": workload_config(cfg, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "roofline_snn": roofline_snn, "cpu_baseline": cpu,
-            "stage_ms_per_step": st, "n_uncertified": last["knn"].get("n_uncertified"),
-            "nnz_snn": g["nnz_snn"], "max_indegree": g.get("max_indegree")}
+            "verify": verify, "stage_ms_per_step": st, "n_uncertified": ks.get("n_uncertified"),
+            "nnz_snn": g["nnz_snn"], "max_indegree": g.get("max_indegree"), "other_workloads": other}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_multi(args, cfg, X, rank, world, local, dev, barrier, main_last):
+    """N > 1: rank 0 drives all N devices through the single-process multi-device C ABI
+    (b200nn_multi_find_neighbors_*): every device uploads its slice of the page-locked host
+    embedding over its own PCIe link, the slices and the kNN index travel between the devices
+    over NVLink, and the complete result (idx, dist, nn Graph, one SNN dgCMatrix) lands in
+    rank 0's host buffers.  The other ranks wait at the barrier."""
+    import torch
+    import torch.distributed as dist
+    from seurat_b200 import _lib
+    n, d, k = cfg["n"], cfg["d"], cfg["k"]
+    res = None
+    torch.cuda.empty_cache()
+    barrier()
+    if rank == 0:
+        try:
+            m = _lib.MultiContext(list(range(world)))
+            Xp = torch.from_numpy(X).pin_memory()
+            Xh = Xp.numpy()
+            nnz_nn = main_last["graphs"]["nnz_nn"]
+            pin = lambda count, dt: torch.empty(count, dtype=dt).pin_memory().numpy()  # noqa: E731
+            out = {"idx": pin(n * k, torch.int32).reshape(n, k), "dist": pin(n * k, torch.float64).reshape(n, k),
+                   "nn_p": pin(n + 1, torch.int32), "nn_i": pin(nnz_nn, torch.int32), "nn_x": pin(nnz_nn, torch.float64)}
+            times = []
+            r = None
+            for s in range(1 + max(1, args.e2e_steps)):
+                t0 = time.perf_counter()
+                r = m.find_neighbors(Xh, k, PRUNE, True, _lib.ROW_MAJOR, args.knn_algo, args.n_cand, out=out,
+                                     scan_mode=args.scan_mode, pinned_snn=True)
+                t1 = time.perf_counter()
+                if s > 0:
+                    times.append(t1 - t0)
+            nnz_snn = r["stats"]["nnz_snn"]
+            res = {"value": n / statistics.median(times), "unit": "cells/s", "h2d_bytes_per_step": n * d * 8,
+                   "d2h_bytes_per_step": n * k * 12 + 2 * 4 * (n + 1) + 12 * (nnz_nn + nnz_snn),
+                   "ms_per_step": 1e3 * statistics.median(times),
+                   "api": f"b200nn_multi_find_neighbors_count/_fill on {world} devices from one process (host buffers, page-locked)",
+                   "stage_ms": {kk: vv for kk, vv in r["stats"].items() if kk.startswith("ms_")},
+                   "delivers": "idx, dist, nn Graph and ONE gathered SNN dgCMatrix in host memory (as at N = 1)"}
+            if not args.no_verify:
+                res["same_as_value_leg"] = bool((r["idx"] - 1 == main_last["idx_full"].cpu().numpy()).all())
+            m.close()
+        except Exception as ex:  # the value leg must still be reported
+            res = {"value": None, "unit": "cells/s", "error": repr(ex)}
+    barrier()
+    return res
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200NN_VERSION 1
+#define B200NN_VERSION 2
 
 #if defined(__GNUC__)
 #define B200NN_API __attribute__((visibility("default")))
@@ -73,6 +73,14 @@ typedef struct b200nn_opts {
   int32_t n_cand;      /* widened candidate count k' of the tensor path, 0 = auto    */
   int32_t scan_mode;   /* tensor path: 0 = auto, 1 = exhaustive (every reference tile),
                           2 = grouped (tile-pruned); same result, for benchmarking   */
+  /* b200nn_dev_knn only: this call computes share `shard_rank` of `shard_world` of a SELF
+     search (d_qry = NULL).  d_idx0 / d_dist are then FULL [nr x k] buffers of which only the
+     rows of this share are written.  Which rows a share owns is the library's choice (whole
+     groups of the tile-pruned search, so that every share keeps full work items); every share
+     of a call with the same data makes the same choice, and the shares partition the rows.
+     Callers zero-fill d_idx0 and combine the shares with a sum (all-reduce).  0 / 0 = off. */
+  int32_t shard_rank;
+  int32_t shard_world;
 } b200nn_opts;
 
 typedef struct b200nn_stats {
@@ -92,6 +100,8 @@ typedef struct b200nn_stats {
   int64_t gpu_launches;   /* kernels launched by this call                           */
   int64_t knn_tiles_visited; /* (work item, reference tile) pairs the tensor kernel scanned  */
   int64_t knn_tiles_total;   /* ... out of this many (equal for the exhaustive scan)         */
+  double ms_knn_pass2;       /* the dominant launch of K1 alone (pass 2 of the grouped search, or the
+                                exhaustive scan); part of ms_knn_cand                         */
 } b200nn_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -184,6 +194,37 @@ B200NN_API int32_t b200nn_index_dims(const b200nn_index *index);
 B200NN_API int b200nn_index_knn(b200nn_ctx *ctx, const b200nn_index *index, const double *qry, int64_t nq,
                                 int32_t k, int32_t *idx_out, double *dist_out, const b200nn_opts *opts,
                                 b200nn_stats *stats);
+
+/* ---- several devices from one process ------------------------------------ */
+/*
+ * FindNeighbors.default is called from a single-threaded R process
+ * (R/clustering.R:633-682), so the sharding over 1/2/4/8 GPUs lives inside the
+ * library: one worker thread, context and stream per device.  Query cells are
+ * split contiguously; every device uploads its slice of the embedding over its
+ * own PCIe link, the slices and later the int32 kNN index are exchanged between
+ * the devices over NVLink (peer copies), every device emits the SNN rows of its
+ * share, and all results land in the caller's host buffers as ONE Neighbor /
+ * dgCMatrix -- same contract as the single-device entry points above.
+ * devices == NULL: devices 0 .. n_devices-1; n_devices <= 0: every visible device.
+ * A device may be listed more than once (the shards then share it).
+ */
+typedef struct b200nn_multi b200nn_multi;
+B200NN_API int b200nn_multi_create(const int32_t *devices, int32_t n_devices, b200nn_multi **multi_out);
+B200NN_API void b200nn_multi_destroy(b200nn_multi *multi);
+B200NN_API int32_t b200nn_multi_size(const b200nn_multi *multi);
+/* same contract as b200nn_knn */
+B200NN_API int b200nn_multi_knn(b200nn_multi *multi, const double *ref, int64_t nr, const double *qry, int64_t nq,
+                                int32_t d, int32_t k, int32_t *idx_out, double *dist_out,
+                                const b200nn_opts *opts, b200nn_stats *stats);
+/* same contract as b200nn_find_neighbors_count / _fill (stats: maximum over the devices of the
+ * stage times, sums of the counters; ms_h2d includes the NVLink exchange of the embedding) */
+B200NN_API int b200nn_multi_find_neighbors_count(b200nn_multi *multi, const double *data, int64_t n, int32_t d,
+                                                 int32_t k, double prune, int32_t compute_snn,
+                                                 int32_t *idx_out, double *dist_out, int32_t *nn_p_out,
+                                                 int32_t *nn_i_out, double *nn_x_out, const b200nn_opts *opts,
+                                                 int64_t *nnz_nn_out, int64_t *nnz_snn_out, b200nn_stats *stats);
+B200NN_API int b200nn_multi_find_neighbors_fill(b200nn_multi *multi, int32_t *nn_p, int32_t *nn_i, double *nn_x,
+                                                int32_t *snn_p, int32_t *snn_i, double *snn_x);
 
 /* ---- device-buffer entry points ---------------------------------------- */
 /* All pointers are device pointers on the context's device.  Work is queued

@@ -1,7 +1,7 @@
 """seurat_b200 -- B200-native (sm_100a) implementation of Seurat's FindNeighbors
 hot path: exact kNN (the nn.method="rann" arm of NNHelper) + nn Graph + SNN
 (ComputeSNN), behind the reference's own interface.  See DESIGN.md."""
-from ._lib import B200Error, Context, default_context, device_count  # noqa: F401
+from ._lib import B200Error, Context, MultiContext, default_context, device_count  # noqa: F401
 from .neighbors import (Cells, ComputeSNN, Distances, Embedding, FindNeighbors,  # noqa: F401
                         FindNeighborsSeurat, Graph, Indices, L2Norm, Neighbor, NNHelper, SeuratLite)
 

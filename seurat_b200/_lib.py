@@ -28,6 +28,8 @@ SYMBOLS = [
     "b200nn_find_neighbors_count", "b200nn_find_neighbors_fill",
     "b200nn_index_create", "b200nn_index_destroy", "b200nn_index_rows", "b200nn_index_dims", "b200nn_index_knn",
     "b200nn_dev_knn", "b200nn_dev_knn_candidates", "b200nn_dev_graphs", "b200nn_dev_result", "b200nn_dev_copy_result",
+    "b200nn_multi_create", "b200nn_multi_destroy", "b200nn_multi_size", "b200nn_multi_knn",
+    "b200nn_multi_find_neighbors_count", "b200nn_multi_find_neighbors_fill",
 ]
 
 
@@ -40,7 +42,7 @@ class B200Error(RuntimeError):
 
 class Opts(C.Structure):
     _fields_ = [("layout", C.c_int32), ("knn_algo", C.c_int32), ("n_cand", C.c_int32),
-                ("scan_mode", C.c_int32)]
+                ("scan_mode", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -49,7 +51,8 @@ class Stats(C.Structure):
                  "ms_nn_graph", "ms_snn", "ms_d2h")] + \
                [(n, C.c_int64) for n in
                 ("n_uncertified", "nnz_nn", "nnz_snn", "snn_expanded", "max_indegree",
-                 "gpu_launches", "knn_tiles_visited", "knn_tiles_total")]
+                 "gpu_launches", "knn_tiles_visited", "knn_tiles_total")] + \
+               [("ms_knn_pass2", C.c_double)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -104,6 +107,16 @@ def load() -> C.CDLL:
                                         C.POINTER(Stats)]
         L.b200nn_dev_result.argtypes = [vp, i32, C.POINTER(DevCsr)]
         L.b200nn_dev_copy_result.argtypes = [vp, i32, vp, vp, vp]
+        L.b200nn_multi_create.argtypes = [vp, i32, C.POINTER(vp)]
+        L.b200nn_multi_destroy.argtypes = [vp]
+        L.b200nn_multi_destroy.restype = None
+        L.b200nn_multi_size.argtypes = [vp]
+        L.b200nn_multi_size.restype = i32
+        L.b200nn_multi_knn.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, C.POINTER(Opts), C.POINTER(Stats)]
+        L.b200nn_multi_find_neighbors_count.argtypes = [vp, vp, i64, i32, i32, dbl, i32, vp, vp, vp, vp, vp,
+                                                        C.POINTER(Opts), C.POINTER(i64), C.POINTER(i64),
+                                                        C.POINTER(Stats)]
+        L.b200nn_multi_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         _lib = L
         return L
 
@@ -262,8 +275,9 @@ class Context:
 
     # ---- device-buffer calls (pointers or torch CUDA tensors) --------------
     def dev_knn(self, d_ref, nr: int, d_qry, nq: int, d: int, k: int, d_idx0, d_dist,
-                algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0) -> dict:
-        o = Opts(ROW_MAJOR, algo, n_cand, scan_mode)
+                algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0, shard_rank: int = 0,
+                shard_world: int = 0) -> dict:
+        o = Opts(ROW_MAJOR, algo, n_cand, scan_mode, shard_rank, shard_world)
         st = Stats()
         check(self._L.b200nn_dev_knn(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, k, _ptr(d_idx0),
                                      _ptr(d_dist), C.byref(o), C.byref(st)))
@@ -294,6 +308,133 @@ class Context:
     def dev_copy_result(self, which: int, d_p, d_i, d_x) -> None:
         """Device-to-device copy of a result into caller buffers (p is int64)."""
         check(self._L.b200nn_dev_copy_result(self._h, which, _ptr(d_p), _ptr(d_i), _ptr(d_x)))
+
+
+class MultiContext:
+    """Several devices driven from this process (b200nn_multi_*): what the R shim creates when more
+    than one GPU is visible.  ``knn`` and ``find_neighbors`` have the signatures of :class:`Context`,
+    so ``FindNeighbors(..., ctx=MultiContext([0, 1, 2, 3]))`` shards the call; the stages that take an
+    existing index (``ComputeSNN`` / nn Graph alone, resident indexes) run on the first device."""
+
+    def __init__(self, devices=None):
+        L = load()
+        self._L = L
+        self._h = C.c_void_p(None)
+        self._single = None
+        if devices is None:
+            arr, n = None, 0
+        else:
+            devices = [int(x) for x in devices]
+            arr, n = (C.c_int32 * len(devices))(*devices), len(devices)
+        check(L.b200nn_multi_create(arr, n, C.byref(self._h)))
+        self.devices = devices if devices is not None else list(range(self.size))
+
+    @property
+    def size(self) -> int:
+        return int(self._L.b200nn_multi_size(self._h))
+
+    @property
+    def device(self) -> int:
+        return self.devices[0]
+
+    def _first(self) -> Context:
+        if self._single is None:
+            self._single = Context(self.devices[0])
+        return self._single
+
+    def close(self) -> None:
+        if getattr(self, "_single", None) is not None:
+            self._single.close()
+            self._single = None
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.b200nn_multi_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def knn(self, ref, qry, k: int, layout: int, algo: int = KNN_AUTO, n_cand: int = 0, scan_mode: int = 0):
+        nr, d = ref.shape
+        nq = nr if qry is None else qry.shape[0]
+        order = "C" if layout == ROW_MAJOR else "F"
+        idx = np.empty((nq, k), dtype=np.int32, order=order)
+        dist = np.empty((nq, k), dtype=np.float64, order=order)
+        o = Opts(layout, algo, n_cand, scan_mode)
+        st = Stats()
+        check(self._L.b200nn_multi_knn(self._h, _ptr(ref), nr, _ptr(qry), nq, d, k, _ptr(idx), _ptr(dist),
+                                       C.byref(o), C.byref(st)))
+        return idx, dist, st.as_dict()
+
+    def find_neighbors(self, data, k: int, prune: float, compute_snn: bool, layout: int,
+                       algo: int = KNN_AUTO, n_cand: int = 0, want_knn: bool = True,
+                       out: dict | None = None, scan_mode: int = 0, pinned_snn: bool = False):
+        """Same contract as :meth:`Context.find_neighbors`.  ``pinned_snn`` allocates the SNN arrays
+        page-locked (through torch) when the caller did not pass ``snn_*`` buffers."""
+        n, d = data.shape
+        order = "C" if layout == ROW_MAJOR else "F"
+        out = out or {}
+        idx = dist = None
+        if want_knn:
+            idx, dist = out.get("idx"), out.get("dist")
+            if idx is None:
+                idx = np.empty((n, k), dtype=np.int32, order=order)
+            if dist is None:
+                dist = np.empty((n, k), dtype=np.float64, order=order)
+        o = Opts(layout, algo, n_cand, scan_mode)
+        st = Stats()
+        nnz_nn, nnz_snn = C.c_int64(0), C.c_int64(0)
+        early = {}
+        for name, count, dt in (("nn_p", n + 1, np.int32), ("nn_i", n * k, np.int32), ("nn_x", n * k, np.float64)):
+            a = out.get(name)
+            if a is not None and a.size >= count and a.dtype == dt and a.flags.c_contiguous:
+                early[name] = a
+        if len(early) != 3:
+            early = {}
+        check(self._L.b200nn_multi_find_neighbors_count(self._h, _ptr(data), n, d, k, float(prune),
+                                                        1 if compute_snn else 0, _ptr(idx), _ptr(dist),
+                                                        _ptr(early.get("nn_p")), _ptr(early.get("nn_i")),
+                                                        _ptr(early.get("nn_x")), C.byref(o), C.byref(nnz_nn),
+                                                        C.byref(nnz_snn), C.byref(st)))
+
+        def buf(name, count, dtype, pinned=False):
+            a = out.get(name)
+            if a is not None and a.size >= count:
+                return a[:count] if a.size != count else a
+            if pinned:
+                import torch
+                return torch.empty(count, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory().numpy()
+            return np.empty(count, dtype=dtype)
+
+        if early:
+            nn_p, nn_i, nn_x = early["nn_p"][:n + 1], early["nn_i"][:nnz_nn.value], early["nn_x"][:nnz_nn.value]
+            fill_nn = (None, None, None)
+        else:
+            nn_p, nn_i, nn_x = buf("nn_p", n + 1, np.int32), buf("nn_i", nnz_nn.value, np.int32), \
+                buf("nn_x", nnz_nn.value, np.float64)
+            fill_nn = (nn_p, nn_i, nn_x)
+        snn = (None, None, None)
+        if compute_snn:
+            snn = (buf("snn_p", n + 1, np.int32, pinned_snn), buf("snn_i", nnz_snn.value, np.int32, pinned_snn),
+                   buf("snn_x", nnz_snn.value, np.float64, pinned_snn))
+        if fill_nn[0] is not None or compute_snn:
+            check(self._L.b200nn_multi_find_neighbors_fill(self._h, _ptr(fill_nn[0]), _ptr(fill_nn[1]),
+                                                           _ptr(fill_nn[2]), _ptr(snn[0]), _ptr(snn[1]),
+                                                           _ptr(snn[2])))
+        return {"idx": idx, "dist": dist, "nn": (nn_p, nn_i, nn_x), "snn": snn if compute_snn else None,
+                "stats": st.as_dict()}
+
+    # stages that start from an existing index run on the first device
+    def compute_snn(self, nn_ranked, prune: float, layout: int):
+        return self._first().compute_snn(nn_ranked, prune, layout)
+
+    def nn_graph(self, nn_ranked, n: int, layout: int):
+        return self._first().nn_graph(nn_ranked, n, layout)
+
+    def index(self, ref, layout: int) -> "Index":
+        return self._first().index(ref, layout)
 
 
 _default_ctx: dict[int, Context] = {}

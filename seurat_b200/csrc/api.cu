@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libb200nn.so (see include/b200nn.h).
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 
 #include "internal.cuh"
@@ -141,6 +142,10 @@ int download_csr(b200nn_ctx *ctx, const CsrResult &r, int32_t *p, int32_t *i, do
   return B200NN_OK;
 }
 
+}  // namespace
+
+b200nn_opts b200nn_default_opts() { return default_opts(); }
+
 int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
                  int d, int k, const b200nn_opts &o, int32_t *d_idx0, double *d_dist,
                  b200nn_stats *stats) {
@@ -160,6 +165,33 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
   if (nq == 0) return B200NN_OK;
   const double *q = d_qry ? d_qry : d_ref;
   int algo = o.knn_algo;
+  ctx->owned_rows = nullptr;
+  ctx->owned_slots = 0;
+  ctx->owned_b = 0;
+  ctx->owned_e = nq;
+  const bool sharded = o.shard_world > 1;
+  if (sharded) {
+    if (q != d_ref || nq != nr || o.shard_rank < 0 || o.shard_rank >= o.shard_world || o.shard_world > 64) {
+      b200nn_set_error("knn: a sharded call must be a self search (d_qry = NULL) with 0 <= rank < world <= 64");
+      return B200NN_ERR_INVALID;
+    }
+    const bool tc = algo != B200NN_KNN_EXACT && knn_tc_applicable(nr, nq, d, k);
+    if (!(tc && knn_tc_grouped(nr, o.scan_mode & 3))) {
+      // no grouping to align the shares with: contiguous rows [b, e) of the full-size outputs
+      const int64_t per = ceil_div64(nr, o.shard_world);
+      const int64_t b = std::min<int64_t>((int64_t)o.shard_rank * per, nr), e = std::min<int64_t>(b + per, nr);
+      ctx->owned_b = b;
+      ctx->owned_e = e;
+      if (e <= b) return B200NN_OK;
+      b200nn_opts o1 = o;
+      o1.shard_rank = o1.shard_world = 0;
+      int rc = knn_dispatch(ctx, d_ref, nr, d_ref + b * d, e - b, d, k, o1, d_idx0 + b * k, d_dist + b * k, stats);
+      ctx->owned_rows = nullptr;
+      ctx->owned_b = b;
+      ctx->owned_e = e;
+      return rc;
+    }
+  }
   if (algo == B200NN_KNN_AUTO)
     algo = knn_tc_applicable(nr, nq, d, k) ? B200NN_KNN_TENSOR : B200NN_KNN_EXACT;
   if (algo == B200NN_KNN_TENSOR) {
@@ -167,8 +199,11 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
       b200nn_set_error("tensor-core kNN path does not cover nr=%lld d=%d k=%d", (long long)nr, d, k);
       return B200NN_ERR_INVALID;
     }
-    return knn_tc_launch(ctx, d_ref, nr, q, nq, d, k, o.n_cand, o.scan_mode & 3, d_idx0, d_dist, stats);
+    return knn_tc_launch(ctx, d_ref, nr, q, nq, d, k, o.n_cand, o.scan_mode & 3, d_idx0, d_dist, stats,
+                         sharded ? o.shard_rank : 0, sharded ? o.shard_world : 0);
   }
+  RC_TRY(check_finite_f64(ctx, d_ref, nr * (int64_t)d, "data"));
+  if (q != d_ref) RC_TRY(check_finite_f64(ctx, q, nq * (int64_t)d, "query"));
   Timer t(ctx, 4);
   RC_TRY(t.start());
   RC_TRY(knn_exact_launch(ctx, d_ref, nr, q, nq, d, k, nullptr, 0, d_idx0, d_dist));
@@ -176,7 +211,6 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
   return B200NN_OK;
 }
 
-}  // namespace
 
 extern "C" {
 
@@ -228,7 +262,9 @@ int b200nn_ctx_create(int device, b200nn_ctx **ctx_out) {
     ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   }
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming);
   for (auto &ev : ctx->ev)
     if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
   if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(DevInfo));
@@ -250,8 +286,14 @@ void b200nn_ctx_destroy(b200nn_ctx *ctx) {
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+  }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;

@@ -87,6 +87,11 @@ enum WsSlot {
   WS_TC_IBUF,      // group ids, permutations, offsets, list counts
   WS_TC_FBUF,      // centroids, radii, item balls
   WS_TC_TILES,     // per-item tile lists
+  WS_FLAG,         // one int32 flag (finite check)
+  WS_TC_CENT16,    // fp16 operand rows of the group centroids (tensor-core assignment)
+  WS_REV_SORTED,   // reverse lists sorted per column (nn Graph side stream)
+  WS_SCAN_TMP2,    // block sums of scans queued on the side stream
+  WS_DIST_FULL,    // multi-device search: full-size distance scratch of a group-aligned share
   WS_NUM
 };
 
@@ -125,15 +130,23 @@ struct b200nn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device->host copies that overlap later stages
+  cudaStream_t side_stream = nullptr;  // nn Graph columns (sort / emit) while the SNN stage runs
   cudaEvent_t ev[16] = {};
   cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_side = nullptr;   // nn Graph side stream: start / end markers
   WsBuf ws[WS_NUM];
+  std::vector<uint8_t> h_keep;     // SNN lookup tables of the last call (host copies must outlive the H2D)
+  std::vector<double> h_jac;
   DevInfo *h_info = nullptr;  // pinned
   int sm_count = 148;
   int64_t launches = 0;
   CsrResult nn_graph, snn;
   // pending host-buffer results (between *_count and *_fill)
   bool pending_nn = false, pending_snn = false;
+  // rows written by the last sharded kNN call (opts.shard_world > 1): either the `owned_slots`
+  // entries of owned_rows (device; -1 = padding) or, when owned_rows is null, rows [owned_b, owned_e)
+  const int32_t *owned_rows = nullptr;
+  int64_t owned_slots = 0, owned_b = 0, owned_e = 0;
 };
 
 // grow-only workspace allocation; returns nullptr + error code via rc
@@ -154,13 +167,16 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // ---------------------------------------------------------------------------
 
 // util.cu
-int scan_exclusive_i32_to_i64(b200nn_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n);
+int scan_exclusive_i32_to_i64(b200nn_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n,
+                              cudaStream_t stream = nullptr, int tmp_slot = -1);
 // out[r * ncol + c] = in[c * nrow + r] (+ add)   (column-major -> row-major)
 int transpose_f64(b200nn_ctx *ctx, const double *d_in, double *d_out, int64_t nrow, int64_t ncol);
 int transpose_i32_add(b200nn_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t nrow,
                       int64_t ncol, int32_t add);
 int add_i32(b200nn_ctx *ctx, const int32_t *d_in, int32_t *d_out, int64_t n, int32_t add);
-int narrow_i64_to_i32(b200nn_ctx *ctx, const int64_t *d_in, int32_t *d_out, int64_t n);
+int narrow_i64_to_i32(b200nn_ctx *ctx, const int64_t *d_in, int32_t *d_out, int64_t n, cudaStream_t stream = nullptr);
+// B200NN_ERR_INVALID ("NA/NaN/Inf in foreign function call") when x holds a non-finite value
+int check_finite_f64(b200nn_ctx *ctx, const double *d_x, int64_t count, const char *what);
 
 // knn_exact.cu : FP64 exhaustive scan.  d_qsel == nullptr: queries 0..nq-1;
 // otherwise the kernel processes the n_sel query rows listed in d_qsel
@@ -197,11 +213,18 @@ int knn_exact_grouped_launch(b200nn_ctx *ctx, const double *d_ref, const double 
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k);
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                   int64_t nq, int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
-                  b200nn_stats *stats);
+                  b200nn_stats *stats, int shard_rank = 0, int shard_world = 0);
+// true when knn_tc_launch would run the grouped (tile-pruned) search for this shape
+bool knn_tc_grouped(int64_t nr, int scan_mode);
 
 int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
                  int d, int kp, int scan_mode, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
                  double *h_scale_mu);
+
+// api.cu : algorithm selection + argument checks of the kNN stage (device pointers, row-major)
+b200nn_opts b200nn_default_opts();
+int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
+                 int d, int k, const b200nn_opts &o, int32_t *d_idx0, double *d_dist, b200nn_stats *stats);
 
 // snn.cu
 // optional host destination of the nn Graph (capacity n_rows * k entries): copied on the

@@ -60,7 +60,11 @@ constexpr int NUM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;  // 16 KB (A tile == B tile)
 constexpr int MAX_D = BK - 3;       // 61
 constexpr int MAX_KP = 48;          // shared-memory budget of the candidate lists
-constexpr double ETA_COEF = 64.0 * 5.9604644775390625e-08;  // 64 * 2^-24
+// FP32 accumulation error of one key: each of the `ksteps` K = 16 MMAs adds 16 products to the
+// running sum; with a truncating aligned adder every partial result is within 2^-23 of the
+// largest magnitude M involved, so |error| <= ksteps * 17 * 2^-23 * M (provable, not
+// the measured 4 * 2^-24 * M)
+constexpr double ETA_PER_KSTEP = 17.0 * 1.1920928955078125e-07;  // 17 * 2^-23
 constexpr double NORM_TARGET = 32000.0;
 
 struct TcMisc {            // small device-resident state of one kNN call
@@ -72,6 +76,8 @@ struct TcMisc {            // small device-resident state of one kNN call
   double qn2_max;
   int32_t n_fail;
   int32_t hang;            // set when an mbarrier wait timed out
+  int32_t nonfinite;       // some input coordinate is NA / NaN / Inf (nn2 refuses those: .C(NAOK = FALSE))
+  int32_t pad_;
   long long tiles_visited; // (item, tile) pairs of the last candidate launch
   long long tiles_total;
 };
@@ -284,6 +290,7 @@ struct TcParams {
   int32_t pass1;         // 1: only item_T is produced
   const int32_t *order;  // items by decreasing list length (null: identity)
   const float *tau_init; // pass 2: per-row threshold found by pass 1 (null: start from +inf)
+  int32_t *argmin_out;   // group assignment: only the reference row with the smallest key is wanted
 };
 
 // Item visited by CTA `b` in its round `i`: positions are dealt out in a snake so that the
@@ -557,7 +564,20 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
       }
       // flush this thread's candidates
       S = merge_pending(lk, li, pk, pi, kp, LSTRIDE, S);
-      if (oq >= 0) {
+      if (oq >= 0 && P.argmin_out) {
+        // nearest-centroid assignment: the smallest key of the list (ties: lower id), deterministic
+        float bk = CUDART_INF_F;
+        int bi = 0;
+        for (int e = 0; e < S.cnt_list; ++e) {
+          const float key = lk[e * LSTRIDE];
+          const int id = li[e * LSTRIDE];
+          if (key < bk || (key == bk && id < bi)) {
+            bk = key;
+            bi = id;
+          }
+        }
+        P.argmin_out[oq] = bi;
+      } else if (oq >= 0) {
         const float tq = S.cnt_list == kp ? S.tau : CUDART_INF_F;
         if (P.pass1) {
           P.tau[oq] = tq;
@@ -632,6 +652,7 @@ k_mean_final(const double *__restrict__ partial, int64_t n, int d, TcMisc *__res
     misc->qn2_max = 0.0;
     misc->n_fail = 0;
     misc->hang = 0;
+    misc->nonfinite = 0;
     misc->tiles_visited = 0;
     misc->tiles_total = 0;
   }
@@ -655,6 +676,7 @@ k_max_norm(const double *__restrict__ X, int64_t n, int d, TcMisc *__restrict__ 
       double y = x[j] - mu[j];
       n2 += y * y;
     }
+    if (!isfinite(n2)) misc->nonfinite = 1;  // any NaN / Inf coordinate (or mean) ends up here
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n2 = fmax(n2, __shfl_xor_sync(0xffffffffu, n2, o));
@@ -812,7 +834,7 @@ __global__ void k_km_init(const __half *__restrict__ y16, int64_t n, int d, int 
 __global__ void __launch_bounds__(128)
 k_km_assign(const __half *__restrict__ y16, int64_t m, int64_t stride, int d, int G,
             const float *__restrict__ cent, const float *__restrict__ cnorm, int32_t *__restrict__ gid,
-            int32_t *__restrict__ counts, float *__restrict__ sums) {
+            int32_t *__restrict__ counts, long long *__restrict__ sums) {
   __shared__ __align__(16) float cs[KM_CH * BK];
   __shared__ float cn[KM_CH];
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -861,19 +883,23 @@ k_km_assign(const __half *__restrict__ y16, int64_t m, int64_t stride, int d, in
     if (sums) {
 #pragma unroll
       for (int j = 0; j < BK; ++j)
-        if (j < d) atomicAdd(&sums[(size_t)bg * BK + j], y[j]);
+        if (j < d)  // exact fixed-point sum: an FP16 value times 2^24 is an integer, and integer addition is
+                    // associative, so the centroids do not depend on the order of the atomics (every
+                    // device / rank derives the SAME grouping from the same data)
+          atomicAdd(reinterpret_cast<unsigned long long *>(&sums[(size_t)bg * BK + j]),
+                    (unsigned long long)(long long)(y[j] * 16777216.f));
     }
   }
 }
 
-__global__ void k_km_update(float *__restrict__ sums, int32_t *__restrict__ counts, int d,
+__global__ void k_km_update(long long *__restrict__ sums, int32_t *__restrict__ counts, int d,
                             float *__restrict__ cent, float *__restrict__ cnorm) {
   const int g = blockIdx.x, j = threadIdx.x;  // 64 threads
   const int c = counts[g];
   float v = cent[g * BK + j];
-  if (c > 0) v = j < d ? sums[(size_t)g * BK + j] / (float)c : 0.f;
+  if (c > 0) v = j < d ? (float)((double)sums[(size_t)g * BK + j] * (1.0 / 16777216.0) / (double)c) : 0.f;
   cent[g * BK + j] = v;
-  sums[(size_t)g * BK + j] = 0.f;
+  sums[(size_t)g * BK + j] = 0;
   float s = v * v;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -884,6 +910,52 @@ __global__ void k_km_update(float *__restrict__ sums, int32_t *__restrict__ coun
     cnorm[g] = part[0] + part[1];
     counts[g] = 0;
   }
+}
+
+// B operand of the centroids for the tensor-core assignment: rows [-2 ch, h1, h2, h3, 0..] with
+// ch = fp16(c) and h1 + h2 + h3 the FP16 split of |ch|^2; rows g >= G carry key = +inf.  One warp per row.
+__global__ void __launch_bounds__(256)
+k_cent_operand(const float *__restrict__ cent, int G, int G_pad, int d, __half *__restrict__ c16) {
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (g >= G_pad) return;
+  __half h0 = __float2half_rn(0.f), h1 = h0;
+  double n2 = 0.0;
+  if (g < G) {
+    const int j0 = lane, j1 = lane + 32;
+    if (j0 < d) h0 = __float2half_rn(cent[(size_t)g * BK + j0]);
+    if (j1 < d) h1 = __float2half_rn(cent[(size_t)g * BK + j1]);
+    const double a = (double)__half2float(h0), b = (double)__half2float(h1);
+    n2 = a * a + b * b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  const __half s1 = __double2half(n2);
+  const double r1 = n2 - (double)__half2float(s1);
+  const __half s2 = __double2half(r1);
+  const __half s3 = __double2half(r1 - (double)__half2float(s2));
+  for (int j = lane; j < BK; j += 32) {
+    __half o = __float2half_rn(0.f);
+    if (g >= G) o = j == d ? __ushort_as_half(0x7c00) : o;
+    else if (j < d) o = __hmul(j < 32 ? h0 : h1, __float2half_rn(-2.0f));
+    else if (j == d) o = s1;
+    else if (j == d + 1) o = s2;
+    else if (j == d + 2) o = s3;
+    c16[(size_t)g * BK + j] = o;
+  }
+}
+
+// rows per group (shared-memory histogram per block, G <= 1024)
+__global__ void __launch_bounds__(256)
+k_count_gid(const int32_t *__restrict__ gid, int64_t n, int G, int32_t *__restrict__ counts) {
+  __shared__ int s_cnt[1024];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) s_cnt[g] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&s_cnt[min(max(gid[i], 0), G - 1)], 1);
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x)
+    if (s_cnt[g] > 0) atomicAdd(&counts[g], s_cnt[g]);
 }
 
 // padded reference offsets (multiples of BN) and query offsets (multiples of an item); zeroes the cursors
@@ -908,7 +980,8 @@ __global__ void k_group_offsets(const int32_t *__restrict__ rcount, const int32_
 // from a shared-memory histogram instead of once per row (G <= 1024)
 __global__ void __launch_bounds__(256)
 k_group_scatter(const int32_t *__restrict__ gid, int64_t n, int G, const int32_t *__restrict__ off,
-                int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+                int32_t *__restrict__ cursor, int32_t *__restrict__ perm, const int32_t *__restrict__ owner = nullptr,
+                int rank = 0) {
   __shared__ int s_cnt[1024];
   __shared__ int s_base[1024];
   for (int g = threadIdx.x; g < G; g += blockDim.x) s_cnt[g] = 0;
@@ -917,13 +990,194 @@ k_group_scatter(const int32_t *__restrict__ gid, int64_t n, int G, const int32_t
   int g = -1, local = 0;
   if (i < n) {
     g = gid[i];
-    local = atomicAdd(&s_cnt[g], 1);
+    if (owner && owner[g] != rank) g = -1;  // a query row of another share
+    if (g >= 0) local = atomicAdd(&s_cnt[g], 1);
   }
   __syncthreads();
   for (int q = threadIdx.x; q < G; q += blockDim.x)
     if (s_cnt[q] > 0) s_base[q] = atomicAdd(&cursor[q], s_cnt[q]);
   __syncthreads();
-  if (i < n) perm[off[g] + s_base[g] + local] = (int32_t)i;
+  if (g >= 0) perm[off[g] + s_base[g] + local] = (int32_t)i;
+}
+
+// ---------------------------------------------------------------------------
+// Hub-first order inside a group.  With c any fixed point,
+//     key(q, r) = |r - c|^2 - 2 (q - c).(r - c) + const(q):
+// reference points close to their group's centre are near neighbours of EVERY query that
+// visits the group (the "hubs" of high-dimensional data).  Storing each group by increasing
+// a_r = |yh_r - c_g|^2 makes the running thresholds of the candidate kernel fall to their
+// final values within the first tiles of a group, after which whole 32-key chunks are
+// rejected by the min-tree; it also gives every 128-row tile an annulus
+// lo_t <= |r - c_g| <= hi_t that prunes tiles inside a kept group (k_build_lists).
+// The order is a counting sort over NB z-score buckets of a_r per group (any order is valid).
+// ---------------------------------------------------------------------------
+constexpr int FINE_NB = 64;
+
+// a_i = |yh_i - c_gid(i)|^2 per row, and per group sum / sum of squares of a (shared-memory
+// partial sums per block, G <= 1024)
+__global__ void __launch_bounds__(128)
+k_row_anorm(const __half *__restrict__ y16, const int32_t *__restrict__ gid, int64_t n, int d, int G,
+            const float *__restrict__ cent, float *__restrict__ anorm, float *__restrict__ gstat) {
+  __shared__ float s_sum[1024];
+  __shared__ float s_sq[1024];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    s_sum[g] = 0.f;
+    s_sq[g] = 0.f;
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float y[BK];
+    load_y_row(y16, i, d, y);
+    const int g = gid[i];
+    const float4 *cv = reinterpret_cast<const float4 *>(cent + (size_t)g * BK);
+    float a = 0.f;
+#pragma unroll
+    for (int q4 = 0; q4 < BK / 4; ++q4) {
+      const float4 c = cv[q4];
+      const float t0 = y[q4 * 4] - c.x, t1 = y[q4 * 4 + 1] - c.y, t2 = y[q4 * 4 + 2] - c.z, t3 = y[q4 * 4 + 3] - c.w;
+      a = fmaf(t0, t0, a);
+      a = fmaf(t1, t1, a);
+      a = fmaf(t2, t2, a);
+      a = fmaf(t3, t3, a);
+    }
+    anorm[i] = a;
+    if (gstat) {
+      atomicAdd(&s_sum[g], a);
+      atomicAdd(&s_sq[g], a * a);
+    }
+  }
+  if (gstat) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x)
+      if (s_sum[g] != 0.f) {
+        atomicAdd(&gstat[2 * g], s_sum[g]);
+        atomicAdd(&gstat[2 * g + 1], s_sq[g]);
+      }
+  }
+}
+
+// (sum, sum of squares) -> (mean, NB / (6 sd)) per group
+__global__ void k_group_stat_final(float *__restrict__ gstat, const int32_t *__restrict__ rcount, int G) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float c = (float)rcount[g];
+  float mean = 0.f, inv = 0.f;
+  if (c > 0.f) {
+    mean = gstat[2 * g] / c;
+    const float var = gstat[2 * g + 1] / c - mean * mean;
+    inv = var > 1e-12f * mean * mean && var > 0.f ? (float)FINE_NB / (6.f * sqrtf(var)) : 0.f;
+  }
+  gstat[2 * g] = mean;
+  gstat[2 * g + 1] = inv;
+}
+
+__device__ __forceinline__ int fine_bucket(float a, float mean, float inv) {
+  const float z = (a - mean) * inv + 0.5f * FINE_NB;
+  int b = z > 0.f ? (z < (float)FINE_NB ? (int)z : FINE_NB - 1) : 0;  // NaN -> 0
+  return b;
+}
+
+__global__ void __launch_bounds__(256)
+k_fine_count(const int32_t *__restrict__ gid, const float *__restrict__ anorm, int64_t n,
+             const float *__restrict__ gstat, int32_t *__restrict__ fcount) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = gid[i];
+  atomicAdd(&fcount[g * FINE_NB + fine_bucket(anorm[i], gstat[2 * g], gstat[2 * g + 1])], 1);
+}
+
+// one block per group: bucket offsets inside the group's (padded) range; cursors zeroed
+__global__ void __launch_bounds__(FINE_NB)
+k_fine_offsets(const int32_t *__restrict__ fcount, const int32_t *__restrict__ off, int32_t *__restrict__ foff,
+               int32_t *__restrict__ fcursor) {
+  __shared__ int s[FINE_NB];
+  const int g = blockIdx.x, b = threadIdx.x;
+  s[b] = fcount[g * FINE_NB + b];
+  __syncthreads();
+  int pre = 0;
+  for (int u = 0; u < b; ++u) pre += s[u];
+  foff[g * FINE_NB + b] = off[g] + pre;
+  fcursor[g * FINE_NB + b] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_fine_scatter(const int32_t *__restrict__ gid, const float *__restrict__ anorm, int64_t n,
+               const float *__restrict__ gstat, const int32_t *__restrict__ foff, int32_t *__restrict__ fcursor,
+               int32_t *__restrict__ perm, const int32_t *__restrict__ owner, int rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = gid[i];
+  if (owner && owner[g] != rank) return;  // a query row of another share
+  const int f = g * FINE_NB + fine_bucket(anorm[i], gstat[2 * g], gstat[2 * g + 1]);
+  perm[foff[f] + atomicAdd(&fcursor[f], 1)] = (int32_t)i;
+}
+
+// annulus [lo, hi] of |yh_r - c_g| over the rows of every 128-row tile (one warp per tile);
+// rounded outwards.  Padding-only tiles get lo = +inf.
+__global__ void __launch_bounds__(256)
+k_tile_annulus(const int32_t *__restrict__ rperm, const float *__restrict__ anorm, int64_t n_tiles,
+               float *__restrict__ tile_lo, float *__restrict__ tile_hi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_tiles) return;
+  float mn = CUDART_INF_F, mx = 0.f;
+  for (int u = lane; u < BN; u += 32) {
+    const int i = rperm[t * BN + u];
+    if (i >= 0) {
+      const float a = anorm[i];
+      mn = fminf(mn, a);
+      mx = fmaxf(mx, a);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+    tile_lo[t] = mn < CUDART_INF_F ? fmaxf(sqrtf(mn) * 0.9999f - 1e-4f, 0.f) : CUDART_INF_F;
+    tile_hi[t] = sqrtf(mx) * 1.0001f + 1e-4f;
+  }
+}
+
+// Sharded self search (opts.shard_world > 1): whole groups are dealt to the shares, largest first,
+// each to the share with the fewest query rows so far (LPT).  rcount, hence the deal, is identical on
+// every device that runs the same data (the grouping is deterministic), so the shares partition the
+// rows.  qcount[g] = rcount[g] for the groups of `rank`, 0 for the others.
+__global__ void __launch_bounds__(1024)
+k_group_owner(const int32_t *__restrict__ rcount, int G, int world, int rank, int32_t *__restrict__ owner,
+              int32_t *__restrict__ qcount) {
+  __shared__ int s_order[1024];
+  __shared__ int s_owner[1024];
+  const int g = threadIdx.x;
+  if (g < G) {
+    const int c = rcount[g];
+    int pos = 0;
+    for (int h = 0; h < G; ++h) {
+      const int ch = rcount[h];
+      pos += (ch > c || (ch == c && h < g)) ? 1 : 0;
+    }
+    s_order[pos] = g;
+  }
+  __syncthreads();
+  if (g == 0) {
+    long long load[64];
+    for (int r = 0; r < world; ++r) load[r] = 0;
+    for (int p = 0; p < G; ++p) {
+      const int gg = s_order[p];
+      int best = 0;
+      for (int r = 1; r < world; ++r)
+        if (load[r] < load[best]) best = r;
+      s_owner[gg] = best;
+      load[best] += rcount[gg];
+    }
+  }
+  __syncthreads();
+  if (g < G) {
+    owner[g] = s_owner[g];
+    qcount[g] = s_owner[g] == rank ? rcount[g] : 0;
+  }
 }
 
 // padding rows [n, n_pad) of an ungrouped reference operand: key = +inf for every query
@@ -1064,17 +1318,20 @@ k_item_stats(const __half *__restrict__ q16, const int32_t *__restrict__ qperm, 
 // pass 2: every group whose ball may hold a key below the item's bound, plus the pass-1 group.
 constexpr int LIST_THREADS = 256;
 constexpr int PASS1_TILES = 8;
+constexpr int LIST_NBK = 64;  // score buckets of the pass-2 visiting order
 __global__ void __launch_bounds__(LIST_THREADS)
 k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_rad,
               const float *__restrict__ item_T, int G, const float *__restrict__ cent,
-              const float *__restrict__ grad, const int32_t *__restrict__ goff, int pass1,
+              const float *__restrict__ grad, const int32_t *__restrict__ goff,
+              const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, int pass1,
               int64_t list_stride, int32_t *__restrict__ tiles, int32_t *__restrict__ list_cnt) {
   __shared__ float cs[BK];
   __shared__ float s_min[LIST_THREADS / 32];
   __shared__ int s_scan[LIST_THREADS / 32];
   __shared__ float s_dmin;
-  __shared__ float s_gd[LIST_THREADS * 4];
-  __shared__ int s_gn[LIST_THREADS * 4];
+  __shared__ int s_hist[LIST_NBK];
+  __shared__ int s_cur[LIST_NBK];
+  __shared__ int s_total;
   const int item = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (item_rad[item] < 0.f) {  // padding-only item
     if (tid == 0) list_cnt[item] = 0;
@@ -1162,35 +1419,54 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
       pos += ntile[u];
     }
   } else {
-    // pass 2 visits the kept groups by increasing centre distance: the thresholds drop to
-    // their final values within the first few tiles and later tiles yield almost no hits
-    // (the set of visited tiles, hence the result, does not depend on the order)
-#pragma unroll
-    for (int u = 0; u < GPT; ++u) {
-      s_gd[tid * GPT + u] = ntile[u] > 0 ? dist[u] : CUDART_INF_F;
-      s_gn[tid * GPT + u] = ntile[u];
-    }
+    // pass 2.  Inside a kept group every tile is tested against its annulus: for r in tile t,
+    // |q - r| >= | |q - c_g| - |r - c_g| | with |q - c_g| in [D - rho_item, D + rho_item].
+    // Kept tiles are visited by increasing expected squared distance D^2 + lo_t^2 (64 score
+    // buckets, counting sort), so the thresholds reach their final values within the first
+    // tiles and later tiles yield almost no hits.  The set of visited tiles -- hence the
+    // result -- does not depend on the order.  The pass-1 tiles are always visited again.
+    for (int b = tid; b < LIST_NBK; b += LIST_THREADS) s_hist[b] = 0;
     __syncthreads();
-    int before[GPT];
-#pragma unroll
-    for (int u = 0; u < GPT; ++u) before[u] = 0;
-    for (int o = 0; o < G; ++o) {
-      const float od = s_gd[o];
-      const int on = s_gn[o];
+    const float s0 = dmin * dmin;
+    const float inv = (T > 0.f && T < CUDART_INF_F) ? (float)LIST_NBK / (4.f * T) : 0.f;
+    for (int phase = 0; phase < 2; ++phase) {
 #pragma unroll
       for (int u = 0; u < GPT; ++u) {
         const int g = tid * GPT + u;
-        if (od < dist[u] || (od == dist[u] && o < g)) before[u] += on;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < GPT; ++u) {
-      const int g = tid * GPT + u;
-      if (ntile[u] > 0) {
+        if (ntile[u] <= 0) continue;
         const int t0 = goff[g] / BN;
-        for (int t = 0; t < ntile[u]; ++t) dst[before[u] + t] = t0 + t;
+        const float D = dist[u];
+        const bool nearest = D <= dmin;
+        for (int t = 0; t < ntile[u]; ++t) {
+          const float lo = tile_lo[t0 + t], hi = tile_hi[t0 + t];
+          bool keep_t = true;
+          if (!(nearest && t < PASS1_TILES)) {
+            const float lb = fmaxf(lo - (D * 1.00001f + ri), (D * 0.99999f - ri) - hi);
+            keep_t = !(lb > 0.f && lb * lb > T);
+          }
+          if (!keep_t) continue;
+          const float z = (D * D + lo * lo - s0) * inv;
+          const int b = z > 0.f ? (z < (float)LIST_NBK ? (int)z : LIST_NBK - 1) : 0;
+          if (phase == 0)
+            atomicAdd(&s_hist[b], 1);
+          else
+            dst[atomicAdd(&s_cur[b], 1)] = t0 + t;
+        }
+      }
+      __syncthreads();
+      if (phase == 0) {
+        if (tid == 0) {
+          int run = 0;
+          for (int b = 0; b < LIST_NBK; ++b) {
+            s_cur[b] = run;
+            run += s_hist[b];
+          }
+          s_total = run;
+        }
+        __syncthreads();
       }
     }
+    total = s_total;
   }
   if (tid == 0) list_cnt[item] = total;
 }
@@ -1279,7 +1555,7 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
          const double *__restrict__ q_n2, const double *__restrict__ q_err,
          TcMisc *__restrict__ misc, int32_t *__restrict__ idx0, double *__restrict__ dist,
          int32_t *__restrict__ fail_list, double *__restrict__ fail_tau,
-         const int32_t *__restrict__ visit, int64_t n_visit) {
+         const int32_t *__restrict__ visit, int64_t n_visit, double eta_coef) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ds = rr_stride(d);
@@ -1372,7 +1648,7 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   const double s = misc->scale;
   const double qn = q_n2[q], eq = q_err[q];
   const double M = misc->rn2_max + 2.0 * sqrt(qn) * sqrt(misc->rn2_max) + 1.0;
-  const double eta = ETA_COEF * M + 1e-4;
+  const double eta = eta_coef * M + 1e-4;
   // every non-candidate has a key >= the threshold of the list that rejected it
   const double tq = (double)tau[q];
   const double dk2 = __longlong_as_double((long long)kth);
@@ -1535,12 +1811,21 @@ static int pick_groups(int64_t nr) {
 
 // candidate stage alone (also used by the debug / profiling entry point).
 // mode: 0 = auto, 1 = exhaustive scan of every tile, 2 = grouped (tile-pruned)
+bool knn_tc_grouped(int64_t nr, int scan_mode) { return scan_mode == 2 || (scan_mode == 0 && nr >= 32768); }
+
 static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                              int64_t nq, int d, int kp, int mode, TcCandidates *out,
-                             float *d_dbg_keys, b200nn_stats *stats) {
+                             float *d_dbg_keys, b200nn_stats *stats, int shard_rank = 0, int shard_world = 0) {
   cudaStream_t st = ctx->stream;
+  bool timed_pass2 = false;
   const bool self = (d_qry == d_ref) && (nq == nr);
-  const bool grouped = mode == 2 || (mode == 0 && nr >= 32768 && d_dbg_keys == nullptr);
+  const bool grouped = d_dbg_keys == nullptr && knn_tc_grouped(nr, mode);
+  const bool sharded = shard_world > 1;
+  if (sharded && !(grouped && self && shard_world <= 64 && shard_rank >= 0 && shard_rank < shard_world)) {
+    b200nn_set_error("sharded tensor search needs a self query in grouped mode (rank %d of %d)", shard_rank,
+                     shard_world);
+    return B200NN_ERR_INVALID;
+  }
   *out = TcCandidates();
   TcMisc *misc;
   double *partial, *q_n2, *q_err;
@@ -1627,9 +1912,10 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     RC_TRY(ws_get(ctx, WS_TC_SPLIT, (size_t)nr, &split));
     RC_TRY(ws_get(ctx, WS_TC_REF16, (size_t)nr_pad * BK, &r16));
     // int scratch: gid_r[nr] gid_q[nq] rperm[nr_pad] qperm[nq] + 8 small arrays of (G+1)
+    const size_t nF = (size_t)G * FINE_NB;  // (group, bucket) bins of the hub-first order
     RC_TRY(ws_get(ctx, WS_TC_IBUF,
                   (size_t)nr + nq + nr_pad + nq_pad + 8 * (size_t)(G + 1) + 2 * (size_t)P.n_items +
-                      (size_t)list_stride + 64,
+                      (size_t)list_stride + 6 * nF + (size_t)(G + 1) + 64,
                   &ibuf));
     gid_r = ibuf;
     gid_q = gid_r + nr;
@@ -1639,11 +1925,20 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
             *qoff = goff + (G + 1), *rcursor = qoff + (G + 1), *qcursor = rcursor + (G + 1),
             *kcount = qcursor + (G + 1), *list_cnt = kcount + (G + 1) * 2, *order = list_cnt + P.n_items,
             *bins = order + P.n_items;
+    int32_t *fcount_r = bins + list_stride + 32, *fcount_q = fcount_r + nF, *foff_r = fcount_q + nF,
+            *foff_q = foff_r + nF, *fcur_r = foff_q + nF, *fcur_q = fcur_r + nF, *owner_buf = fcur_q + nF;
+    const int32_t *owner = sharded ? owner_buf : nullptr;
     // float scratch: cent[G*64] cnorm[G] sums[G*64] grad[G] item_c[nI*64] item_rad[nI] item_T[nI]
+    //                gstat[2G] tile_lo/hi[n_tiles] anorm_r[nr] anorm_q[nq]
     const size_t nI = (size_t)P.n_items;
-    RC_TRY(ws_get(ctx, WS_TC_FBUF, (size_t)G * BK * 2 + 2 * (size_t)G + nI * BK + 2 * nI + 64, &fbuf));
-    float *cent = fbuf, *sums = cent + (size_t)G * BK, *cnorm = sums + (size_t)G * BK, *grad = cnorm + G,
+    RC_TRY(ws_get(ctx, WS_TC_FBUF,
+                  (size_t)G * BK * 3 + 2 * (size_t)G + nI * BK + 2 * nI + 2 * (size_t)G + 2 * (size_t)n_tiles_max +
+                      (size_t)nr + (size_t)nq + 64,
+                  &fbuf));
+    float *cent = fbuf, *cnorm = cent + (size_t)G * BK * 3, *grad = cnorm + G,
           *item_c = grad + G, *item_rad = item_c + nI * BK, *item_T = item_rad + nI;
+    float *gstat = item_T + nI, *tile_lo = gstat + 2 * (size_t)G, *tile_hi = tile_lo + n_tiles_max,
+          *anorm_r = tile_hi + n_tiles_max, *anorm_q = anorm_r + nr;
     int32_t *tiles;
     RC_TRY(ws_get(ctx, WS_TC_TILES, nI * (size_t)list_stride, &tiles));
 
@@ -1662,7 +1957,8 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     // 2. coarse k-means on a strided sample of the reference rows
     const int64_t m = nr < KM_SAMPLE ? nr : KM_SAMPLE;
     const int64_t stride = nr / m;
-    CU_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)G * BK, st));
+    long long *sums = reinterpret_cast<long long *>(cent + (size_t)G * BK);  // [G x 64] fixed-point sums
+    CU_TRY(cudaMemsetAsync(sums, 0, sizeof(long long) * (size_t)G * BK, st));
     CU_TRY(cudaMemsetAsync(rcount, 0, sizeof(int32_t) * 8 * (size_t)(G + 1), st));
     k_km_init<<<G, 64, 0, st>>>(yr16, m * stride, d, G, cent, cnorm);
     KERNEL_CHECK(ctx);
@@ -1673,25 +1969,107 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       k_km_update<<<G, 64, 0, st>>>(sums, kcount, d, cent, cnorm);
       KERNEL_CHECK(ctx);
     }
-    // 3. assign every reference / query row, sort by group
-    k_km_assign<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, nr, 1, d, G, cent, cnorm, gid_r, rcount,
-                                                                nullptr);
-    KERNEL_CHECK(ctx);
-    if (self) {
-      CU_TRY(cudaMemcpyAsync(qcount, rcount, sizeof(int32_t) * G, cudaMemcpyDeviceToDevice, st));
-      gid_q = gid_r;
+    // 3. assign every reference / query row to its nearest centroid, sort by group.  The assignment is
+    // itself a nearest-neighbour search of n rows against G centroids: it runs on the tensor cores
+    // through the candidate kernel (2 - 8 centroid tiles per work item), ~6x faster than the FP32
+    // FMA kernel (k_km_assign; B200NN_KM_ASSIGN_FMA=1 keeps it for comparison).  Any assignment is
+    // valid (only the pruning depends on it); this one is deterministic.
+    static const bool assign_fma = getenv("B200NN_KM_ASSIGN_FMA") != nullptr;
+    const int G_pad = ((G + BN - 1) / BN) * BN;
+    __half *c16 = nullptr;
+    if (!assign_fma) {
+      RC_TRY(ws_get(ctx, WS_TC_CENT16, (size_t)G_pad * BK, &c16));
+      k_cent_operand<<<(unsigned)ceil_div64((int64_t)G_pad * 32, 256), 256, 0, st>>>(cent, G, G_pad, d, c16);
+      KERNEL_CHECK(ctx);
+    }
+    auto assign_tc = [&](const __half *y16, int64_t n_rows, int32_t *gid_out, int32_t *counts) -> int {
+      CUtensorMap mq, mr;
+      RC_TRY(make_operand_map(&mq, y16, n_rows));
+      RC_TRY(make_operand_map(&mr, c16, G_pad));
+      TcParams A;
+      memset(&A, 0, sizeof(A));
+      A.nq = n_rows;
+      A.nr = G_pad;
+      A.n_items = (int32_t)ceil_div64(n_rows, QT * BM);
+      A.n_btiles = G_pad / BN;
+      A.ksteps = P.ksteps;
+      A.kp = 8;
+      A.stages = pick_stages(8);
+      A.cand = cand;
+      A.tau = tau;
+      A.misc = misc;
+      A.argmin_out = gid_out;
+      RC_TRY(launch_tc(ctx, mq, mr, A, false));
+      k_count_gid<<<ctx->sm_count * 4, 256, 0, st>>>(gid_out, n_rows, G, counts);
+      KERNEL_CHECK(ctx);
+      return B200NN_OK;
+    };
+    if (assign_fma) {
+      k_km_assign<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, nr, 1, d, G, cent, cnorm, gid_r, rcount,
+                                                                  nullptr);
+      KERNEL_CHECK(ctx);
     } else {
+      RC_TRY(assign_tc(yr16, nr, gid_r, rcount));
+    }
+    if (self) {
+      if (sharded) {  // this share takes whole groups
+        k_group_owner<<<1, 1024, 0, st>>>(rcount, G, shard_world, shard_rank, owner_buf, qcount);
+        KERNEL_CHECK(ctx);
+      } else {
+        CU_TRY(cudaMemcpyAsync(qcount, rcount, sizeof(int32_t) * G, cudaMemcpyDeviceToDevice, st));
+      }
+      gid_q = gid_r;
+    } else if (assign_fma) {
       k_km_assign<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(yq16, nq, 1, d, G, cent, cnorm, gid_q, qcount,
                                                                   nullptr);
       KERNEL_CHECK(ctx);
+    } else {
+      RC_TRY(assign_tc(yq16, nq, gid_q, qcount));
     }
     k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor);
     KERNEL_CHECK(ctx);
     CU_TRY(cudaMemsetAsync(rperm, 0xff, sizeof(int32_t) * (size_t)(nr_pad + nq_pad), st));  // rperm and qperm
-    k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, G, goff, rcursor, rperm);
+    // 3b. squared distance of every row to its group's centre; groups are stored hub-first
+    static const bool no_hub = getenv("B200NN_NO_HUB") != nullptr;  // arrival order (for comparison)
+    CU_TRY(cudaMemsetAsync(gstat, 0, sizeof(float) * 2 * (size_t)G, st));
+    k_row_anorm<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, gid_r, nr, d, G, cent, anorm_r, gstat);
     KERNEL_CHECK(ctx);
-    k_group_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, nq, G, qoff, qcursor, qperm);
-    KERNEL_CHECK(ctx);
+    if (self) {
+      anorm_q = anorm_r;
+    } else {
+      k_row_anorm<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(yq16, gid_q, nq, d, G, cent, anorm_q, nullptr);
+      KERNEL_CHECK(ctx);
+    }
+    if (no_hub) {
+      k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, G, goff, rcursor, rperm);
+      KERNEL_CHECK(ctx);
+      k_group_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, nq, G, qoff, qcursor, qperm, owner,
+                                                                      shard_rank);
+      KERNEL_CHECK(ctx);
+    } else {
+      k_group_stat_final<<<(G + 127) / 128, 128, 0, st>>>(gstat, rcount, G);
+      KERNEL_CHECK(ctx);
+      CU_TRY(cudaMemsetAsync(fcount_r, 0, sizeof(int32_t) * 2 * nF, st));  // fcount_r and fcount_q
+      k_fine_count<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, fcount_r);
+      KERNEL_CHECK(ctx);
+      k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_r, goff, foff_r, fcur_r);
+      KERNEL_CHECK(ctx);
+      if (self) {
+        k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_r, qoff, foff_q, fcur_q);
+        KERNEL_CHECK(ctx);
+      } else {
+        k_fine_count<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, anorm_q, nq, gstat, fcount_q);
+        KERNEL_CHECK(ctx);
+        k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_q, qoff, foff_q, fcur_q);
+        KERNEL_CHECK(ctx);
+      }
+      k_fine_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, foff_r, fcur_r, rperm,
+                                                                     nullptr, 0);
+      KERNEL_CHECK(ctx);
+      k_fine_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, anorm_q, nq, gstat, foff_q, fcur_q, qperm,
+                                                                     owner, shard_rank);
+      KERNEL_CHECK(ctx);
+    }
     // 4. operands in sorted order
     k_gather_ref<<<(unsigned)ceil_div64(nr_pad * 8, 256), 256, 0, st>>>(yr16, split, rperm, nr_pad, d, r16);
     KERNEL_CHECK(ctx);
@@ -1700,6 +2078,9 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     // 5. balls
     CU_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)G, st));
     k_group_radius<<<dim3(G, 8), 128, 0, st>>>(yr16, rperm, goff, d, cent, grad);
+    KERNEL_CHECK(ctx);
+    k_tile_annulus<<<(unsigned)ceil_div64(n_tiles_max * 32, 256), 256, 0, st>>>(rperm, anorm_r, n_tiles_max, tile_lo,
+                                                                                 tile_hi);
     KERNEL_CHECK(ctx);
     k_item_stats<<<P.n_items, 64, 0, st>>>(q16, qperm, nq_pad, d, item_c, item_rad);
     KERNEL_CHECK(ctx);
@@ -1717,14 +2098,14 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     P.rperm = rperm;
     P.qperm = qperm;
     P.item_T = item_T;
-    k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, 1,
-                                                      P.list_stride, tiles, list_cnt);
+    k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, tile_lo, tile_hi,
+                                                      1, P.list_stride, tiles, list_cnt);
     KERNEL_CHECK(ctx);
     P.pass1 = 1;
     RC_TRY(debug_list_stats(ctx, "pass 1", list_cnt, P.n_items));
     RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
-    k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, 0,
-                                                      P.list_stride, tiles, list_cnt);
+    k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, tile_lo, tile_hi,
+                                                      0, P.list_stride, tiles, list_cnt);
     KERNEL_CHECK(ctx);
     out->visit = qperm;
     out->n_visit = nq_pad;
@@ -1745,7 +2126,10 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     KERNEL_CHECK(ctx);
     P.order = order;
     RC_TRY(debug_list_stats(ctx, "pass 2", list_cnt, P.n_items, item_T, item_rad));
+    CU_TRY(cudaEventRecord(ctx->ev[14], st));
     RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
+    CU_TRY(cudaEventRecord(ctx->ev[15], st));
+    timed_pass2 = true;
   }
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));
@@ -1755,6 +2139,12 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     stats->ms_prep += ms;
     CU_TRY(cudaEventElapsedTime(&ms, e1, e2));
     stats->ms_knn_cand += ms;
+    if (timed_pass2) {
+      CU_TRY(cudaEventElapsedTime(&ms, ctx->ev[14], ctx->ev[15]));
+      stats->ms_knn_pass2 += ms;
+    } else {
+      stats->ms_knn_pass2 += ms;  // exhaustive scan: the one candidate launch
+    }
   }
   out->cand = cand;
   out->tau = tau;
@@ -1766,7 +2156,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
 
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
                   int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
-                  b200nn_stats *stats) {
+                  b200nn_stats *stats, int shard_rank, int shard_world) {
   cudaStream_t st = ctx->stream;
   int kp = pick_kp(k, n_cand);
   if (kp > MAX_KP) kp = MAX_KP;
@@ -1775,7 +2165,12 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
     return B200NN_ERR_INVALID;
   }
   TcCandidates C;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, scan_mode, &C, nullptr, stats));
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, scan_mode, &C, nullptr, stats, shard_rank,
+                           shard_world));
+  if (shard_world > 1) {  // the rows this share wrote (the group-sorted query order, -1 = padding)
+    ctx->owned_rows = C.visit;
+    ctx->owned_slots = C.n_visit;
+  }
   int32_t *cand = C.cand;
   float *tau = C.tau;
   double *q_n2 = C.q_n2, *q_err = C.q_err;
@@ -1796,7 +2191,7 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)ceil_div64(n_visit, RR_WARPS), RR_WARPS * 32, smem, st>>>(
       d_ref, d_qry, nq, d, k, kp, cand, tau, q_n2, q_err, misc, d_idx0, d_dist, fail_list, fail_tau,
-      C.visit, n_visit);
+      C.visit, n_visit, ETA_PER_KSTEP * (double)((d + 3 + 15) / 16));
   KERNEL_CHECK(ctx);
   CU_TRY(cudaEventRecord(e1, st));
   TcMisc h;
@@ -1805,6 +2200,10 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   if (h.hang) {
     b200nn_set_error("tensor-core kNN kernel: mbarrier wait timed out (pipeline protocol error)");
     return B200NN_ERR_CUDA;
+  }
+  if (h.nonfinite) {
+    b200nn_set_error("NA/NaN/Inf in foreign function call (the embedding holds a non-finite value)");
+    return B200NN_ERR_INVALID;
   }
   if (h.n_fail > 0) {
     CU_TRY(cudaMemcpyAsync(flags, &misc->n_fail, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));

@@ -22,6 +22,7 @@
 // Rows are binned by expanded work E_i = sum_c |R(c)| into classes that differ
 // only in table size / threads per row; the "huge" class hashes in HBM.
 #include <limits.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -98,7 +99,7 @@ __device__ __forceinline__ void bitonic_sort_asc(T *a, int m, int g, int nthr, S
 // K3: transpose
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_hist(const int32_t *__restrict__ idx0, int64_t total, int64_t n, int32_t *__restrict__ indeg,
+k_hist(const int32_t *__restrict__ idx0, int64_t total, int k, int64_t n, int32_t *__restrict__ indeg,
        DevInfo *__restrict__ info) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -107,6 +108,23 @@ k_hist(const int32_t *__restrict__ idx0, int64_t total, int64_t n, int32_t *__re
     info->err_index_range = 1;
   else
     atomicAdd(&indeg[c], 1);
+  // a row that lists the same neighbour twice (A_ic = 2): the SNN kernels must know before they start,
+  // and every row counts (row j's duplicate changes S_ij of every row i)
+  const int p = (int)(t % k);
+  const int32_t *row = idx0 + (t - p);
+  bool dup = false;
+  for (int q = 0; q < p; ++q) dup |= row[q] == c;
+  if (dup) info->has_dups = 1;
+}
+
+// longest reverse list (statistics; the work classes use the per-row sums)
+__global__ void __launch_bounds__(256)
+k_max_indeg(const int32_t *__restrict__ indeg, int64_t n, DevInfo *__restrict__ info) {
+  int m = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, indeg[i]);
+  m = warp_max_i32(m);
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&info->max_indegree, m);
 }
 
 __global__ void __launch_bounds__(256)
@@ -124,11 +142,12 @@ k_scatter(const int32_t *__restrict__ idx0, int64_t total, int k, int64_t n,
 constexpr int SORT_WARPS = 8;
 constexpr int SORT_WARP_CAP = 1024;  // elements a warp sorts in shared memory
 
-// one warp per column: sort the reverse list, count distinct rows
+// one warp per column: sorted copy of the reverse list (the nn Graph's column), distinct rows counted.
+// Out of place: the SNN kernels read the unsorted lists concurrently (they do not need an order).
 __global__ void __launch_bounds__(SORT_WARPS * 32)
-k_sort_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr, int64_t n,
-               int32_t *__restrict__ uniq, int32_t *__restrict__ long_list,
-               DevInfo *__restrict__ info) {
+k_sort_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, const int64_t *__restrict__ colptr,
+               int64_t n, int32_t *__restrict__ uniq, int32_t *__restrict__ long_list,
+               int32_t *__restrict__ n_long) {
   __shared__ int32_t sbuf[SORT_WARPS][SORT_WARP_CAP];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * SORT_WARPS + w;
@@ -136,9 +155,11 @@ k_sort_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr, in
   const int64_t beg = colptr[c];
   const int64_t len64 = colptr[c + 1] - beg;
   const int len = (int)len64;
-  if (lane == 0 && len > info->max_indegree) atomicMax(&info->max_indegree, len);
   if (len <= 1) {
-    if (lane == 0) uniq[c] = len;
+    if (lane == 0) {
+      uniq[c] = len;
+      if (len == 1) out[beg] = rev[beg];
+    }
     return;
   }
   int ndup = 0;
@@ -154,7 +175,7 @@ k_sort_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr, in
       }
     }
     int32_t prev = __shfl_up_sync(0xffffffffu, v, 1);
-    if (lane < len) rev[beg + lane] = v;
+    if (lane < len) out[beg + lane] = v;
     ndup = (lane > 0 && lane < len && v == prev) ? 1 : 0;
   } else if (len <= SORT_WARP_CAP) {
     int32_t *a = sbuf[w];
@@ -163,21 +184,18 @@ k_sort_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr, in
     bitonic_sort_asc(a, len, lane, 32, [] { __syncwarp(); });
     for (int t = lane; t < len; t += 32) {
       int32_t v = a[t];
-      rev[beg + t] = v;
+      out[beg + t] = v;
       if (t > 0 && a[t - 1] == v) ndup++;
     }
   } else {
     if (lane == 0) {
-      int pos = atomicAdd(&info->n_long, 1);
+      int pos = atomicAdd(n_long, 1);
       long_list[pos] = (int32_t)c;
     }
     return;  // uniq[c] is written by k_sort_long_columns
   }
   ndup = warp_sum_i32(ndup);
-  if (lane == 0) {
-    uniq[c] = len - ndup;
-    if (ndup) info->has_dups = 1;
-  }
+  if (lane == 0) uniq[c] = len - ndup;
 }
 
 constexpr int LONG_THREADS = 1024;
@@ -185,12 +203,12 @@ constexpr int LONG_SMEM_CAP = 32768;  // elements (128 KB)
 
 // one CTA per long column (hubs)
 __global__ void __launch_bounds__(LONG_THREADS)
-k_sort_long_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colptr,
+k_sort_long_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, const int64_t *__restrict__ colptr,
                     int32_t *__restrict__ uniq, const int32_t *__restrict__ long_list,
-                    DevInfo *__restrict__ info) {
+                    const int32_t *__restrict__ n_long_p) {
   extern __shared__ int32_t lbuf[];
   __shared__ int red[32];
-  const int n_long = info->n_long;
+  const int n_long = *n_long_p;
   for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
     const int64_t c = long_list[li];
     const int64_t beg = colptr[c];
@@ -198,10 +216,10 @@ k_sort_long_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colpt
     int32_t *a;
     if (len <= LONG_SMEM_CAP) {
       a = lbuf;
-      for (int t = threadIdx.x; t < len; t += LONG_THREADS) a[t] = rev[beg + t];
     } else {
-      a = rev + beg;  // in place in HBM (block-scope visibility via __syncthreads)
+      a = out + beg;  // sorted in HBM (block-scope visibility via __syncthreads)
     }
+    for (int t = threadIdx.x; t < len; t += LONG_THREADS) a[t] = rev[beg + t];
     __syncthreads();
     bitonic_sort_asc(a, len, (int)threadIdx.x, LONG_THREADS, [] { __syncthreads(); });
     int ndup = 0;
@@ -211,16 +229,13 @@ k_sort_long_columns(int32_t *__restrict__ rev, const int64_t *__restrict__ colpt
     }
     __syncthreads();
     if (len <= LONG_SMEM_CAP)
-      for (int t = threadIdx.x; t < len; t += LONG_THREADS) rev[beg + t] = a[t];
+      for (int t = threadIdx.x; t < len; t += LONG_THREADS) out[beg + t] = a[t];
     ndup = warp_sum_i32(ndup);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ndup;
     __syncthreads();
     if (threadIdx.x < 32) {
       int v = warp_sum_i32(red[threadIdx.x]);
-      if (threadIdx.x == 0) {
-        uniq[c] = len - v;
-        if (v) info->has_dups = 1;
-      }
+      if (threadIdx.x == 0) uniq[c] = len - v;
     }
     __syncthreads();
   }
@@ -786,6 +801,306 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
   }
 }
 
+// ---------------------------------------------------------------------------
+// Single-walk warp-per-row kernel with BYTE-FLAG levels (default for 2 <= s_min <= 5, k <= 32,
+// no duplicated neighbours).
+//
+// The two-walk kernel above is bound by shared-memory atomics: an ATOMS with spread addresses
+// retires 2 cycles per LANE, and pass A issues one per candidate occurrence (measured round 1:
+// ~1 occurrence / clk / SM; round 2, a single-walk variant with the same 4-bit atomic counters
+// was no faster: profiles/r02_ab1_*.txt).  This kernel counts without any atomic:
+//   * level flags: L1, L2, .. L(s_min-1) are byte arrays.  An occurrence of key j climbs the
+//     levels: at the first level whose flag (at j's slot) is still 0 it writes 1 and stops;
+//     if all s_min - 1 flags are already set it is "hot".  A byte store of the constant 1 is
+//     idempotent, so colliding lanes need no atomic, and a collision can only help a key climb
+//     faster (false positive), never slower: after its t-th occurrence the flags L1..Lt of a key
+//     are set, hence the s_min-th occurrence of every surviving key is hot.
+//   * hot keys are de-duplicated in a small exact key table;
+//   * the exact count of each distinct hot key j comes from the FORWARD lists:
+//         S_ij = |N(i) ∩ N(j)|      (A is 0/1 without duplicated neighbours, src/snn.cpp:27)
+//     one lane per hot key reads N(j) and probes a 64-word hash set of N(i); ~40 keys per row
+//     are verified instead of ~1800 occurrences walked a second time.
+//   * pigeonhole: a surviving key occurs in >= s_min of the k lists, hence in at least one list
+//     other than the s_min - 1 LONGEST ones; those lists (hubs) are walked last and never set a
+//     level-1 flag, which removes most of their false positives.
+// Output, cut-off and x values are exactly those of the kernels above (same LUTs).
+// ---------------------------------------------------------------------------
+constexpr int HOT_NSET = 64;  // hash set of N(i): k <= 32 keys in 64 words
+constexpr int flag_level_bytes(int lv1_log, int l) { return 1 << (lv1_log - (l < 2 ? l : 2)); }
+constexpr int flag_total_bytes(int lv1_log, int levels) {
+  int b = 0;
+  for (int l = 0; l < levels; ++l) b += flag_level_bytes(lv1_log, l);
+  return b;
+}
+constexpr int hot_bytes(int lv1_log, int levels, int tx_log) {
+  return flag_total_bytes(lv1_log, levels) + (1 << tx_log) * 4 + ((filt_slot_cap(tx_log) * 2 + 15) & ~15) + 64 * 4 +
+         HOT_NSET * 4;
+}
+
+// batch insert of hot keys into the de-duplicating key table (keys only)
+template <int F_TX_LOG>
+__device__ __forceinline__ void hot_insert_batch(uint32_t *tab, uint16_t *slots, int &nslots, uint32_t j,
+                                                 bool active, int lane) {
+  constexpr uint32_t mask = (1u << F_TX_LOG) - 1;
+  constexpr int F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
+  uint32_t h = (j * 2654435761u) >> (32 - F_TX_LOG);
+  volatile uint32_t *vt = tab;
+  bool won = false, todo = active;
+  while (todo) {
+    uint32_t cur = vt[h];
+    if (cur == 0xffffffffu) {
+      cur = atomicCAS(&tab[h], 0xffffffffu, j);
+      if (cur == 0xffffffffu) {
+        won = true;
+        break;
+      }
+    }
+    if (cur == j) break;
+    h = (h + 1) & mask;
+  }
+  __syncwarp();
+  const unsigned wb = __ballot_sync(0xffffffffu, won);
+  if (won) {
+    const int pos = nslots + __popc(wb & ((1u << lane) - 1));
+    if (pos < F_SLOT_CAP) slots[pos] = (uint16_t)h;
+  }
+  nslots += __popc(wb);
+  __syncwarp();
+}
+
+__device__ __forceinline__ int nset_probe(const uint32_t *nset, uint32_t c) {
+  uint32_t h = (c * 2654435761u) >> (32 - 6);
+  while (true) {
+    const uint32_t e = nset[h];
+    if (e == c) return 1;
+    if (e == 0xffffffffu) return 0;
+    h = (h + 1) & (HOT_NSET - 1);
+  }
+}
+
+template <int LV1_LOG, int LEVELS, int F_TX_LOG, int F_WARPS>
+__global__ void __launch_bounds__(F_WARPS * 32)
+k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+  constexpr int F_BYTES = hot_bytes(LV1_LOG, LEVELS, F_TX_LOG);
+  constexpr int FLAG_BYTES = flag_total_bytes(LV1_LOG, LEVELS);
+  constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
+  static_assert(FLAG_BYTES >= F_SLOT_CAP * 4, "the flag area doubles as the hot-key buffer");
+  static_assert(LEVELS >= 1 && LEVELS <= 4, "s_min - 1 levels");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem_raw + (size_t)w * F_BYTES;
+  volatile uint8_t *flags = base;
+  uint32_t *tab = reinterpret_cast<uint32_t *>(base + FLAG_BYTES);
+  uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
+  uint32_t *pend = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(slots) +
+                                                ((F_SLOT_CAP * 2 + 15) & ~15));
+  uint32_t *nset = pend + 64;
+  const int k = P.k;
+  for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+  const int n_warps = gridDim.x * F_WARPS;
+  for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
+    const int row_l = P.row_list[r];
+    const int64_t row = P.row_begin + row_l;
+    {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      uint4 *c4 = reinterpret_cast<uint4 *>(base);
+      for (int s = lane; s < FLAG_BYTES / 16; s += 32) c4[s] = z;
+      nset[lane] = 0xffffffffu;
+      nset[lane + 32] = 0xffffffffu;
+    }
+    __syncwarp();
+    // list descriptors (k <= 32: one list per lane) and the hash set of N(i)
+    int64_t beg = 0;
+    int len = 0;
+    if (lane < k) {
+      const uint32_t c = (uint32_t)P.idx0[row * k + lane];
+      beg = P.colptr[c];
+      len = (int)(P.colptr[c + 1] - beg);
+      uint32_t h = (c * 2654435761u) >> (32 - 6);
+      while (true) {
+        const uint32_t old = atomicCAS(&nset[h], 0xffffffffu, c);
+        if (old == 0xffffffffu || old == c) break;
+        h = (h + 1) & (HOT_NSET - 1);
+      }
+    }
+    // the n_ro longest lists are walked last and never set a level-1 flag
+    bool ro = false;
+    {
+      const int key = lane < k ? (len << 5) | lane : -1;
+      for (int t = 0; t < n_ro; ++t) {
+        int m = ro ? -1 : key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m >= 0 && key == m) ro = true;
+      }
+    }
+    const unsigned ro_mask = __ballot_sync(0xffffffffu, ro);
+    int nslots = 0, npend = 0;
+    bool ovf = false;
+    // walk (phase, list, 128-element block); the next block's loads are issued before the
+    // current block is processed
+    int ph = 0, pl = -1, t0 = 0, l = 0;
+    int64_t b = 0;
+    auto advance = [&](int &aph, int &apl, int &at0, int &al, int64_t &ab) -> bool {
+      at0 += 128;
+      while (true) {
+        if (apl >= 0 && at0 < al) return true;
+        ++apl;
+        at0 = 0;
+        al = 0;
+        if (apl >= k) {
+          if (aph == 1 || ro_mask == 0) return false;
+          aph = 1;
+          apl = -1;
+          continue;
+        }
+        if ((((ro_mask >> apl) & 1u) != 0) != (aph == 1)) continue;
+        ab = __shfl_sync(0xffffffffu, beg, apl);
+        al = __shfl_sync(0xffffffffu, len, apl);
+      }
+    };
+    int32_t v[4], nv[4];
+    bool have = advance(ph, pl, t0, l, b);
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (t0 + 32 * u + lane < l) ? P.rev[b + t0 + 32 * u + lane] : -1;
+    }
+    while (have && !ovf) {
+      int nph = ph, npl = pl, nt0 = t0, nl = l;
+      int64_t nb = b;
+      const bool nhave = advance(nph, npl, nt0, nl, nb);
+      if (nhave) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nv[u] = (nt0 + 32 * u + lane < nl) ? P.rev[nb + nt0 + 32 * u + lane] : -1;
+      }
+      // climb the levels: plain byte loads / stores only
+      bool go[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) go[u] = v[u] >= 0;
+      {
+        int off = 0;
+#pragma unroll
+        for (int lv = 0; lv < LEVELS; ++lv) {
+          constexpr uint32_t MUL[4] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu};
+          const int lg = LV1_LOG - (lv < 2 ? lv : 2);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (go[u]) {
+              volatile uint8_t *fp = flags + off + (((uint32_t)v[u] * MUL[lv]) >> (32 - lg));
+              if (*fp == 0) {
+                if (lv > 0 || ph == 0) *fp = 1;
+                go[u] = false;
+              }
+            }
+          }
+          off += 1 << lg;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (t0 + 32 * u >= l) break;  // warp-uniform
+        const unsigned bal = __ballot_sync(0xffffffffu, go[u]);
+        if (bal) {
+          if (go[u]) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
+          npend += __popc(bal);
+          __syncwarp();
+          if (npend >= 32) {
+            hot_insert_batch<F_TX_LOG>(tab, slots, nslots, pend[lane], true, lane);
+            const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
+            __syncwarp();
+            if (32 + lane < npend) pend[lane] = mv;
+            npend -= 32;
+            __syncwarp();
+            if (nslots > F_SLOTS) ovf = true;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = nv[u];
+      ph = nph;
+      pl = npl;
+      t0 = nt0;
+      l = nl;
+      b = nb;
+      have = nhave;
+    }
+    if (!ovf && npend > 0) {
+      hot_insert_batch<F_TX_LOG>(tab, slots, nslots, lane < npend ? pend[lane] : 0, lane < npend, lane);
+      if (nslots > F_SLOTS) ovf = true;
+    }
+    __syncwarp();
+    if (ovf) {
+      // hand the row to the big-table kernel; leave the table clean
+      for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+      if (lane == 0) {
+        P.row_nnz[row_l] = 0;
+        ovf_list[atomicAdd(&info->n_ovf, 1)] = row_l;
+      }
+      __syncwarp();
+      continue;
+    }
+    // distinct hot keys -> the (now free) flag area, table cleaned, ascending order
+    uint32_t *keys = reinterpret_cast<uint32_t *>(base);
+    for (int t = lane; t < nslots; t += 32) {
+      const int sl = slots[t];
+      keys[t] = tab[sl];
+      tab[sl] = 0xffffffffu;
+    }
+    __syncwarp();
+    bitonic_sort_asc(keys, nslots, lane, 32, [] { __syncwarp(); });
+    // exact counts from the forward lists (one lane per key, eight loads in flight), cut-off,
+    // emit (already in column order)
+    uint32_t *dst = reinterpret_cast<uint32_t *>(P.tmp) + P.tmp_off[row_l];
+    int m = 0;
+    for (int tb = 0; tb < nslots; tb += 32) {
+      const int t = tb + lane;
+      const bool act = t < nslots;
+      const uint32_t j = act ? keys[t] : (uint32_t)row;
+      const int32_t *nj = P.idx0 + (int64_t)j * k;
+      int sc = 0;
+      for (int q0 = 0; q0 < k; q0 += 8) {
+        int32_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = (q0 + u < k) ? nj[q0 + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c[u] >= 0) sc += nset_probe(nset, (uint32_t)c[u]);
+      }
+      const bool kp = act && P.keep[sc] != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, kp);
+      if (kp) dst[m + __popc(bal & ((1u << lane) - 1))] = (j << P.cbits) | (uint32_t)sc;
+      m += __popc(bal);
+    }
+    if (lane == 0) P.row_nnz[row_l] = m;
+    __syncwarp();
+  }
+}
+
+template <int LV1_LOG, int LEVELS, int F_TX_LOG, int F_WARPS>
+int launch_flags(b200nn_ctx *ctx, const SnnParams &P, int n_ro, int32_t *ovf_list, DevInfo *d_info) {
+  auto kern = k_snn_rows_flags<LV1_LOG, LEVELS, F_TX_LOG, F_WARPS>;
+  constexpr int bytes = hot_bytes(LV1_LOG, LEVELS, F_TX_LOG) * F_WARPS;
+  static_assert(2 * (bytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, F_WARPS), (int64_t)ctx->sm_count * 2);
+  kern<<<blocks, F_WARPS * 32, bytes, ctx->stream>>>(P, n_ro, ovf_list, d_info);
+  KERNEL_CHECK(ctx);
+  return B200NN_OK;
+}
+
+// rows with E <= 3.3 k: 8 k level-1 flags, 512-word key table; larger rows: 16 k flags, 1024 words.
+// Warps per CTA are what two CTAs per SM can hold.
+template <int LEVELS>
+int launch_flags_class(b200nn_ctx *ctx, const SnnParams &P, bool big, int lv1_small, int n_ro, int32_t *ovf_list,
+                       DevInfo *d_info) {
+  constexpr int budget = 113 * 1024;
+  if (big) return launch_flags<14, LEVELS, 10, budget / hot_bytes(14, LEVELS, 10)>(ctx, P, n_ro, ovf_list, d_info);
+  if (lv1_small == 12)
+    return launch_flags<12, LEVELS, 9, (budget / hot_bytes(12, LEVELS, 9) > 16 ? 16 : budget / hot_bytes(12, LEVELS, 9))>(
+        ctx, P, n_ro, ovf_list, d_info);
+  return launch_flags<13, LEVELS, 9, budget / hot_bytes(13, LEVELS, 9)>(ctx, P, n_ro, ovf_list, d_info);
+}
+
 // expanded work, survivor bound and work class of every row
 struct RowWorkParams {
   const int32_t *idx0;
@@ -795,7 +1110,8 @@ struct RowWorkParams {
   int32_t k;
   int32_t s_min;   // smallest kept count (0: nothing is ever kept)
   int64_t n;
-  int32_t class_lim[4];
+  int32_t class_lim[4];      // no row lists a neighbour twice
+  int32_t class_lim_dup[4];  // some row does (info->has_dups, set by k_hist earlier on the stream)
   int32_t *row_bound;
   int32_t *class_list;  // 5 x n_rows
   DevInfo *info;
@@ -820,7 +1136,8 @@ __global__ void __launch_bounds__(256) k_row_work(RowWorkParams P) {
   }
   if (act) P.row_bound[rl] = (int32_t)bound;
   int cls = -1;
-  if (act) cls = e <= P.class_lim[0] ? 0 : e <= P.class_lim[1] ? 1 : e <= P.class_lim[2] ? 2 : e <= P.class_lim[3] ? 3 : 4;
+  const int32_t *lim = P.info->has_dups ? P.class_lim_dup : P.class_lim;
+  if (act) cls = e <= lim[0] ? 0 : e <= lim[1] ? 1 : e <= lim[2] ? 2 : e <= lim[3] ? 3 : 4;
   // warp-aggregated append to the class lists
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
@@ -863,7 +1180,7 @@ k_snn_fill(const Word *__restrict__ tmp, const int64_t *__restrict__ tmp_off,
 }
 
 template <typename Word, int LOG_T, int G, int RPB>
-int launch_class(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm) {
+int launch_class(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, int64_t max_blocks = 0) {
   if (P.n_rows_class <= 0) return B200NN_OK;
   constexpr bool HUGE = (LOG_T == 0);
   constexpr bool INPLACE = (G == 32) && !HUGE;
@@ -876,6 +1193,7 @@ int launch_class(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm) {
   }
   int64_t want = ceil_div64(P.n_rows_class, RPB);
   int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
+  if (max_blocks > 0 && cap > max_blocks) cap = max_blocks;
   int blocks = (int)std::min<int64_t>(want, cap);
   k_snn_rows<Word, LOG_T, G, RPB><<<blocks, G * RPB, smem, ctx->stream>>>(P);
   KERNEL_CHECK(ctx);
@@ -897,7 +1215,7 @@ static inline int32_t class_limit(int log_t) { return (int32_t)(((int64_t)1 << l
 constexpr int HUGE_BLOCKS_PER_SM = 1;
 
 template <typename Cfg>
-int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int32_t n_rows,
+int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int32_t n_rows, int64_t n_cols,
                     const int32_t *class_count, int max_row_e, bool has_dups, int filter_s_min,
                     int32_t *ovf_list, DevInfo *d_info) {
   typedef typename Cfg::Word Word;
@@ -910,26 +1228,49 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     // positives in the counters; measured best: class 0 (E <= 2.8 k) 8 k counters, 30 warps/SM;
     // class 1 (E <= 3.2 k) 16 k counters, 20 warps/SM; class 2 (E <= 6.5 k) 16 k counters, 16.
     constexpr int WA = 15, WB = 10, WC = 8;
-    auto kA = k_snn_rows_filter<13, 9, WA>;
-    auto kB = k_snn_rows_filter<14, 9, WB>;
-    auto kC = k_snn_rows_filter<14, 10, WC>;
-    constexpr int bytesA = filt_bytes(13, 9) * WA, bytesB = filt_bytes(14, 9) * WB, bytesC = filt_bytes(14, 10) * WC;
-    CU_TRY(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesA));
-    CU_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesB));
-    CU_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesC));
-    for (int c = 0; c < 3; ++c) {
-      P.row_list = class_list + c * (int64_t)n_rows;
-      P.n_rows_class = class_count[c];
-      if (P.n_rows_class <= 0) continue;
-      const int w = c == 0 ? WA : c == 1 ? WB : WC;
-      const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, w), (int64_t)ctx->sm_count * 2);
-      if (c == 0)
-        kA<<<blocks, WA * 32, bytesA, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
-      else if (c == 1)
-        kB<<<blocks, WB * 32, bytesB, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
-      else
-        kC<<<blocks, WC * 32, bytesC, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
-      KERNEL_CHECK(ctx);
+    // single-walk kernel (k <= 32: one reverse list per lane); B200NN_SNN_TWO_WALK=1 keeps the
+    // two-walk kernel for comparison.  B200NN_SNN_NO_RO=1 switches the read-only lists off.
+    static const bool two_walk_env = getenv("B200NN_SNN_TWO_WALK") != nullptr;
+    static const bool no_ro_env = getenv("B200NN_SNN_NO_RO") != nullptr;
+    static const char *lv1_env = getenv("B200NN_SNN_LV1");  // 12: 4 k level-1 flags for the small rows
+    const int lv1_small = lv1_env ? atoi(lv1_env) : 13;
+    const bool single_walk = P.k <= 32 && filter_s_min <= 5 && !two_walk_env;
+    if (single_walk) {
+      const int n_ro = no_ro_env ? 0 : filter_s_min - 1;
+      for (int c = 0; c < 3; ++c) {
+        P.row_list = class_list + c * (int64_t)n_rows;
+        P.n_rows_class = class_count[c];
+        if (P.n_rows_class <= 0) continue;
+        const bool big = c == 2;
+        switch (filter_s_min - 1) {
+          case 1: RC_TRY(launch_flags_class<1>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
+          case 2: RC_TRY(launch_flags_class<2>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
+          case 3: RC_TRY(launch_flags_class<3>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
+          default: RC_TRY(launch_flags_class<4>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
+        }
+      }
+    } else {
+      auto kA = k_snn_rows_filter<13, 9, WA>;
+      auto kB = k_snn_rows_filter<14, 9, WB>;
+      auto kC = k_snn_rows_filter<14, 10, WC>;
+      constexpr int bytesA = filt_bytes(13, 9) * WA, bytesB = filt_bytes(14, 9) * WB, bytesC = filt_bytes(14, 10) * WC;
+      CU_TRY(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesA));
+      CU_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesB));
+      CU_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesC));
+      for (int c = 0; c < 3; ++c) {
+        P.row_list = class_list + c * (int64_t)n_rows;
+        P.n_rows_class = class_count[c];
+        if (P.n_rows_class <= 0) continue;
+        const int w = c == 0 ? WA : c == 1 ? WB : WC;
+        const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, w), (int64_t)ctx->sm_count * 2);
+        if (c == 0)
+          kA<<<blocks, WA * 32, bytesA, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
+        else if (c == 1)
+          kB<<<blocks, WB * 32, bytesB, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
+        else
+          kC<<<blocks, WC * 32, bytesC, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
+        KERNEL_CHECK(ctx);
+      }
     }
   } else {
     P.row_list = class_list + 0 * (int64_t)n_rows;
@@ -946,16 +1287,24 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
   P.n_rows_class = class_count[3];
   RC_TRY((launch_class<Word, Cfg::L3, 256, 1>(ctx, P, 1)));
   if (class_count[4] > 0) {
+    // a row has at most n distinct candidates, however large its expanded work E is (hubs,
+    // duplicated cells): 2 * min(E, n) words per table suffice
+    const int64_t distinct_max = std::min<int64_t>((int64_t)max_row_e, n_cols);
     int log_t = 1;
-    while (((int64_t)1 << log_t) < 2 * (int64_t)max_row_e) ++log_t;
+    while (((int64_t)1 << log_t) < 2 * distinct_max) ++log_t;
     int64_t blocks = std::min<int64_t>(class_count[4], (int64_t)ctx->sm_count * HUGE_BLOCKS_PER_SM);
-    Word *tables;
-    RC_TRY(ws_get(ctx, WS_HUGE_TABLE, (size_t)blocks << log_t, &tables));
+    Word *tables = nullptr;
+    int rc_t = ws_get(ctx, WS_HUGE_TABLE, (size_t)blocks << log_t, &tables);
+    while (rc_t == B200NN_ERR_NOMEM && blocks > 1) {  // fewer concurrent hub rows instead of failing
+      blocks = (blocks + 1) / 2;
+      rc_t = ws_get(ctx, WS_HUGE_TABLE, (size_t)blocks << log_t, &tables);
+    }
+    RC_TRY(rc_t);
     P.huge_tables = tables;
     P.huge_log_t = log_t;
     P.row_list = class_list + 4 * (int64_t)n_rows;
     P.n_rows_class = class_count[4];
-    RC_TRY((launch_class<Word, 0, 256, 1>(ctx, P, HUGE_BLOCKS_PER_SM)));
+    RC_TRY((launch_class<Word, 0, 256, 1>(ctx, P, HUGE_BLOCKS_PER_SM, blocks)));
   }
   if (filter_s_min >= 2) {
     // rows whose exact table overflowed in the filtered kernel (E <= 0.8 * 2^L2 <= 2^L3 / 2)
@@ -1027,98 +1376,102 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
   CU_TRY(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * ((size_t)n + 1), st));
 
   // ---- K3 ----
+  // Main stream: histogram, scan, scatter -- all the SNN stage needs (unsorted reverse lists).
+  // Side stream: the nn Graph proper (sorted columns, duplicates merged, emission, early copy to
+  // the caller's buffers) runs concurrently with the SNN stage.
   if (total > 0) {
-    k_hist<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(d_idx0, total, n, indeg, d_info);
+    k_hist<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(d_idx0, total, k, n, indeg, d_info);
     KERNEL_CHECK(ctx);
   }
   RC_TRY(scan_exclusive_i32_to_i64(ctx, indeg, colptr, n));
+  k_max_indeg<<<ctx->sm_count, 256, 0, st>>>(indeg, n, d_info);
+  KERNEL_CHECK(ctx);
   if (total > 0) {
     k_scatter<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(d_idx0, total, k, n, colptr, cursor,
                                                                  rev);
     KERNEL_CHECK(ctx);
   }
-  k_sort_columns<<<(unsigned)ceil_div64(n, SORT_WARPS), SORT_WARPS * 32, 0, st>>>(
-      rev, colptr, n, uniq, long_list, d_info);
-  KERNEL_CHECK(ctx);
-  {
-    size_t smem = sizeof(int32_t) * LONG_SMEM_CAP;
-    CU_TRY(cudaFuncSetAttribute(k_sort_long_columns, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-    k_sort_long_columns<<<ctx->sm_count, LONG_THREADS, smem, st>>>(rev, colptr, uniq, long_list,
-                                                                   d_info);
-    KERNEL_CHECK(ctx);
-  }
-
   int64_t *nn_p = nullptr;
+  int32_t *nn_i = nullptr;
+  double *nn_x = nullptr;
   if (want_nn_graph) {
+    cudaStream_t ss = ctx->side_stream;
+    int32_t *rev_sorted;
+    RC_TRY(ws_get(ctx, WS_REV_SORTED, (size_t)total + 1, &rev_sorted));
     RC_TRY(ws_get(ctx, WS_NN_P, (size_t)n + 1, &nn_p));
-    RC_TRY(scan_exclusive_i32_to_i64(ctx, uniq, nn_p, n));
-  }
-  // sync #1: flags of the transpose
-  RC_TRY(fetch_info(ctx, d_info));
-  DevInfo hi = *ctx->h_info;
-  if (hi.err_index_range) {
-    b200nn_set_error("neighbour index out of range: every entry must lie in [1, %lld]",
-                     (long long)n);
-    return B200NN_ERR_INDEX_RANGE;
-  }
-  if (want_nn_graph) {
-    int64_t nnz_nn = 0;
-    CU_TRY(cudaMemcpyAsync(&nnz_nn, nn_p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    int32_t *nn_i;
-    double *nn_x;
-    RC_TRY(ws_get(ctx, WS_NN_I, (size_t)nnz_nn + 1, &nn_i));
-    RC_TRY(ws_get(ctx, WS_NN_X, (size_t)nnz_nn + 1, &nn_x));
-    k_emit_nn_graph<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, st>>>(rev, colptr, uniq, nn_p, n,
+    // the graph has at most `total` entries (fewer only when a row lists a neighbour twice)
+    RC_TRY(ws_get(ctx, WS_NN_I, (size_t)total + 1, &nn_i));
+    RC_TRY(ws_get(ctx, WS_NN_X, (size_t)total + 1, &nn_x));
+    CU_TRY(cudaEventRecord(ctx->ev_side, st));
+    CU_TRY(cudaStreamWaitEvent(ss, ctx->ev_side, 0));
+    k_sort_columns<<<(unsigned)ceil_div64(n, SORT_WARPS), SORT_WARPS * 32, 0, ss>>>(
+        rev, rev_sorted, colptr, n, uniq, long_list, &d_info->n_long);
+    KERNEL_CHECK(ctx);
+    {
+      size_t smem = sizeof(int32_t) * LONG_SMEM_CAP;
+      CU_TRY(cudaFuncSetAttribute(k_sort_long_columns, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+      k_sort_long_columns<<<ctx->sm_count, LONG_THREADS, smem, ss>>>(rev, rev_sorted, colptr, uniq, long_list,
+                                                                     &d_info->n_long);
+      KERNEL_CHECK(ctx);
+    }
+    RC_TRY(scan_exclusive_i32_to_i64(ctx, uniq, nn_p, n, ss, WS_SCAN_TMP2));
+    k_emit_nn_graph<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ss>>>(rev_sorted, colptr, uniq, nn_p, n,
                                                                         nn_i, nn_x);
     KERNEL_CHECK(ctx);
-    ctx->nn_graph.valid = true;
-    ctx->nn_graph.n_rows = n;
-    ctx->nn_graph.nnz = nnz_nn;
-    ctx->nn_graph.p = nn_p;
-    ctx->nn_graph.i = nn_i;
-    ctx->nn_graph.x = nn_x;
-    if (stats) stats->nnz_nn = nnz_nn;
     if (early_nn && (early_nn->p || early_nn->i || early_nn->x)) {
-      // the caller's nn Graph buffers are known already: copy on the copy stream, behind the SNN stage
+      // the caller's nn Graph buffers (capacity n_rows * k) are known already: they are filled on the
+      // copy stream while the SNN stage runs; entries past nnz_nn are unspecified
       int32_t *p32 = nullptr;
       if (early_nn->p) {
         RC_TRY(ws_get(ctx, WS_OUT_P32, (size_t)n + 1, &p32));
-        RC_TRY(narrow_i64_to_i32(ctx, nn_p, p32, n + 1));
+        RC_TRY(narrow_i64_to_i32(ctx, nn_p, p32, n + 1, ss));
       }
-      CU_TRY(cudaEventRecord(ctx->ev_copy, st));
+      CU_TRY(cudaEventRecord(ctx->ev_copy, ss));
       CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
       if (early_nn->p)
         CU_TRY(cudaMemcpyAsync(early_nn->p, p32, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
-      if (early_nn->i && nnz_nn)
-        CU_TRY(cudaMemcpyAsync(early_nn->i, nn_i, sizeof(int32_t) * (size_t)nnz_nn, cudaMemcpyDeviceToHost,
+      if (early_nn->i && total)
+        CU_TRY(cudaMemcpyAsync(early_nn->i, nn_i, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
-      if (early_nn->x && nnz_nn)
-        CU_TRY(cudaMemcpyAsync(early_nn->x, nn_x, sizeof(double) * (size_t)nnz_nn, cudaMemcpyDeviceToHost,
+      if (early_nn->x && total)
+        CU_TRY(cudaMemcpyAsync(early_nn->x, nn_x, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
     }
+    CU_TRY(cudaEventRecord(ctx->ev_side, ss));  // end of the side work (joined below)
   }
-  if (stats) stats->max_indegree = hi.max_indegree;
   CU_TRY(cudaEventRecord(e1, st));
+  DevInfo hi;
+  memset(&hi, 0, sizeof(hi));
 
   // ---- K4 ----
   if (compute_snn) {
     const int64_t rows = row_end - row_begin;
     if (rows >= 0x7fffffffLL) return B200NN_ERR_INVALID;
-    // count range: without duplicates |N(i) ∩ N(j)| <= k; with duplicates <= k^2
-    const bool has_dups = hi.has_dups != 0;
-    int64_t smax = has_dups ? (int64_t)k * k : (int64_t)k;
-    if (smax > (1 << 20)) {
+    // lookup tables for BOTH count ranges (no duplicates: s <= k; duplicated neighbours: s <= k^2), so
+    // that nothing has to be read back before the per-row work is known; huge k asks first
+    DevInfo early;
+    memset(&early, 0, sizeof(early));
+    const bool lut_all = (int64_t)k * k <= 65536;
+    if (!lut_all) {
+      RC_TRY(fetch_info(ctx, d_info));
+      early = *ctx->h_info;
+    }
+    const int64_t lut_max = (lut_all || early.has_dups) ? (int64_t)k * k : (int64_t)k;
+    if (lut_max > (1 << 20)) {
+      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
       b200nn_set_error("k = %d with duplicated neighbours exceeds the supported count range", k);
       return B200NN_ERR_INVALID;
     }
-    // lookup tables from the exact double expression of the reference
-    std::vector<uint8_t> h_keep((size_t)smax + 1);
-    std::vector<double> h_jac((size_t)smax + 1);
+    // lookup tables from the exact double expression of the reference (host copies live in the
+    // context so that the asynchronous upload needs no synchronisation)
+    std::vector<uint8_t> &h_keep = ctx->h_keep;
+    std::vector<double> &h_jac = ctx->h_jac;
+    h_keep.assign((size_t)lut_max + 1, 0);
+    h_jac.assign((size_t)lut_max + 1, 0.0);
     int32_t s_min = 0;
-    for (int64_t s = 0; s <= smax; ++s) {
+    for (int64_t s = 0; s <= lut_max; ++s) {
       double v = jaccard_of((double)s, (double)k);
       if (v < prune) v = 0;
       bool kp = (s > 0) && (v != 0);  // s == 0 entries are never stored by the product
@@ -1128,19 +1481,11 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     }
     uint8_t *d_keep;
     double *d_jac;
-    RC_TRY(ws_get(ctx, WS_LUT_KEEP, (size_t)smax + 1, &d_keep));
-    RC_TRY(ws_get(ctx, WS_LUT_JAC, (size_t)smax + 1, &d_jac));
+    RC_TRY(ws_get(ctx, WS_LUT_KEEP, (size_t)lut_max + 1, &d_keep));
+    RC_TRY(ws_get(ctx, WS_LUT_JAC, (size_t)lut_max + 1, &d_jac));
     CU_TRY(cudaMemcpyAsync(d_keep, h_keep.data(), h_keep.size(), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_jac, h_jac.data(), h_jac.size() * sizeof(double),
                            cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));  // the host vectors go out of scope below
-
-    // word format
-    int kbits = 1;
-    while (((int64_t)1 << kbits) < n) ++kbits;
-    bool use32 = kbits < 32 && smax <= (((int64_t)1 << (32 - kbits)) - 2);
-    const int cbits = use32 ? 32 - kbits : 32;
-    const size_t wbytes = use32 ? 4 : 8;
 
     int32_t *row_bound, *class_list, *row_nnz;
     int64_t *tmp_off, *snn_p;
@@ -1158,17 +1503,28 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     rw.k = k;
     rw.s_min = s_min;
     rw.n = n;
-    // the filtered kernel needs 32-bit words, no duplicated neighbours, byte-sized counts
+    // word format of the survivors: key << cbits | count.  The class limits are those of the 32-bit
+    // configuration whenever the key fits; a row that lists a neighbour twice (known only after the
+    // read-back below) may force 64-bit words, whose smaller tables take the same classes at half
+    // the limits -- those are applied inside k_row_work through has_dups.
+    int kbits = 1;
+    while (((int64_t)1 << kbits) < n) ++kbits;
+    const bool fits32_nodup = kbits < 32 && (int64_t)k <= (((int64_t)1 << (32 - kbits)) - 2);
+    const bool fits32_dup = kbits < 32 && (int64_t)k * k <= (((int64_t)1 << (32 - kbits)) - 2);
+    // the filtered kernels need 32-bit words, no duplicated neighbours, byte-sized counts
     // and a cut-off that actually removes single overlaps
-    const int filter_s_min = (use32 && !has_dups && k <= 255 && s_min >= 2 && s_min <= F_SMIN_MAX) ? s_min : 0;
-    // Class 0 is bounded by the 2^L0-word table of the plain warp kernel; the filtered kernel's
-    // tables are independent of it and its 30-warps-per-SM configuration is the fastest up to
-    // E ~ 2.8 k (measured: 1638 -> 13.2 ms, 2200 -> 12.8, 2800 -> 12.7, 3277 -> 12.8, 4000 -> 15.1)
-    rw.class_lim[0] = filter_s_min >= 2 ? 2800 : class_limit(use32 ? WordCfg32::L0 : WordCfg64::L0);
-    rw.class_lim[1] = class_limit(use32 ? WordCfg32::L1 : WordCfg64::L1);
-    rw.class_lim[2] = class_limit(use32 ? WordCfg32::L2 : WordCfg64::L2);
-    // the block-per-row kernel keeps survivors in a buffer of T/2 words: E <= T/2 there
-    rw.class_lim[3] = (1 << (use32 ? WordCfg32::L3 : WordCfg64::L3)) / 2;
+    const int filter_if_nodup = (fits32_nodup && k <= 255 && s_min >= 2 && s_min <= F_SMIN_MAX) ? s_min : 0;
+    // Class 0 is bounded by the 2^L0-word table of the plain warp kernel; the filtered kernels'
+    // tables are independent of it (measured best split for them: E <= 2.8 k)
+    for (int v = 0; v < 2; ++v) {  // v = 0: no duplicated neighbours, v = 1: some
+      const bool u32 = v == 0 ? fits32_nodup : fits32_dup;
+      int32_t *lim = v == 0 ? rw.class_lim : rw.class_lim_dup;
+      lim[0] = (v == 0 && filter_if_nodup >= 2) ? 2800 : class_limit(u32 ? WordCfg32::L0 : WordCfg64::L0);
+      lim[1] = class_limit(u32 ? WordCfg32::L1 : WordCfg64::L1);
+      lim[2] = class_limit(u32 ? WordCfg32::L2 : WordCfg64::L2);
+      // the block-per-row kernel keeps survivors in a buffer of T/2 words: E <= T/2 there
+      lim[3] = (1 << (u32 ? WordCfg32::L3 : WordCfg64::L3)) / 2;
+    }
     rw.row_bound = row_bound;
     rw.class_list = class_list;
     rw.info = d_info;
@@ -1177,9 +1533,26 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
       KERNEL_CHECK(ctx);
     }
     RC_TRY(scan_exclusive_i32_to_i64(ctx, row_bound, tmp_off, rows));
-    // sync #2: class sizes and the survivor-buffer bound
+    // the one read-back before the row kernels: flags of the transpose (index range, duplicated
+    // neighbours), class sizes and the survivor-buffer bound
     RC_TRY(fetch_info(ctx, d_info));
     hi = *ctx->h_info;
+    if (hi.err_index_range) {
+      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      b200nn_set_error("neighbour index out of range: every entry must lie in [1, %lld]", (long long)n);
+      return B200NN_ERR_INDEX_RANGE;
+    }
+    const bool has_dups = hi.has_dups != 0;
+    const int64_t smax = has_dups ? (int64_t)k * k : (int64_t)k;
+    if (smax > lut_max) {
+      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      b200nn_set_error("k = %d with duplicated neighbours exceeds the supported count range", k);
+      return B200NN_ERR_INVALID;
+    }
+    const bool use32 = has_dups ? fits32_dup : fits32_nodup;
+    const int cbits = use32 ? 32 - kbits : 32;
+    const size_t wbytes = use32 ? 4 : 8;
+    const int filter_s_min = has_dups ? 0 : filter_if_nodup;
     void *tmp;
     RC_TRY(ws_reserve(ctx, WS_TMP, ((size_t)hi.sum_bound + 1) * wbytes, &tmp));
     CU_TRY(cudaMemsetAsync(row_nnz, 0, sizeof(int32_t) * ((size_t)rows + 1), st));
@@ -1202,10 +1575,10 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     int32_t *ovf_list;
     RC_TRY(ws_get(ctx, WS_OVF_LIST, (size_t)rows + 1, &ovf_list));
     if (use32)
-      RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, hi.class_count,
+      RC_TRY(run_snn_classes<WordCfg32>(ctx, P, class_list, (int32_t)rows, n, hi.class_count,
                                         hi.max_row_e, has_dups, filter_s_min, ovf_list, d_info));
     else
-      RC_TRY(run_snn_classes<WordCfg64>(ctx, P, class_list, (int32_t)rows, hi.class_count,
+      RC_TRY(run_snn_classes<WordCfg64>(ctx, P, class_list, (int32_t)rows, n, hi.class_count,
                                         hi.max_row_e, has_dups, 0, ovf_list, d_info));
     RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
     // sync #3: nnz
@@ -1239,9 +1612,35 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
       stats->snn_expanded = hi.sum_row_e;
     }
   }
+  if (!compute_snn) {  // nothing was read back yet
+    RC_TRY(fetch_info(ctx, d_info));
+    hi = *ctx->h_info;
+    if (hi.err_index_range) {
+      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      b200nn_set_error("neighbour index out of range: every entry must lie in [1, %lld]", (long long)n);
+      return B200NN_ERR_INDEX_RANGE;
+    }
+  }
+  if (want_nn_graph) {
+    // join the side stream: the nn Graph is complete (its early copies may still be in flight on the
+    // copy stream; the host-buffer entry points wait for those)
+    int64_t nnz_nn = 0;
+    CU_TRY(cudaMemcpyAsync(&nnz_nn, nn_p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->side_stream));
+    CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+    ctx->nn_graph.valid = true;
+    ctx->nn_graph.n_rows = n;
+    ctx->nn_graph.nnz = nnz_nn;
+    ctx->nn_graph.p = nn_p;
+    ctx->nn_graph.i = nn_i;
+    ctx->nn_graph.x = nn_x;
+    if (stats) stats->nnz_nn = nnz_nn;
+  }
+  if (stats) stats->max_indegree = hi.max_indegree;
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));
   if (stats) {
+    // ms_nn_graph: the transpose the SNN stage waits for (histogram, scan, scatter); the sorted nn
+    // Graph columns are produced on the side stream while the SNN rows are computed
     float ms = 0;
     CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
     stats->ms_nn_graph = ms;

@@ -131,15 +131,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(const int32_t *__res
   }
 }
 
-int scan_exclusive_i32_to_i64(b200nn_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n) {
+int scan_exclusive_i32_to_i64(b200nn_ctx *ctx, const int32_t *d_in, int64_t *d_out, int64_t n,
+                              cudaStream_t stream, int tmp_slot) {
+  // a scan queued on another stream than the context's needs its own block-sum scratch
+  cudaStream_t st = stream ? stream : ctx->stream;
   int64_t nb = ceil_div64(n > 0 ? n : 1, SCAN_TILE);
   int64_t *bsum;
-  RC_TRY(ws_get(ctx, WS_SCAN_TMP, (size_t)nb + 1, &bsum));
-  k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, bsum);
+  RC_TRY(ws_get(ctx, tmp_slot >= 0 ? (WsSlot)tmp_slot : WS_SCAN_TMP, (size_t)nb + 1, &bsum));
+  k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, n, bsum);
   KERNEL_CHECK(ctx);
-  k_scan_bsums<<<1, 1024, 0, ctx->stream>>>(bsum, nb, d_out + n);
+  k_scan_bsums<<<1, 1024, 0, st>>>(bsum, nb, d_out + n);
   KERNEL_CHECK(ctx);
-  k_scan_down<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, bsum, d_out);
+  k_scan_down<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, n, bsum, d_out);
   KERNEL_CHECK(ctx);
   return B200NN_OK;
 }
@@ -209,9 +212,39 @@ __global__ void k_narrow(const int64_t *__restrict__ in, int32_t *__restrict__ o
   if (i < n) out[i] = (int32_t)in[i];
 }
 
-int narrow_i64_to_i32(b200nn_ctx *ctx, const int64_t *d_in, int32_t *d_out, int64_t n) {
+int narrow_i64_to_i32(b200nn_ctx *ctx, const int64_t *d_in, int32_t *d_out, int64_t n, cudaStream_t stream) {
   if (n <= 0) return B200NN_OK;
-  k_narrow<<<(unsigned)ceil_div64(n, 256), 256, 0, ctx->stream>>>(d_in, d_out, n);
+  k_narrow<<<(unsigned)ceil_div64(n, 256), 256, 0, stream ? stream : ctx->stream>>>(d_in, d_out, n);
   KERNEL_CHECK(ctx);
+  return B200NN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// RANN::nn2 goes through .C(..., NAOK = FALSE): R refuses NA / NaN / Inf before the search
+// starts.  The tensor path folds this test into its norm pass; the FP64 scan calls this.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_check_finite(const double *__restrict__ x, int64_t n, int32_t *flag) {
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    bad |= !isfinite(x[i]);
+  if (bad) *flag = 1;
+}
+
+int check_finite_f64(b200nn_ctx *ctx, const double *d_x, int64_t count, const char *what) {
+  if (count <= 0) return B200NN_OK;
+  int32_t *flag;
+  RC_TRY(ws_get(ctx, WS_FLAG, 4, &flag));
+  CU_TRY(cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+  int64_t blocks = ceil_div64(count, 256 * 8);
+  if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+  k_check_finite<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_x, count, flag);
+  KERNEL_CHECK(ctx);
+  int32_t h = 0;
+  CU_TRY(cudaMemcpyAsync(&h, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (h) {
+    b200nn_set_error("NA/NaN/Inf in foreign function call (arg %s)", what);
+    return B200NN_ERR_INVALID;
+  }
   return B200NN_OK;
 }

@@ -2,10 +2,16 @@
 
 The path shards naturally with ONE exchange step:
 
-  rank g owns query rows [g*ceil(n/G), ...)      -- kNN rows are independent
-  all-gather of the int32 kNN index (4*n*k bytes) -- the only collective
+  rank g computes the kNN rows of its share       -- kNN rows are independent
+  one collective on the int32 kNN index           -- the only exchange (4*n*k bytes)
   every rank transposes the full index locally    -- K3, cheap, HBM-bound
-  rank g emits SNN rows of its shard              -- K4 rows are independent
+  rank g emits SNN rows [g*ceil(n/G), ...)        -- K4 rows are independent
+
+Which kNN rows a rank computes is the library's choice when the backend offers
+``knn_owned`` (b200nn_opts.shard_rank / shard_world): whole groups of the tile-pruned
+search, so that every rank keeps full work items; the shares partition the rows and are
+combined by a sum all-reduce over zero-filled index buffers.  Otherwise (query != reference
+calls, the CPU test backend) rows are split contiguously and the index is all-gathered.
 
 The reference embedding is replicated on every GPU (<= 1 GB at 4M x 30).
 Distances never travel.  `torch.distributed` (NCCL over NVLink on GPUs, gloo
@@ -51,6 +57,22 @@ class CudaBackend:
                                                self.scan_mode)
         return idx0, dst
 
+    def knn_owned(self, ref: torch.Tensor, rank: int, world: int, k: int):
+        """Self search, share `rank` of `world`.  Returns (idx0 int32 [n, k] zero except the rows of this
+        share, dist float64 [n, k] NaN except those rows); the buffers are reused between calls."""
+        n, d = ref.shape
+        key = (n, k)
+        if getattr(self, "_owned_key", None) != key:
+            self._owned_idx = torch.empty((n, k), dtype=torch.int32, device=self.device)
+            self._owned_dist = torch.empty((n, k), dtype=torch.float64, device=self.device)
+            self._owned_key = key
+        self._owned_idx.zero_()
+        self._owned_dist.fill_(float("nan"))
+        torch.cuda.current_stream(self.device).synchronize()
+        self.last_stats = self.ctx.dev_knn(ref, n, None, n, d, k, self._owned_idx, self._owned_dist, self.knn_algo,
+                                           self.n_cand, self.scan_mode, rank, world)
+        return self._owned_idx, self._owned_dist
+
     def graph_rows(self, idx0_full: torch.Tensor, k: int, prune: float, compute_snn: bool,
                    row_begin: int, row_end: int) -> dict:
         n = idx0_full.shape[0]
@@ -87,6 +109,13 @@ def all_gather_index(idx_local: torch.Tensor, n: int, group=None) -> torch.Tenso
     return recv[:n]
 
 
+def all_reduce_index(idx_owned: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the zero-filled per-rank index buffers = the full index (the shares partition the rows)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(idx_owned, op=dist.ReduceOp.SUM, group=group)
+    return idx_owned
+
+
 def find_neighbors_sharded(ref: torch.Tensor, k: int, prune: float = 1 / 15, compute_snn: bool = True,
                            backend=None, group=None, qry: torch.Tensor | None = None) -> dict:
     """One rank's part of FindNeighbors on a replicated embedding.
@@ -101,6 +130,17 @@ def find_neighbors_sharded(ref: torch.Tensor, k: int, prune: float = 1 / 15, com
     n = ref.shape[0]
     nq = n if qry is None else qry.shape[0]
     b, e = shard_bounds(nq, world)[rank]
+    if qry is None and world > 1 and hasattr(backend, "knn_owned"):
+        # group-aligned shares: this rank's kNN rows are scattered over [0, n); "dist" is the full-size
+        # buffer (NaN rows belong to other ranks), "owned" the mask of the rows computed here
+        idx_owned, dist_owned = backend.knn_owned(ref, rank, world, k)
+        owned = ~torch.isnan(dist_owned[:, 0])
+        idx_full = all_reduce_index(idx_owned, group)
+        out = {"rows": (b, e), "idx0": idx_full[b:e], "dist": dist_owned, "owned": owned}
+        g = backend.graph_rows(idx_full, k, prune, compute_snn, b, e)
+        out.update(g)
+        out["idx0_full"] = idx_full
+        return out
     idx_local, dist_local = backend.knn_shard(ref, b, e, k, qry)
     out = {"rows": (b, e), "idx0": idx_local, "dist": dist_local}
     if qry is not None:

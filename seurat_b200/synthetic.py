@@ -13,6 +13,8 @@ CONFIGS = {
     "C": dict(n=1_000_000, d=50, k=20, seed=1),
     "D": dict(n=4_000_000, d=30, k=30, seed=2),
 }
+# config E (query path): 500k queries (seed 4, same centres) against 2M reference cells (seed 3)
+CONFIG_E = dict(nr=2_000_000, nq=500_000, d=50, k=20, seed_ref=3, seed_qry=4)
 
 
 def gaussian_mixture(n: int, d: int, seed: int, n_centres: int = 32, centre_sd: float = 6.0,
@@ -27,6 +29,36 @@ def gaussian_mixture(n: int, d: int, seed: int, n_centres: int = 32, centre_sd: 
         e = min(n, s + chunk)
         X[s:e] = centres[lab[s:e]] + rng.normal(0.0, 1.0, size=(e - s, d))
     return X, centres
+
+
+def shaped_embedding(kind: str, n: int, d: int = 50, seed: int = 7) -> np.ndarray:
+    """Inputs without the benchmark mixture's coarse cluster structure (VERDICT r1 "what's weak" 4):
+    the tile-pruned search has to stay exact -- and should stay fast -- on these too.
+
+      pca_like    decaying spectrum + 40 clusters of very different sizes (closest to a real PCA embedding)
+      manifold10  10 latent dimensions mapped linearly into d, small isotropic noise
+      uniform     uniform cube (nothing can be pruned in d = 50)
+      dups        benchmark mixture with a tenth of the rows replaced by exact copies of other rows
+    """
+    rng = np.random.default_rng(seed)
+    if kind == "mixture32":
+        return gaussian_mixture(n, d, 1)[0]
+    if kind == "uniform":
+        return rng.uniform(-1, 1, size=(n, d))
+    if kind == "manifold10":
+        z = rng.normal(size=(n, 10)) * np.linspace(3, 0.5, 10)
+        return np.ascontiguousarray(z @ rng.normal(size=(10, d)) + 0.05 * rng.normal(size=(n, d)))
+    if kind == "pca_like":
+        sizes = rng.dirichlet(np.ones(40) * 0.3)
+        lab = rng.choice(40, size=n, p=sizes)
+        cen = rng.normal(size=(40, d)) * np.linspace(8, 0.3, d)
+        return np.ascontiguousarray(cen[lab] + rng.normal(size=(n, d)) * np.linspace(2, 0.2, d))
+    if kind == "dups":
+        X = gaussian_mixture(n, d, 3)[0]
+        src = rng.integers(0, n, size=n // 10)
+        X[rng.integers(0, n, size=n // 10)] = X[src]
+        return X
+    raise ValueError(kind)
 
 
 def cell_names(n: int) -> list[str]:

@@ -9,7 +9,9 @@
 # the reference embedding kept on the GPU (an external pointer with a finaliser); NNHelper's
 # unchanged tail stores results$idx in the Neighbor's alg.idx slot.
 b200_nn2 <- function(data, query = data, k, cache.index = FALSE, index = NULL, ...) {
-  self <- identical(query, data)
+  # NNHelper passes query = data as the SAME object for the self search: identical() returns at
+  # its pointer check then, without comparing 400 MB; only equal-shaped distinct matrices are compared
+  self <- missing(query) || (identical(dim(query), dim(data)) && identical(query, data))
   if (!self) storage.mode(query) <- "double"
   if (is.null(index) && isTRUE(cache.index)) {
     storage.mode(data) <- "double"

@@ -16,6 +16,9 @@
  *   b200_FindNeighbors(data, k, prune, compute_snn)  the body of FindNeighbors.default,
  *                                   R/clustering.R:633-682, with the index kept on the GPU
  *                                   -> list(nn = dgCMatrix, snn = dgCMatrix)
+ *   With more than one GPU visible b200_nn2 and b200_FindNeighbors go through b200nn_multi_*:
+ *   the call is sharded over the devices inside the library (B200NN_NUM_DEVICES limits it,
+ *   B200NN_DEVICE pins it to one device).
  *   b200_index(data) / b200_index_nn2(index, query, k)  the cache.index = TRUE / index =
  *                                   arguments of NNHelper / FindNeighbors, R/clustering.R:596-597,
  *                                   :1686-1688: the reference embedding stays on the GPU behind an
@@ -35,7 +38,9 @@
 
 #include "b200nn.h"
 
-static b200nn_ctx *g_ctx = NULL;
+static b200nn_ctx *g_ctx = NULL;      /* first device: stages that start from an existing index */
+static b200nn_multi *g_multi = NULL;  /* every visible device: kNN and the fused FindNeighbors    */
+static int g_live_indexes = 0;        /* resident reference sets that still point into g_ctx      */
 
 static b200nn_ctx *get_ctx(void) {
   if (g_ctx == NULL) {
@@ -43,6 +48,26 @@ static b200nn_ctx *get_ctx(void) {
     if (b200nn_ctx_create(dev ? atoi(dev) : 0, &g_ctx) != B200NN_OK) Rf_error("%s", b200nn_last_error());
   }
   return g_ctx;
+}
+
+/* All visible GPUs (or the first B200NN_NUM_DEVICES of them) behind one handle; NULL when only
+ * one device is to be used, in which case the single-device entry points are called. */
+static b200nn_multi *get_multi(void) {
+  if (g_multi == NULL) {
+    const char *nd = getenv("B200NN_NUM_DEVICES");
+    int want = nd ? atoi(nd) : b200nn_device_count();
+    if (getenv("B200NN_DEVICE") != NULL) want = 1; /* an explicit device pins the call to it */
+    if (want <= 1) return NULL;
+    if (b200nn_multi_create(NULL, want, &g_multi) != B200NN_OK) Rf_error("%s", b200nn_last_error());
+  }
+  return g_multi;
+}
+
+/* nn2 accepts integer matrices as well (R coerces for .C): hand back a REALSXP, PROTECTed by the caller */
+static SEXP as_real_matrix(SEXP m, const char *what) {
+  if (!Rf_isMatrix(m) || !(Rf_isReal(m) || Rf_isInteger(m) || Rf_isLogical(m)))
+    Rf_error("%s must be a numeric matrix", what);
+  return Rf_isReal(m) ? m : Rf_coerceVector(m, REALSXP);
 }
 
 static SEXP make_dgCMatrix(int n, int64_t nnz, SEXP p, SEXP i, SEXP x) {
@@ -60,21 +85,26 @@ static SEXP make_dgCMatrix(int n, int64_t nnz, SEXP p, SEXP i, SEXP x) {
   return m;
 }
 
-/* RANN::nn2 drop-in: data, query are double matrices (column-major); query may be R_NilValue */
-SEXP b200_nn2(SEXP data, SEXP query, SEXP k_) {
-  if (!Rf_isReal(data) || !Rf_isMatrix(data)) Rf_error("data must be a numeric matrix");
+/* RANN::nn2 drop-in: data, query are numeric matrices (column-major); query may be R_NilValue */
+SEXP b200_nn2(SEXP data_, SEXP query_, SEXP k_) {
+  SEXP data = PROTECT(as_real_matrix(data_, "data"));
+  const int self = Rf_isNull(query_);
+  SEXP query = PROTECT(self ? R_NilValue : as_real_matrix(query_, "query"));
   const int nr = Rf_nrows(data), d = Rf_ncols(data), k = Rf_asInteger(k_);
-  const int self = Rf_isNull(query);
   const int nq = self ? nr : Rf_nrows(query);
   if (!self && Rf_ncols(query) != d) Rf_error("Query and data tables must have same dimensions");
   if (k > nr) Rf_error("Cannot find more nearest neighbours than there are points");
   SEXP idx = PROTECT(Rf_allocMatrix(INTSXP, nq, k));
   SEXP dist = PROTECT(Rf_allocMatrix(REALSXP, nq, k));
   b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
-  int rc = b200nn_knn(get_ctx(), REAL(data), nr, self ? NULL : REAL(query), nq, d, k, INTEGER(idx),
-                      REAL(dist), &o, NULL);
+  b200nn_multi *mu = get_multi();
+  /* non-finite input is refused inside the library (nn2's .C(NAOK = FALSE) behaviour) */
+  int rc = mu ? b200nn_multi_knn(mu, REAL(data), nr, self ? NULL : REAL(query), nq, d, k, INTEGER(idx),
+                                 REAL(dist), &o, NULL)
+              : b200nn_knn(get_ctx(), REAL(data), nr, self ? NULL : REAL(query), nq, d, k, INTEGER(idx),
+                           REAL(dist), &o, NULL);
   if (rc != B200NN_OK) {
-    UNPROTECT(2);
+    UNPROTECT(4);
     Rf_error("%s", b200nn_last_error());
   }
   SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
@@ -84,7 +114,7 @@ SEXP b200_nn2(SEXP data, SEXP query, SEXP k_) {
   SET_STRING_ELT(nms, 0, Rf_mkChar("nn.idx"));
   SET_STRING_ELT(nms, 1, Rf_mkChar("nn.dists"));
   Rf_setAttrib(res, R_NamesSymbol, nms);
-  UNPROTECT(4);
+  UNPROTECT(6);
   return res;
 }
 
@@ -117,29 +147,38 @@ SEXP b200_ComputeSNN(SEXP nn_ranked, SEXP prune_) {
   return m;
 }
 
-/* fused FindNeighbors.default body for query == object */
-SEXP b200_FindNeighbors(SEXP data, SEXP k_, SEXP prune_, SEXP compute_snn_) {
-  if (!Rf_isReal(data) || !Rf_isMatrix(data)) Rf_error("object must be a numeric matrix");
+/* fused FindNeighbors.default body for query == object; all visible GPUs take a share */
+SEXP b200_FindNeighbors(SEXP data_, SEXP k_, SEXP prune_, SEXP compute_snn_) {
+  SEXP data = PROTECT(as_real_matrix(data_, "object"));
   const int n = Rf_nrows(data), d = Rf_ncols(data), k = Rf_asInteger(k_);
   const int snn = Rf_asLogical(compute_snn_);
   int64_t nnz_nn = 0, nnz_snn = 0;
   b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
-  int rc = b200nn_find_neighbors_count(get_ctx(), REAL(data), n, d, k, Rf_asReal(prune_), snn, NULL, NULL,
-                                       NULL, NULL, NULL, &o, &nnz_nn, &nnz_snn, NULL);
-  if (rc != B200NN_OK) Rf_error("%s", b200nn_last_error());
-  R_CheckUserInterrupt();
+  b200nn_multi *mu = get_multi();
+  int rc = mu ? b200nn_multi_find_neighbors_count(mu, REAL(data), n, d, k, Rf_asReal(prune_), snn, NULL, NULL,
+                                                  NULL, NULL, NULL, &o, &nnz_nn, &nnz_snn, NULL)
+              : b200nn_find_neighbors_count(get_ctx(), REAL(data), n, d, k, Rf_asReal(prune_), snn, NULL, NULL,
+                                            NULL, NULL, NULL, &o, &nnz_nn, &nnz_snn, NULL);
+  if (rc != B200NN_OK) {
+    UNPROTECT(1);
+    Rf_error("%s", b200nn_last_error());
+  }
   SEXP np = PROTECT(Rf_allocVector(INTSXP, n + 1));
   SEXP ni = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz_nn));
   SEXP nx = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz_nn));
   SEXP sp = PROTECT(Rf_allocVector(INTSXP, snn ? n + 1 : 0));
   SEXP si = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)nnz_snn));
   SEXP sx = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)nnz_snn));
-  rc = b200nn_find_neighbors_fill(get_ctx(), INTEGER(np), INTEGER(ni), REAL(nx), snn ? INTEGER(sp) : NULL,
-                                  snn ? INTEGER(si) : NULL, snn ? REAL(sx) : NULL);
+  rc = mu ? b200nn_multi_find_neighbors_fill(mu, INTEGER(np), INTEGER(ni), REAL(nx), snn ? INTEGER(sp) : NULL,
+                                             snn ? INTEGER(si) : NULL, snn ? REAL(sx) : NULL)
+          : b200nn_find_neighbors_fill(get_ctx(), INTEGER(np), INTEGER(ni), REAL(nx), snn ? INTEGER(sp) : NULL,
+                                       snn ? INTEGER(si) : NULL, snn ? REAL(sx) : NULL);
   if (rc != B200NN_OK) {
-    UNPROTECT(6);
+    UNPROTECT(7);
     Rf_error("%s", b200nn_last_error());
   }
+  /* nothing of the library is pending any more: a user interrupt may unwind from here */
+  R_CheckUserInterrupt();
   SEXP res = PROTECT(Rf_allocVector(VECSXP, snn ? 2 : 1));
   SEXP nms = PROTECT(Rf_allocVector(STRSXP, snn ? 2 : 1));
   SET_VECTOR_ELT(res, 0, make_dgCMatrix(n, nnz_nn, np, ni, nx));
@@ -149,7 +188,7 @@ SEXP b200_FindNeighbors(SEXP data, SEXP k_, SEXP prune_, SEXP compute_snn_) {
     SET_STRING_ELT(nms, 1, Rf_mkChar("snn"));
   }
   Rf_setAttrib(res, R_NamesSymbol, nms);
-  UNPROTECT(8);
+  UNPROTECT(9);
   return res;
 }
 
@@ -157,29 +196,33 @@ SEXP b200_FindNeighbors(SEXP data, SEXP k_, SEXP prune_, SEXP compute_snn_) {
 static void index_finalizer(SEXP ptr) {
   b200nn_index *ix = (b200nn_index *)R_ExternalPtrAddr(ptr);
   if (ix != NULL) {
-    b200nn_index_destroy(g_ctx, ix);
+    b200nn_index_destroy(g_ctx, ix); /* g_ctx outlives every index: b200_release refuses otherwise */
     R_ClearExternalPtr(ptr);
+    if (g_live_indexes > 0) --g_live_indexes;
   }
 }
 
-SEXP b200_index(SEXP data) {
-  if (!Rf_isReal(data) || !Rf_isMatrix(data)) Rf_error("data must be a numeric matrix");
+SEXP b200_index(SEXP data_) {
+  SEXP data = PROTECT(as_real_matrix(data_, "data"));
   b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
   b200nn_index *ix = NULL;
-  if (b200nn_index_create(get_ctx(), REAL(data), Rf_nrows(data), Rf_ncols(data), &o, &ix) != B200NN_OK)
-    Rf_error("%s", b200nn_last_error());
+  int rc = b200nn_index_create(get_ctx(), REAL(data), Rf_nrows(data), Rf_ncols(data), &o, &ix);
+  UNPROTECT(1);
+  if (rc != B200NN_OK) Rf_error("%s", b200nn_last_error());
   SEXP ptr = PROTECT(R_MakeExternalPtr(ix, Rf_install("b200nn_index"), R_NilValue));
   R_RegisterCFinalizerEx(ptr, index_finalizer, TRUE);
+  ++g_live_indexes;
   UNPROTECT(1);
   return ptr;
 }
 
 /* nn2 against a resident reference set; query may be R_NilValue (self) */
-SEXP b200_index_nn2(SEXP index, SEXP query, SEXP k_) {
+SEXP b200_index_nn2(SEXP index, SEXP query_, SEXP k_) {
   b200nn_index *ix = (b200nn_index *)R_ExternalPtrAddr(index);
   if (ix == NULL) Rf_error("the cached index is no longer valid");
   const int nr = (int)b200nn_index_rows(ix), d = b200nn_index_dims(ix), k = Rf_asInteger(k_);
-  const int self = Rf_isNull(query);
+  const int self = Rf_isNull(query_);
+  SEXP query = PROTECT(self ? R_NilValue : as_real_matrix(query_, "query"));
   const int nq = self ? nr : Rf_nrows(query);
   if (!self && Rf_ncols(query) != d) Rf_error("Query and data tables must have same dimensions");
   SEXP idx = PROTECT(Rf_allocMatrix(INTSXP, nq, k));
@@ -187,7 +230,7 @@ SEXP b200_index_nn2(SEXP index, SEXP query, SEXP k_) {
   b200nn_opts o = {B200NN_COL_MAJOR, B200NN_KNN_AUTO, 0, 0};
   int rc = b200nn_index_knn(get_ctx(), ix, self ? NULL : REAL(query), nq, k, INTEGER(idx), REAL(dist), &o, NULL);
   if (rc != B200NN_OK) {
-    UNPROTECT(2);
+    UNPROTECT(3);
     Rf_error("%s", b200nn_last_error());
   }
   SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
@@ -197,16 +240,22 @@ SEXP b200_index_nn2(SEXP index, SEXP query, SEXP k_) {
   SET_STRING_ELT(nms, 0, Rf_mkChar("nn.idx"));
   SET_STRING_ELT(nms, 1, Rf_mkChar("nn.dists"));
   Rf_setAttrib(res, R_NamesSymbol, nms);
-  UNPROTECT(4);
+  UNPROTECT(5);
   return res;
 }
 
+/* Frees the device state.  Resident indexes live inside the single-device context: while any
+ * external pointer to one is still alive the context stays (their finaliser needs it). */
 SEXP b200_release(void) {
-  if (g_ctx) {
+  if (g_multi) {
+    b200nn_multi_destroy(g_multi);
+    g_multi = NULL;
+  }
+  if (g_ctx && g_live_indexes == 0) {
     b200nn_ctx_destroy(g_ctx);
     g_ctx = NULL;
   }
-  return R_NilValue;
+  return Rf_ScalarLogical(g_ctx == NULL);
 }
 
 static const R_CallMethodDef CallEntries[] = {

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_all_header_symbols():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in b200nn.h but not exported"
     assert sorted(_lib.SYMBOLS) == syms, "the ctypes binding must cover exactly the header's entry points"
-    assert L.b200nn_version() == 1
+    assert L.b200nn_version() == 2
 
 
 def test_no_torch_types_in_abi():

@@ -33,6 +33,21 @@ class OracleBackend:
         return out
 
 
+class OwnedOracleBackend(OracleBackend):
+    """a backend that, like libb200nn's grouped search, chooses a NON-contiguous share of the rows"""
+
+    def knn_owned(self, ref, rank, world, k):
+        n = ref.shape[0]
+        mine = np.nonzero((np.arange(n) * 7 + 3) % world == rank)[0]
+        idx = torch.zeros((n, k), dtype=torch.int32)
+        d = torch.full((n, k), float("nan"), dtype=torch.float64)
+        if mine.size:
+            wi, wd = oracle.knn(ref.numpy(), ref.numpy()[mine], k)
+            idx[mine] = torch.from_numpy(wi - 1)
+            d[mine] = torch.from_numpy(wd)
+        return idx, d
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -41,15 +56,19 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n, d, k, prune, tmpdir):
+def _worker(rank, world, port, n, d, k, prune, tmpdir, owned=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         rng = np.random.default_rng(42)
         X = torch.from_numpy(rng.normal(size=(n, d)))
-        r = sdist.find_neighbors_sharded(X, k, prune, True, backend=OracleBackend())
+        r = sdist.find_neighbors_sharded(X, k, prune, True, backend=OwnedOracleBackend() if owned else OracleBackend())
         b, e = r["rows"]
+        if owned:   # the distances of the rows this rank computed, at their original positions
+            wi, wd = oracle.knn(X.numpy(), k=k)
+            own = r["owned"].numpy()
+            assert own.sum() > 0 and (r["dist"].numpy()[own] == wd[own]).all()
         assert (b, e) == sdist.shard_bounds(n, world)[rank]
         full = sdist.gather_csr_rows(*r["snn"], dst=0)
         # kNN rows gathered for the check
@@ -68,10 +87,11 @@ def _worker(rank, world, port, n, d, k, prune, tmpdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 501), (3, 100), (2, 64)])
-def test_sharded_pipeline_equals_single_process(tmp_path, world, n):
+@pytest.mark.parametrize("world,n,owned", [(2, 501, False), (3, 100, False), (2, 64, False), (2, 333, True),
+                                            (3, 200, True)])
+def test_sharded_pipeline_equals_single_process(tmp_path, world, n, owned):
     d, k, prune = 6, 10, 1 / 15
-    mp.spawn(_worker, args=(world, _free_port(), n, d, k, prune, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, d, k, prune, str(tmp_path), owned), nprocs=world, join=True)
     got = np.load(os.path.join(str(tmp_path), "out.npz"))
     X = np.random.default_rng(42).normal(size=(n, d))
     idx, _ = oracle.knn(X, k=k)

@@ -11,32 +11,14 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import seurat_b200 as sb  # noqa: E402
-from seurat_b200.synthetic import gaussian_mixture  # noqa: E402
+from seurat_b200.synthetic import shaped_embedding  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 d, k = 50, 20
-rng = np.random.default_rng(7)
 
 
 def make(kind):
-    if kind == "mixture32":
-        return gaussian_mixture(n, d, 1)[0]
-    if kind == "uniform":
-        return rng.uniform(-1, 1, size=(n, d))
-    if kind == "manifold10":          # 10 latent dimensions mapped linearly into 50, small isotropic noise
-        z = rng.normal(size=(n, 10)) * np.linspace(3, 0.5, 10)
-        return z @ rng.normal(size=(10, d)) + 0.05 * rng.normal(size=(n, d))
-    if kind == "pca_like":            # decaying spectrum + 40 clusters of very different sizes
-        sizes = rng.dirichlet(np.ones(40) * 0.3)
-        lab = rng.choice(40, size=n, p=sizes)
-        cen = rng.normal(size=(40, d)) * np.linspace(8, 0.3, d)
-        return cen[lab] + rng.normal(size=(n, d)) * np.linspace(2, 0.2, d)
-    if kind == "dups":                # a tenth of the rows are exact copies of other rows
-        X = gaussian_mixture(n, d, 3)[0]
-        src = rng.integers(0, n, size=n // 10)
-        X[rng.integers(0, n, size=n // 10)] = X[src]
-        return X
-    raise ValueError(kind)
+    return shaped_embedding(kind, n, d)
 
 
 ctx = sb.Context(0)
