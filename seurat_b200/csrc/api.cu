@@ -290,10 +290,12 @@ void b200nn_ctx_destroy(b200nn_ctx *ctx) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
   }
-  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
-  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;

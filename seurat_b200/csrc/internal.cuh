@@ -88,6 +88,10 @@ enum WsSlot {
   WS_TC_FBUF,      // centroids, radii, item balls
   WS_TC_TILES,     // per-item tile lists
   WS_FLAG,         // one int32 flag (finite check)
+  WS_LOW_OFF,      // symmetric SNN: offsets of the mirrored (lower-triangle) segments
+  WS_LOW_WORDS,    //                packed words of the lower triangle, unsorted / sorted per row
+  WS_LOW_SORTED,
+  WS_LONG_LIST2,
   WS_TC_CENT16,    // fp16 operand rows of the group centroids (tensor-core assignment)
   WS_REV_SORTED,   // reverse lists sorted per column (nn Graph side stream)
   WS_SCAN_TMP2,    // block sums of scans queued on the side stream
@@ -115,6 +119,9 @@ struct DevInfo {
   int32_t n_long;            // columns too long for the warp-level sort
   int32_t n_ovf;             // rows the filtered SNN kernel handed to the big-table kernel
   int32_t pad_;
+  long long dbg_hot_keys;    // experimental single-walk kernel: distinct hot keys verified (all rows)
+  int32_t n_long2;           // long lower-triangle segments of the symmetric SNN assembly
+  int32_t pad2_;
 };
 
 struct CsrResult {

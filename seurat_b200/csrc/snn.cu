@@ -144,11 +144,13 @@ constexpr int SORT_WARP_CAP = 1024;  // elements a warp sorts in shared memory
 
 // one warp per column: sorted copy of the reverse list (the nn Graph's column), distinct rows counted.
 // Out of place: the SNN kernels read the unsorted lists concurrently (they do not need an order).
+template <typename T>  // int32_t: reverse lists (uniq counted); uint32_t: packed SNN words (uniq == nullptr)
 __global__ void __launch_bounds__(SORT_WARPS * 32)
-k_sort_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, const int64_t *__restrict__ colptr,
+k_sort_columns(const T *__restrict__ rev, T *__restrict__ out, const int64_t *__restrict__ colptr,
                int64_t n, int32_t *__restrict__ uniq, int32_t *__restrict__ long_list,
                int32_t *__restrict__ n_long) {
-  __shared__ int32_t sbuf[SORT_WARPS][SORT_WARP_CAP];
+  __shared__ T sbuf[SORT_WARPS][SORT_WARP_CAP];
+  constexpr T TMAX = (T)(~(T)0) > 0 ? (T)(~(T)0) : (T)INT_MAX;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * SORT_WARPS + w;
   if (c >= n) return;
@@ -157,33 +159,33 @@ k_sort_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, const
   const int len = (int)len64;
   if (len <= 1) {
     if (lane == 0) {
-      uniq[c] = len;
+      if (uniq) uniq[c] = len;
       if (len == 1) out[beg] = rev[beg];
     }
     return;
   }
   int ndup = 0;
   if (len <= 32) {
-    int32_t v = lane < len ? rev[beg + lane] : INT_MAX;
+    T v = lane < len ? rev[beg + lane] : TMAX;
 #pragma unroll
     for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
       for (int j = kk >> 1; j > 0; j >>= 1) {
-        int32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+        T o = __shfl_xor_sync(0xffffffffu, v, j);
         bool up = (lane & kk) == 0, lower = (lane & j) == 0;
         v = (lower == up) ? min(v, o) : max(v, o);
       }
     }
-    int32_t prev = __shfl_up_sync(0xffffffffu, v, 1);
+    T prev = __shfl_up_sync(0xffffffffu, v, 1);
     if (lane < len) out[beg + lane] = v;
     ndup = (lane > 0 && lane < len && v == prev) ? 1 : 0;
   } else if (len <= SORT_WARP_CAP) {
-    int32_t *a = sbuf[w];
+    T *a = sbuf[w];
     for (int t = lane; t < len; t += 32) a[t] = rev[beg + t];
     __syncwarp();
     bitonic_sort_asc(a, len, lane, 32, [] { __syncwarp(); });
     for (int t = lane; t < len; t += 32) {
-      int32_t v = a[t];
+      T v = a[t];
       out[beg + t] = v;
       if (t > 0 && a[t - 1] == v) ndup++;
     }
@@ -195,25 +197,27 @@ k_sort_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, const
     return;  // uniq[c] is written by k_sort_long_columns
   }
   ndup = warp_sum_i32(ndup);
-  if (lane == 0) uniq[c] = len - ndup;
+  if (lane == 0 && uniq) uniq[c] = len - ndup;
 }
 
 constexpr int LONG_THREADS = 1024;
 constexpr int LONG_SMEM_CAP = 32768;  // elements (128 KB)
 
 // one CTA per long column (hubs)
+template <typename T>
 __global__ void __launch_bounds__(LONG_THREADS)
-k_sort_long_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, const int64_t *__restrict__ colptr,
+k_sort_long_columns(const T *__restrict__ rev, T *__restrict__ out, const int64_t *__restrict__ colptr,
                     int32_t *__restrict__ uniq, const int32_t *__restrict__ long_list,
                     const int32_t *__restrict__ n_long_p) {
-  extern __shared__ int32_t lbuf[];
+  extern __shared__ int32_t lbuf_raw[];
+  T *lbuf = reinterpret_cast<T *>(lbuf_raw);
   __shared__ int red[32];
   const int n_long = *n_long_p;
   for (int li = blockIdx.x; li < n_long; li += gridDim.x) {
     const int64_t c = long_list[li];
     const int64_t beg = colptr[c];
     const int len = (int)(colptr[c + 1] - beg);
-    int32_t *a;
+    T *a;
     if (len <= LONG_SMEM_CAP) {
       a = lbuf;
     } else {
@@ -224,7 +228,7 @@ k_sort_long_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, 
     bitonic_sort_asc(a, len, (int)threadIdx.x, LONG_THREADS, [] { __syncthreads(); });
     int ndup = 0;
     for (int t = threadIdx.x; t < len; t += LONG_THREADS) {
-      int32_t v = a[t];
+      T v = a[t];
       if (t > 0 && a[t - 1] == v) ndup++;
     }
     __syncthreads();
@@ -235,7 +239,7 @@ k_sort_long_columns(const int32_t *__restrict__ rev, int32_t *__restrict__ out, 
     __syncthreads();
     if (threadIdx.x < 32) {
       int v = warp_sum_i32(red[threadIdx.x]);
-      if (threadIdx.x == 0) uniq[c] = len - v;
+      if (threadIdx.x == 0 && uniq) uniq[c] = len - v;
     }
     __syncthreads();
   }
@@ -292,6 +296,8 @@ struct SnnParams {
   int32_t *row_nnz;        // [rows]
   void *huge_tables;       // HBM hash tables (huge class)
   int32_t huge_log_t;
+  int32_t sym;             // 1: only candidates j > i are counted (upper triangle; S is symmetric and
+                           //    the lower triangle + diagonal are mirrored afterwards)
 };
 
 template <typename Word>
@@ -417,8 +423,10 @@ __global__ void __launch_bounds__(G *RPB) k_snn_rows(SnnParams P) {
       const int32_t c = nbr[p];
       const int64_t beg = P.colptr[c];
       const int len = (int)(P.colptr[c + 1] - beg);
-      for (int t = g; t < len; t += G)
-        hash_insert<Word>(tab, mask, log_t, P.cbits, (uint32_t)P.rev[beg + t]);
+      for (int t = g; t < len; t += G) {
+        const int32_t j = P.rev[beg + t];
+        if (!P.sym || (int64_t)j > row) hash_insert<Word>(tab, mask, log_t, P.cbits, (uint32_t)j);
+      }
     }
     gsync();
     // 3. keep the entries that pass the prune cut-off
@@ -505,12 +513,17 @@ __global__ void __launch_bounds__(WARPS * 32) k_snn_rows_warp(SnnParams P) {
         const int32_t *src = P.rev + b;
         for (int t = lane; ATOMIC && t < l; t += 128) {
           // up to four independent loads in flight, then the (serialising) inserts
-          const int32_t v0 = src[t];
-          const int32_t v1 = (t + 32 < l) ? src[t + 32] : -1;
-          const int32_t v2 = (t + 64 < l) ? src[t + 64] : -1;
-          const int32_t v3 = (t + 96 < l) ? src[t + 96] : -1;
+          const int lowkey = P.sym ? (int)row : -1;
+          int32_t v0 = src[t];
+          int32_t v1 = (t + 32 < l) ? src[t + 32] : -1;
+          int32_t v2 = (t + 64 < l) ? src[t + 64] : -1;
+          int32_t v3 = (t + 96 < l) ? src[t + 96] : -1;
+          if (v0 <= lowkey) v0 = -1;
+          if (v1 <= lowkey) v1 = -1;
+          if (v2 <= lowkey) v2 = -1;
+          if (v3 <= lowkey) v3 = -1;
           if (ATOMIC) {
-            hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v0);
+            if (v0 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v0);
             if (v1 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v1);
             if (v2 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v2);
             if (v3 >= 0) hash_insert<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v3);
@@ -520,10 +533,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_snn_rows_warp(SnnParams P) {
           // warp-synchronous variant: the loop bound must be warp-uniform
           for (int t0 = 0; t0 < l; t0 += 128) {
             const int t = t0 + lane;
-            const int32_t v0 = (t < l) ? src[t] : -1;
-            const int32_t v1 = (t + 32 < l) ? src[t + 32] : -1;
-            const int32_t v2 = (t + 64 < l) ? src[t + 64] : -1;
-            const int32_t v3 = (t + 96 < l) ? src[t + 96] : -1;
+            const int lowkey = P.sym ? (int)row : -1;
+            int32_t v0 = (t < l) ? src[t] : -1;
+            int32_t v1 = (t + 32 < l) ? src[t + 32] : -1;
+            int32_t v2 = (t + 64 < l) ? src[t + 64] : -1;
+            int32_t v3 = (t + 96 < l) ? src[t + 96] : -1;
+            if (v0 <= lowkey) v0 = -1;
+            if (v1 <= lowkey) v1 = -1;
+            if (v2 <= lowkey) v2 = -1;
+            if (v3 <= lowkey) v3 = -1;
             hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v0, v0 >= 0);
             if (t0 + 32 < l) hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v1, v1 >= 0);
             if (t0 + 64 < l) hash_insert_warp<Word>(tab, mask, LOG_T, P.cbits, (uint32_t)v2, v2 >= 0);
@@ -690,8 +708,12 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
         int64_t b = __shfl_sync(0xffffffffu, beg, 0);
         int l = __shfl_sync(0xffffffffu, len, 0);
         int32_t v[4], nv[4];
+        const int lowkey = P.sym ? (int)row : -1;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (32 * u + lane < l) ? P.rev[b + 32 * u + lane] : -1;
+        for (int u = 0; u < 4; ++u) {
+          v[u] = (32 * u + lane < l) ? P.rev[b + 32 * u + lane] : -1;
+          if (v[u] <= lowkey) v[u] = -1;
+        }
         while (pl < np && !ovf) {
           int pn = pl, tn = t0 + 128;
           int64_t bn = b;
@@ -706,7 +728,10 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
           }
           if (pn < np) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) nv[u] = (tn + 32 * u + lane < ln) ? P.rev[bn + tn + 32 * u + lane] : -1;
+            for (int u = 0; u < 4; ++u) {
+              nv[u] = (tn + 32 * u + lane < ln) ? P.rev[bn + tn + 32 * u + lane] : -1;
+              if (nv[u] <= lowkey) nv[u] = -1;
+            }
           }
           uint32_t hc[4];
 #pragma unroll
@@ -802,38 +827,247 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
 }
 
 // ---------------------------------------------------------------------------
-// Single-walk warp-per-row kernel with BYTE-FLAG levels (default for 2 <= s_min <= 5, k <= 32,
-// no duplicated neighbours).
-//
-// The two-walk kernel above is bound by shared-memory atomics: an ATOMS with spread addresses
-// retires 2 cycles per LANE, and pass A issues one per candidate occurrence (measured round 1:
-// ~1 occurrence / clk / SM; round 2, a single-walk variant with the same 4-bit atomic counters
-// was no faster: profiles/r02_ab1_*.txt).  This kernel counts without any atomic:
-//   * level flags: L1, L2, .. L(s_min-1) are byte arrays.  An occurrence of key j climbs the
-//     levels: at the first level whose flag (at j's slot) is still 0 it writes 1 and stops;
-//     if all s_min - 1 flags are already set it is "hot".  A byte store of the constant 1 is
-//     idempotent, so colliding lanes need no atomic, and a collision can only help a key climb
-//     faster (false positive), never slower: after its t-th occurrence the flags L1..Lt of a key
-//     are set, hence the s_min-th occurrence of every surviving key is hot.
+// Walker over the k reverse lists of a row (k <= 32: lane p holds the descriptor of list p), in
+// 128-element blocks.  Lists flagged in ro_mask are visited after all the others (phase 1).
+// Pigeonhole: a key that survives the cut-off occurs in >= s_min of the k lists, hence in at least
+// one list other than the s_min - 1 LONGEST ones; those lists (the hubs, ~1/3 of all occurrences)
+// therefore never have to create a counter, only to bump the ones that exist.
+// ---------------------------------------------------------------------------
+struct ListWalk {
+  int64_t beg;   // per lane: start of list `lane` in rev
+  int len;       // per lane: its length
+  unsigned ro_mask;
+  int k;
+  // warp-uniform cursor
+  int ph, pl, t0, l;
+  int64_t b;
+  __device__ __forceinline__ void start(unsigned mask) {
+    ro_mask = mask;
+    ph = 0;
+    pl = -1;
+    t0 = 0;
+    l = 0;
+    b = 0;
+  }
+  // next 128-element block; false when every list has been walked
+  __device__ __forceinline__ bool advance() {
+    t0 += 128;
+    while (true) {
+      if (pl >= 0 && t0 < l) return true;
+      ++pl;
+      t0 = 0;
+      l = 0;
+      if (pl >= k) {
+        if (ph == 1 || ro_mask == 0) return false;
+        ph = 1;
+        pl = -1;
+        continue;
+      }
+      if ((((ro_mask >> pl) & 1u) != 0) != (ph == 1)) continue;
+      b = __shfl_sync(0xffffffffu, beg, pl);
+      l = __shfl_sync(0xffffffffu, len, pl);
+    }
+  }
+  __device__ __forceinline__ void load(const int32_t *__restrict__ rev, int lane, int lowkey, int32_t (&v)[4]) const {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = (t0 + 32 * u + lane < l) ? rev[b + t0 + 32 * u + lane] : -1;
+      if (v[u] <= lowkey) v[u] = -1;  // symmetric mode: only candidates j > i
+    }
+  }
+};
+
+// the n_ro longest of the (<= 32) lists, as a lane mask (ties: higher lane first)
+__device__ __forceinline__ unsigned longest_lists(int len, int lane, int k, int n_ro) {
+  bool ro = false;
+  const int key = lane < k ? (len << 5) | lane : -1;
+  for (int t = 0; t < n_ro; ++t) {
+    int m = ro ? -1 : key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (m >= 0 && key == m) ro = true;
+  }
+  return __ballot_sync(0xffffffffu, ro);
+}
+
+// ---------------------------------------------------------------------------
+// Two-walk filtered kernel for k <= 32 (the default): pass A (4-bit saturating counters) and pass B
+// (exact table for the occurrences whose counter reached s_min) as in k_snn_rows_filter, plus
+//   * read-only handling of the s_min - 1 longest lists in pass A (see ListWalk): pass A is bound
+//     by shared-memory atomics (an ATOMS with spread addresses retires 2 cycles per LANE; measured
+//     ~1 occurrence / clk / SM), and this removes the atomics of most hub occurrences;
+//   * symmetric mode (P.sym): only candidates j > i are counted -- half the occurrences.
+// ---------------------------------------------------------------------------
+template <int CW_LOG, int F_TX_LOG, int F_WARPS>
+__global__ void __launch_bounds__(F_WARPS * 32)
+k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+  constexpr int F_BYTES = filt_bytes(CW_LOG, F_TX_LOG);
+  constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
+  static_assert((1 << CW_LOG) / 2 >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem_raw + (size_t)w * F_BYTES;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(base);  // eight 4-bit counters per word
+  uint32_t *tab = reinterpret_cast<uint32_t *>(base + (1 << CW_LOG) / 2);
+  uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
+  uint32_t *pend = reinterpret_cast<uint32_t *>(slots + F_SLOT_CAP);
+  const uint32_t cmask = (1u << P.cbits) - 1;
+  const int k = P.k;
+  for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+  const int n_warps = gridDim.x * F_WARPS;
+  for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
+    const int row_l = P.row_list[r];
+    const int64_t row = P.row_begin + row_l;
+    const int lowkey = P.sym ? (int)row : -1;
+    {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
+      for (int s = lane; s < (1 << CW_LOG) / 32; s += 32) c4[s] = z;
+    }
+    __syncwarp();
+    ListWalk W;
+    W.k = k;
+    W.beg = 0;
+    W.len = 0;
+    if (lane < k) {
+      const int32_t c = P.idx0[row * k + lane];
+      W.beg = P.colptr[c];
+      W.len = (int)(P.colptr[c + 1] - W.beg);
+    }
+    const unsigned ro_mask = longest_lists(W.len, lane, k, n_ro);
+    int nslots = 0, npend = 0;
+    bool ovf = false, sat = false;
+    int32_t v[4], nv[4];
+    // ---- pass A: count (atomics only where a counter may still matter) ----
+    W.start(ro_mask);
+    bool have = W.advance();
+    if (have) W.load(P.rev, lane, lowkey, v);
+    while (have) {
+      const int ph = W.ph, t0 = W.t0, l = W.l;
+      have = W.advance();
+      if (have) W.load(P.rev, lane, lowkey, nv);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (t0 + 32 * u >= l) break;  // warp-uniform
+        if (v[u] >= 0) {
+          const uint32_t hc = hash_cnt<CW_LOG>((uint32_t)v[u]);
+          const uint32_t sh = (hc & 7u) * 4u;
+          volatile uint32_t *wp = cnt + (hc >> 3);
+          const int c4 = (int)((*wp >> sh) & 15u);
+          if (c4 < s_min && (ph == 0 || c4 > 0)) {
+            const uint32_t old = atomicAdd(cnt + (hc >> 3), 1u << sh);
+            sat |= ((old >> sh) & 15u) == 15u;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = nv[u];
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, sat)) ovf = true;  // a counter wrapped: the big-table kernel takes the row
+    // ---- pass B: exact counts of the occurrences whose counter reached s_min ----
+    if (!ovf) {
+      W.start(0u);
+      have = W.advance();
+      if (have) W.load(P.rev, lane, lowkey, v);
+      while (have && !ovf) {
+        const int t0 = W.t0, l = W.l;
+        have = W.advance();
+        if (have) W.load(P.rev, lane, lowkey, nv);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (t0 + 32 * u >= l) break;  // warp-uniform
+          bool pass_f = false;
+          if (v[u] >= 0) {
+            const uint32_t hc = hash_cnt<CW_LOG>((uint32_t)v[u]);
+            pass_f = (int)((cnt[hc >> 3] >> ((hc & 7u) * 4u)) & 15u) >= s_min;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
+          if (bal) {
+            if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
+            npend += __popc(bal);
+            __syncwarp();
+            if (npend >= 32) {
+              filt_insert_batch<F_TX_LOG>(tab, slots, nslots, P.cbits, pend[lane], true, lane);
+              const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
+              __syncwarp();
+              if (32 + lane < npend) pend[lane] = mv;
+              npend -= 32;
+              __syncwarp();
+              if (nslots > F_SLOTS) ovf = true;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = nv[u];
+      }
+      if (!ovf && npend > 0) {
+        filt_insert_batch<F_TX_LOG>(tab, slots, nslots, P.cbits, lane < npend ? pend[lane] : 0, lane < npend, lane);
+        if (nslots > F_SLOTS) ovf = true;
+      }
+    }
+    __syncwarp();
+    if (ovf) {
+      for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+      if (lane == 0) {
+        P.row_nnz[row_l] = 0;
+        ovf_list[atomicAdd(&info->n_ovf, 1)] = row_l;
+      }
+      __syncwarp();
+      continue;
+    }
+    // survivors: exact counts against the cut-off, compacted into the (now free) counter area
+    uint32_t *out = reinterpret_cast<uint32_t *>(cnt);
+    int m = 0;
+    for (int t0 = 0; t0 < nslots; t0 += 32) {
+      const int t = t0 + lane;
+      uint32_t wv = 0;
+      bool kp = false;
+      if (t < nslots) {
+        const int sl = slots[t];
+        wv = tab[sl];
+        tab[sl] = 0xffffffffu;
+        kp = P.keep[wv & cmask] != 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, kp);
+      if (kp) out[m + __popc(bal & ((1u << lane) - 1))] = wv;
+      m += __popc(bal);
+    }
+    __syncwarp();
+    bitonic_sort_asc(out, m, lane, 32, [] { __syncwarp(); });
+    uint32_t *dst = reinterpret_cast<uint32_t *>(P.tmp) + P.tmp_off[row_l];
+    for (int t = lane; t < m; t += 32) dst[t] = out[t];
+    if (lane == 0) P.row_nnz[row_l] = m;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Experimental single-walk kernel (B200NN_SNN_BITS=1): no shared-memory atomics at all.
+//   * level bit maps L1 .. L(s_min-1): an occurrence of key j climbs the levels; at the first level
+//     whose bit (at j's position) is still 0 it sets the bit and stops; if all s_min - 1 bits are
+//     already set it is "hot".  After its t-th occurrence the bits L1..Lt of a key are set, so the
+//     s_min-th occurrence of every surviving key is hot; collisions only add false positives.
+//     Bits are set with a plain 32-bit read-modify-write followed by a read-back: lanes that lose a
+//     same-word race in the same instruction see their bit missing and retry.
+//     (A variant with BYTE flags was measured 2x slower than the two-walk kernel: divergent
+//     sub-word shared-memory accesses cost about as much as the atomics they replaced,
+//     profiles/r02_ab2_snn_byte_flags.txt.)
 //   * hot keys are de-duplicated in a small exact key table;
 //   * the exact count of each distinct hot key j comes from the FORWARD lists:
 //         S_ij = |N(i) ∩ N(j)|      (A is 0/1 without duplicated neighbours, src/snn.cpp:27)
-//     one lane per hot key reads N(j) and probes a 64-word hash set of N(i); ~40 keys per row
-//     are verified instead of ~1800 occurrences walked a second time.
-//   * pigeonhole: a surviving key occurs in >= s_min of the k lists, hence in at least one list
-//     other than the s_min - 1 LONGEST ones; those lists (hubs) are walked last and never set a
-//     level-1 flag, which removes most of their false positives.
-// Output, cut-off and x values are exactly those of the kernels above (same LUTs).
+//     one lane per hot key reads N(j) and probes a 64-word hash set of N(i).
+// Output, cut-off and x values are exactly those of the other kernels (same LUTs).
 // ---------------------------------------------------------------------------
 constexpr int HOT_NSET = 64;  // hash set of N(i): k <= 32 keys in 64 words
-constexpr int flag_level_bytes(int lv1_log, int l) { return 1 << (lv1_log - (l < 2 ? l : 2)); }
-constexpr int flag_total_bytes(int lv1_log, int levels) {
+constexpr int bits_level_words(int lv1_log, int l) { return (1 << (lv1_log - (l < 2 ? l : 2))) / 32; }
+constexpr int bits_total_words(int lv1_log, int levels) {
   int b = 0;
-  for (int l = 0; l < levels; ++l) b += flag_level_bytes(lv1_log, l);
+  for (int l = 0; l < levels; ++l) b += bits_level_words(lv1_log, l);
   return b;
 }
 constexpr int hot_bytes(int lv1_log, int levels, int tx_log) {
-  return flag_total_bytes(lv1_log, levels) + (1 << tx_log) * 4 + ((filt_slot_cap(tx_log) * 2 + 15) & ~15) + 64 * 4 +
+  return bits_total_words(lv1_log, levels) * 4 + (1 << tx_log) * 4 + ((filt_slot_cap(tx_log) * 2 + 15) & ~15) + 64 * 4 +
          HOT_NSET * 4;
 }
 
@@ -880,17 +1114,18 @@ __device__ __forceinline__ int nset_probe(const uint32_t *nset, uint32_t c) {
 
 template <int LV1_LOG, int LEVELS, int F_TX_LOG, int F_WARPS>
 __global__ void __launch_bounds__(F_WARPS * 32)
-k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+k_snn_rows_bits(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
   constexpr int F_BYTES = hot_bytes(LV1_LOG, LEVELS, F_TX_LOG);
-  constexpr int FLAG_BYTES = flag_total_bytes(LV1_LOG, LEVELS);
+  constexpr int BIT_WORDS = bits_total_words(LV1_LOG, LEVELS);
   constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
-  static_assert(FLAG_BYTES >= F_SLOT_CAP * 4, "the flag area doubles as the hot-key buffer");
+  static_assert(BIT_WORDS >= F_SLOT_CAP, "the bit maps double as the hot-key buffer");
+  static_assert(BIT_WORDS % 4 == 0, "cleared with 16-byte stores");
   static_assert(LEVELS >= 1 && LEVELS <= 4, "s_min - 1 levels");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + (size_t)w * F_BYTES;
-  volatile uint8_t *flags = base;
-  uint32_t *tab = reinterpret_cast<uint32_t *>(base + FLAG_BYTES);
+  volatile uint32_t *bits = reinterpret_cast<uint32_t *>(base);
+  uint32_t *tab = reinterpret_cast<uint32_t *>(base) + BIT_WORDS;
   uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
   uint32_t *pend = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(slots) +
                                                 ((F_SLOT_CAP * 2 + 15) & ~15));
@@ -901,21 +1136,24 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
   for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
     const int row_l = P.row_list[r];
     const int64_t row = P.row_begin + row_l;
+    const int lowkey = P.sym ? (int)row : -1;
     {
       const uint4 z = make_uint4(0, 0, 0, 0);
       uint4 *c4 = reinterpret_cast<uint4 *>(base);
-      for (int s = lane; s < FLAG_BYTES / 16; s += 32) c4[s] = z;
+      for (int s = lane; s < BIT_WORDS / 4; s += 32) c4[s] = z;
       nset[lane] = 0xffffffffu;
       nset[lane + 32] = 0xffffffffu;
     }
     __syncwarp();
     // list descriptors (k <= 32: one list per lane) and the hash set of N(i)
-    int64_t beg = 0;
-    int len = 0;
+    ListWalk W;
+    W.k = k;
+    W.beg = 0;
+    W.len = 0;
     if (lane < k) {
       const uint32_t c = (uint32_t)P.idx0[row * k + lane];
-      beg = P.colptr[c];
-      len = (int)(P.colptr[c + 1] - beg);
+      W.beg = P.colptr[c];
+      W.len = (int)(P.colptr[c + 1] - W.beg);
       uint32_t h = (c * 2654435761u) >> (32 - 6);
       while (true) {
         const uint32_t old = atomicCAS(&nset[h], 0xffffffffu, c);
@@ -923,57 +1161,18 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
         h = (h + 1) & (HOT_NSET - 1);
       }
     }
-    // the n_ro longest lists are walked last and never set a level-1 flag
-    bool ro = false;
-    {
-      const int key = lane < k ? (len << 5) | lane : -1;
-      for (int t = 0; t < n_ro; ++t) {
-        int m = ro ? -1 : key;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (m >= 0 && key == m) ro = true;
-      }
-    }
-    const unsigned ro_mask = __ballot_sync(0xffffffffu, ro);
+    const unsigned ro_mask = longest_lists(W.len, lane, k, n_ro);
     int nslots = 0, npend = 0;
     bool ovf = false;
-    // walk (phase, list, 128-element block); the next block's loads are issued before the
-    // current block is processed
-    int ph = 0, pl = -1, t0 = 0, l = 0;
-    int64_t b = 0;
-    auto advance = [&](int &aph, int &apl, int &at0, int &al, int64_t &ab) -> bool {
-      at0 += 128;
-      while (true) {
-        if (apl >= 0 && at0 < al) return true;
-        ++apl;
-        at0 = 0;
-        al = 0;
-        if (apl >= k) {
-          if (aph == 1 || ro_mask == 0) return false;
-          aph = 1;
-          apl = -1;
-          continue;
-        }
-        if ((((ro_mask >> apl) & 1u) != 0) != (aph == 1)) continue;
-        ab = __shfl_sync(0xffffffffu, beg, apl);
-        al = __shfl_sync(0xffffffffu, len, apl);
-      }
-    };
     int32_t v[4], nv[4];
-    bool have = advance(ph, pl, t0, l, b);
-    if (have) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = (t0 + 32 * u + lane < l) ? P.rev[b + t0 + 32 * u + lane] : -1;
-    }
+    W.start(ro_mask);
+    bool have = W.advance();
+    if (have) W.load(P.rev, lane, lowkey, v);
     while (have && !ovf) {
-      int nph = ph, npl = pl, nt0 = t0, nl = l;
-      int64_t nb = b;
-      const bool nhave = advance(nph, npl, nt0, nl, nb);
-      if (nhave) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) nv[u] = (nt0 + 32 * u + lane < nl) ? P.rev[nb + nt0 + 32 * u + lane] : -1;
-      }
-      // climb the levels: plain byte loads / stores only
+      const int ph = W.ph, t0 = W.t0, l = W.l;
+      have = W.advance();
+      if (have) W.load(P.rev, lane, lowkey, nv);
+      // climb the levels: plain 32-bit loads / stores only
       bool go[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) go[u] = v[u] >= 0;
@@ -986,14 +1185,22 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (go[u]) {
-              volatile uint8_t *fp = flags + off + (((uint32_t)v[u] * MUL[lv]) >> (32 - lg));
-              if (*fp == 0) {
-                if (lv > 0 || ph == 0) *fp = 1;
+              const uint32_t hb = ((uint32_t)v[u] * MUL[lv]) >> (32 - lg);
+              volatile uint32_t *wp = bits + off + (hb >> 5);
+              const uint32_t bit = 1u << (hb & 31u);
+              uint32_t wv = *wp;
+              if (!(wv & bit)) {
+                if (lv > 0 || ph == 0) {
+                  do {  // a lane that loses a same-word race sees its bit missing and writes again
+                    *wp = wv | bit;
+                    wv = *wp;
+                  } while (!(wv & bit));
+                }
                 go[u] = false;
               }
             }
           }
-          off += 1 << lg;
+          off += (1 << lg) / 32;
         }
       }
 #pragma unroll
@@ -1017,12 +1224,6 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = nv[u];
-      ph = nph;
-      pl = npl;
-      t0 = nt0;
-      l = nl;
-      b = nb;
-      have = nhave;
     }
     if (!ovf && npend > 0) {
       hot_insert_batch<F_TX_LOG>(tab, slots, nslots, lane < npend ? pend[lane] : 0, lane < npend, lane);
@@ -1039,7 +1240,7 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
       __syncwarp();
       continue;
     }
-    // distinct hot keys -> the (now free) flag area, table cleaned, ascending order
+    // distinct hot keys -> the (now free) bit-map area, table cleaned, ascending order
     uint32_t *keys = reinterpret_cast<uint32_t *>(base);
     for (int t = lane; t < nslots; t += 32) {
       const int sl = slots[t];
@@ -1052,6 +1253,7 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
     // emit (already in column order)
     uint32_t *dst = reinterpret_cast<uint32_t *>(P.tmp) + P.tmp_off[row_l];
     int m = 0;
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&info->dbg_hot_keys), (unsigned long long)nslots);
     for (int tb = 0; tb < nslots; tb += 32) {
       const int t = tb + lane;
       const bool act = t < nslots;
@@ -1077,8 +1279,8 @@ k_snn_rows_flags(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo 
 }
 
 template <int LV1_LOG, int LEVELS, int F_TX_LOG, int F_WARPS>
-int launch_flags(b200nn_ctx *ctx, const SnnParams &P, int n_ro, int32_t *ovf_list, DevInfo *d_info) {
-  auto kern = k_snn_rows_flags<LV1_LOG, LEVELS, F_TX_LOG, F_WARPS>;
+int launch_bits(b200nn_ctx *ctx, const SnnParams &P, int n_ro, int32_t *ovf_list, DevInfo *d_info) {
+  auto kern = k_snn_rows_bits<LV1_LOG, LEVELS, F_TX_LOG, F_WARPS>;
   constexpr int bytes = hot_bytes(LV1_LOG, LEVELS, F_TX_LOG) * F_WARPS;
   static_assert(2 * (bytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -1088,17 +1290,14 @@ int launch_flags(b200nn_ctx *ctx, const SnnParams &P, int n_ro, int32_t *ovf_lis
   return B200NN_OK;
 }
 
-// rows with E <= 3.3 k: 8 k level-1 flags, 512-word key table; larger rows: 16 k flags, 1024 words.
-// Warps per CTA are what two CTAs per SM can hold.
+// 32 k level-1 bits (4 KB) and a 512-word key table for rows with E <= 3.3 k, 64 k bits and 1024
+// words for the larger ones; warps per CTA are what two CTAs per SM can hold (at most 16)
 template <int LEVELS>
-int launch_flags_class(b200nn_ctx *ctx, const SnnParams &P, bool big, int lv1_small, int n_ro, int32_t *ovf_list,
-                       DevInfo *d_info) {
+int launch_bits_class(b200nn_ctx *ctx, const SnnParams &P, bool big, int n_ro, int32_t *ovf_list, DevInfo *d_info) {
   constexpr int budget = 113 * 1024;
-  if (big) return launch_flags<14, LEVELS, 10, budget / hot_bytes(14, LEVELS, 10)>(ctx, P, n_ro, ovf_list, d_info);
-  if (lv1_small == 12)
-    return launch_flags<12, LEVELS, 9, (budget / hot_bytes(12, LEVELS, 9) > 16 ? 16 : budget / hot_bytes(12, LEVELS, 9))>(
-        ctx, P, n_ro, ovf_list, d_info);
-  return launch_flags<13, LEVELS, 9, budget / hot_bytes(13, LEVELS, 9)>(ctx, P, n_ro, ovf_list, d_info);
+  constexpr int wb = budget / hot_bytes(16, LEVELS, 10), ws = budget / hot_bytes(15, LEVELS, 9);
+  if (big) return launch_bits<16, LEVELS, 10, (wb > 16 ? 16 : wb)>(ctx, P, n_ro, ovf_list, d_info);
+  return launch_bits<15, LEVELS, 9, (ws > 16 ? 16 : ws)>(ctx, P, n_ro, ovf_list, d_info);
 }
 
 // expanded work, survivor bound and work class of every row
@@ -1156,6 +1355,84 @@ __global__ void __launch_bounds__(256) k_row_work(RowWorkParams P) {
     if (emax > P.info->max_row_e) atomicMax(&P.info->max_row_e, emax);
     atomicAdd(reinterpret_cast<unsigned long long *>(&P.info->sum_row_e), (unsigned long long)esum);
     atomicAdd(reinterpret_cast<unsigned long long *>(&P.info->sum_bound), (unsigned long long)bsum);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Symmetric mode (all rows, no duplicated neighbours): the row kernels emit only the upper
+// triangle (j > i); S = A A^T is symmetric, so the lower triangle is its mirror image and the
+// diagonal is S_ii = k.  Half the candidate occurrences are walked.
+// ---------------------------------------------------------------------------
+// incoming (mirrored) entries per row
+__global__ void __launch_bounds__(256)
+k_low_count(const uint32_t *__restrict__ tmp, const int64_t *__restrict__ tmp_off, const int32_t *__restrict__ up_cnt,
+            int cbits, int32_t n_rows, int32_t *__restrict__ low_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const uint32_t *src = tmp + tmp_off[r];
+  const int m = up_cnt[r];
+  for (int t = lane; t < m; t += 32) atomicAdd(&low_cnt[src[t] >> cbits], 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_row_total(const int32_t *__restrict__ low_cnt, const int32_t *__restrict__ up_cnt, int diag, int32_t n_rows,
+            int32_t *__restrict__ total) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) total[r] = low_cnt[r] + diag + up_cnt[r];
+}
+
+// upper entry (i -> j, s) becomes the word (i << cbits | s) in row j's (unsorted) lower segment
+__global__ void __launch_bounds__(256)
+k_low_scatter(const uint32_t *__restrict__ tmp, const int64_t *__restrict__ tmp_off, const int32_t *__restrict__ up_cnt,
+              int cbits, int32_t n_rows, const int64_t *__restrict__ low_off, int32_t *__restrict__ low_cur,
+              uint32_t *__restrict__ low_words) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const uint32_t *src = tmp + tmp_off[r];
+  const int m = up_cnt[r];
+  const uint32_t cmask = (1u << cbits) - 1;
+  for (int t = lane; t < m; t += 32) {
+    const uint32_t w = src[t];
+    const uint32_t j = w >> cbits;
+    const int pos = atomicAdd(&low_cur[j], 1);
+    low_words[low_off[j] + pos] = ((uint32_t)r << cbits) | (w & cmask);
+  }
+}
+
+// row i of the final CSR: sorted lower words, the diagonal, the upper words
+__global__ void __launch_bounds__(256)
+k_snn_fill_sym(const uint32_t *__restrict__ tmp, const int64_t *__restrict__ tmp_off, const int32_t *__restrict__ up_cnt,
+               const uint32_t *__restrict__ low_sorted, const int64_t *__restrict__ low_off,
+               const int64_t *__restrict__ snn_p, const double *__restrict__ jac, int cbits, int diag, int k,
+               int32_t n_rows, int32_t *__restrict__ snn_i, double *__restrict__ snn_x) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const uint32_t cmask = (1u << cbits) - 1;
+  int64_t ob = snn_p[r];
+  const int64_t lb = low_off[r];
+  const int lc = (int)(low_off[r + 1] - lb);
+  for (int t = lane; t < lc; t += 32) {
+    const uint32_t w = low_sorted[lb + t];
+    snn_i[ob + t] = (int32_t)(w >> cbits);
+    snn_x[ob + t] = jac[w & cmask];
+  }
+  ob += lc;
+  if (diag) {
+    if (lane == 0) {
+      snn_i[ob] = (int32_t)r;
+      snn_x[ob] = jac[k];
+    }
+    ob += 1;
+  }
+  const uint32_t *src = tmp + tmp_off[r];
+  const int m = up_cnt[r];
+  for (int t = lane; t < m; t += 32) {
+    const uint32_t w = src[t];
+    snn_i[ob + t] = (int32_t)(w >> cbits);
+    snn_x[ob + t] = jac[w & cmask];
   }
 }
 
@@ -1228,26 +1505,46 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     // positives in the counters; measured best: class 0 (E <= 2.8 k) 8 k counters, 30 warps/SM;
     // class 1 (E <= 3.2 k) 16 k counters, 20 warps/SM; class 2 (E <= 6.5 k) 16 k counters, 16.
     constexpr int WA = 15, WB = 10, WC = 8;
-    // single-walk kernel (k <= 32: one reverse list per lane); B200NN_SNN_TWO_WALK=1 keeps the
-    // two-walk kernel for comparison.  B200NN_SNN_NO_RO=1 switches the read-only lists off.
-    static const bool two_walk_env = getenv("B200NN_SNN_TWO_WALK") != nullptr;
+    // k <= 32 (one reverse list per lane): two-walk kernel with read-only hub lists;
+    // B200NN_SNN_NO_RO=1 switches those off, B200NN_SNN_ROUND1=1 selects the round-1 kernel.
     static const bool no_ro_env = getenv("B200NN_SNN_NO_RO") != nullptr;
-    static const char *lv1_env = getenv("B200NN_SNN_LV1");  // 12: 4 k level-1 flags for the small rows
-    const int lv1_small = lv1_env ? atoi(lv1_env) : 13;
-    const bool single_walk = P.k <= 32 && filter_s_min <= 5 && !two_walk_env;
-    if (single_walk) {
-      const int n_ro = no_ro_env ? 0 : filter_s_min - 1;
+    static const bool bits_env = getenv("B200NN_SNN_BITS") != nullptr;   // experimental single-walk kernel
+    static const bool old_env = getenv("B200NN_SNN_ROUND1") != nullptr;  // round-1 kernel (no read-only lists)
+    const int n_ro = no_ro_env ? 0 : filter_s_min - 1;
+    if (P.k <= 32 && bits_env && filter_s_min <= 5) {
       for (int c = 0; c < 3; ++c) {
         P.row_list = class_list + c * (int64_t)n_rows;
         P.n_rows_class = class_count[c];
         if (P.n_rows_class <= 0) continue;
         const bool big = c == 2;
         switch (filter_s_min - 1) {
-          case 1: RC_TRY(launch_flags_class<1>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
-          case 2: RC_TRY(launch_flags_class<2>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
-          case 3: RC_TRY(launch_flags_class<3>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
-          default: RC_TRY(launch_flags_class<4>(ctx, P, big, lv1_small, n_ro, ovf_list, d_info)); break;
+          case 1: RC_TRY(launch_bits_class<1>(ctx, P, big, n_ro, ovf_list, d_info)); break;
+          case 2: RC_TRY(launch_bits_class<2>(ctx, P, big, n_ro, ovf_list, d_info)); break;
+          case 3: RC_TRY(launch_bits_class<3>(ctx, P, big, n_ro, ovf_list, d_info)); break;
+          default: RC_TRY(launch_bits_class<4>(ctx, P, big, n_ro, ovf_list, d_info)); break;
         }
+      }
+    } else if (P.k <= 32 && !old_env) {
+      auto kA = k_snn_rows_filter2<13, 9, WA>;
+      auto kB = k_snn_rows_filter2<14, 9, WB>;
+      auto kC = k_snn_rows_filter2<14, 10, WC>;
+      constexpr int bytesA = filt_bytes(13, 9) * WA, bytesB = filt_bytes(14, 9) * WB, bytesC = filt_bytes(14, 10) * WC;
+      CU_TRY(cudaFuncSetAttribute(kA, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesA));
+      CU_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesB));
+      CU_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, bytesC));
+      for (int c = 0; c < 3; ++c) {
+        P.row_list = class_list + c * (int64_t)n_rows;
+        P.n_rows_class = class_count[c];
+        if (P.n_rows_class <= 0) continue;
+        const int w = c == 0 ? WA : c == 1 ? WB : WC;
+        const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, w), (int64_t)ctx->sm_count * 2);
+        if (c == 0)
+          kA<<<blocks, WA * 32, bytesA, ctx->stream>>>(P, filter_s_min, n_ro, ovf_list, d_info);
+        else if (c == 1)
+          kB<<<blocks, WB * 32, bytesB, ctx->stream>>>(P, filter_s_min, n_ro, ovf_list, d_info);
+        else
+          kC<<<blocks, WC * 32, bytesC, ctx->stream>>>(P, filter_s_min, n_ro, ovf_list, d_info);
+        KERNEL_CHECK(ctx);
       }
     } else {
       auto kA = k_snn_rows_filter<13, 9, WA>;
@@ -1404,15 +1701,15 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     RC_TRY(ws_get(ctx, WS_NN_X, (size_t)total + 1, &nn_x));
     CU_TRY(cudaEventRecord(ctx->ev_side, st));
     CU_TRY(cudaStreamWaitEvent(ss, ctx->ev_side, 0));
-    k_sort_columns<<<(unsigned)ceil_div64(n, SORT_WARPS), SORT_WARPS * 32, 0, ss>>>(
+    k_sort_columns<int32_t><<<(unsigned)ceil_div64(n, SORT_WARPS), SORT_WARPS * 32, 0, ss>>>(
         rev, rev_sorted, colptr, n, uniq, long_list, &d_info->n_long);
     KERNEL_CHECK(ctx);
     {
       size_t smem = sizeof(int32_t) * LONG_SMEM_CAP;
-      CU_TRY(cudaFuncSetAttribute(k_sort_long_columns, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CU_TRY(cudaFuncSetAttribute(k_sort_long_columns<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-      k_sort_long_columns<<<ctx->sm_count, LONG_THREADS, smem, ss>>>(rev, rev_sorted, colptr, uniq, long_list,
-                                                                     &d_info->n_long);
+      k_sort_long_columns<int32_t><<<ctx->sm_count, LONG_THREADS, smem, ss>>>(rev, rev_sorted, colptr, uniq,
+                                                                              long_list, &d_info->n_long);
       KERNEL_CHECK(ctx);
     }
     RC_TRY(scan_exclusive_i32_to_i64(ctx, uniq, nn_p, n, ss, WS_SCAN_TMP2));
@@ -1572,6 +1869,9 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     P.row_nnz = row_nnz;
     P.huge_tables = nullptr;
     P.huge_log_t = 0;
+    // all rows, 0/1 adjacency, packed 32-bit words: count only j > i and mirror (B200NN_SNN_NO_SYM=1: off)
+    static const bool no_sym_env = getenv("B200NN_SNN_NO_SYM") != nullptr;
+    P.sym = (row_begin == 0 && row_end == n && !has_dups && use32 && rows > 1 && !no_sym_env) ? 1 : 0;
     int32_t *ovf_list;
     RC_TRY(ws_get(ctx, WS_OVF_LIST, (size_t)rows + 1, &ovf_list));
     if (use32)
@@ -1580,25 +1880,72 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     else
       RC_TRY(run_snn_classes<WordCfg64>(ctx, P, class_list, (int32_t)rows, n, hi.class_count,
                                         hi.max_row_e, has_dups, 0, ovf_list, d_info));
-    RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
-    // sync #3: nnz
     int64_t nnz = 0;
-    CU_TRY(cudaMemcpyAsync(&nnz, snn_p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
     int32_t *snn_i;
     double *snn_x;
-    RC_TRY(ws_get(ctx, WS_SNN_I, (size_t)nnz + 1, &snn_i));
-    RC_TRY(ws_get(ctx, WS_SNN_X, (size_t)nnz + 1, &snn_x));
-    if (rows > 0) {
-      unsigned blocks = (unsigned)ceil_div64(rows * 32, 256);
-      if (use32)
-        k_snn_fill<uint32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t *>(tmp), tmp_off,
-                                                     snn_p, d_jac, cbits, (int32_t)rows, snn_i,
-                                                     snn_x);
-      else
-        k_snn_fill<uint64_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint64_t *>(tmp), tmp_off,
-                                                     snn_p, d_jac, cbits, (int32_t)rows, snn_i,
-                                                     snn_x);
+    if (!P.sym) {
+      RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
+      // read-back: nnz (sizes the result arrays)
+      CU_TRY(cudaMemcpyAsync(&nnz, snn_p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      RC_TRY(ws_get(ctx, WS_SNN_I, (size_t)nnz + 1, &snn_i));
+      RC_TRY(ws_get(ctx, WS_SNN_X, (size_t)nnz + 1, &snn_x));
+      if (rows > 0) {
+        unsigned blocks = (unsigned)ceil_div64(rows * 32, 256);
+        if (use32)
+          k_snn_fill<uint32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t *>(tmp), tmp_off,
+                                                       snn_p, d_jac, cbits, (int32_t)rows, snn_i,
+                                                       snn_x);
+        else
+          k_snn_fill<uint64_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint64_t *>(tmp), tmp_off,
+                                                       snn_p, d_jac, cbits, (int32_t)rows, snn_i,
+                                                       snn_x);
+        KERNEL_CHECK(ctx);
+      }
+    } else {
+      // the row kernels emitted the upper triangle: mirror it (count, scatter, sort the short
+      // lower segments), add the diagonal S_ii = k, assemble the rows
+      const uint32_t *tmp32 = reinterpret_cast<const uint32_t *>(tmp);
+      int32_t *low_cnt = indeg, *low_cur = cursor, *total_row = row_bound;  // free since the transpose
+      const int diag = h_keep[(size_t)k] ? 1 : 0;
+      const unsigned wblocks = (unsigned)ceil_div64(rows * 32, 256);
+      CU_TRY(cudaMemsetAsync(low_cnt, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+      CU_TRY(cudaMemsetAsync(low_cur, 0, sizeof(int32_t) * ((size_t)n + 1), st));
+      k_low_count<<<wblocks, 256, 0, st>>>(tmp32, tmp_off, row_nnz, cbits, (int32_t)rows, low_cnt);
+      KERNEL_CHECK(ctx);
+      k_row_total<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(low_cnt, row_nnz, diag, (int32_t)rows, total_row);
+      KERNEL_CHECK(ctx);
+      int64_t *low_off;
+      RC_TRY(ws_get(ctx, WS_LOW_OFF, (size_t)rows + 1, &low_off));
+      RC_TRY(scan_exclusive_i32_to_i64(ctx, low_cnt, low_off, rows));
+      RC_TRY(scan_exclusive_i32_to_i64(ctx, total_row, snn_p, rows));
+      // read-back: nnz (sizes the result arrays)
+      CU_TRY(cudaMemcpyAsync(&nnz, snn_p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      const int64_t nnz_low = (nnz - (int64_t)diag * rows) / 2;
+      uint32_t *low_words, *low_sorted;
+      int32_t *long_list2;
+      RC_TRY(ws_get(ctx, WS_SNN_I, (size_t)nnz + 1, &snn_i));
+      RC_TRY(ws_get(ctx, WS_SNN_X, (size_t)nnz + 1, &snn_x));
+      RC_TRY(ws_get(ctx, WS_LOW_WORDS, (size_t)nnz_low + 1, &low_words));
+      RC_TRY(ws_get(ctx, WS_LOW_SORTED, (size_t)nnz_low + 1, &low_sorted));
+      RC_TRY(ws_get(ctx, WS_LONG_LIST2, (size_t)(nnz_low / SORT_WARP_CAP) + 2, &long_list2));
+      k_low_scatter<<<wblocks, 256, 0, st>>>(tmp32, tmp_off, row_nnz, cbits, (int32_t)rows, low_off, low_cur,
+                                             low_words);
+      KERNEL_CHECK(ctx);
+      k_sort_columns<uint32_t><<<(unsigned)ceil_div64(rows, SORT_WARPS), SORT_WARPS * 32, 0, st>>>(
+          low_words, low_sorted, low_off, rows, nullptr, long_list2, &d_info->n_long2);
+      KERNEL_CHECK(ctx);
+      {
+        size_t smem = sizeof(int32_t) * LONG_SMEM_CAP;
+        CU_TRY(cudaFuncSetAttribute(k_sort_long_columns<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+        k_sort_long_columns<uint32_t><<<ctx->sm_count, LONG_THREADS, smem, st>>>(low_words, low_sorted, low_off,
+                                                                                 nullptr, long_list2, &d_info->n_long2);
+        KERNEL_CHECK(ctx);
+      }
+      k_snn_fill_sym<<<wblocks, 256, 0, st>>>(tmp32, tmp_off, row_nnz, low_sorted, low_off, snn_p, d_jac, cbits, diag,
+                                              k, (int32_t)rows, snn_i, snn_x);
       KERNEL_CHECK(ctx);
     }
     ctx->snn.valid = true;
