@@ -148,7 +148,7 @@ b200nn_opts b200nn_default_opts() { return default_opts(); }
 
 int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
                  int d, int k, const b200nn_opts &o, int32_t *d_idx0, double *d_dist,
-                 b200nn_stats *stats) {
+                 b200nn_stats *stats, TcRefCache *cache) {
   if (!d_ref || nr <= 0 || nq < 0 || d <= 0 || k <= 0 || !d_idx0 || !d_dist) {
     b200nn_set_error("knn: invalid argument (nr=%lld nq=%lld d=%d k=%d)", (long long)nr,
                      (long long)nq, d, k);
@@ -200,7 +200,7 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
       return B200NN_ERR_INVALID;
     }
     return knn_tc_launch(ctx, d_ref, nr, q, nq, d, k, o.n_cand, o.scan_mode & 3, d_idx0, d_dist, stats,
-                         sharded ? o.shard_rank : 0, sharded ? o.shard_world : 0);
+                         sharded ? o.shard_rank : 0, sharded ? o.shard_world : 0, cache);
   }
   RC_TRY(check_finite_f64(ctx, d_ref, nr * (int64_t)d, "data"));
   if (q != d_ref) RC_TRY(check_finite_f64(ctx, q, nq * (int64_t)d, "query"));
@@ -265,9 +265,11 @@ int b200nn_ctx_create(int device, b200nn_ctx **ctx_out) {
   if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
   if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming);
   for (auto &ev : ctx->ev)
     if (ce == cudaSuccess) ce = cudaEventCreate(&ev);
   if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_info), sizeof(DevInfo));
+  if (ce == cudaSuccess) ce = cudaMallocHost(reinterpret_cast<void **>(&ctx->h_scalars), 8 * sizeof(long long));
   if (ce != cudaSuccess) {
     b200nn_set_error("ctx_create: %s", cudaGetErrorString(ce));
     b200nn_ctx_destroy(ctx);
@@ -286,6 +288,7 @@ void b200nn_ctx_destroy(b200nn_ctx *ctx) {
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   if (ctx->h_info) cudaFreeHost(ctx->h_info);
+  if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
   if (ctx->side_stream) {
     cudaStreamSynchronize(ctx->side_stream);
     cudaStreamDestroy(ctx->side_stream);
@@ -296,6 +299,7 @@ void b200nn_ctx_destroy(b200nn_ctx *ctx) {
   }
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->ev_side) cudaEventDestroy(ctx->ev_side);
+  if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;
@@ -436,6 +440,9 @@ struct b200nn_index {
   double *d_ref = nullptr;  // [nr x d] row-major, own allocation (not a workspace slot)
   int64_t nr = 0;
   int32_t d = 0;
+  // prepared operands of the tensor search (centring / scale, group-sorted FP16 rows, grouping, balls):
+  // filled by the first query, reused by the later ones
+  TcRefCache *cache = nullptr;
 };
 
 int b200nn_index_create(b200nn_ctx *ctx, const double *ref, int64_t nr, int32_t d, const b200nn_opts *opts,
@@ -476,6 +483,7 @@ int b200nn_index_create(b200nn_ctx *ctx, const double *ref, int64_t nr, int32_t 
   ix->owner = ctx;
   ix->nr = nr;
   ix->d = d;
+  ix->cache = tc_ref_cache_create();
   *index_out = ix;
   return B200NN_OK;
 }
@@ -487,6 +495,7 @@ void b200nn_index_destroy(b200nn_ctx *ctx, b200nn_index *index) {
     cudaStreamSynchronize(ctx->stream);
   }
   if (index->d_ref) cudaFree(index->d_ref);
+  tc_ref_cache_destroy(index->cache);
   delete index;
 }
 
@@ -523,7 +532,7 @@ int b200nn_index_knn(b200nn_ctx *ctx, const b200nn_index *index, const double *q
   double *d_dist;
   RC_TRY(ws_get(ctx, WS_IDX0, (size_t)nq * k, &d_idx0));
   RC_TRY(ws_get(ctx, WS_DIST, (size_t)nq * k, &d_dist));
-  RC_TRY(knn_dispatch(ctx, index->d_ref, nr, d_qry, nq, d, k, o, d_idx0, d_dist, stats));
+  RC_TRY(knn_dispatch(ctx, index->d_ref, nr, d_qry, nq, d, k, o, d_idx0, d_dist, stats, index->cache));
   RC_TRY(th.start());
   RC_TRY(download_knn(ctx, d_idx0, d_dist, nq, k, o.layout, idx_out, dist_out));
   RC_TRY(th.stop(stats ? &stats->ms_d2h : nullptr));

@@ -140,11 +140,13 @@ struct b200nn_ctx {
   cudaStream_t side_stream = nullptr;  // nn Graph columns (sort / emit) while the SNN stage runs
   cudaEvent_t ev[16] = {};
   cudaEvent_t ev_copy = nullptr;
-  cudaEvent_t ev_side = nullptr;   // nn Graph side stream: start / end markers
+  cudaEvent_t ev_side = nullptr;   // nn Graph side stream: start marker
+  cudaEvent_t ev_sorted = nullptr; // ... its sorted columns are complete
   WsBuf ws[WS_NUM];
   std::vector<uint8_t> h_keep;     // SNN lookup tables of the last call (host copies must outlive the H2D)
   std::vector<double> h_jac;
-  DevInfo *h_info = nullptr;  // pinned
+  DevInfo *h_info = nullptr;  // pinned (device-visible: small read-backs are stored here by a kernel)
+  long long *h_scalars = nullptr;  // pinned, 8 values
   int sm_count = 148;
   int64_t launches = 0;
   CsrResult nn_graph, snn;
@@ -218,9 +220,12 @@ int knn_exact_grouped_launch(b200nn_ctx *ctx, const double *d_ref, const double 
 // knn_tc.cu : tcgen05 candidate generation + FP64 re-rank + certificate
 // scan_mode: 0 = auto, 1 = exhaustive scan of every key tile, 2 = grouped (tile-pruned) search
 bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k);
+struct TcRefCache;  // reference-side state of the grouped search, kept by a resident index
+TcRefCache *tc_ref_cache_create();
+void tc_ref_cache_destroy(TcRefCache *c);
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                   int64_t nq, int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
-                  b200nn_stats *stats, int shard_rank = 0, int shard_world = 0);
+                  b200nn_stats *stats, int shard_rank = 0, int shard_world = 0, TcRefCache *cache = nullptr);
 // true when knn_tc_launch would run the grouped (tile-pruned) search for this shape
 bool knn_tc_grouped(int64_t nr, int scan_mode);
 
@@ -231,7 +236,8 @@ int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
 // api.cu : algorithm selection + argument checks of the kNN stage (device pointers, row-major)
 b200nn_opts b200nn_default_opts();
 int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
-                 int d, int k, const b200nn_opts &o, int32_t *d_idx0, double *d_dist, b200nn_stats *stats);
+                 int d, int k, const b200nn_opts &o, int32_t *d_idx0, double *d_dist, b200nn_stats *stats,
+                 TcRefCache *cache = nullptr);
 
 // snn.cu
 // optional host destination of the nn Graph (capacity n_rows * k entries): copied on the

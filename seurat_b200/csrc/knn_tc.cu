@@ -43,6 +43,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+#include <utility>
+
 #include "internal.cuh"
 
 namespace {
@@ -1813,14 +1816,46 @@ static int pick_groups(int64_t nr) {
 // mode: 0 = auto, 1 = exhaustive scan of every tile, 2 = grouped (tile-pruned)
 bool knn_tc_grouped(int64_t nr, int scan_mode) { return scan_mode == 2 || (scan_mode == 0 && nr >= 32768); }
 
+// Reference-side state of the grouped search kept by a resident index (b200nn_index):
+// centring / scale, the group-sorted FP16 operand, the grouping with its balls and tile annuli.
+// One device blob; the segments are copied back into the workspace at the start of a later call,
+// which then only prepares the queries.
+struct TcRefCache {
+  bool valid = false;
+  int64_t nr = 0;
+  int d = 0, G = 0;
+  void *blob = nullptr;
+  size_t bytes = 0;
+};
+TcRefCache *tc_ref_cache_create() { return new (std::nothrow) TcRefCache(); }
+void tc_ref_cache_destroy(TcRefCache *c) {
+  if (!c) return;
+  if (c->blob) cudaFree(c->blob);
+  delete c;
+}
+
+// per-call fields of the restored prep state
+__global__ void k_misc_reset(TcMisc *misc) {
+  misc->qn2_max = 0.0;
+  misc->n_fail = 0;
+  misc->hang = 0;
+  misc->nonfinite = 0;
+  misc->tiles_visited = 0;
+  misc->tiles_total = 0;
+}
+
 static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
                              int64_t nq, int d, int kp, int mode, TcCandidates *out,
-                             float *d_dbg_keys, b200nn_stats *stats, int shard_rank = 0, int shard_world = 0) {
+                             float *d_dbg_keys, b200nn_stats *stats, int shard_rank = 0, int shard_world = 0,
+                             TcRefCache *cache = nullptr) {
   cudaStream_t st = ctx->stream;
   bool timed_pass2 = false;
-  const bool self = (d_qry == d_ref) && (nq == nr);
   const bool grouped = d_dbg_keys == nullptr && knn_tc_grouped(nr, mode);
   const bool sharded = shard_world > 1;
+  if (!grouped || sharded) cache = nullptr;  // only the grouped search has reference-side state worth keeping
+  const bool cached = cache && cache->valid && cache->nr == nr && cache->d == d;
+  // with restored reference-side state the queries are prepared on their own, also for a self search
+  const bool self = (d_qry == d_ref) && (nq == nr) && !cached;
   if (sharded && !(grouped && self && shard_world <= 64 && shard_rank >= 0 && shard_rank < shard_world)) {
     b200nn_set_error("sharded tensor search needs a self query in grouped mode (rank %d of %d)", shard_rank,
                      shard_world);
@@ -1842,18 +1877,30 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
 
   cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10];
   CU_TRY(cudaEventRecord(e0, st));
-  k_mean_partial<<<MEAN_BLOCKS, 64, 0, st>>>(d_ref, nr, d, partial);
-  KERNEL_CHECK(ctx);
-  k_mean_final<<<1, 64, 0, st>>>(partial, nr, d, misc);
-  KERNEL_CHECK(ctx);
-  k_max_norm<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(d_ref, nr, d, misc);
-  KERNEL_CHECK(ctx);
-  if (!self) {
-    k_max_norm<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(d_qry, nq, d, misc);
+  if (!cached) {
+    k_mean_partial<<<MEAN_BLOCKS, 64, 0, st>>>(d_ref, nr, d, partial);
     KERNEL_CHECK(ctx);
+    k_mean_final<<<1, 64, 0, st>>>(partial, nr, d, misc);
+    KERNEL_CHECK(ctx);
+    k_max_norm<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(d_ref, nr, d, misc);
+    KERNEL_CHECK(ctx);
+    // a resident index fixes centre and scale from the reference set alone: later query batches must
+    // see the same operands (a far-away query only costs that row its certificate)
+    if (!self && !cache) {
+      k_max_norm<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(d_qry, nq, d, misc);
+      KERNEL_CHECK(ctx);
+    }
+    k_pick_scale<<<1, 1, 0, st>>>(misc);
+    KERNEL_CHECK(ctx);
+    if (!self && cache) {  // non-finite queries must still be refused
+      k_max_norm<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(d_qry, nq, d, misc);
+      KERNEL_CHECK(ctx);
+    }
   }
-  k_pick_scale<<<1, 1, 0, st>>>(misc);
-  KERNEL_CHECK(ctx);
+  // segments of the reference-side state, in a fixed order (saved after the first call on an index,
+  // copied back at the start of the later ones)
+  std::vector<std::pair<void *, size_t>> segs;
+  segs.emplace_back((void *)misc, sizeof(TcMisc));
 
   TcParams P;
   memset(&P, 0, sizeof(P));
@@ -1942,10 +1989,37 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     int32_t *tiles;
     RC_TRY(ws_get(ctx, WS_TC_TILES, nI * (size_t)list_stride, &tiles));
 
+    segs.emplace_back((void *)r16, sizeof(__half) * (size_t)nr_pad * BK);
+    segs.emplace_back((void *)rperm, sizeof(int32_t) * (size_t)nr_pad);
+    segs.emplace_back((void *)rcount, sizeof(int32_t) * (size_t)(G + 1));
+    segs.emplace_back((void *)cent, sizeof(float) * (size_t)G * BK);
+    segs.emplace_back((void *)grad, sizeof(float) * (size_t)G);
+    segs.emplace_back((void *)gstat, sizeof(float) * 2 * (size_t)G);
+    segs.emplace_back((void *)tile_lo, sizeof(float) * (size_t)n_tiles_max);
+    segs.emplace_back((void *)tile_hi, sizeof(float) * (size_t)n_tiles_max);
+    CU_TRY(cudaMemsetAsync(rcount, 0, sizeof(int32_t) * 8 * (size_t)(G + 1), st));
+    if (cached) {
+      if (cache->G != G) {
+        b200nn_set_error("resident index: cached grouping does not match (%d groups, expected %d)", cache->G, G);
+        return B200NN_ERR_STATE;
+      }
+      const char *src = static_cast<const char *>(cache->blob);
+      for (auto &sg : segs) {
+        CU_TRY(cudaMemcpyAsync(sg.first, src, sg.second, cudaMemcpyDeviceToDevice, st));
+        src += (sg.second + 255) & ~(size_t)255;
+      }
+      k_misc_reset<<<1, 1, 0, st>>>(misc);
+      KERNEL_CHECK(ctx);
+      k_max_norm<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(d_qry, nq, d, misc);  // refuses NaN / Inf queries
+      KERNEL_CHECK(ctx);
+    }
+
     // 1. FP16 rows (original order), residuals, norms
-    k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, yr16, nullptr, self ? q_n2 : nullptr,
-                                                              self ? q_err : nullptr, misc, split, 1);
-    KERNEL_CHECK(ctx);
+    if (!cached) {
+      k_convert<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(d_ref, nr, d, yr16, nullptr, self ? q_n2 : nullptr,
+                                                                self ? q_err : nullptr, misc, split, 1);
+      KERNEL_CHECK(ctx);
+    }
     if (self) {
       yq16 = yr16;
     } else {
@@ -1958,11 +2032,12 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     const int64_t m = nr < KM_SAMPLE ? nr : KM_SAMPLE;
     const int64_t stride = nr / m;
     long long *sums = reinterpret_cast<long long *>(cent + (size_t)G * BK);  // [G x 64] fixed-point sums
-    CU_TRY(cudaMemsetAsync(sums, 0, sizeof(long long) * (size_t)G * BK, st));
-    CU_TRY(cudaMemsetAsync(rcount, 0, sizeof(int32_t) * 8 * (size_t)(G + 1), st));
-    k_km_init<<<G, 64, 0, st>>>(yr16, m * stride, d, G, cent, cnorm);
-    KERNEL_CHECK(ctx);
-    for (int itn = 0; itn < KM_ITERS; ++itn) {
+    if (!cached) {
+      CU_TRY(cudaMemsetAsync(sums, 0, sizeof(long long) * (size_t)G * BK, st));
+      k_km_init<<<G, 64, 0, st>>>(yr16, m * stride, d, G, cent, cnorm);
+      KERNEL_CHECK(ctx);
+    }
+    for (int itn = 0; itn < (cached ? 0 : KM_ITERS); ++itn) {
       k_km_assign<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(yr16, m, stride, d, G, cent, cnorm, nullptr,
                                                                  kcount, sums);
       KERNEL_CHECK(ctx);
@@ -1977,7 +2052,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     static const bool assign_fma = getenv("B200NN_KM_ASSIGN_FMA") != nullptr;
     const int G_pad = ((G + BN - 1) / BN) * BN;
     __half *c16 = nullptr;
-    if (!assign_fma) {
+    if (!assign_fma || cached) {
       RC_TRY(ws_get(ctx, WS_TC_CENT16, (size_t)G_pad * BK, &c16));
       k_cent_operand<<<(unsigned)ceil_div64((int64_t)G_pad * 32, 256), 256, 0, st>>>(cent, G, G_pad, d, c16);
       KERNEL_CHECK(ctx);
@@ -2004,7 +2079,9 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       KERNEL_CHECK(ctx);
       return B200NN_OK;
     };
-    if (assign_fma) {
+    if (cached) {
+      // the reference rows keep their groups
+    } else if (assign_fma) {
       k_km_assign<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, nr, 1, d, G, cent, cnorm, gid_r, rcount,
                                                                   nullptr);
       KERNEL_CHECK(ctx);
@@ -2019,7 +2096,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
         CU_TRY(cudaMemcpyAsync(qcount, rcount, sizeof(int32_t) * G, cudaMemcpyDeviceToDevice, st));
       }
       gid_q = gid_r;
-    } else if (assign_fma) {
+    } else if (assign_fma && !cached) {
       k_km_assign<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(yq16, nq, 1, d, G, cent, cnorm, gid_q, qcount,
                                                                   nullptr);
       KERNEL_CHECK(ctx);
@@ -2028,12 +2105,17 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     }
     k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor);
     KERNEL_CHECK(ctx);
-    CU_TRY(cudaMemsetAsync(rperm, 0xff, sizeof(int32_t) * (size_t)(nr_pad + nq_pad), st));  // rperm and qperm
+    if (cached)  // rperm was restored
+      CU_TRY(cudaMemsetAsync(qperm, 0xff, sizeof(int32_t) * (size_t)nq_pad, st));
+    else
+      CU_TRY(cudaMemsetAsync(rperm, 0xff, sizeof(int32_t) * (size_t)(nr_pad + nq_pad), st));  // rperm and qperm
     // 3b. squared distance of every row to its group's centre; groups are stored hub-first
     static const bool no_hub = getenv("B200NN_NO_HUB") != nullptr;  // arrival order (for comparison)
-    CU_TRY(cudaMemsetAsync(gstat, 0, sizeof(float) * 2 * (size_t)G, st));
-    k_row_anorm<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, gid_r, nr, d, G, cent, anorm_r, gstat);
-    KERNEL_CHECK(ctx);
+    if (!cached) {
+      CU_TRY(cudaMemsetAsync(gstat, 0, sizeof(float) * 2 * (size_t)G, st));
+      k_row_anorm<<<(unsigned)ceil_div64(nr, 128), 128, 0, st>>>(yr16, gid_r, nr, d, G, cent, anorm_r, gstat);
+      KERNEL_CHECK(ctx);
+    }
     if (self) {
       anorm_q = anorm_r;
     } else {
@@ -2041,19 +2123,23 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       KERNEL_CHECK(ctx);
     }
     if (no_hub) {
-      k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, G, goff, rcursor, rperm);
-      KERNEL_CHECK(ctx);
+      if (!cached) {
+        k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, G, goff, rcursor, rperm);
+        KERNEL_CHECK(ctx);
+      }
       k_group_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, nq, G, qoff, qcursor, qperm, owner,
                                                                       shard_rank);
       KERNEL_CHECK(ctx);
     } else {
-      k_group_stat_final<<<(G + 127) / 128, 128, 0, st>>>(gstat, rcount, G);
-      KERNEL_CHECK(ctx);
       CU_TRY(cudaMemsetAsync(fcount_r, 0, sizeof(int32_t) * 2 * nF, st));  // fcount_r and fcount_q
-      k_fine_count<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, fcount_r);
-      KERNEL_CHECK(ctx);
-      k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_r, goff, foff_r, fcur_r);
-      KERNEL_CHECK(ctx);
+      if (!cached) {
+        k_group_stat_final<<<(G + 127) / 128, 128, 0, st>>>(gstat, rcount, G);
+        KERNEL_CHECK(ctx);
+        k_fine_count<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, fcount_r);
+        KERNEL_CHECK(ctx);
+        k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_r, goff, foff_r, fcur_r);
+        KERNEL_CHECK(ctx);
+      }
       if (self) {
         k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_r, qoff, foff_q, fcur_q);
         KERNEL_CHECK(ctx);
@@ -2063,25 +2149,31 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
         k_fine_offsets<<<G, FINE_NB, 0, st>>>(fcount_q, qoff, foff_q, fcur_q);
         KERNEL_CHECK(ctx);
       }
-      k_fine_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, foff_r, fcur_r, rperm,
-                                                                     nullptr, 0);
-      KERNEL_CHECK(ctx);
+      if (!cached) {
+        k_fine_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, foff_r, fcur_r, rperm,
+                                                                       nullptr, 0);
+        KERNEL_CHECK(ctx);
+      }
       k_fine_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, anorm_q, nq, gstat, foff_q, fcur_q, qperm,
                                                                      owner, shard_rank);
       KERNEL_CHECK(ctx);
     }
     // 4. operands in sorted order
-    k_gather_ref<<<(unsigned)ceil_div64(nr_pad * 8, 256), 256, 0, st>>>(yr16, split, rperm, nr_pad, d, r16);
-    KERNEL_CHECK(ctx);
+    if (!cached) {
+      k_gather_ref<<<(unsigned)ceil_div64(nr_pad * 8, 256), 256, 0, st>>>(yr16, split, rperm, nr_pad, d, r16);
+      KERNEL_CHECK(ctx);
+    }
     k_gather_qry<<<(unsigned)ceil_div64(nq_pad * 8, 256), 256, 0, st>>>(yq16, qperm, nq_pad, q16);
     KERNEL_CHECK(ctx);
     // 5. balls
-    CU_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)G, st));
-    k_group_radius<<<dim3(G, 8), 128, 0, st>>>(yr16, rperm, goff, d, cent, grad);
-    KERNEL_CHECK(ctx);
-    k_tile_annulus<<<(unsigned)ceil_div64(n_tiles_max * 32, 256), 256, 0, st>>>(rperm, anorm_r, n_tiles_max, tile_lo,
-                                                                                 tile_hi);
-    KERNEL_CHECK(ctx);
+    if (!cached) {
+      CU_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)G, st));
+      k_group_radius<<<dim3(G, 8), 128, 0, st>>>(yr16, rperm, goff, d, cent, grad);
+      KERNEL_CHECK(ctx);
+      k_tile_annulus<<<(unsigned)ceil_div64(n_tiles_max * 32, 256), 256, 0, st>>>(rperm, anorm_r, n_tiles_max, tile_lo,
+                                                                                   tile_hi);
+      KERNEL_CHECK(ctx);
+    }
     k_item_stats<<<P.n_items, 64, 0, st>>>(q16, qperm, nq_pad, d, item_c, item_rad);
     KERNEL_CHECK(ctx);
     CU_TRY(cudaMemsetAsync(item_T, 0, sizeof(float) * nI, st));
@@ -2130,6 +2222,33 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
     CU_TRY(cudaEventRecord(ctx->ev[15], st));
     timed_pass2 = true;
+    if (cache && !cached) {
+      // first call on a resident index: keep the reference-side state (stream-ordered copies)
+      size_t total = 0;
+      for (auto &sg : segs) total += (sg.second + 255) & ~(size_t)255;
+      if (cache->blob && cache->bytes < total) {
+        cudaFree(cache->blob);
+        cache->blob = nullptr;
+      }
+      if (!cache->blob) {
+        if (cudaMalloc(&cache->blob, total) != cudaSuccess) {
+          (void)cudaGetLastError();
+          cache->blob = nullptr;  // not fatal: the index simply stays uncached
+        }
+        cache->bytes = cache->blob ? total : 0;
+      }
+      if (cache->blob) {
+        char *dst = static_cast<char *>(cache->blob);
+        for (auto &sg : segs) {
+          CU_TRY(cudaMemcpyAsync(dst, sg.first, sg.second, cudaMemcpyDeviceToDevice, st));
+          dst += (sg.second + 255) & ~(size_t)255;
+        }
+        cache->nr = nr;
+        cache->d = d;
+        cache->G = G;
+        cache->valid = true;
+      }
+    }
   }
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));
@@ -2156,7 +2275,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
 
 int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry, int64_t nq,
                   int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
-                  b200nn_stats *stats, int shard_rank, int shard_world) {
+                  b200nn_stats *stats, int shard_rank, int shard_world, TcRefCache *cache) {
   cudaStream_t st = ctx->stream;
   int kp = pick_kp(k, n_cand);
   if (kp > MAX_KP) kp = MAX_KP;
@@ -2166,7 +2285,7 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
   }
   TcCandidates C;
   RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, scan_mode, &C, nullptr, stats, shard_rank,
-                           shard_world));
+                           shard_world, cache));
   if (shard_world > 1) {  // the rows this share wrote (the group-sorted query order, -1 = padding)
     ctx->owned_rows = C.visit;
     ctx->owned_slots = C.n_visit;

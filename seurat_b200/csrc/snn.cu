@@ -298,6 +298,7 @@ struct SnnParams {
   int32_t huge_log_t;
   int32_t sym;             // 1: only candidates j > i are counted (upper triangle; S is symmetric and
                            //    the lower triangle + diagonal are mirrored afterwards)
+  int32_t sorted;          // 1: `rev` holds the sorted lists (nn Graph columns)
 };
 
 template <typename Word>
@@ -828,22 +829,16 @@ k_snn_rows_filter(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInf
 
 // ---------------------------------------------------------------------------
 // Walker over the k reverse lists of a row (k <= 32: lane p holds the descriptor of list p), in
-// 128-element blocks.  Lists flagged in ro_mask are visited after all the others (phase 1).
-// Pigeonhole: a key that survives the cut-off occurs in >= s_min of the k lists, hence in at least
-// one list other than the s_min - 1 LONGEST ones; those lists (the hubs, ~1/3 of all occurrences)
-// therefore never have to create a counter, only to bump the ones that exist.
+// 128-element blocks; offsets are 32-bit (the transpose has fewer than 2^31 entries).
 // ---------------------------------------------------------------------------
 struct ListWalk {
-  int64_t beg;   // per lane: start of list `lane` in rev
+  uint32_t beg;  // per lane: start of list `lane` in rev
   int len;       // per lane: its length
-  unsigned ro_mask;
   int k;
   // warp-uniform cursor
-  int ph, pl, t0, l;
-  int64_t b;
-  __device__ __forceinline__ void start(unsigned mask) {
-    ro_mask = mask;
-    ph = 0;
+  int pl, t0, l;
+  uint32_t b;
+  __device__ __forceinline__ void start() {
     pl = -1;
     t0 = 0;
     l = 0;
@@ -852,55 +847,38 @@ struct ListWalk {
   // next 128-element block; false when every list has been walked
   __device__ __forceinline__ bool advance() {
     t0 += 128;
-    while (true) {
-      if (pl >= 0 && t0 < l) return true;
-      ++pl;
+    while (t0 >= l) {
+      if (++pl >= k) return false;
       t0 = 0;
-      l = 0;
-      if (pl >= k) {
-        if (ph == 1 || ro_mask == 0) return false;
-        ph = 1;
-        pl = -1;
-        continue;
-      }
-      if ((((ro_mask >> pl) & 1u) != 0) != (ph == 1)) continue;
       b = __shfl_sync(0xffffffffu, beg, pl);
       l = __shfl_sync(0xffffffffu, len, pl);
     }
+    return true;
   }
   __device__ __forceinline__ void load(const int32_t *__restrict__ rev, int lane, int lowkey, int32_t (&v)[4]) const {
+    const int32_t *src = rev + b + t0 + lane;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      v[u] = (t0 + 32 * u + lane < l) ? rev[b + t0 + 32 * u + lane] : -1;
-      if (v[u] <= lowkey) v[u] = -1;  // symmetric mode: only candidates j > i
+      v[u] = (t0 + 32 * u + lane < l) ? src[32 * u] : -1;
+      if (v[u] <= lowkey) v[u] = -1;  // symmetric mode on unsorted lists: only candidates j > i
     }
   }
 };
 
-// the n_ro longest of the (<= 32) lists, as a lane mask (ties: higher lane first)
-__device__ __forceinline__ unsigned longest_lists(int len, int lane, int k, int n_ro) {
-  bool ro = false;
-  const int key = lane < k ? (len << 5) | lane : -1;
-  for (int t = 0; t < n_ro; ++t) {
-    int m = ro ? -1 : key;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (m >= 0 && key == m) ro = true;
-  }
-  return __ballot_sync(0xffffffffu, ro);
-}
-
 // ---------------------------------------------------------------------------
 // Two-walk filtered kernel for k <= 32 (the default): pass A (4-bit saturating counters) and pass B
-// (exact table for the occurrences whose counter reached s_min) as in k_snn_rows_filter, plus
-//   * read-only handling of the s_min - 1 longest lists in pass A (see ListWalk): pass A is bound
-//     by shared-memory atomics (an ATOMS with spread addresses retires 2 cycles per LANE; measured
-//     ~1 occurrence / clk / SM), and this removes the atomics of most hub occurrences;
-//   * symmetric mode (P.sym): only candidates j > i are counted -- half the occurrences.
+// (exact table for the occurrences whose counter reached s_min) as in k_snn_rows_filter.
+// ncu (profiles/r02_ncu_k_snn_rows_filter2.txt): the kernel is instruction-issue bound (73 % issue
+// utilisation, ~80 warp instructions per 32 occurrences and pass), not bound by the shared-memory
+// atomics or by bandwidth, so what counts is how many occurrences are walked:
+//   * symmetric mode (P.sym): only candidates j > i are counted.  With P.sorted the reverse lists
+//     are sorted (the nn Graph's columns), and since row i is itself a member of each of its k
+//     lists, a binary search for i gives the start of the suffix j > i: half of every list is
+//     neither loaded nor looped over.
 // ---------------------------------------------------------------------------
 template <int CW_LOG, int F_TX_LOG, int F_WARPS>
 __global__ void __launch_bounds__(F_WARPS * 32)
-k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+k_snn_rows_filter2(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
   constexpr int F_BYTES = filt_bytes(CW_LOG, F_TX_LOG);
   constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
   static_assert((1 << CW_LOG) / 2 >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
@@ -918,7 +896,8 @@ k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_l
   for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
     const int row_l = P.row_list[r];
     const int64_t row = P.row_begin + row_l;
-    const int lowkey = P.sym ? (int)row : -1;
+    // per-element filter only when the lists are unsorted; sorted lists are cut at the row itself
+    const int lowkey = (P.sym && !P.sorted) ? (int)row : -1;
     {
       uint4 z = make_uint4(0, 0, 0, 0);
       uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
@@ -931,19 +910,32 @@ k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_l
     W.len = 0;
     if (lane < k) {
       const int32_t c = P.idx0[row * k + lane];
-      W.beg = P.colptr[c];
-      W.len = (int)(P.colptr[c + 1] - W.beg);
+      const int64_t cb = P.colptr[c];
+      int len = (int)(P.colptr[c + 1] - cb);
+      uint32_t beg = (uint32_t)cb;
+      if (P.sym && P.sorted) {
+        // first position whose row id exceeds `row` (the list is ascending and contains `row`)
+        int lo = 0, hi = len;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (P.rev[beg + mid] <= (int32_t)row) lo = mid + 1;
+          else hi = mid;
+        }
+        beg += (uint32_t)lo;
+        len -= lo;
+      }
+      W.beg = beg;
+      W.len = len;
     }
-    const unsigned ro_mask = longest_lists(W.len, lane, k, n_ro);
     int nslots = 0, npend = 0;
     bool ovf = false, sat = false;
     int32_t v[4], nv[4];
-    // ---- pass A: count (atomics only where a counter may still matter) ----
-    W.start(ro_mask);
+    // ---- pass A: count ----
+    W.start();
     bool have = W.advance();
     if (have) W.load(P.rev, lane, lowkey, v);
     while (have) {
-      const int ph = W.ph, t0 = W.t0, l = W.l;
+      const int t0 = W.t0, l = W.l;
       have = W.advance();
       if (have) W.load(P.rev, lane, lowkey, nv);
 #pragma unroll
@@ -953,8 +945,7 @@ k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_l
           const uint32_t hc = hash_cnt<CW_LOG>((uint32_t)v[u]);
           const uint32_t sh = (hc & 7u) * 4u;
           volatile uint32_t *wp = cnt + (hc >> 3);
-          const int c4 = (int)((*wp >> sh) & 15u);
-          if (c4 < s_min && (ph == 0 || c4 > 0)) {
+          if ((int)((*wp >> sh) & 15u) < s_min) {
             const uint32_t old = atomicAdd(cnt + (hc >> 3), 1u << sh);
             sat |= ((old >> sh) & 15u) == 15u;
           }
@@ -967,7 +958,7 @@ k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_l
     if (__any_sync(0xffffffffu, sat)) ovf = true;  // a counter wrapped: the big-table kernel takes the row
     // ---- pass B: exact counts of the occurrences whose counter reached s_min ----
     if (!ovf) {
-      W.start(0u);
+      W.start();
       have = W.advance();
       if (have) W.load(P.rev, lane, lowkey, v);
       while (have && !ovf) {
@@ -1040,264 +1031,6 @@ k_snn_rows_filter2(SnnParams P, int s_min, int n_ro, int32_t *__restrict__ ovf_l
     if (lane == 0) P.row_nnz[row_l] = m;
     __syncwarp();
   }
-}
-
-// ---------------------------------------------------------------------------
-// Experimental single-walk kernel (B200NN_SNN_BITS=1): no shared-memory atomics at all.
-//   * level bit maps L1 .. L(s_min-1): an occurrence of key j climbs the levels; at the first level
-//     whose bit (at j's position) is still 0 it sets the bit and stops; if all s_min - 1 bits are
-//     already set it is "hot".  After its t-th occurrence the bits L1..Lt of a key are set, so the
-//     s_min-th occurrence of every surviving key is hot; collisions only add false positives.
-//     Bits are set with a plain 32-bit read-modify-write followed by a read-back: lanes that lose a
-//     same-word race in the same instruction see their bit missing and retry.
-//     (A variant with BYTE flags was measured 2x slower than the two-walk kernel: divergent
-//     sub-word shared-memory accesses cost about as much as the atomics they replaced,
-//     profiles/r02_ab2_snn_byte_flags.txt.)
-//   * hot keys are de-duplicated in a small exact key table;
-//   * the exact count of each distinct hot key j comes from the FORWARD lists:
-//         S_ij = |N(i) ∩ N(j)|      (A is 0/1 without duplicated neighbours, src/snn.cpp:27)
-//     one lane per hot key reads N(j) and probes a 64-word hash set of N(i).
-// Output, cut-off and x values are exactly those of the other kernels (same LUTs).
-// ---------------------------------------------------------------------------
-constexpr int HOT_NSET = 64;  // hash set of N(i): k <= 32 keys in 64 words
-constexpr int bits_level_words(int lv1_log, int l) { return (1 << (lv1_log - (l < 2 ? l : 2))) / 32; }
-constexpr int bits_total_words(int lv1_log, int levels) {
-  int b = 0;
-  for (int l = 0; l < levels; ++l) b += bits_level_words(lv1_log, l);
-  return b;
-}
-constexpr int hot_bytes(int lv1_log, int levels, int tx_log) {
-  return bits_total_words(lv1_log, levels) * 4 + (1 << tx_log) * 4 + ((filt_slot_cap(tx_log) * 2 + 15) & ~15) + 64 * 4 +
-         HOT_NSET * 4;
-}
-
-// batch insert of hot keys into the de-duplicating key table (keys only)
-template <int F_TX_LOG>
-__device__ __forceinline__ void hot_insert_batch(uint32_t *tab, uint16_t *slots, int &nslots, uint32_t j,
-                                                 bool active, int lane) {
-  constexpr uint32_t mask = (1u << F_TX_LOG) - 1;
-  constexpr int F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
-  uint32_t h = (j * 2654435761u) >> (32 - F_TX_LOG);
-  volatile uint32_t *vt = tab;
-  bool won = false, todo = active;
-  while (todo) {
-    uint32_t cur = vt[h];
-    if (cur == 0xffffffffu) {
-      cur = atomicCAS(&tab[h], 0xffffffffu, j);
-      if (cur == 0xffffffffu) {
-        won = true;
-        break;
-      }
-    }
-    if (cur == j) break;
-    h = (h + 1) & mask;
-  }
-  __syncwarp();
-  const unsigned wb = __ballot_sync(0xffffffffu, won);
-  if (won) {
-    const int pos = nslots + __popc(wb & ((1u << lane) - 1));
-    if (pos < F_SLOT_CAP) slots[pos] = (uint16_t)h;
-  }
-  nslots += __popc(wb);
-  __syncwarp();
-}
-
-__device__ __forceinline__ int nset_probe(const uint32_t *nset, uint32_t c) {
-  uint32_t h = (c * 2654435761u) >> (32 - 6);
-  while (true) {
-    const uint32_t e = nset[h];
-    if (e == c) return 1;
-    if (e == 0xffffffffu) return 0;
-    h = (h + 1) & (HOT_NSET - 1);
-  }
-}
-
-template <int LV1_LOG, int LEVELS, int F_TX_LOG, int F_WARPS>
-__global__ void __launch_bounds__(F_WARPS * 32)
-k_snn_rows_bits(SnnParams P, int n_ro, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
-  constexpr int F_BYTES = hot_bytes(LV1_LOG, LEVELS, F_TX_LOG);
-  constexpr int BIT_WORDS = bits_total_words(LV1_LOG, LEVELS);
-  constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
-  static_assert(BIT_WORDS >= F_SLOT_CAP, "the bit maps double as the hot-key buffer");
-  static_assert(BIT_WORDS % 4 == 0, "cleared with 16-byte stores");
-  static_assert(LEVELS >= 1 && LEVELS <= 4, "s_min - 1 levels");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *base = smem_raw + (size_t)w * F_BYTES;
-  volatile uint32_t *bits = reinterpret_cast<uint32_t *>(base);
-  uint32_t *tab = reinterpret_cast<uint32_t *>(base) + BIT_WORDS;
-  uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
-  uint32_t *pend = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(slots) +
-                                                ((F_SLOT_CAP * 2 + 15) & ~15));
-  uint32_t *nset = pend + 64;
-  const int k = P.k;
-  for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
-  const int n_warps = gridDim.x * F_WARPS;
-  for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
-    const int row_l = P.row_list[r];
-    const int64_t row = P.row_begin + row_l;
-    const int lowkey = P.sym ? (int)row : -1;
-    {
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      uint4 *c4 = reinterpret_cast<uint4 *>(base);
-      for (int s = lane; s < BIT_WORDS / 4; s += 32) c4[s] = z;
-      nset[lane] = 0xffffffffu;
-      nset[lane + 32] = 0xffffffffu;
-    }
-    __syncwarp();
-    // list descriptors (k <= 32: one list per lane) and the hash set of N(i)
-    ListWalk W;
-    W.k = k;
-    W.beg = 0;
-    W.len = 0;
-    if (lane < k) {
-      const uint32_t c = (uint32_t)P.idx0[row * k + lane];
-      W.beg = P.colptr[c];
-      W.len = (int)(P.colptr[c + 1] - W.beg);
-      uint32_t h = (c * 2654435761u) >> (32 - 6);
-      while (true) {
-        const uint32_t old = atomicCAS(&nset[h], 0xffffffffu, c);
-        if (old == 0xffffffffu || old == c) break;
-        h = (h + 1) & (HOT_NSET - 1);
-      }
-    }
-    const unsigned ro_mask = longest_lists(W.len, lane, k, n_ro);
-    int nslots = 0, npend = 0;
-    bool ovf = false;
-    int32_t v[4], nv[4];
-    W.start(ro_mask);
-    bool have = W.advance();
-    if (have) W.load(P.rev, lane, lowkey, v);
-    while (have && !ovf) {
-      const int ph = W.ph, t0 = W.t0, l = W.l;
-      have = W.advance();
-      if (have) W.load(P.rev, lane, lowkey, nv);
-      // climb the levels: plain 32-bit loads / stores only
-      bool go[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) go[u] = v[u] >= 0;
-      {
-        int off = 0;
-#pragma unroll
-        for (int lv = 0; lv < LEVELS; ++lv) {
-          constexpr uint32_t MUL[4] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu};
-          const int lg = LV1_LOG - (lv < 2 ? lv : 2);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (go[u]) {
-              const uint32_t hb = ((uint32_t)v[u] * MUL[lv]) >> (32 - lg);
-              volatile uint32_t *wp = bits + off + (hb >> 5);
-              const uint32_t bit = 1u << (hb & 31u);
-              uint32_t wv = *wp;
-              if (!(wv & bit)) {
-                if (lv > 0 || ph == 0) {
-                  do {  // a lane that loses a same-word race sees its bit missing and writes again
-                    *wp = wv | bit;
-                    wv = *wp;
-                  } while (!(wv & bit));
-                }
-                go[u] = false;
-              }
-            }
-          }
-          off += (1 << lg) / 32;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (t0 + 32 * u >= l) break;  // warp-uniform
-        const unsigned bal = __ballot_sync(0xffffffffu, go[u]);
-        if (bal) {
-          if (go[u]) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)v[u];
-          npend += __popc(bal);
-          __syncwarp();
-          if (npend >= 32) {
-            hot_insert_batch<F_TX_LOG>(tab, slots, nslots, pend[lane], true, lane);
-            const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
-            __syncwarp();
-            if (32 + lane < npend) pend[lane] = mv;
-            npend -= 32;
-            __syncwarp();
-            if (nslots > F_SLOTS) ovf = true;
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = nv[u];
-    }
-    if (!ovf && npend > 0) {
-      hot_insert_batch<F_TX_LOG>(tab, slots, nslots, lane < npend ? pend[lane] : 0, lane < npend, lane);
-      if (nslots > F_SLOTS) ovf = true;
-    }
-    __syncwarp();
-    if (ovf) {
-      // hand the row to the big-table kernel; leave the table clean
-      for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
-      if (lane == 0) {
-        P.row_nnz[row_l] = 0;
-        ovf_list[atomicAdd(&info->n_ovf, 1)] = row_l;
-      }
-      __syncwarp();
-      continue;
-    }
-    // distinct hot keys -> the (now free) bit-map area, table cleaned, ascending order
-    uint32_t *keys = reinterpret_cast<uint32_t *>(base);
-    for (int t = lane; t < nslots; t += 32) {
-      const int sl = slots[t];
-      keys[t] = tab[sl];
-      tab[sl] = 0xffffffffu;
-    }
-    __syncwarp();
-    bitonic_sort_asc(keys, nslots, lane, 32, [] { __syncwarp(); });
-    // exact counts from the forward lists (one lane per key, eight loads in flight), cut-off,
-    // emit (already in column order)
-    uint32_t *dst = reinterpret_cast<uint32_t *>(P.tmp) + P.tmp_off[row_l];
-    int m = 0;
-    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&info->dbg_hot_keys), (unsigned long long)nslots);
-    for (int tb = 0; tb < nslots; tb += 32) {
-      const int t = tb + lane;
-      const bool act = t < nslots;
-      const uint32_t j = act ? keys[t] : (uint32_t)row;
-      const int32_t *nj = P.idx0 + (int64_t)j * k;
-      int sc = 0;
-      for (int q0 = 0; q0 < k; q0 += 8) {
-        int32_t c[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) c[u] = (q0 + u < k) ? nj[q0 + u] : -1;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (c[u] >= 0) sc += nset_probe(nset, (uint32_t)c[u]);
-      }
-      const bool kp = act && P.keep[sc] != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, kp);
-      if (kp) dst[m + __popc(bal & ((1u << lane) - 1))] = (j << P.cbits) | (uint32_t)sc;
-      m += __popc(bal);
-    }
-    if (lane == 0) P.row_nnz[row_l] = m;
-    __syncwarp();
-  }
-}
-
-template <int LV1_LOG, int LEVELS, int F_TX_LOG, int F_WARPS>
-int launch_bits(b200nn_ctx *ctx, const SnnParams &P, int n_ro, int32_t *ovf_list, DevInfo *d_info) {
-  auto kern = k_snn_rows_bits<LV1_LOG, LEVELS, F_TX_LOG, F_WARPS>;
-  constexpr int bytes = hot_bytes(LV1_LOG, LEVELS, F_TX_LOG) * F_WARPS;
-  static_assert(2 * (bytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, F_WARPS), (int64_t)ctx->sm_count * 2);
-  kern<<<blocks, F_WARPS * 32, bytes, ctx->stream>>>(P, n_ro, ovf_list, d_info);
-  KERNEL_CHECK(ctx);
-  return B200NN_OK;
-}
-
-// 32 k level-1 bits (4 KB) and a 512-word key table for rows with E <= 3.3 k, 64 k bits and 1024
-// words for the larger ones; warps per CTA are what two CTAs per SM can hold (at most 16)
-template <int LEVELS>
-int launch_bits_class(b200nn_ctx *ctx, const SnnParams &P, bool big, int n_ro, int32_t *ovf_list, DevInfo *d_info) {
-  constexpr int budget = 113 * 1024;
-  constexpr int wb = budget / hot_bytes(16, LEVELS, 10), ws = budget / hot_bytes(15, LEVELS, 9);
-  if (big) return launch_bits<16, LEVELS, 10, (wb > 16 ? 16 : wb)>(ctx, P, n_ro, ovf_list, d_info);
-  return launch_bits<15, LEVELS, 9, (ws > 16 ? 16 : ws)>(ctx, P, n_ro, ovf_list, d_info);
 }
 
 // expanded work, survivor bound and work class of every row
@@ -1477,6 +1210,8 @@ int launch_class(b200nn_ctx *ctx, SnnParams P, int blocks_per_sm, int64_t max_bl
   return B200NN_OK;
 }
 
+int fetch_info(b200nn_ctx *ctx, const DevInfo *d_info);
+
 // table sizes (log2 words) of the three warp-per-row classes and the block-per-row class
 struct WordCfg32 {
   typedef uint32_t Word;
@@ -1505,26 +1240,9 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     // positives in the counters; measured best: class 0 (E <= 2.8 k) 8 k counters, 30 warps/SM;
     // class 1 (E <= 3.2 k) 16 k counters, 20 warps/SM; class 2 (E <= 6.5 k) 16 k counters, 16.
     constexpr int WA = 15, WB = 10, WC = 8;
-    // k <= 32 (one reverse list per lane): two-walk kernel with read-only hub lists;
-    // B200NN_SNN_NO_RO=1 switches those off, B200NN_SNN_ROUND1=1 selects the round-1 kernel.
-    static const bool no_ro_env = getenv("B200NN_SNN_NO_RO") != nullptr;
-    static const bool bits_env = getenv("B200NN_SNN_BITS") != nullptr;   // experimental single-walk kernel
-    static const bool old_env = getenv("B200NN_SNN_ROUND1") != nullptr;  // round-1 kernel (no read-only lists)
-    const int n_ro = no_ro_env ? 0 : filter_s_min - 1;
-    if (P.k <= 32 && bits_env && filter_s_min <= 5) {
-      for (int c = 0; c < 3; ++c) {
-        P.row_list = class_list + c * (int64_t)n_rows;
-        P.n_rows_class = class_count[c];
-        if (P.n_rows_class <= 0) continue;
-        const bool big = c == 2;
-        switch (filter_s_min - 1) {
-          case 1: RC_TRY(launch_bits_class<1>(ctx, P, big, n_ro, ovf_list, d_info)); break;
-          case 2: RC_TRY(launch_bits_class<2>(ctx, P, big, n_ro, ovf_list, d_info)); break;
-          case 3: RC_TRY(launch_bits_class<3>(ctx, P, big, n_ro, ovf_list, d_info)); break;
-          default: RC_TRY(launch_bits_class<4>(ctx, P, big, n_ro, ovf_list, d_info)); break;
-        }
-      }
-    } else if (P.k <= 32 && !old_env) {
+    // k <= 32 (one reverse list per lane): k_snn_rows_filter2; B200NN_SNN_ROUND1=1 selects the round-1 kernel
+    static const bool old_env = getenv("B200NN_SNN_ROUND1") != nullptr;  // round-1 kernel (any k)
+    if (P.k <= 32 && !old_env) {
       auto kA = k_snn_rows_filter2<13, 9, WA>;
       auto kB = k_snn_rows_filter2<14, 9, WB>;
       auto kC = k_snn_rows_filter2<14, 10, WC>;
@@ -1539,11 +1257,11 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
         const int w = c == 0 ? WA : c == 1 ? WB : WC;
         const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, w), (int64_t)ctx->sm_count * 2);
         if (c == 0)
-          kA<<<blocks, WA * 32, bytesA, ctx->stream>>>(P, filter_s_min, n_ro, ovf_list, d_info);
+          kA<<<blocks, WA * 32, bytesA, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
         else if (c == 1)
-          kB<<<blocks, WB * 32, bytesB, ctx->stream>>>(P, filter_s_min, n_ro, ovf_list, d_info);
+          kB<<<blocks, WB * 32, bytesB, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
         else
-          kC<<<blocks, WC * 32, bytesC, ctx->stream>>>(P, filter_s_min, n_ro, ovf_list, d_info);
+          kC<<<blocks, WC * 32, bytesC, ctx->stream>>>(P, filter_s_min, ovf_list, d_info);
         KERNEL_CHECK(ctx);
       }
     } else {
@@ -1605,9 +1323,8 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
   }
   if (filter_s_min >= 2) {
     // rows whose exact table overflowed in the filtered kernel (E <= 0.8 * 2^L2 <= 2^L3 / 2)
-    int32_t n_ovf = 0;
-    CU_TRY(cudaMemcpyAsync(&n_ovf, &d_info->n_ovf, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    RC_TRY(fetch_info(ctx, d_info));
+    const int32_t n_ovf = ctx->h_info->n_ovf;
     if (n_ovf > 0) {
       P.row_list = ovf_list;
       P.n_rows_class = n_ovf;
@@ -1617,9 +1334,34 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
   return B200NN_OK;
 }
 
+// Small read-backs go through a kernel that stores into the context's page-locked host block (device-
+// visible under unified addressing) instead of cudaMemcpyAsync: a D2H copy would queue on the copy engine
+// behind the multi-100-MB result transfers of the end-to-end path (measured: +6 ms per call).
+__global__ void k_info_to_host(const DevInfo *__restrict__ d_info, DevInfo *__restrict__ h_info) {
+  const int t = threadIdx.x;
+  const int32_t *src = reinterpret_cast<const int32_t *>(d_info);
+  volatile int32_t *dst = reinterpret_cast<volatile int32_t *>(h_info);
+  for (int i = t; i < (int)(sizeof(DevInfo) / sizeof(int32_t)); i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+__global__ void k_i64_to_host(const int64_t *__restrict__ src, long long *__restrict__ h_dst) {
+  *reinterpret_cast<volatile long long *>(h_dst) = (long long)*src;
+  __threadfence_system();
+}
+
 int fetch_info(b200nn_ctx *ctx, const DevInfo *d_info) {
-  CU_TRY(cudaMemcpyAsync(ctx->h_info, d_info, sizeof(DevInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  k_info_to_host<<<1, 32, 0, ctx->stream>>>(d_info, ctx->h_info);
+  KERNEL_CHECK(ctx);
   CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+// one 64-bit device value -> host, on `stream` (slot 0 / 1 of the context's host scalars)
+int fetch_i64(b200nn_ctx *ctx, const int64_t *d_val, int64_t *out, cudaStream_t stream, int slot) {
+  k_i64_to_host<<<1, 1, 0, stream>>>(d_val, &ctx->h_scalars[slot]);
+  KERNEL_CHECK(ctx);
+  CU_TRY(cudaStreamSynchronize(stream));
+  *out = (int64_t)ctx->h_scalars[slot];
   return B200NN_OK;
 }
 
@@ -1691,14 +1433,15 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
   int64_t *nn_p = nullptr;
   int32_t *nn_i = nullptr;
   double *nn_x = nullptr;
-  if (want_nn_graph) {
-    cudaStream_t ss = ctx->side_stream;
-    int32_t *rev_sorted;
+  int32_t *rev_sorted = nullptr;
+  static const bool no_sym_env = getenv("B200NN_SNN_NO_SYM") != nullptr;
+  // the symmetric SNN mode (all rows) cuts every sorted list at the row itself: it wants the sorted
+  // columns too, and waits for them (only for them) before its row kernels start
+  const bool sym_possible = compute_snn && row_begin == 0 && row_end == n && n > 1 && !no_sym_env;
+  const bool need_sort = want_nn_graph || sym_possible;
+  cudaStream_t ss = ctx->side_stream;
+  if (need_sort) {
     RC_TRY(ws_get(ctx, WS_REV_SORTED, (size_t)total + 1, &rev_sorted));
-    RC_TRY(ws_get(ctx, WS_NN_P, (size_t)n + 1, &nn_p));
-    // the graph has at most `total` entries (fewer only when a row lists a neighbour twice)
-    RC_TRY(ws_get(ctx, WS_NN_I, (size_t)total + 1, &nn_i));
-    RC_TRY(ws_get(ctx, WS_NN_X, (size_t)total + 1, &nn_x));
     CU_TRY(cudaEventRecord(ctx->ev_side, st));
     CU_TRY(cudaStreamWaitEvent(ss, ctx->ev_side, 0));
     k_sort_columns<int32_t><<<(unsigned)ceil_div64(n, SORT_WARPS), SORT_WARPS * 32, 0, ss>>>(
@@ -1712,6 +1455,13 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
                                                                               long_list, &d_info->n_long);
       KERNEL_CHECK(ctx);
     }
+    CU_TRY(cudaEventRecord(ctx->ev_sorted, ss));
+  }
+  if (want_nn_graph) {
+    RC_TRY(ws_get(ctx, WS_NN_P, (size_t)n + 1, &nn_p));
+    // the graph has at most `total` entries (fewer only when a row lists a neighbour twice)
+    RC_TRY(ws_get(ctx, WS_NN_I, (size_t)total + 1, &nn_i));
+    RC_TRY(ws_get(ctx, WS_NN_X, (size_t)total + 1, &nn_x));
     RC_TRY(scan_exclusive_i32_to_i64(ctx, uniq, nn_p, n, ss, WS_SCAN_TMP2));
     k_emit_nn_graph<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, ss>>>(rev_sorted, colptr, uniq, nn_p, n,
                                                                         nn_i, nn_x);
@@ -1736,7 +1486,6 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
         CU_TRY(cudaMemcpyAsync(early_nn->x, nn_x, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost,
                                ctx->copy_stream));
     }
-    CU_TRY(cudaEventRecord(ctx->ev_side, ss));  // end of the side work (joined below)
   }
   CU_TRY(cudaEventRecord(e1, st));
   DevInfo hi;
@@ -1757,7 +1506,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     }
     const int64_t lut_max = (lut_all || early.has_dups) ? (int64_t)k * k : (int64_t)k;
     if (lut_max > (1 << 20)) {
-      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      if (need_sort) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
       b200nn_set_error("k = %d with duplicated neighbours exceeds the supported count range", k);
       return B200NN_ERR_INVALID;
     }
@@ -1835,14 +1584,14 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     RC_TRY(fetch_info(ctx, d_info));
     hi = *ctx->h_info;
     if (hi.err_index_range) {
-      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      if (need_sort) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
       b200nn_set_error("neighbour index out of range: every entry must lie in [1, %lld]", (long long)n);
       return B200NN_ERR_INDEX_RANGE;
     }
     const bool has_dups = hi.has_dups != 0;
     const int64_t smax = has_dups ? (int64_t)k * k : (int64_t)k;
     if (smax > lut_max) {
-      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      if (need_sort) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
       b200nn_set_error("k = %d with duplicated neighbours exceeds the supported count range", k);
       return B200NN_ERR_INVALID;
     }
@@ -1870,8 +1619,16 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     P.huge_tables = nullptr;
     P.huge_log_t = 0;
     // all rows, 0/1 adjacency, packed 32-bit words: count only j > i and mirror (B200NN_SNN_NO_SYM=1: off)
-    static const bool no_sym_env = getenv("B200NN_SNN_NO_SYM") != nullptr;
-    P.sym = (row_begin == 0 && row_end == n && !has_dups && use32 && rows > 1 && !no_sym_env) ? 1 : 0;
+    P.sym = (sym_possible && !has_dups && use32) ? 1 : 0;
+    P.sorted = 0;
+    if (P.sym) {
+      static const bool unsorted_env = getenv("B200NN_SNN_SYM_UNSORTED") != nullptr;  // per-element filter instead
+      if (!unsorted_env) {
+        CU_TRY(cudaStreamWaitEvent(st, ctx->ev_sorted, 0));
+        P.rev = rev_sorted;
+        P.sorted = 1;
+      }
+    }
     int32_t *ovf_list;
     RC_TRY(ws_get(ctx, WS_OVF_LIST, (size_t)rows + 1, &ovf_list));
     if (use32)
@@ -1886,8 +1643,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     if (!P.sym) {
       RC_TRY(scan_exclusive_i32_to_i64(ctx, row_nnz, snn_p, rows));
       // read-back: nnz (sizes the result arrays)
-      CU_TRY(cudaMemcpyAsync(&nnz, snn_p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-      CU_TRY(cudaStreamSynchronize(st));
+      RC_TRY(fetch_i64(ctx, snn_p + rows, &nnz, st, 0));
       RC_TRY(ws_get(ctx, WS_SNN_I, (size_t)nnz + 1, &snn_i));
       RC_TRY(ws_get(ctx, WS_SNN_X, (size_t)nnz + 1, &snn_x));
       if (rows > 0) {
@@ -1920,8 +1676,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
       RC_TRY(scan_exclusive_i32_to_i64(ctx, low_cnt, low_off, rows));
       RC_TRY(scan_exclusive_i32_to_i64(ctx, total_row, snn_p, rows));
       // read-back: nnz (sizes the result arrays)
-      CU_TRY(cudaMemcpyAsync(&nnz, snn_p + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-      CU_TRY(cudaStreamSynchronize(st));
+      RC_TRY(fetch_i64(ctx, snn_p + rows, &nnz, st, 0));
       const int64_t nnz_low = (nnz - (int64_t)diag * rows) / 2;
       uint32_t *low_words, *low_sorted;
       int32_t *long_list2;
@@ -1963,7 +1718,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     RC_TRY(fetch_info(ctx, d_info));
     hi = *ctx->h_info;
     if (hi.err_index_range) {
-      if (want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+      if (need_sort) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
       b200nn_set_error("neighbour index out of range: every entry must lie in [1, %lld]", (long long)n);
       return B200NN_ERR_INDEX_RANGE;
     }
@@ -1972,8 +1727,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     // join the side stream: the nn Graph is complete (its early copies may still be in flight on the
     // copy stream; the host-buffer entry points wait for those)
     int64_t nnz_nn = 0;
-    CU_TRY(cudaMemcpyAsync(&nnz_nn, nn_p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->side_stream));
-    CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+    RC_TRY(fetch_i64(ctx, nn_p + n, &nnz_nn, ctx->side_stream, 1));
     ctx->nn_graph.valid = true;
     ctx->nn_graph.n_rows = n;
     ctx->nn_graph.nnz = nnz_nn;
@@ -1982,6 +1736,7 @@ int graphs_launch(b200nn_ctx *ctx, const int32_t *d_idx0, int64_t n_rows, int k,
     ctx->nn_graph.x = nn_x;
     if (stats) stats->nnz_nn = nnz_nn;
   }
+  if (need_sort && !want_nn_graph) CU_TRY(cudaStreamSynchronize(ctx->side_stream));
   if (stats) stats->max_indegree = hi.max_indegree;
   CU_TRY(cudaEventRecord(e2, st));
   CU_TRY(cudaEventSynchronize(e2));

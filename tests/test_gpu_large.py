@@ -118,6 +118,36 @@ def test_config_e_query_path(ctx):
     ix.close()
 
 
+def test_resident_index_keeps_prepared_reference(ctx):
+    """b200nn_index (NNHelper(cache.index = TRUE)) in the grouped regime: the first query prepares
+    the reference side (FP16 operands, grouping, balls) and later queries reuse it -- same answers as fresh
+    calls, for other query sets, other k, the self query, and after unrelated calls on the same context"""
+    R, cen = gaussian_mixture(120_000, 50, seed=61, n_centres=16)
+    Q1, _ = gaussian_mixture(30_000, 50, seed=62, centres=cen)
+    Q2, _ = gaussian_mixture(7_001, 50, seed=63, centres=cen)
+    Q2[5] *= 40.0                                   # far outside the reference's range: still exact
+    ix = ctx.index(R, _lib.ROW_MAJOR)
+    stats = []
+    for q, k in ((Q1, 20), (Q2, 20), (Q1, 7), (None, 20), (Q2, 31)):
+        gi, gd, st = ix.knn(q, k)
+        stats.append(st)
+        wi, wd, _ = ctx.knn(R, q, k, _lib.ROW_MAJOR)      # a fresh call (also disturbs the shared workspace)
+        assert (gi == wi).all() and (gd == wd).all()
+        rows = sample_rows(gi.shape[0], 300)
+        qq = R if q is None else q
+        oi, od = oracle.knn(R, qq[rows], k, method="kdtree")
+        assert (gi[rows] == oi).all() and (gd[rows] == od).all()
+    assert stats[1]["ms_prep"] < 0.6 * stats[0]["ms_prep"], [s["ms_prep"] for s in stats]
+    bad = Q1[:100].copy()
+    bad[3, 3] = np.inf
+    with pytest.raises(sb.B200Error, match="NA/NaN/Inf"):
+        ix.knn(bad, 5)
+    gi, gd, _ = ix.knn(Q1[:100], 5)                 # the index survives the refusal
+    wi, wd, _ = ctx.knn(R, Q1[:100], 5, _lib.ROW_MAJOR)
+    assert (gi == wi).all() and (gd == wd).all()
+    ix.close()
+
+
 @pytest.mark.parametrize("kind", ["pca_like", "manifold10", "uniform", "dups"])
 def test_shaped_inputs_250k(ctx, kind):
     """inputs without the benchmark's coarse clusters: still exact (and the pruning must not assume them)"""

@@ -22,9 +22,49 @@ ap = argparse.ArgumentParser()
 ap.add_argument("config", choices=["D", "E"])
 ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--multi", type=int, default=0, help="shard over this many devices through b200nn_multi_* (host buffers)")
 a = ap.parse_args()
-ctx = sb.Context(0)
 out = {"config": a.config}
+if a.multi:
+    # the single-process multi-device C ABI, end to end from (pageable) host buffers
+    from seurat_b200 import _lib
+    m = sb.MultiContext(list(range(a.multi)))
+    out["devices"] = a.multi
+    if a.config == "D":
+        n, d, k = a.n or 4_000_000, 30, 30
+        X, _ = gaussian_mixture(n, d, 2)
+        for r in range(a.reps):
+            t0 = time.perf_counter()
+            g = m.find_neighbors(X, k, 1 / 15, True, _lib.ROW_MAJOR)
+            t1 = time.perf_counter()
+        out.update(n=n, d=d, k=k, e2e_ms=(t1 - t0) * 1e3, cells_per_s_e2e=n / (t1 - t0), stats=g["stats"])
+        rows = np.random.default_rng(0).choice(n, 400, replace=False)
+        wi, wd = oracle.knn(X, X[rows], k, method="kdtree")
+        out["knn_sample_exact"] = bool((g["idx"][rows] == wi).all() and (g["dist"][rows] == wd).all())
+        p, i, x = g["snn"]
+        per = -(-n // a.multi)
+        b = max(0, per - 10000)
+        wp, wi2, wx = oracle.compute_snn_rows(g["idx"], 1 / 15, b, b + 20000)
+        out["snn_block_across_shards_exact"] = bool((p[b:b + 20001].astype(np.int64) - p[b] == wp).all()
+                                                    and (i[p[b]:p[b + 20000]] == wi2).all()
+                                                    and (x[p[b]:p[b + 20000]] == wx).all())
+        out["nnz_per_row"] = float(p[-1]) / n
+    else:
+        nr, nq, d, k = a.n or 2_000_000, (a.n // 4 if a.n else 500_000), 50, 20
+        R, c = gaussian_mixture(nr, d, 3)
+        Q, _ = gaussian_mixture(nq, d, 4, centres=c)
+        for r in range(a.reps):
+            t0 = time.perf_counter()
+            idx, dist, st = m.knn(R, Q, k, _lib.ROW_MAJOR)
+            t1 = time.perf_counter()
+        out.update(nr=nr, nq=nq, d=d, k=k, e2e_ms=(t1 - t0) * 1e3, queries_per_s_e2e=nq / (t1 - t0), stats=st)
+        rows = np.random.default_rng(0).choice(nq, 400, replace=False)
+        wi, wd = oracle.knn(R, Q[rows], k, method="kdtree")
+        out["knn_sample_exact"] = bool((idx[rows] == wi).all() and (dist[rows] == wd).all())
+    m.close()
+    print(json.dumps(out))
+    sys.exit(0)
+ctx = sb.Context(0)
 if a.config == "D":
     n, d, k = a.n or 4_000_000, 30, 30
     X, _ = gaussian_mixture(n, d, 2)
