@@ -961,6 +961,23 @@ k_count_gid(const int32_t *__restrict__ gid, int64_t n, int G, int32_t *__restri
     if (s_cnt[g] > 0) atomicAdd(&counts[g], s_cnt[g]);
 }
 
+// Lloyd step: fixed-point sums of the sampled rows per assigned group (exact, order-independent)
+__global__ void __launch_bounds__(128)
+k_km_accum(const __half *__restrict__ y16, int64_t m, int64_t stride, int d, int G, const int32_t *__restrict__ gid,
+           int32_t *__restrict__ counts, long long *__restrict__ sums) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  float y[BK];
+  load_y_row(y16, r * stride, d, y);
+  const int g = min(max(gid[r], 0), G - 1);
+  atomicAdd(&counts[g], 1);
+#pragma unroll
+  for (int j = 0; j < BK; ++j)
+    if (j < d)
+      atomicAdd(reinterpret_cast<unsigned long long *>(&sums[(size_t)g * BK + j]),
+                (unsigned long long)(long long)(y[j] * 16777216.f));
+}
+
 // padded reference offsets (multiples of BN) and query offsets (multiples of an item); zeroes the cursors
 __global__ void k_group_offsets(const int32_t *__restrict__ rcount, const int32_t *__restrict__ qcount, int G,
                                 int32_t *__restrict__ goff, int32_t *__restrict__ qoff,
@@ -1678,7 +1695,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_operand_map(CUtensorMap *map, const void *ptr, int64_t rows) {
+int make_operand_map(CUtensorMap *map, const void *ptr, int64_t rows, int64_t row_stride = 1) {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -1691,7 +1708,7 @@ int make_operand_map(CUtensorMap *map, const void *ptr, int64_t rows) {
     fn = reinterpret_cast<PFN_encodeTiled>(p);
   }
   cuuint64_t gdim[2] = {(cuuint64_t)BK, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)BK * 2};
+  cuuint64_t gstr[1] = {(cuuint64_t)BK * 2 * (cuuint64_t)row_stride};  // row_stride > 1: every stride-th row
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box,
@@ -2037,29 +2054,16 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       k_km_init<<<G, 64, 0, st>>>(yr16, m * stride, d, G, cent, cnorm);
       KERNEL_CHECK(ctx);
     }
-    for (int itn = 0; itn < (cached ? 0 : KM_ITERS); ++itn) {
-      k_km_assign<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(yr16, m, stride, d, G, cent, cnorm, nullptr,
-                                                                 kcount, sums);
-      KERNEL_CHECK(ctx);
-      k_km_update<<<G, 64, 0, st>>>(sums, kcount, d, cent, cnorm);
-      KERNEL_CHECK(ctx);
-    }
-    // 3. assign every reference / query row to its nearest centroid, sort by group.  The assignment is
-    // itself a nearest-neighbour search of n rows against G centroids: it runs on the tensor cores
-    // through the candidate kernel (2 - 8 centroid tiles per work item), ~6x faster than the FP32
-    // FMA kernel (k_km_assign; B200NN_KM_ASSIGN_FMA=1 keeps it for comparison).  Any assignment is
-    // valid (only the pruning depends on it); this one is deterministic.
     static const bool assign_fma = getenv("B200NN_KM_ASSIGN_FMA") != nullptr;
     const int G_pad = ((G + BN - 1) / BN) * BN;
     __half *c16 = nullptr;
-    if (!assign_fma || cached) {
-      RC_TRY(ws_get(ctx, WS_TC_CENT16, (size_t)G_pad * BK, &c16));
+    if (!assign_fma || cached) RC_TRY(ws_get(ctx, WS_TC_CENT16, (size_t)G_pad * BK, &c16));
+    // nearest centroid of n_rows rows (every row_stride-th row of y16) on the tensor cores
+    auto assign_tc = [&](const __half *y16, int64_t n_rows, int64_t row_stride, int32_t *gid_out, int32_t *counts) -> int {
       k_cent_operand<<<(unsigned)ceil_div64((int64_t)G_pad * 32, 256), 256, 0, st>>>(cent, G, G_pad, d, c16);
       KERNEL_CHECK(ctx);
-    }
-    auto assign_tc = [&](const __half *y16, int64_t n_rows, int32_t *gid_out, int32_t *counts) -> int {
       CUtensorMap mq, mr;
-      RC_TRY(make_operand_map(&mq, y16, n_rows));
+      RC_TRY(make_operand_map(&mq, y16, n_rows, row_stride));
       RC_TRY(make_operand_map(&mr, c16, G_pad));
       TcParams A;
       memset(&A, 0, sizeof(A));
@@ -2075,10 +2079,31 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       A.misc = misc;
       A.argmin_out = gid_out;
       RC_TRY(launch_tc(ctx, mq, mr, A, false));
-      k_count_gid<<<ctx->sm_count * 4, 256, 0, st>>>(gid_out, n_rows, G, counts);
-      KERNEL_CHECK(ctx);
+      if (counts) {
+        k_count_gid<<<ctx->sm_count * 4, 256, 0, st>>>(gid_out, n_rows, G, counts);
+        KERNEL_CHECK(ctx);
+      }
       return B200NN_OK;
     };
+    for (int itn = 0; itn < (cached ? 0 : KM_ITERS); ++itn) {
+      if (assign_fma) {
+        k_km_assign<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(yr16, m, stride, d, G, cent, cnorm, nullptr,
+                                                                   kcount, sums);
+        KERNEL_CHECK(ctx);
+      } else {
+        // the Lloyd assignment of the sample also runs through the candidate kernel
+        RC_TRY(assign_tc(yr16, m, stride, gid_r, nullptr));
+        k_km_accum<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(yr16, m, stride, d, G, gid_r, kcount, sums);
+        KERNEL_CHECK(ctx);
+      }
+      k_km_update<<<G, 64, 0, st>>>(sums, kcount, d, cent, cnorm);
+      KERNEL_CHECK(ctx);
+    }
+    // 3. assign every reference / query row to its nearest centroid, sort by group.  The assignment is
+    // itself a nearest-neighbour search of n rows against G centroids: it runs on the tensor cores
+    // through the candidate kernel (2 - 8 centroid tiles per work item), ~6x faster than the FP32
+    // FMA kernel (k_km_assign; B200NN_KM_ASSIGN_FMA=1 keeps it for comparison).  Any assignment is
+    // valid (only the pruning depends on it); this one is deterministic.
     if (cached) {
       // the reference rows keep their groups
     } else if (assign_fma) {
@@ -2086,7 +2111,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
                                                                   nullptr);
       KERNEL_CHECK(ctx);
     } else {
-      RC_TRY(assign_tc(yr16, nr, gid_r, rcount));
+      RC_TRY(assign_tc(yr16, nr, 1, gid_r, rcount));
     }
     if (self) {
       if (sharded) {  // this share takes whole groups
@@ -2101,7 +2126,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
                                                                   nullptr);
       KERNEL_CHECK(ctx);
     } else {
-      RC_TRY(assign_tc(yq16, nq, gid_q, qcount));
+      RC_TRY(assign_tc(yq16, nq, 1, gid_q, qcount));
     }
     k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor);
     KERNEL_CHECK(ctx);
