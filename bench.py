@@ -286,9 +286,13 @@ def main():
             raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # host-side barrier for the phase in which rank 0 alone drives every GPU: the waiting ranks must
+        # not keep a spinning NCCL kernel on their devices
+        cpu_group = dist.new_group(backend="gloo")
 
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
     X, _ = gaussian_mixture(n, d, cfg["seed"])           # identical on every rank (seeded)
@@ -425,7 +429,7 @@ def main():
                                             and r["stats"]["nnz_snn"] == nnz_snn)
         del out
     else:
-        e2e = e2e_multi(args, cfg, X, rank, world, local, dev, barrier, main_last)
+        e2e = e2e_multi(args, cfg, X, rank, world, local, dev, cpu_group, main_last)
 
     # ---- a second workload without the mixture's coarse cluster structure (1 GPU only) ------
     other = None
@@ -512,19 +516,20 @@ def main():
         dist.destroy_process_group()
 
 
-def e2e_multi(args, cfg, X, rank, world, local, dev, barrier, main_last):
+def e2e_multi(args, cfg, X, rank, world, local, dev, cpu_group, main_last):
     """N > 1: rank 0 drives all N devices through the single-process multi-device C ABI
     (b200nn_multi_find_neighbors_*): every device uploads its slice of the page-locked host
     embedding over its own PCIe link, the slices and the kNN index travel between the devices
     over NVLink, and the complete result (idx, dist, nn Graph, one SNN dgCMatrix) lands in
-    rank 0's host buffers.  The other ranks wait at the barrier."""
+    rank 0's host buffers.  The other ranks wait on the HOST (gloo barrier) with idle GPUs."""
     import torch
     import torch.distributed as dist
     from seurat_b200 import _lib
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
     res = None
+    torch.cuda.synchronize()
     torch.cuda.empty_cache()
-    barrier()
+    dist.barrier(group=cpu_group)
     if rank == 0:
         try:
             m = _lib.MultiContext(list(range(world)))
@@ -555,7 +560,7 @@ def e2e_multi(args, cfg, X, rank, world, local, dev, barrier, main_last):
             m.close()
         except Exception as ex:  # the value leg must still be reported
             res = {"value": None, "unit": "cells/s", "error": repr(ex)}
-    barrier()
+    dist.barrier(group=cpu_group)
     return res
 
 

@@ -1033,6 +1033,205 @@ k_snn_rows_filter2(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevIn
   }
 }
 
+// ---------------------------------------------------------------------------
+// Staged variant of k_snn_rows_filter2 (the default for k <= 32).  The profile of filter2 shows ~110 warp
+// instructions per (list, pass) against ~25 per 32 occurrences of real work: the lists are short (45
+// entries on average after the suffix cut), so per-list bookkeeping dominates and is paid in both passes.
+// Here the row's occurrences are first copied into a flat shared-memory buffer (one lean copy loop per
+// list); pass A and pass B then run over the flat array with full warps and no per-list logic.  Rows
+// with more occurrences than the buffer holds are processed in chunks (and staged again for pass B).
+// ---------------------------------------------------------------------------
+constexpr int STAGE_CAP = 1024;  // occurrences staged per chunk (4 KB per warp)
+constexpr int filt3_bytes(int cw_log, int tx_log) { return filt_bytes(cw_log, tx_log) + STAGE_CAP * 4; }
+
+template <int CW_LOG, int F_TX_LOG, int F_WARPS>
+__global__ void __launch_bounds__(F_WARPS * 32)
+k_snn_rows_filter3(SnnParams P, int s_min, int32_t *__restrict__ ovf_list, DevInfo *__restrict__ info) {
+  constexpr int F_BYTES = filt3_bytes(CW_LOG, F_TX_LOG);
+  constexpr int F_SLOTS = filt_slots(F_TX_LOG), F_SLOT_CAP = filt_slot_cap(F_TX_LOG);
+  static_assert((1 << CW_LOG) / 2 >= F_SLOT_CAP * 4, "the counter area doubles as the survivor buffer");
+  static_assert(filt_bytes(CW_LOG, F_TX_LOG) % 16 == 0, "stage buffer alignment");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem_raw + (size_t)w * F_BYTES;
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(base);  // eight 4-bit counters per word
+  uint32_t *tab = reinterpret_cast<uint32_t *>(base + (1 << CW_LOG) / 2);
+  uint16_t *slots = reinterpret_cast<uint16_t *>(tab + (1 << F_TX_LOG));
+  uint32_t *pend = reinterpret_cast<uint32_t *>(slots + F_SLOT_CAP);
+  int32_t *stage = reinterpret_cast<int32_t *>(base + filt_bytes(CW_LOG, F_TX_LOG));
+  const uint32_t cmask = (1u << P.cbits) - 1;
+  const int k = P.k;
+  for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+  const int n_warps = gridDim.x * F_WARPS;
+  for (int r = blockIdx.x * F_WARPS + w; r < P.n_rows_class; r += n_warps) {
+    const int row_l = P.row_list[r];
+    const int64_t row = P.row_begin + row_l;
+    // per-element filter only when the lists are unsorted; sorted lists are cut at the row itself
+    const int lowkey = (P.sym && !P.sorted) ? (int)row : -1;
+    {
+      uint4 z = make_uint4(0, 0, 0, 0);
+      uint4 *c4 = reinterpret_cast<uint4 *>(cnt);
+      for (int s = lane; s < (1 << CW_LOG) / 32; s += 32) c4[s] = z;
+    }
+    // list descriptors: lane p < k holds (start, length) of the part of list p that is walked
+    uint32_t beg = 0;
+    int len = 0;
+    if (lane < k) {
+      const int32_t c = P.idx0[row * k + lane];
+      const int64_t cb = P.colptr[c];
+      len = (int)(P.colptr[c + 1] - cb);
+      beg = (uint32_t)cb;
+      if (P.sym && P.sorted) {
+        // first position whose row id exceeds `row` (the list is ascending and contains `row`)
+        int lo = 0, hi = len;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (P.rev[beg + mid] <= (int32_t)row) lo = mid + 1;
+          else hi = mid;
+        }
+        beg += (uint32_t)lo;
+        len -= lo;
+      }
+    }
+    const int total = warp_sum_i32(len);
+    const bool one_chunk = total <= STAGE_CAP;  // warp-uniform
+    __syncwarp();
+    int nslots = 0, npend = 0;
+    bool ovf = false, sat = false;
+    for (int pass = 0; pass < 2 && !ovf; ++pass) {
+      if (pass == 1) {
+        __syncwarp();
+        if (__any_sync(0xffffffffu, sat)) {  // a counter wrapped: the big-table kernel takes the row
+          ovf = true;
+          break;
+        }
+      }
+      int pl = 0, toff = 0;  // next list / offset inside it (warp-uniform)
+      while (pl < k && !ovf) {
+        // ---- stage up to STAGE_CAP occurrences (a one-chunk row keeps its pass-A staging for pass B)
+        int cntc = 0;
+        if (pass == 1 && one_chunk) {
+          cntc = total;
+          pl = k;
+        } else {
+          while (pl < k && cntc < STAGE_CAP) {
+            const uint32_t b = __shfl_sync(0xffffffffu, beg, pl);
+            const int l = __shfl_sync(0xffffffffu, len, pl);
+            const int take = min(l - toff, STAGE_CAP - cntc);
+            const int32_t *src = P.rev + b + toff;
+            for (int t = lane; t < take; t += 32) {
+              const int32_t x = src[t];
+              stage[cntc + t] = x > lowkey ? x : -1;
+            }
+            cntc += take;
+            toff += take;
+            if (toff >= l) {
+              ++pl;
+              toff = 0;
+            }
+          }
+          __syncwarp();
+        }
+        // ---- process the staged occurrences with full warps
+        if (pass == 0) {
+          for (int f0 = 0; f0 < cntc; f0 += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int f = f0 + 32 * u + lane;
+              if (f0 + 32 * u >= cntc) break;  // warp-uniform
+              const int32_t x = f < cntc ? stage[f] : -1;
+              if (x >= 0) {
+                const uint32_t hc = hash_cnt<CW_LOG>((uint32_t)x);
+                const uint32_t sh = (hc & 7u) * 4u;
+                volatile uint32_t *wp = cnt + (hc >> 3);
+                if ((int)((*wp >> sh) & 15u) < s_min) {
+                  const uint32_t old = atomicAdd(cnt + (hc >> 3), 1u << sh);
+                  sat |= ((old >> sh) & 15u) == 15u;
+                }
+              }
+            }
+          }
+        } else {
+          for (int f0 = 0; f0 < cntc && !ovf; f0 += 32) {
+            const int f = f0 + lane;
+            const int32_t x = f < cntc ? stage[f] : -1;
+            bool pass_f = false;
+            if (x >= 0) {
+              const uint32_t hc = hash_cnt<CW_LOG>((uint32_t)x);
+              pass_f = (int)((cnt[hc >> 3] >> ((hc & 7u) * 4u)) & 15u) >= s_min;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass_f);
+            if (bal) {
+              if (pass_f) pend[npend + __popc(bal & ((1u << lane) - 1))] = (uint32_t)x;
+              npend += __popc(bal);
+              __syncwarp();
+              if (npend >= 32) {
+                filt_insert_batch<F_TX_LOG>(tab, slots, nslots, P.cbits, pend[lane], true, lane);
+                const uint32_t mv = (32 + lane < npend) ? pend[32 + lane] : 0;
+                __syncwarp();
+                if (32 + lane < npend) pend[lane] = mv;
+                npend -= 32;
+                __syncwarp();
+                if (nslots > F_SLOTS) ovf = true;
+              }
+            }
+          }
+        }
+        __syncwarp();  // the stage buffer may be refilled
+      }
+    }
+    if (!ovf && npend > 0) {
+      filt_insert_batch<F_TX_LOG>(tab, slots, nslots, P.cbits, lane < npend ? pend[lane] : 0, lane < npend, lane);
+      if (nslots > F_SLOTS) ovf = true;
+    }
+    __syncwarp();
+    if (ovf) {
+      for (int s = lane; s < (1 << F_TX_LOG); s += 32) tab[s] = 0xffffffffu;
+      if (lane == 0) {
+        P.row_nnz[row_l] = 0;
+        ovf_list[atomicAdd(&info->n_ovf, 1)] = row_l;
+      }
+      __syncwarp();
+      continue;
+    }
+    // survivors: exact counts against the cut-off, compacted into the (now free) counter area
+    uint32_t *out = reinterpret_cast<uint32_t *>(cnt);
+    int m = 0;
+    for (int t0 = 0; t0 < nslots; t0 += 32) {
+      const int t = t0 + lane;
+      uint32_t wv = 0;
+      bool kp = false;
+      if (t < nslots) {
+        const int sl = slots[t];
+        wv = tab[sl];
+        tab[sl] = 0xffffffffu;
+        kp = P.keep[wv & cmask] != 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, kp);
+      if (kp) out[m + __popc(bal & ((1u << lane) - 1))] = wv;
+      m += __popc(bal);
+    }
+    __syncwarp();
+    bitonic_sort_asc(out, m, lane, 32, [] { __syncwarp(); });
+    uint32_t *dst = reinterpret_cast<uint32_t *>(P.tmp) + P.tmp_off[row_l];
+    for (int t = lane; t < m; t += 32) dst[t] = out[t];
+    if (lane == 0) P.row_nnz[row_l] = m;
+    __syncwarp();
+  }
+}
+
+template <int CW_LOG, int F_TX_LOG, int F_WARPS>
+int launch_filter3(b200nn_ctx *ctx, const SnnParams &P, int s_min, int32_t *ovf_list, DevInfo *d_info) {
+  auto kern = k_snn_rows_filter3<CW_LOG, F_TX_LOG, F_WARPS>;
+  constexpr int bytes = filt3_bytes(CW_LOG, F_TX_LOG) * F_WARPS;
+  static_assert(2 * (bytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int blocks = (int)std::min<int64_t>(ceil_div64(P.n_rows_class, F_WARPS), (int64_t)ctx->sm_count * 2);
+  kern<<<blocks, F_WARPS * 32, bytes, ctx->stream>>>(P, s_min, ovf_list, d_info);
+  KERNEL_CHECK(ctx);
+  return B200NN_OK;
+}
+
 // expanded work, survivor bound and work class of every row
 struct RowWorkParams {
   const int32_t *idx0;
@@ -1242,7 +1441,21 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     constexpr int WA = 15, WB = 10, WC = 8;
     // k <= 32 (one reverse list per lane): k_snn_rows_filter2; B200NN_SNN_ROUND1=1 selects the round-1 kernel
     static const bool old_env = getenv("B200NN_SNN_ROUND1") != nullptr;  // round-1 kernel (any k)
-    if (P.k <= 32 && !old_env) {
+    static const bool unstaged_env = getenv("B200NN_SNN_UNSTAGED") != nullptr;  // k_snn_rows_filter2 instead
+    if (P.k <= 32 && !old_env && !unstaged_env) {
+      // (counters, exact table, warps per CTA): two CTAs per SM, 113 KB each
+      for (int c = 0; c < 3; ++c) {
+        P.row_list = class_list + c * (int64_t)n_rows;
+        P.n_rows_class = class_count[c];
+        if (P.n_rows_class <= 0) continue;
+        if (c == 0)
+          RC_TRY((launch_filter3<13, 9, 113 * 1024 / filt3_bytes(13, 9)>(ctx, P, filter_s_min, ovf_list, d_info)));
+        else if (c == 1)
+          RC_TRY((launch_filter3<14, 9, 113 * 1024 / filt3_bytes(14, 9)>(ctx, P, filter_s_min, ovf_list, d_info)));
+        else
+          RC_TRY((launch_filter3<14, 10, 113 * 1024 / filt3_bytes(14, 10)>(ctx, P, filter_s_min, ovf_list, d_info)));
+      }
+    } else if (P.k <= 32 && !old_env) {
       auto kA = k_snn_rows_filter2<13, 9, WA>;
       auto kB = k_snn_rows_filter2<14, 9, WB>;
       auto kC = k_snn_rows_filter2<14, 10, WC>;
