@@ -244,8 +244,13 @@ int shard_count_phase(b200nn_multi *m, int g, const Job &J, Gate &gate) {
   memset(&s.st, 0, sizeof(s.st));
   s.nnz_snn = s.nnz_nn = 0;
   bool ok = true;
+  static const bool trace = getenv("B200NN_TRACE") != nullptr;  // phase progress of every shard on stderr
+  int phase_no = 0;
   auto phase = [&](int rc) {  // all shards leave a phase together; a failure anywhere ends the call
+    if (trace) fprintf(stderr, "[b200nn multi] shard %d/%d (device %d) finished phase %d rc=%d, waits\n", g, G, s.dev, phase_no, rc);
     ok = gate.wait(rc == B200NN_OK) && rc == B200NN_OK;
+    if (trace) fprintf(stderr, "[b200nn multi] shard %d/%d leaves phase %d (%s)\n", g, G, phase_no, ok ? "ok" : "failed");
+    ++phase_no;
     return ok;
   };
   const bool self = J.qry == nullptr;

@@ -172,6 +172,21 @@ def _check_finite(a: np.ndarray, what: str) -> None:
         raise ValueError(f"NA/NaN/Inf in foreign function call (arg {what})")
 
 
+def _warn_slow_path(st: dict, nq: int) -> None:
+    """The result is exact either way; these inputs only make the search slow: rows whose
+    certificate failed are recomputed by the FP64 scan, and an input without cluster structure (or one far
+    outlier that dictates the FP16 scale) defeats the tile pruning."""
+    if nq >= 10_000 and st.get("n_uncertified", 0) > 0.02 * nq:
+        warnings.warn(f"{st['n_uncertified']} of {nq} query rows needed the FP64 fallback scan (exact duplicates, "
+                      "lattice ties or badly scaled coordinates, e.g. a far outlier); the result is exact but slow",
+                      RuntimeWarning, stacklevel=3)
+    tot = st.get("knn_tiles_total", 0)
+    if nq >= 200_000 and tot and st.get("knn_tiles_visited", 0) > 0.5 * tot:
+        warnings.warn("the embedding has no cluster structure the tile pruning could use: the tensor-core search "
+                      "scans nearly every tile (exact, but several times slower than on clustered data)",
+                      RuntimeWarning, stacklevel=3)
+
+
 def _nn2(data: np.ndarray, query: np.ndarray | None, k: int, ctx: _lib.Context, algo: int,
          n_cand: int, stats_out: dict | None, cache_index: bool = False, index: "_lib.Index | None" = None):
     """Drop-in for ``RANN::nn2(data, query, k, searchtype="standard", eps=0)``.
@@ -201,6 +216,7 @@ def _nn2(data: np.ndarray, query: np.ndarray | None, k: int, ctx: _lib.Context, 
         idx, dist, st = ctx.knn(data, query, int(k), _layout_of(data), algo, n_cand)
     if stats_out is not None:
         stats_out.update(st)
+    _warn_slow_path(st, idx.shape[0])
     out = {"nn.idx": idx, "nn.dists": dist}
     if cache_index:
         out["idx"] = index
@@ -317,6 +333,7 @@ def FindNeighbors(object, query=None, distance_matrix: bool = False, k_param: in
                                    _layout_of(object.values), knn_algo, n_cand, want_knn=False)
             if stats_out is not None:
                 stats_out.update(r["stats"])
+            _warn_slow_path(r["stats"], n_cells)
             names = object.rownames
             graphs = {"nn": Graph(*r["nn"], (n_cells, n_cells), (names, names))}
             if compute_SNN:
