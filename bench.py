@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-extra-workload", action="store_true")
+    ap.add_argument("--e2e-deadline", type=float, default=150.0,
+                    help="N > 1: seconds the single-process multi-device e2e leg may take before it is abandoned")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.n:
@@ -511,7 +513,11 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "roofline_snn": roofline_snn, "cpu_baseline": cpu,
             "verify": verify, "stage_ms_per_step": st, "n_uncertified": ks.get("n_uncertified"),
             "nnz_snn": g["nnz_snn"], "max_indegree": g.get("max_indegree"), "other_workloads": other}
+    hung = bool(e2e and e2e.pop("_hung", False))
     print(json.dumps(line))
+    sys.stdout.flush()
+    if hung:            # a worker thread is stuck inside the library: no orderly teardown possible
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
 
@@ -521,16 +527,32 @@ def e2e_multi(args, cfg, X, rank, world, local, dev, cpu_group, main_last):
     (b200nn_multi_find_neighbors_*): every device uploads its slice of the page-locked host
     embedding over its own PCIe link, the slices and the kNN index travel between the devices
     over NVLink, and the complete result (idx, dist, nn Graph, one SNN dgCMatrix) lands in
-    rank 0's host buffers.  The other ranks wait on the HOST (gloo barrier) with idle GPUs."""
+    rank 0's host buffers.  The other ranks wait on the HOST (store key, no NCCL kernel spinning
+    on their devices) with idle GPUs.  The leg runs under a deadline: if the multi-device call does
+    not come back in time the value leg is still reported and e2e carries the error."""
+    import datetime
     import torch
     import torch.distributed as dist
     from seurat_b200 import _lib
     n, d, k = cfg["n"], cfg["d"], cfg["k"]
-    res = None
+    deadline_s = args.e2e_deadline
+    store = dist.distributed_c10d._get_default_store()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     dist.barrier(group=cpu_group)
-    if rank == 0:
+    if rank != 0:
+        try:
+            store.wait(["b200nn_e2e_done"], datetime.timedelta(seconds=deadline_s + 60))
+            hung = store.get("b200nn_e2e_done") != b"1"
+        except Exception:
+            hung = True
+        if hung:        # rank 0 abandoned a stuck multi-device call: leave without touching NCCL again
+            sys.stdout.flush()
+            os._exit(0)
+        return None
+    box = {}
+
+    def work():
         try:
             m = _lib.MultiContext(list(range(world)))
             Xp = torch.from_numpy(X).pin_memory()
@@ -558,9 +580,25 @@ def e2e_multi(args, cfg, X, rank, world, local, dev, cpu_group, main_last):
             if not args.no_verify:
                 res["same_as_value_leg"] = bool((r["idx"] - 1 == main_last["idx_full"].cpu().numpy()).all())
             m.close()
+            box["res"] = res
         except Exception as ex:  # the value leg must still be reported
-            res = {"value": None, "unit": "cells/s", "error": repr(ex)}
-    dist.barrier(group=cpu_group)
+            box["res"] = {"value": None, "unit": "cells/s", "error": repr(ex)}
+
+    th = threading.Thread(target=work, daemon=True)
+    th.start()
+    th.join(deadline_s)
+    if th.is_alive():
+        box["timed_out"] = True
+        res = {"value": None, "unit": "cells/s",
+               "error": f"multi-device e2e leg did not finish within {deadline_s} s; value leg reported without it"}
+    else:
+        res = box.get("res")
+    try:
+        store.set("b200nn_e2e_done", "hung" if box.get("timed_out") else "1")
+    except Exception:
+        pass
+    if box.get("timed_out"):
+        res["_hung"] = True
     return res
 
 

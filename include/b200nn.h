@@ -284,6 +284,46 @@ B200NN_API int b200nn_dev_result(b200nn_ctx *ctx, int32_t which, b200nn_dev_csr 
 B200NN_API int b200nn_dev_copy_result(b200nn_ctx *ctx, int32_t which, int64_t *d_p, int32_t *d_i,
                                       double *d_x);
 
+/* ---- modularity optimiser (the step after FindNeighbors) --- */
+/*
+ * Replaces RunModularityClusteringCpp, /root/reference/src/RModularityOptimizer.cpp:21-173
+ * (registered as _Seurat_RunModularityClusteringCpp, /root/reference/src/RcppExports.cpp; called from
+ * RunModularityClustering, /root/reference/R/clustering.R:1881-1906, i.e. FindClusters with
+ * algorithm = 1 / 2).  Same arguments, same result for the same random_seed: the cluster of every
+ * node, 0-based, clusters ordered by decreasing size.  Only the strict lower triangle of the matrix
+ * is read (RModularityOptimizer.cpp:72-81), weights must be positive.
+ *   algorithm 1 = Louvain, 2 = Louvain with multilevel refinement; 3 (smart local moving) and 4
+ *   (Leiden, an R-side package in the reference) return B200NN_ERR_INVALID.
+ * Error texts are the wrapper's stop() messages.
+ */
+typedef struct b200nn_modopt_stats {
+  int64_t n_nodes, n_edges;
+  int32_t n_clusters, pad_;
+  double modularity;           /* quality function of the returned clustering (best start)      */
+  int64_t windows;             /* windows of the node permutation executed in parallel           */
+  int64_t rounds;              /* fixed-point rounds over all windows                            */
+  int64_t sequential_steps;    /* nodes handled by the single-node (reference) step              */
+  int64_t window_retries;      /* windows repeated with a smaller size                           */
+  int64_t local_moving_calls, levels, max_window;
+  double ms_total, ms_build, ms_local_moving, ms_reduce, ms_quality;
+  int64_t gpu_launches;
+} b200nn_modopt_stats;
+
+/* p [n + 1], i [nnz], x [nnz]: dgCMatrix slots of the n x n graph in HOST memory (p[0] = 0).
+ * cluster_out [n] int32 in host memory. */
+B200NN_API int b200nn_modularity_cluster(b200nn_ctx *ctx, int64_t n, const int32_t *p, const int32_t *i,
+                                         const double *x, int32_t modularity_function, double resolution,
+                                         int32_t algorithm, int32_t n_random_starts, int32_t n_iterations,
+                                         uint64_t random_seed, int32_t *cluster_out, b200nn_modopt_stats *stats);
+/* The same on the SNN graph the context still holds in HBM after b200nn_find_neighbors_count /
+ * b200nn_dev_graphs (all rows): no D2H + H2D of the graph between FindNeighbors and FindClusters.
+ * n_expected > 0 is checked against the resident graph's size. */
+B200NN_API int b200nn_modularity_cluster_resident(b200nn_ctx *ctx, int32_t modularity_function, double resolution,
+                                                  int32_t algorithm, int32_t n_random_starts,
+                                                  int32_t n_iterations, uint64_t random_seed,
+                                                  int32_t *cluster_out, int64_t n_expected,
+                                                  b200nn_modopt_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

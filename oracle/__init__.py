@@ -4,9 +4,14 @@ TEST INFRASTRUCTURE ONLY -- see the header of oracle.c.  The product package
 ``seurat_b200`` never imports this module; only ``tests/``,
 ``__graft_entry__.smoke()`` and the CPU legs of ``bench.py`` do.
 
-Parity status: unpinned against the real reference (no R / RANN / Eigen in the
-container); pinned against the SURVEY.md 8c known-answer vectors in
+Parity status: kNN / SNN unpinned against the real reference (no R / RANN / Eigen in
+the container); pinned against the SURVEY.md 8c known-answer vectors in
 ``tests/golden`` and cross-checked against scipy / sklearn in ``tests/``.
+
+The modularity optimiser is different: ``modularity_cluster_ref`` runs the REAL reference
+(``/root/reference/src/ModularityOptimizer.cpp`` compiled where it lies into
+``oracle/_ref/libmodopt_ref.so`` by ``make -C oracle ref``) and is pinned by the known answers
+the reference's own tests hold (``tests/testthat/test_modularity_optimizer.R``).
 """
 from __future__ import annotations
 
@@ -164,3 +169,54 @@ def find_neighbors(data, k: int = 20, prune: float = 1.0 / 15.0, nthreads: int =
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+# ----------------------------------------------------------------------------------------------
+# modularity optimiser: the real reference (oracle/_ref), see modopt_ref_driver.cpp
+# ----------------------------------------------------------------------------------------------
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libmodopt_ref.so")
+_ref_lib = None
+
+
+def build_ref(force: bool = False) -> str | None:
+    """Compile oracle/_ref/libmodopt_ref.so from the reference sources where they lie.  Returns the
+    path, or None when /root/reference is absent (the GPU box: the prebuilt file travels there)."""
+    src = "/root/reference/src/ModularityOptimizer.cpp"
+    if os.path.exists(src) and (force or not os.path.exists(_REF_LIB_PATH)
+                                or os.path.getmtime(_REF_LIB_PATH) < os.path.getmtime(
+                                    os.path.join(_HERE, "modopt_ref_driver.cpp"))):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "ref"], stdout=subprocess.DEVNULL)
+    return _REF_LIB_PATH if os.path.exists(_REF_LIB_PATH) else None
+
+
+def have_ref() -> bool:
+    return build_ref() is not None
+
+
+def modularity_cluster_ref(p, i, x, modularity_function=1, resolution=0.8, algorithm=1, n_random_starts=10,
+                           n_iterations=10, random_seed=0):
+    """RunModularityClusteringCpp of the reference itself on dgCMatrix slots (p, i, x).
+    Returns (cluster ids int32 [n], n_clusters, modularity of the best start)."""
+    global _ref_lib
+    if _ref_lib is None:
+        path = build_ref()
+        if path is None:
+            raise RuntimeError("oracle/_ref/libmodopt_ref.so is not built and /root/reference is absent")
+        L = C.CDLL(path)
+        L.ref_modularity_cluster.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                             C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ref_modularity_cluster.restype = C.c_int
+        _ref_lib = L
+    p = np.ascontiguousarray(p, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = p.size - 1
+    out = np.zeros(n, dtype=np.int32)
+    q = C.c_double(0.0)
+    rc = _ref_lib.ref_modularity_cluster(n, _p(p), _p(i), _p(x), int(modularity_function), float(resolution),
+                                         int(algorithm), int(n_random_starts), int(n_iterations),
+                                         int(random_seed), _p(out), C.addressof(q))
+    if rc < 0:
+        raise ValueError({-1: "invalid argument", -2: "Matrix contained no network data.  Check format.",
+                          -3: "Clustering step failed.", -4: "C++ exception"}.get(rc, str(rc)))
+    return out, rc, q.value

@@ -30,6 +30,7 @@ SYMBOLS = [
     "b200nn_dev_knn", "b200nn_dev_knn_candidates", "b200nn_dev_graphs", "b200nn_dev_result", "b200nn_dev_copy_result",
     "b200nn_multi_create", "b200nn_multi_destroy", "b200nn_multi_size", "b200nn_multi_knn",
     "b200nn_multi_find_neighbors_count", "b200nn_multi_find_neighbors_fill",
+    "b200nn_modularity_cluster", "b200nn_modularity_cluster_resident",
 ]
 
 
@@ -56,6 +57,18 @@ class Stats(C.Structure):
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class ModoptStats(C.Structure):
+    _fields_ = [("n_nodes", C.c_int64), ("n_edges", C.c_int64), ("n_clusters", C.c_int32), ("pad_", C.c_int32),
+                ("modularity", C.c_double)] + \
+               [(n, C.c_int64) for n in ("windows", "rounds", "sequential_steps", "window_retries",
+                                         "local_moving_calls", "levels", "max_window")] + \
+               [(n, C.c_double) for n in ("ms_total", "ms_build", "ms_local_moving", "ms_reduce", "ms_quality")] + \
+               [("gpu_launches", C.c_int64)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "pad_"}
 
 
 class DevCsr(C.Structure):
@@ -117,6 +130,10 @@ def load() -> C.CDLL:
                                                         C.POINTER(Opts), C.POINTER(i64), C.POINTER(i64),
                                                         C.POINTER(Stats)]
         L.b200nn_multi_find_neighbors_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.b200nn_modularity_cluster.argtypes = [vp, i64, vp, vp, vp, i32, dbl, i32, i32, i32, C.c_uint64, vp,
+                                                C.POINTER(ModoptStats)]
+        L.b200nn_modularity_cluster_resident.argtypes = [vp, i32, dbl, i32, i32, i32, C.c_uint64, vp, i64,
+                                                         C.POINTER(ModoptStats)]
         _lib = L
         return L
 
@@ -170,6 +187,35 @@ class Context:
     @property
     def stream_ptr(self) -> int:
         return int(self._L.b200nn_ctx_stream(self._h) or 0)
+
+    # ---- modularity optimiser (the step after FindNeighbors) -------------------
+    def modularity_cluster(self, p, i, x, modularity_function: int = 1, resolution: float = 0.8,
+                           algorithm: int = 1, n_random_starts: int = 10, n_iterations: int = 10,
+                           random_seed: int = 0):
+        """dgCMatrix slots (p, i, x) of an n x n graph in host memory -> (cluster ids int32 [n], stats)."""
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = p.size - 1
+        out = np.empty(max(n, 0), dtype=np.int32)
+        st = ModoptStats()
+        check(self._L.b200nn_modularity_cluster(self._h, n, _ptr(p), _ptr(i), _ptr(x), int(modularity_function),
+                                                float(resolution), int(algorithm), int(n_random_starts),
+                                                int(n_iterations), int(random_seed) & (2 ** 64 - 1), _ptr(out),
+                                                C.byref(st)))
+        return out, st.as_dict()
+
+    def modularity_cluster_resident(self, n: int, modularity_function: int = 1, resolution: float = 0.8,
+                                    algorithm: int = 1, n_random_starts: int = 10, n_iterations: int = 10,
+                                    random_seed: int = 0):
+        """The same on the SNN graph still resident in HBM after find_neighbors / dev_graphs."""
+        out = np.empty(n, dtype=np.int32)
+        st = ModoptStats()
+        check(self._L.b200nn_modularity_cluster_resident(self._h, int(modularity_function), float(resolution),
+                                                         int(algorithm), int(n_random_starts), int(n_iterations),
+                                                         int(random_seed) & (2 ** 64 - 1), _ptr(out), n,
+                                                         C.byref(st)))
+        return out, st.as_dict()
 
     def index(self, ref, layout: int) -> "Index":
         """Keep the reference embedding `ref` [nr, d] on the device for repeated queries."""
@@ -432,6 +478,35 @@ class MultiContext:
 
     def nn_graph(self, nn_ranked, n: int, layout: int):
         return self._first().nn_graph(nn_ranked, n, layout)
+
+    # ---- modularity optimiser (the step after FindNeighbors) -------------------
+    def modularity_cluster(self, p, i, x, modularity_function: int = 1, resolution: float = 0.8,
+                           algorithm: int = 1, n_random_starts: int = 10, n_iterations: int = 10,
+                           random_seed: int = 0):
+        """dgCMatrix slots (p, i, x) of an n x n graph in host memory -> (cluster ids int32 [n], stats)."""
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = p.size - 1
+        out = np.empty(max(n, 0), dtype=np.int32)
+        st = ModoptStats()
+        check(self._L.b200nn_modularity_cluster(self._h, n, _ptr(p), _ptr(i), _ptr(x), int(modularity_function),
+                                                float(resolution), int(algorithm), int(n_random_starts),
+                                                int(n_iterations), int(random_seed) & (2 ** 64 - 1), _ptr(out),
+                                                C.byref(st)))
+        return out, st.as_dict()
+
+    def modularity_cluster_resident(self, n: int, modularity_function: int = 1, resolution: float = 0.8,
+                                    algorithm: int = 1, n_random_starts: int = 10, n_iterations: int = 10,
+                                    random_seed: int = 0):
+        """The same on the SNN graph still resident in HBM after find_neighbors / dev_graphs."""
+        out = np.empty(n, dtype=np.int32)
+        st = ModoptStats()
+        check(self._L.b200nn_modularity_cluster_resident(self._h, int(modularity_function), float(resolution),
+                                                         int(algorithm), int(n_random_starts), int(n_iterations),
+                                                         int(random_seed) & (2 ** 64 - 1), _ptr(out), n,
+                                                         C.byref(st)))
+        return out, st.as_dict()
 
     def index(self, ref, layout: int) -> "Index":
         return self._first().index(ref, layout)

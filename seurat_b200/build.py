@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libb200nn.so")
-SOURCES = ["util.cu", "knn_exact.cu", "knn_tc.cu", "snn.cu", "api.cu", "multi.cu"]
+SOURCES = ["util.cu", "knn_exact.cu", "knn_tc.cu", "snn.cu", "api.cu", "multi.cu", "modopt.cu"]
 HEADERS = [os.path.join(CSRC, "internal.cuh"), os.path.join(HERE, "..", "include", "b200nn.h")]
 
 NVCC_FLAGS = [
@@ -46,7 +46,7 @@ def _digest(paths) -> str:
 
 
 def _extra_headers():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inl")))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

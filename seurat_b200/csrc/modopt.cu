@@ -1,0 +1,351 @@
+// modopt.cu -- modularity optimiser on the device: CUDA backend of modopt_core.inl and
+// the C entry points b200nn_modularity_cluster*.
+//
+// Replaces RunModularityClusteringCpp (/root/reference/src/RModularityOptimizer.cpp:21-173) with
+// results identical to the reference for the same seed; see modopt_core.inl for how the sequential
+// algorithm is executed in parallel.  Here: the kernels behind the backend's parallel steps
+// (k_pfor: one logical thread per element, grid-stride; CUB radix sort / scan for the grouping
+// steps; k_seq_sum: the order-fixed running sums), a stream-ordered memory pool so that the many
+// short-lived buffers cost no cudaMalloc, and argument checks with the wrapper's messages.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <time.h>
+
+#include "internal.cuh"
+
+#define MO_HD __device__
+template <typename T>
+__device__ __forceinline__ void be_atomic_min(T *a, T v) { atomicMin(a, v); }
+template <typename T>
+__device__ __forceinline__ void be_atomic_max(T *a, T v) { atomicMax(a, v); }
+__device__ __forceinline__ void be_atomic_max64(int64_t *a, int64_t v) {
+  atomicMax(reinterpret_cast<long long *>(a), (long long)v);
+}
+
+#include "modopt_core.inl"
+
+namespace {
+
+template <class F>
+__global__ void __launch_bounds__(256) k_pfor(int64_t n, F f) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+template <class F>
+__global__ void k_single(F f) {
+  f();
+}
+
+// running sum in the order of the array (the reference's std::accumulate / += loops): one warp,
+// coalesced loads, the additions themselves strictly one after the other
+__global__ void __launch_bounds__(32) k_seq_sum(const double *__restrict__ x, int64_t n, double init, double *out) {
+  const int lane = threadIdx.x;
+  double s = init;
+  double nxt = lane < n ? x[lane] : 0.0;
+  for (int64_t base = 0; base < n; base += 32) {
+    const double v = nxt;
+    const int64_t nb = base + 32 + lane;
+    nxt = nb < n ? x[nb] : 0.0;
+    const int cnt = (int)(n - base < 32 ? n - base : 32);
+    if (cnt == 32) {
+#pragma unroll
+      for (int l = 0; l < 32; ++l) s = __dadd_rn(s, __shfl_sync(0xffffffffu, v, l));
+    } else {
+      for (int l = 0; l < cnt; ++l) s = __dadd_rn(s, __shfl_sync(0xffffffffu, v, l));
+    }
+  }
+  if (lane == 0) *out = s;
+}
+
+struct CudaBackend {
+  b200nn_ctx *ctx;
+  cudaStream_t st;
+  int rc = B200NN_OK;  // first failure; later steps become no-ops
+  int64_t win0 = 8192, winmax = (int64_t)1 << 40;
+  double *d_scalar = nullptr;
+
+  explicit CudaBackend(b200nn_ctx *c) : ctx(c), st(c->stream) {
+    if (const char *e = getenv("B200NN_MODOPT_WIN0")) win0 = atoll(e);
+    if (const char *e = getenv("B200NN_MODOPT_WINMAX")) winmax = atoll(e);
+    // keep the stream-ordered pool's memory between the many short-lived buffers of a call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
+  void fail(cudaError_t e, const char *what) {
+    if (rc != B200NN_OK) return;
+    b200nn_set_error("modularity optimiser: CUDA error %s in %s: %s", cudaGetErrorName(e), what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    rc = e == cudaErrorMemoryAllocation ? B200NN_ERR_NOMEM : B200NN_ERR_CUDA;
+  }
+  template <typename T>
+  T *alloc(int64_t n) {
+    void *p = nullptr;
+    if (rc != B200NN_OK) return nullptr;
+    cudaError_t e = cudaMallocAsync(&p, sizeof(T) * (size_t)(n > 0 ? n : 1), st);
+    if (e != cudaSuccess) {
+      fail(e, "cudaMallocAsync");
+      return nullptr;
+    }
+    return static_cast<T *>(p);
+  }
+  void free(void *p) {
+    if (p) cudaFreeAsync(p, st);
+  }
+  template <class F>
+  void pfor(int64_t n, F f) {
+    if (rc != B200NN_OK || n <= 0) return;
+    const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_pfor<<<(unsigned)blocks, 256, 0, st>>>(n, f);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail(e, "k_pfor launch");
+  }
+  template <class F>
+  void single(F f) {
+    if (rc != B200NN_OK) return;
+    k_single<<<1, 1, 0, st>>>(f);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail(e, "k_single launch");
+  }
+  void sort_keys(const uint64_t *in, uint64_t *out, int64_t n, int bits) {
+    if (rc != B200NN_OK || n <= 0) return;
+    size_t tb = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(nullptr, tb, in, out, n, 0, bits, st);
+    if (e != cudaSuccess) return fail(e, "SortKeys (size)");
+    void *tmp = alloc<uint8_t>((int64_t)tb);
+    if (!tmp) return;
+    e = cub::DeviceRadixSort::SortKeys(tmp, tb, in, out, n, 0, bits, st);
+    ctx->launches += 3;
+    if (e != cudaSuccess) fail(e, "SortKeys");
+    free(tmp);
+  }
+  void sort_pairs(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int64_t n, int bits) {
+    if (rc != B200NN_OK || n <= 0) return;
+    size_t tb = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, bits, st);
+    if (e != cudaSuccess) return fail(e, "SortPairs (size)");
+    void *tmp = alloc<uint8_t>((int64_t)tb);
+    if (!tmp) return;
+    e = cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, 0, bits, st);
+    ctx->launches += 3;
+    if (e != cudaSuccess) fail(e, "SortPairs");
+    free(tmp);
+  }
+  // out[0..n]: exclusive prefix sums of in[0..n-1]; out[n] = the total (in[] has n + 1 slots)
+  void excl_scan(const int64_t *in, int64_t *out, int64_t n) {
+    if (rc != B200NN_OK) return;
+    size_t tb = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n + 1, st);
+    if (e != cudaSuccess) return fail(e, "ExclusiveSum (size)");
+    void *tmp = alloc<uint8_t>((int64_t)tb);
+    if (!tmp) return;
+    e = cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n + 1, st);
+    ctx->launches += 2;
+    if (e != cudaSuccess) fail(e, "ExclusiveSum");
+    free(tmp);
+  }
+  void h2d(void *d, const void *s, size_t b) {
+    if (rc != B200NN_OK || !d) return;
+    cudaError_t e = cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the host buffer may be a temporary
+    if (e != cudaSuccess) fail(e, "h2d");
+  }
+  void d2h(void *d, const void *s, size_t b) {
+    if (rc != B200NN_OK || !s) {
+      memset(d, 0, b);
+      return;
+    }
+    cudaError_t e = cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      fail(e, "d2h");
+      memset(d, 0, b);
+    }
+  }
+  void d2d(void *d, const void *s, size_t b) {
+    if (rc != B200NN_OK || !d || !s) return;
+    cudaError_t e = cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) fail(e, "d2d");
+  }
+  double seq_sum(const double *x, int64_t n, double init) {
+    if (rc != B200NN_OK) return 0.0;
+    if (!d_scalar) d_scalar = alloc<double>(1);
+    if (!d_scalar) return 0.0;
+    k_seq_sum<<<1, 32, 0, st>>>(x, n, init, d_scalar);
+    ctx->launches++;
+    double h = 0.0;
+    d2h(&h, d_scalar, sizeof(double));
+    return h;
+  }
+  bool failed() const { return rc != B200NN_OK; }
+  int64_t initial_window(int64_t) { return win0; }
+  int64_t max_window(int64_t) { return winmax; }
+  double now_ms() {
+    cudaStreamSynchronize(st);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+};
+
+int check_args(int modularity_function, double resolution, int algorithm, int n_random_starts, int n_iterations) {
+  // the wrapper's stop() messages, RModularityOptimizer.cpp:32-41
+  if (modularity_function != 1 && modularity_function != 2) {
+    b200nn_set_error("Modularity parameter must be equal to 1 or 2.");
+    return B200NN_ERR_INVALID;
+  }
+  if (algorithm != 1 && algorithm != 2 && algorithm != 3 && algorithm != 4) {
+    b200nn_set_error("Algorithm for modularity optimization must be 1, 2, 3, or 4");
+    return B200NN_ERR_INVALID;
+  }
+  if (n_random_starts < 1) {
+    b200nn_set_error("Have to have at least one start");
+    return B200NN_ERR_INVALID;
+  }
+  if (n_iterations < 1) {
+    b200nn_set_error("Need at least one interation");
+    return B200NN_ERR_INVALID;
+  }
+  if (modularity_function == 2 && resolution > 1.0) {
+    b200nn_set_error("error: resolution<1 for alternative modularity");
+    return B200NN_ERR_INVALID;
+  }
+  if (algorithm == 3 || algorithm == 4) {
+    b200nn_set_error("modularity optimiser: algorithm %d (%s) is not available on the device; 1 = Louvain and "
+                     "2 = Louvain with multilevel refinement are",
+                     algorithm, algorithm == 3 ? "smart local moving" : "Leiden, an R-side package in the reference");
+    return B200NN_ERR_INVALID;
+  }
+  return B200NN_OK;
+}
+
+void fill_stats(const modopt::Stats &s, int64_t n, int64_t edges, int32_t n_clusters, double q, double ms_total,
+                int64_t launches, b200nn_modopt_stats *out) {
+  if (!out) return;
+  memset(out, 0, sizeof(*out));
+  out->n_nodes = n;
+  out->n_edges = edges;
+  out->n_clusters = n_clusters;
+  out->modularity = q;
+  out->windows = s.windows;
+  out->rounds = s.rounds;
+  out->sequential_steps = s.seq_steps;
+  out->window_retries = s.shrinks;
+  out->local_moving_calls = s.local_moving_calls;
+  out->levels = s.levels;
+  out->max_window = s.max_window;
+  out->ms_total = ms_total;
+  out->ms_build = s.ms_build;
+  out->ms_local_moving = s.ms_local_moving;
+  out->ms_reduce = s.ms_reduce;
+  out->ms_quality = s.ms_quality;
+  out->gpu_launches = launches;
+}
+
+template <typename PT>
+int cluster_device_csc(b200nn_ctx *ctx, int64_t n, const PT *d_p, const int32_t *d_i, const double *d_x,
+                       int modularity_function, double resolution, int algorithm, int n_random_starts,
+                       int n_iterations, uint64_t seed, int32_t *cluster_out, b200nn_modopt_stats *stats) {
+  CudaBackend be(ctx);
+  const int64_t l0 = ctx->launches;
+  const double t0 = be.now_ms();
+  modopt::Net net;
+  modopt::Stats st;
+  const int64_t E = modopt::build_network(be, (int32_t)n, d_p, d_i, d_x, modularity_function, net);
+  st.ms_build = be.now_ms() - t0;
+  if (be.rc != B200NN_OK) return be.rc;
+  if (E == 0) {
+    b200nn_set_error("Matrix contained no network data.  Check format.");
+    return B200NN_ERR_INVALID;
+  }
+  double q = 0;
+  const int32_t k = modopt::run_clustering(be, net, algorithm, resolution, modularity_function, n_random_starts,
+                                           n_iterations, seed, cluster_out, &q, &st);
+  modopt::free_net(be, net);
+  be.free(be.d_scalar);
+  const double t1 = be.now_ms();
+  if (be.rc != B200NN_OK) return be.rc;
+  if (k < 0) {
+    b200nn_set_error("Clustering step failed.");
+    return B200NN_ERR_STATE;
+  }
+  fill_stats(st, n, E, k, q, t1 - t0, ctx->launches - l0, stats);
+  return B200NN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200nn_modularity_cluster(b200nn_ctx *ctx, int64_t n, const int32_t *p, const int32_t *i, const double *x,
+                              int32_t modularity_function, double resolution, int32_t algorithm,
+                              int32_t n_random_starts, int32_t n_iterations, uint64_t random_seed,
+                              int32_t *cluster_out, b200nn_modopt_stats *stats) {
+  if (!ctx) {
+    b200nn_set_error("NULL context");
+    return B200NN_ERR_INVALID;
+  }
+  if (!p || !i || !x || !cluster_out || n <= 0 || n >= 0x7fffffffLL) {
+    b200nn_set_error("modularity_cluster: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  RC_TRY(check_args(modularity_function, resolution, algorithm, n_random_starts, n_iterations));
+  const int64_t nnz = p[n];
+  if (p[0] != 0 || nnz < 0) {
+    b200nn_set_error("modularity_cluster: p is not a dgCMatrix column pointer");
+    return B200NN_ERR_INVALID;
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  int32_t *d_p = nullptr, *d_i = nullptr;
+  double *d_x = nullptr;
+  CU_TRY(cudaMallocAsync(&d_p, sizeof(int32_t) * (size_t)(n + 1), ctx->stream));
+  CU_TRY(cudaMallocAsync(&d_i, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), ctx->stream));
+  CU_TRY(cudaMallocAsync(&d_x, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1), ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_p, p, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz > 0) {
+    CU_TRY(cudaMemcpyAsync(d_i, i, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = cluster_device_csc(ctx, n, d_p, d_i, d_x, modularity_function, resolution, algorithm, n_random_starts,
+                              n_iterations, random_seed, cluster_out, stats);
+  cudaFreeAsync(d_p, ctx->stream);
+  cudaFreeAsync(d_i, ctx->stream);
+  cudaFreeAsync(d_x, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+int b200nn_modularity_cluster_resident(b200nn_ctx *ctx, int32_t modularity_function, double resolution,
+                                       int32_t algorithm, int32_t n_random_starts, int32_t n_iterations,
+                                       uint64_t random_seed, int32_t *cluster_out, int64_t n_expected,
+                                       b200nn_modopt_stats *stats) {
+  if (!ctx) {
+    b200nn_set_error("NULL context");
+    return B200NN_ERR_INVALID;
+  }
+  RC_TRY(check_args(modularity_function, resolution, algorithm, n_random_starts, n_iterations));
+  const CsrResult &r = ctx->snn;
+  if (!r.valid || !r.p || !cluster_out) {
+    b200nn_set_error("modularity_cluster_resident: no SNN graph is resident (run b200nn_find_neighbors_count / "
+                     "b200nn_dev_graphs with compute_snn first)");
+    return B200NN_ERR_STATE;
+  }
+  if (n_expected > 0 && r.n_rows != n_expected) {
+    b200nn_set_error("modularity_cluster_resident: the resident SNN holds %lld rows (a shard?), expected %lld",
+                     (long long)r.n_rows, (long long)n_expected);
+    return B200NN_ERR_STATE;
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  // S is symmetric, so its CSR arrays are its CSC arrays (semantics item 5)
+  return cluster_device_csc(ctx, r.n_rows, r.p, r.i, r.x, modularity_function, resolution, algorithm,
+                            n_random_starts, n_iterations, random_seed, cluster_out, stats);
+}
+
+}  // extern "C"

@@ -264,10 +264,14 @@ int shard_count_phase(b200nn_multi *m, int g, const Job &J, Gate &gate) {
     const int64_t per_r = ceil_div64(J.nr, G);
     const int64_t rb = std::min<int64_t>(g * per_r, J.nr), re = std::min<int64_t>(rb + per_r, J.nr);
     SH_TRY(upload_rows(s, J.ref, J.nr, J.d, J.o.layout, s.d_ref, rb, re));
+    // NA / NaN / Inf are refused before any search kernel sees them (nn2's .C(NAOK = FALSE)): every
+    // shard checks the slice it uploaded, and a failure anywhere stops all shards at this phase
+    SH_TRY(check_finite_f64(ctx, s.d_ref + rb * J.d, (re - rb) * (int64_t)J.d, "data"));
     s.d_qry = nullptr;
     if (!self) {  // every device needs only its own query rows
       SH_TRY(ws_get(ctx, WS_QRY64, (size_t)nq * J.d, &s.d_qry));
       SH_TRY(upload_rows(s, J.qry, nq, J.d, J.o.layout, s.d_qry, s.b, s.e));
+      SH_TRY(check_finite_f64(ctx, s.d_qry + s.b * J.d, (s.e - s.b) * (int64_t)J.d, "query"));
     }
     SH_TRY(ws_get(ctx, WS_IDX0, (size_t)nq * J.k, &s.d_idx));
     SH_TRY(ws_get(ctx, WS_DIST, (size_t)std::max<int64_t>(s.e - s.b, 1) * J.k, &s.d_dist));

@@ -1441,8 +1441,10 @@ int run_snn_classes(b200nn_ctx *ctx, SnnParams P, const int32_t *class_list, int
     constexpr int WA = 15, WB = 10, WC = 8;
     // k <= 32 (one reverse list per lane): k_snn_rows_filter2; B200NN_SNN_ROUND1=1 selects the round-1 kernel
     static const bool old_env = getenv("B200NN_SNN_ROUND1") != nullptr;  // round-1 kernel (any k)
-    static const bool unstaged_env = getenv("B200NN_SNN_UNSTAGED") != nullptr;  // k_snn_rows_filter2 instead
-    if (P.k <= 32 && !old_env && !unstaged_env) {
+    // the staged variant (flat shared-memory occurrence buffer) measured slower on config C
+    // (15.1 ms vs 11.6 ms for the stage, gpurun_out r02e vs profiles/r02_bench_C.json): opt-in only
+    static const bool staged_env = getenv("B200NN_SNN_STAGED") != nullptr;
+    if (P.k <= 32 && !old_env && staged_env) {
       // (counters, exact table, warps per CTA): two CTAs per SM, 113 KB each
       for (int c = 0; c < 3; ++c) {
         P.row_list = class_list + c * (int64_t)n_rows;

@@ -18,7 +18,8 @@ from conftest import assert_csr_equal
 from seurat_b200 import _lib
 from seurat_b200.synthetic import CONFIGS, cell_names, gaussian_mixture
 
-pytestmark = pytest.mark.gpu
+# a wedged multi-device call must end the run, not hold the box (pytest-timeout kills the process)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 PRUNE = 1 / 15
 

@@ -1,0 +1,97 @@
+"""CPU suite of the modularity optimiser.
+
+  * oracle/_ref (the reference's own ModularityOptimizer.cpp, compiled where it lies) reproduces the
+    known answers of the reference's tests -- the pin;
+  * the committed golden vectors were made by it (tests/golden/make_modopt_golden.py);
+  * the step functions the CUDA library launches (seurat_b200/csrc/modopt_core.inl), run serially by
+    tests/emul, give exactly those vectors -- labels AND the bits of the modularity -- for every
+    window size, including windows of one node (the reference step) and whole-sweep windows.
+No GPU is used here; the product library itself is exercised by tests/test_gpu_modopt.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import emul_modopt
+import modopt_cases as mc
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "modopt_fixtures.json")) as f:
+    GOLD = json.load(f)["cases"]
+GRAPHS = {name: build for name, build, _ in mc.small_cases()}
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built and /root/reference absent")
+
+
+@needs_ref
+def test_ref_build_reproduces_the_reference_tests_known_answers():
+    p, i, x = mc.slots(mc.karate())
+    for params, want in mc.KARATE_KAT + mc.KARATE_KAT_SLM:
+        got, nc, _ = oracle.modularity_cluster_ref(p, i, x, *params)
+        assert got.tolist() == want and nc == max(want) + 1
+
+
+def test_emulated_device_steps_reproduce_the_reference_tests_known_answers():
+    p, i, x = mc.slots(mc.karate())
+    for params, want in mc.KARATE_KAT:
+        for w0 in (1, 2, 5, 34):
+            got, nc, _, _ = emul_modopt.cluster(p, i, x, *params, win0=w0, winmax=34)
+            assert got.tolist() == want and nc == max(want) + 1
+
+
+@pytest.mark.parametrize("case", [c for c in GOLD if not c["graph"].startswith("snn:")],
+                         ids=lambda c: c["graph"] + "-" + "-".join(map(str, c["params"])))
+def test_emulated_device_steps_match_golden(case):
+    p, i, x = mc.slots(GRAPHS[case["graph"]]())
+    n = p.size - 1
+    for w0, wm in ((1, 1), (3, 64), (256, n), (n, n)):
+        lab, nc, q, st = emul_modopt.cluster(p, i, x, *case["params"], win0=w0, winmax=wm)
+        assert nc == case["n_clusters"], (w0, wm, st)
+        assert mc.digest(lab) == case["sha256"], (w0, wm, st)
+        assert q == float.fromhex(case["modularity"]), "modularity must agree to the last bit"
+        if w0 == 1 and wm == 1:
+            assert st["windows"] == 0, "window size 1 must take the single-node step only"
+
+
+def test_emulated_device_steps_match_golden_snn_20k():
+    from seurat_b200.synthetic import gaussian_mixture
+    case = [c for c in GOLD if c["graph"] == "snn:20000:50:7:12:20"]
+    X, _ = gaussian_mixture(20000, 50, seed=7, n_centres=12)
+    p, i, x = oracle.find_neighbors(X, k=20, prune=1 / 15, method="kdtree")["snn"]
+    for c in case[:2]:
+        lab, nc, q, st = emul_modopt.cluster(p, i, x, *c["params"])
+        assert nc == c["n_clusters"] and mc.digest(lab) == c["sha256"] and q == float.fromhex(c["modularity"])
+        assert st["rounds"] < 12 * max(1, st["windows"]), "the fixed point should need few rounds per window"
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(6))
+def test_emulated_device_steps_match_the_reference_on_random_graphs(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(40, 900))
+    M = mc.random_graph(n, float(rng.uniform(2, 12)), seed=seed + 50, weighted=bool(seed % 2),
+                        symmetric=bool(seed % 3), isolated=int(rng.integers(0, 4)))
+    p, i, x = mc.slots(M)
+    for _ in range(4):
+        mf = int(rng.integers(1, 3))
+        res = float(rng.choice([0.01, 0.2, 0.8, 1.0])) if mf == 2 else float(rng.choice([0.1, 0.8, 1.0, 4.0, 40.0]))
+        params = (mf, res, int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(1, 6)),
+                  int(rng.integers(0, 2 ** 40)))
+        want, wc, wq = oracle.modularity_cluster_ref(p, i, x, *params)
+        got, gc, gq, st = emul_modopt.cluster(p, i, x, *params, win0=int(rng.integers(1, 64)), winmax=n)
+        assert gc == wc and (got == want).all() and gq == wq, (params, st)
+
+
+def test_python_mirror_argument_checks():
+    import seurat_b200 as sb
+    with pytest.raises(ValueError, match="Please provide an SNN graph"):
+        sb.FindClusters(None)
+    with pytest.raises(ValueError, match="algorithm not recognised"):
+        sb.FindClusters((np.zeros(2, np.int32), np.zeros(0, np.int32), np.zeros(0)), algorithm=7)
+    ids = sb.GroupSingletons([0, 0, 1, 2, 2], (np.array([0, 2, 4, 7, 9, 11], np.int32),
+                                               np.array([0, 1, 0, 1, 2, 3, 4, 2, 3, 2, 4], np.int32),
+                                               np.array([1, .5, .5, 1, 1, .2, .6, .2, 1, .6, 1])), verbose=False)
+    assert ids == [0, 0, 2, 2, 2]
+    assert sb.GroupSingletons([0, 0, 1], None, group_singletons=False) == [0, 0, "singleton"]
