@@ -12,6 +12,10 @@
 
 #include <time.h>
 
+#include <string>
+#include <utility>
+#include <vector>
+
 #include "internal.cuh"
 
 #define MO_HD __device__
@@ -19,6 +23,7 @@ template <typename T>
 __device__ __forceinline__ void be_atomic_min(T *a, T v) { atomicMin(a, v); }
 template <typename T>
 __device__ __forceinline__ void be_atomic_max(T *a, T v) { atomicMax(a, v); }
+__device__ __forceinline__ int be_atomic_add(int *a, int v) { return atomicAdd(a, v); }
 __device__ __forceinline__ void be_atomic_max64(int64_t *a, int64_t v) {
   atomicMax(reinterpret_cast<long long *>(a), (long long)v);
 }
@@ -59,6 +64,57 @@ __global__ void __launch_bounds__(32) k_seq_sum(const double *__restrict__ x, in
   if (lane == 0) *out = s;
 }
 
+// The long chains of a local-moving round, one warp per chain (modopt_core.inl chain_walk is the
+// definition): 32 events are loaded coalesced, the running weight takes them one after the other
+// (every lane keeps the same running value; a leave is the addition of the negated weight, which is
+// the same IEEE operation as the subtraction), each lane keeps the value after its own event.
+__global__ void __launch_bounds__(256)
+k_long_chains(const uint64_t *__restrict__ ks, double *__restrict__ ev_cw, int32_t *__restrict__ ev_nn,
+              const int32_t *__restrict__ hend, const double *__restrict__ cw, const int32_t *__restrict__ nn,
+              const int32_t *__restrict__ list, const int32_t *__restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int n_long = *count;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_long; q += warps) {
+    const int s = list[q], e = hend[s];
+    const int32_t c = (int32_t)(ks[s] >> 32);
+    double w = cw[c];
+    int cnt = nn[c];
+    for (int base = s; base < e; base += 32) {
+      const int p = base + lane;
+      const bool in = p < e;
+      const bool join = in && ((uint32_t)ks[p] & 1u);
+      const double x = in ? (join ? ev_cw[p] : -ev_cw[p]) : 0.0;
+      // node count after my event: inclusive prefix of +1 / -1
+      int d = in ? (join ? 1 : -1) : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, d, o);
+        if (lane >= o) d += v;
+      }
+      const int m = e - base < 32 ? e - base : 32;
+      double mine = 0.0;
+      if (m == 32) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+          w = __dadd_rn(w, __shfl_sync(0xffffffffu, x, l));
+          if (l == lane) mine = w;
+        }
+      } else {
+        for (int l = 0; l < m; ++l) {
+          w = __dadd_rn(w, __shfl_sync(0xffffffffu, x, l));
+          if (l == lane) mine = w;
+        }
+      }
+      if (in) {
+        ev_cw[p] = mine;
+        ev_nn[p] = cnt + d;
+      }
+      cnt += __shfl_sync(0xffffffffu, d, 31);
+    }
+  }
+}
+
 struct CudaBackend {
   b200nn_ctx *ctx;
   cudaStream_t st;
@@ -69,6 +125,7 @@ struct CudaBackend {
   explicit CudaBackend(b200nn_ctx *c) : ctx(c), st(c->stream) {
     if (const char *e = getenv("B200NN_MODOPT_WIN0")) win0 = atoll(e);
     if (const char *e = getenv("B200NN_MODOPT_WINMAX")) winmax = atoll(e);
+    trace = getenv("B200NN_MODOPT_TRACE") != nullptr;
     // keep the stream-ordered pool's memory between the many short-lived buffers of a call
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
@@ -174,7 +231,7 @@ struct CudaBackend {
     cudaError_t e = cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) fail(e, "d2d");
   }
-  double seq_sum(const double *x, int64_t n, double init) {
+  double seq_sum_plain(const double *x, int64_t n, double init) {
     if (rc != B200NN_OK) return 0.0;
     if (!d_scalar) d_scalar = alloc<double>(1);
     if (!d_scalar) return 0.0;
@@ -185,6 +242,39 @@ struct CudaBackend {
     return h;
   }
   bool failed() const { return rc != B200NN_OK; }
+  void long_chains(const uint64_t *ks, double *ev_cw, int32_t *ev_nn, const int32_t *hend, const double *cw,
+                   const int32_t *nn, const int32_t *list, const int32_t *count) {
+    if (rc != B200NN_OK) return;
+    k_long_chains<<<ctx->sm_count * 2, 256, 0, st>>>(ks, ev_cw, ev_nn, hend, cw, nn, list, count);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) fail(e, "k_long_chains launch");
+  }
+  // B200NN_MODOPT_TRACE=1: time between marks (stream synchronised), summed per name, printed at the end
+  bool trace = false;
+  double t_mark = 0;
+  std::vector<std::pair<std::string, double>> acc;
+  void mark(const char *name) {
+    if (!trace) return;
+    const double t = now_ms();
+    for (auto &a : acc)
+      if (a.first == name) {
+        a.second += t - t_mark;
+        t_mark = now_ms();
+        return;
+      }
+    acc.push_back({name, t - t_mark});
+    t_mark = now_ms();
+  }
+  void note_window(int64_t n, int64_t w, int rounds, bool converged, int64_t max_chain) {
+    if (trace) fprintf(stderr, "[b200nn modopt] network %lld nodes: window %lld, %d rounds, longest chain %lld%s\n",
+                       (long long)n, (long long)w, rounds, (long long)max_chain,
+                       converged ? "" : " (not converged, retried smaller)");
+  }
+  void report() {
+    if (!trace) return;
+    for (auto &a : acc) fprintf(stderr, "[b200nn modopt] %-22s %10.2f ms\n", a.first.c_str(), a.second);
+  }
   int64_t initial_window(int64_t) { return win0; }
   int64_t max_window(int64_t) { return winmax; }
   double now_ms() {
@@ -270,6 +360,7 @@ int cluster_device_csc(b200nn_ctx *ctx, int64_t n, const PT *d_p, const int32_t 
                                            n_iterations, seed, cluster_out, &q, &st);
   modopt::free_net(be, net);
   be.free(be.d_scalar);
+  be.report();
   const double t1 = be.now_ms();
   if (be.rc != B200NN_OK) return be.rc;
   if (k < 0) {

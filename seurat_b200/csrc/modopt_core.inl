@@ -116,6 +116,27 @@ struct Stats {
 
 MO_HD inline u32 hash_cluster(i32 c) { return (u32)c * 0x9E3779B1u; }
 
+// chains of at least this many events go to the backend's cooperative walker
+constexpr i64 LONG_CHAIN = 96;
+
+// Replays one cluster's events [s, e) of the sorted event list: ev_cw[] holds the weight of each
+// event's node on entry and the cluster's weight right after the event on exit (a leave subtracts,
+// a join adds: the reference's -= / += in visiting order); ev_nn[] the node count after the event.
+MO_HD inline void chain_walk(const u64 *ks, double *ev_cw, i32 *ev_nn, i64 s, i64 e, double w, i32 cnt) {
+  for (i64 q = s; q < e; ++q) {
+    const double wj = ev_cw[q];
+    if ((u32)ks[q] & 1u) {
+      w = dadd(w, wj);
+      ++cnt;
+    } else {
+      w = dsub(w, wj);
+      --cnt;
+    }
+    ev_cw[q] = w;
+    ev_nn[q] = cnt;
+  }
+}
+
 // =================================================================================================
 // Local moving (VOSClusteringTechnique::runLocalMovingAlgorithm, ModularityOptimizer.cpp:474-581)
 // =================================================================================================
@@ -145,6 +166,7 @@ struct LocalMoving {
   double *ev_cw = nullptr;           // [2W] cluster weight after the event
   i32 *ev_nn = nullptr;              // [2W] node count after the event
   i32 *hend = nullptr;               // [2W] at a segment head: end of the segment
+  i32 *long_list = nullptr;          // [2W / LONG_CHAIN + 1] heads of the long chains of a round
   i32 *segfirst = nullptr;           // [n] first event of a cluster in keys_s, -1 = none this round
   i64 *pushflag = nullptr, *pushoff = nullptr;  // [W + 1]
   i32 *flags = nullptr;              // device: [0] changed, [1] first popper, [2] first unstable, [3] last unstable
@@ -167,6 +189,7 @@ struct LocalMoving {
       ev_cw = be.template alloc<double>(2 * W);
       ev_nn = be.template alloc<i32>(2 * W);
       hend = be.template alloc<i32>(2 * W);
+      long_list = be.template alloc<i32>(2 * W / LONG_CHAIN + 2);
       pushflag = be.template alloc<i64>(W + 1);
       pushoff = be.template alloc<i64>(W + 1);
     }
@@ -180,10 +203,10 @@ struct LocalMoving {
   }
   void free_window_w() {
     be.free(D); be.free(D2); be.free(c0); be.free(leave_nn); be.free(toff); be.free(tcap_in);
-    be.free(keys); be.free(keys_s); be.free(ev_cw); be.free(ev_nn); be.free(hend);
+    be.free(keys); be.free(keys_s); be.free(ev_cw); be.free(ev_nn); be.free(hend); be.free(long_list);
     be.free(pushflag); be.free(pushoff);
     D = D2 = c0 = leave_nn = nullptr; toff = tcap_in = nullptr; keys = keys_s = nullptr;
-    ev_cw = nullptr; ev_nn = hend = nullptr; pushflag = pushoff = nullptr;
+    ev_cw = nullptr; ev_nn = hend = nullptr; long_list = nullptr; pushflag = pushoff = nullptr;
   }
   void free_all() {
     free_window_w();
@@ -371,6 +394,7 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
     }
     int rounds = 0;
     bool converged = false;
+    i64 max_chain = 0;
     while (rounds < round_cap && !be.failed()) {
       ++rounds;
       const i64 t0 = i;
@@ -379,6 +403,7 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
       double *tsum_ = tsum, *cw_ = cw, *evcw_ = ev_cw;
       i64 *toff_ = toff;
       u64 *keys_ = keys, *ks_ = keys_s;
+      be.mark("lm.other");
       // (1) clear the tables, reset the flags
       be.pfor(T, [=] MO_HD(i64 s) { tcl_[s] = -1; });
       be.single([=] MO_HD() {
@@ -386,7 +411,10 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
         flags_[1] = 0x7fffffff;
         flags_[2] = 0x7fffffff;
         flags_[3] = -1;
+        flags_[6] = 0;  // longest chain of the round (diagnostics)
+        flags_[7] = 0;  // number of long chains
       });
+      be.mark("lm.clear");
       // (2) edge weight towards every neighbouring cluster, summed in edge order (:507-516);
       //     neighbours visited earlier in this window count with last round's decision
       be.pfor(Wn, [=] MO_HD(i64 t) {
@@ -409,33 +437,37 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
         keys_[2 * t] = ((u64)(u32)c0_[t] << 32) | ((u64)t << 1);
         keys_[2 * t + 1] = ((u64)(u32)D_[t] << 32) | ((u64)t << 1) | 1ull;
       });
+      be.mark("lm.gather");
       // (3b) events grouped by cluster, in visiting order
       be.sort_keys(keys, keys_s, 2 * Wn, 64);
+      be.mark("lm.sort");
       // (4) every cluster's weight and size replayed along its chain (:518-519, :547-548);
       //     ev_cw first holds the weight of the event's node so that the chain streams
       be.pfor(2 * Wn, [=] MO_HD(i64 s) { evcw_[s] = nt.nw[perm_[t0 + ((u32)ks_[s] >> 1)]]; });
+      // short chains: the thread that finds the head walks it; long chains (a large cluster owns a
+      // large share of the window) are listed and replayed by the backend's cooperative walker
+      // (one warp per chain on the device: coalesced loads, the additions still strictly in order)
+      i32 *longl_ = long_list;
       be.pfor(2 * Wn, [=] MO_HD(i64 s) {
         const i32 c = (i32)(ks_[s] >> 32);
         if (s > 0 && (i32)(ks_[s - 1] >> 32) == c) return;
-        double w = cw_[c];
-        i32 cnt = nn_[c];
-        i64 e = s;
-        for (; e < 2 * Wn && (i32)(ks_[e] >> 32) == c; ++e) {
-          const u32 lo = (u32)ks_[e];
-          const double wj = evcw_[e];
-          if (lo & 1u) {
-            w = dadd(w, wj);
-            ++cnt;
-          } else {
-            w = dsub(w, wj);
-            --cnt;
-          }
-          evcw_[e] = w;
-          evnn_[e] = cnt;
+        i64 lo = s + 1, hi = 2 * Wn;  // end of the segment: first key of a later cluster
+        while (lo < hi) {
+          const i64 mid = (lo + hi) >> 1;
+          if ((i32)(ks_[mid] >> 32) == c) lo = mid + 1; else hi = mid;
         }
+        const i64 e = lo;
         seg_[c] = (i32)s;
         hend_[s] = (i32)e;
+        be_atomic_max(&flags_[6], (i32)(e - s));  // longest chain (diagnostics)
+        if (e - s >= LONG_CHAIN) {
+          longl_[be_atomic_add(&flags_[7], 1)] = (i32)s;
+          return;
+        }
+        chain_walk(ks_, evcw_, evnn_, s, e, cw_[c], nn_[c]);
       });
+      be.long_chains(ks_, evcw_, evnn_, hend_, cw_, nn_, long_list, flags + 7);
+      be.mark("lm.chain");
       // (5) every node decides (:521-545)
       be.pfor(Wn, [=] MO_HD(i64 t) {
         const i32 j = perm_[t0 + t];
@@ -492,20 +524,24 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
         D2_[t] = best;
         if (best != D_[t]) flags_[0] = 1;
       });
+      be.mark("lm.decide");
       // (6) forget this round's segments
       be.pfor(2 * Wn, [=] MO_HD(i64 s) {
         const i32 c = (i32)(ks_[s] >> 32);
         if (s > 0 && (i32)(ks_[s - 1] >> 32) == c) return;
         seg_[c] = -1;
       });
-      i32 hf[2];
-      be.d2h(hf, flags, 2 * sizeof(i32));
+      i32 hf[7];
+      be.d2h(hf, flags, 7 * sizeof(i32));
+      max_chain = std::max<i64>(max_chain, hf[6]);
+      be.mark("lm.unseg+readback");
       std::swap(D, D2);
       if (!hf[0]) {
         converged = true;
         break;
       }
     }
+    be.note_window(n, Wn, rounds, converged, max_chain);
     if (stats) {
       stats->rounds += rounds;
       stats->windows++;
@@ -616,6 +652,123 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
   }
   free_all();
   return update;
+}
+
+// =================================================================================================
+// Order-fixed running sums (std::accumulate / `+=` loops of the reference) without walking them
+// element by element.  For s in [2^e, 2^(e+1)) and x >= 0 with s + x < 2^(e+1), fl(s + x) is
+// s + rn(x / u) * u with u = ulp(s) = 2^(e-52): while the running sum stays inside one binade the
+// sequence of rounded additions is an INTEGER prefix sum of r_t = rn(x_t / u), exact and
+// associative -- except for exact ties (frac(x_t / u) = 1/2), whose rounding depends on the parity
+// of the running sum.  So: block sums of r_t in parallel, one pass over the block sums to find the
+// first block that leaves the binade or holds a tie (or a negative / non-finite term), that block
+// alone with real additions, then on with the next binade.  About 25 binades cover 15 M terms.
+// =================================================================================================
+constexpr i64 SUM_BLOCK = 2048;
+constexpr u64 TWO53 = 1ull << 53;
+
+template <class B>
+double seq_sum(B &be, const double *x, i64 n, double init) {
+  double s = init;
+  i64 pos = 0;
+  if (n < 4 * SUM_BLOCK) return be.seq_sum_plain(x, n, s);
+  const i64 nb_all = (n + SUM_BLOCK - 1) / SUM_BLOCK;
+  u64 *bsum = be.template alloc<u64>(nb_all);
+  i32 *bflag = be.template alloc<i32>(nb_all);
+  u64 *res = be.template alloc<u64>(2);
+  u64 *gsum = be.template alloc<u64>(nb_all / 64 + 1);
+  i32 *gflag = be.template alloc<i32>(nb_all / 64 + 1);
+  while (pos < n && !be.failed()) {
+    int e = 0;
+    const bool ok = s > 0.0 && s < 1e300 && s >= 2.3e-308 && (frexp(s, &e), true);
+    if (!ok) {  // zero / subnormal / huge / negative running sum: this block with real additions
+      const i64 len = std::min<i64>(SUM_BLOCK, n - pos);
+      s = be.seq_sum_plain(x + pos, len, s);
+      pos += len;
+      continue;
+    }
+    const int ex = e - 1;             // s in [2^ex, 2^(ex+1))
+    const int shift = 52 - ex;        // x / u = ldexp(x, shift)
+    const u64 S = (u64)ldexp(s, shift);
+    const i64 nb = (n - pos + SUM_BLOCK - 1) / SUM_BLOCK;
+    const double *xp = x + pos;
+    const i64 rem = n - pos;
+    be.pfor(nb, [=] MO_HD(i64 b) {
+      u64 acc = 0;
+      i32 flag = 0;
+      const i64 hi = (b + 1) * SUM_BLOCK < rem ? (b + 1) * SUM_BLOCK : rem;
+      for (i64 t = b * SUM_BLOCK; t < hi; ++t) {
+        const double v = xp[t];
+        if (!(v >= 0.0) || v > 1e300) {  // negative, NaN or huge: real additions
+          flag = 1;
+          break;
+        }
+        const double y = ldexp(v, shift);
+        if (y >= 9007199254740992.0) {   // >= 2^53: certainly leaves the binade
+          flag = 1;
+          break;
+        }
+        const double fl = floor(y);
+        const double fr = y - fl;        // exact
+        if (fr == 0.5) {                 // tie: depends on the parity of the running sum
+          flag = 1;
+          break;
+        }
+        acc += (u64)fl + (fr > 0.5 ? 1ull : 0ull);
+        if (acc >= TWO53) {
+          acc = TWO53;
+          break;
+        }
+      }
+      bsum[b] = acc;
+      bflag[b] = flag;
+    });
+    // first block that cannot be taken wholesale: groups of 64 blocks first, then inside the group
+    const i64 ng = (nb + 63) / 64;
+    be.pfor(ng, [=] MO_HD(i64 g) {
+      u64 acc = 0;
+      i32 flag = 0;
+      const i64 hi = (g + 1) * 64 < nb ? (g + 1) * 64 : nb;
+      for (i64 b = g * 64; b < hi; ++b) {
+        flag |= bflag[b];
+        acc += bsum[b];
+        if (acc >= TWO53) acc = TWO53;
+      }
+      gsum[g] = acc;
+      gflag[g] = flag;
+    });
+    be.single([=] MO_HD() {
+      u64 acc = S;
+      i64 g = 0;
+      for (; g < ng; ++g) {
+        if (gflag[g] || acc + gsum[g] >= TWO53) break;
+        acc += gsum[g];
+      }
+      i64 b = g * 64;
+      for (; b < nb; ++b) {
+        if (bflag[b] || acc + bsum[b] >= TWO53) break;
+        acc += bsum[b];
+      }
+      res[0] = acc;
+      res[1] = (u64)b;
+    });
+    u64 h[2];
+    be.d2h(h, res, sizeof(h));
+    s = ldexp((double)h[0], -shift);   // exact: an integer below 2^53 times a power of two
+    pos += (i64)h[1] * SUM_BLOCK;
+    if (pos >= n) break;
+    if ((i64)h[1] < nb) {               // the block that could not be taken wholesale
+      const i64 len = std::min<i64>(SUM_BLOCK, n - pos);
+      s = be.seq_sum_plain(x + pos, len, s);
+      pos += len;
+    }
+  }
+  be.free(bsum);
+  be.free(bflag);
+  be.free(res);
+  be.free(gsum);
+  be.free(gflag);
+  return s;
 }
 
 // =================================================================================================
@@ -840,7 +993,7 @@ double quality_function(B &be, const Net &nt, const i32 *cl, i32 nC, double reso
   be.pfor(m2, [=] MO_HD(i64 e) {
     if (f[e]) xs[o[e]] = c.ew[e];
   });
-  double q = be.seq_sum(xs, K, 0.0);
+  double q = seq_sum(be, xs, K, 0.0);
   q = q + self_links;
   // cluster weights in node order, then the penalty cluster by cluster
   u64 *k1 = be.template alloc<u64>(n), *k2 = be.template alloc<u64>(n);
@@ -858,7 +1011,7 @@ double quality_function(B &be, const Net &nt, const i32 *cl, i32 nC, double reso
   });
   double *pen = be.template alloc<double>(nC);
   be.pfor(nC, [=] MO_HD(i64 cc) { pen[cc] = -dmul(dmul(cw[cc], cw[cc]), resolution); });
-  q = be.seq_sum(pen, nC, q);
+  q = seq_sum(be, pen, nC, q);
   q /= 2 * total_edge_weight + self_links;
   be.free(f); be.free(o); be.free(xs); be.free(k1); be.free(k2); be.free(nws); be.free(cw); be.free(pen);
   return q;
@@ -915,7 +1068,7 @@ template <class B>
 i32 run_clustering(B &be, const Net &net, int algorithm, double resolution, int modularityFunction, int nRandomStarts,
                    int nIterations, u64 seed, i32 *cluster_out, double *modularity_out, Stats *stats) {
   const i32 n = net.n;
-  const double total_edge_weight = be.seq_sum(net.ew, net.m2, 0.0) / 2.0;  // getTotalEdgeWeight (:242-244)
+  const double total_edge_weight = seq_sum(be, net.ew, net.m2, 0.0) / 2.0;  // getTotalEdgeWeight (:242-244)
   const double self_links = 0.0;  // matrixToNetwork drops nothing onto the diagonal
   const double resolution2 =
       modularityFunction == 1 ? resolution / (2 * total_edge_weight + self_links) : resolution;

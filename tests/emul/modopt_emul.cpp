@@ -6,6 +6,7 @@
 // Never linked into libb200nn.so; the product path has no CPU fallback.
 //
 //   g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC tests/emul/modopt_emul.cpp -o tests/emul/libmodopt_emul.so
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -17,6 +18,7 @@
 template <typename T> static inline void be_atomic_min(T *a, T v) { if (v < *a) *a = v; }
 template <typename T> static inline void be_atomic_max(T *a, T v) { if (v > *a) *a = v; }
 static inline void be_atomic_max64(int64_t *a, int64_t v) { if (v > *a) *a = v; }
+static inline int be_atomic_add(int *a, int v) { const int o = *a; *a += v; return o; }
 
 #include "../../seurat_b200/csrc/modopt_core.inl"
 
@@ -45,12 +47,23 @@ struct EmulBackend {
   void h2d(void *d, const void *s, size_t b) { memcpy(d, s, b); }
   void d2h(void *d, const void *s, size_t b) { memcpy(d, s, b); }
   void d2d(void *d, const void *s, size_t b) { memcpy(d, s, b); }
-  double seq_sum(const double *x, int64_t n, double init) {
+  double seq_sum_plain(const double *x, int64_t n, double init) {
     double s = init;
     for (int64_t i = 0; i < n; ++i) s = s + x[i];
     return s;
   }
   bool failed() const { return false; }
+  void mark(const char *) {}
+  void long_chains(const uint64_t *ks, double *ev_cw, int32_t *ev_nn, const int32_t *hend, const double *cw,
+                   const int32_t *nn, const int32_t *list, const int32_t *count) {
+    for (int32_t q = 0; q < *count; ++q) {
+      const int32_t s = list[q];
+      const int32_t c = (int32_t)(ks[s] >> 32);
+      modopt::chain_walk(ks, ev_cw, ev_nn, s, hend[s], cw[c], nn[c]);
+    }
+  }
+  void note_window(int64_t n, int64_t w, int r, bool, int64_t mc) { if (getenv("EMUL_TRACE")) fprintf(stderr, "net %lld window %lld rounds %d max_chain %lld\n", (long long)n, (long long)w, r, (long long)mc); }
+
   int64_t initial_window(int64_t) { return win0; }
   int64_t max_window(int64_t) { return winmax; }
   double now_ms() {
@@ -82,4 +95,9 @@ extern "C" int emul_modularity_cluster(int n, const int *p, const int *i, const 
   }
   free_net(be, net);
   return k;
+}
+
+extern "C" double emul_seq_sum(const double *x, int64_t n, double init) {
+  EmulBackend be;
+  return modopt::seq_sum(be, x, n, init);
 }

@@ -40,3 +40,12 @@ def cluster(p, i, x, mf, res, alg, ns, ni, seed, win0=0, winmax=0):
                                        seed, out.ctypes.data, C.addressof(q), win0, winmax, st.ctypes.data)
     names = ("windows", "rounds", "sequential_steps", "window_retries", "local_moving_calls", "levels", "max_window")
     return out, rc, q.value, dict(zip(names, st.tolist()))
+
+
+def seq_sum(x, init=0.0):
+    """the order-fixed running sum of modopt_core.inl (binade-wise integer prefix sums)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    L = lib()
+    L.emul_seq_sum.argtypes = [C.c_void_p, C.c_int64, C.c_double]
+    L.emul_seq_sum.restype = C.c_double
+    return float(L.emul_seq_sum(x.ctypes.data, x.size, float(init)))

@@ -95,3 +95,37 @@ def test_python_mirror_argument_checks():
                                                np.array([1, .5, .5, 1, 1, .2, .6, .2, 1, .6, 1])), verbose=False)
     assert ids == [0, 0, 2, 2, 2]
     assert sb.GroupSingletons([0, 0, 1], None, group_singletons=False) == [0, 0, "singleton"]
+
+
+def test_order_fixed_running_sum_is_exact():
+    """seq_sum (binade-wise integer prefix sums) == the element-by-element running sum, bit for bit:
+    uniform terms, Jaccard-like rationals, powers of two (ties and absorbed terms), mixed magnitudes,
+    zeros, and a negative / a huge term (those blocks take real additions)"""
+    rng = np.random.default_rng(5)
+
+    def plain(x, init):
+        s = np.float64(init)
+        for v in x:
+            s = s + v
+        return float(s)
+
+    for trial in range(6):
+        n = int(rng.integers(9000, 60000))
+        if trial == 0:
+            x = rng.random(n)
+        elif trial == 1:
+            s_ = rng.integers(1, 21, n)
+            x = s_ / (40 - s_)
+        elif trial == 2:
+            x = np.ldexp(rng.integers(1, 8, n).astype(float), rng.integers(-60, 3, n))
+        elif trial == 3:
+            x = rng.random(n) * 10.0 ** rng.integers(-12, 6, n)
+        elif trial == 4:
+            x = np.ones(n)
+            x[rng.integers(0, n, 50)] = 0.0
+        else:
+            x = rng.random(n)
+            x[n // 2] = -0.3
+            x[n // 3] = 1e18
+        init = 0.0 if trial % 2 else float(rng.random() * 1000)
+        assert emul_modopt.seq_sum(x, init) == plain(x, init), trial
