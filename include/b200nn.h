@@ -292,8 +292,8 @@ B200NN_API int b200nn_dev_copy_result(b200nn_ctx *ctx, int32_t which, int64_t *d
  * algorithm = 1 / 2).  Same arguments, same result for the same random_seed: the cluster of every
  * node, 0-based, clusters ordered by decreasing size.  Only the strict lower triangle of the matrix
  * is read (RModularityOptimizer.cpp:72-81), weights must be positive.
- *   algorithm 1 = Louvain, 2 = Louvain with multilevel refinement; 3 (smart local moving) and 4
- *   (Leiden, an R-side package in the reference) return B200NN_ERR_INVALID.
+ *   algorithm 1 = Louvain, 2 = Louvain with multilevel refinement, 3 = smart local moving; 4
+ *   (Leiden: FindClusters routes it to an R-side package, never here) returns B200NN_ERR_INVALID.
  * Error texts are the wrapper's stop() messages.
  */
 typedef struct b200nn_modopt_stats {
@@ -306,6 +306,7 @@ typedef struct b200nn_modopt_stats {
   int64_t window_retries;      /* windows repeated with a smaller size                           */
   int64_t local_moving_calls, levels, max_window;
   double ms_total, ms_build, ms_local_moving, ms_reduce, ms_quality;
+  double ms_subnetworks;       /* SLM: local moving inside the clusters                          */
   int64_t gpu_launches;
 } b200nn_modopt_stats;
 

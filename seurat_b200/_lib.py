@@ -64,7 +64,7 @@ class ModoptStats(C.Structure):
                 ("modularity", C.c_double)] + \
                [(n, C.c_int64) for n in ("windows", "rounds", "sequential_steps", "window_retries",
                                          "local_moving_calls", "levels", "max_window")] + \
-               [(n, C.c_double) for n in ("ms_total", "ms_build", "ms_local_moving", "ms_reduce", "ms_quality")] + \
+               [(n, C.c_double) for n in ("ms_total", "ms_build", "ms_local_moving", "ms_reduce", "ms_quality", "ms_subnetworks")] + \
                [("gpu_launches", C.c_int64)]
 
     def as_dict(self) -> dict:

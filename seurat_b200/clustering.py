@@ -6,9 +6,9 @@ Mirrors, argument for argument, the reference's R functions
   * ``FindClusters.default``      R/clustering.R:307-432
   * ``GroupSingletons``           R/clustering.R:1373-1415
 over the C ABI (``b200nn_modularity_cluster*``).  All compute is in libb200nn.so; there is no
-CPU fallback.  Algorithms 1 (Louvain) and 2 (Louvain with multilevel refinement) run on the
-device and give the reference's clusters for the same ``random.seed``; 3 (SLM) and 4 (Leiden, an
-R package in the reference) are refused with an error.
+CPU fallback.  Algorithms 1 (Louvain), 2 (Louvain with multilevel refinement) and 3 (smart local
+moving) run on the device and give the reference's clusters for the same ``random.seed``; 4
+(Leiden, an R package in the reference) is refused with an error.
 """
 from __future__ import annotations
 
@@ -52,7 +52,8 @@ def RunModularityClustering(SNN, modularity: int = 1, resolution: float = 0.8, a
     if print_output:  # the wrapper's Rprintf lines (RModularityOptimizer.cpp:88-96, 152-163)
         _message("Modularity Optimizer version 1.3.0 by Ludo Waltman and Nees Jan van Eck\n")
         _message(f"Number of nodes: {st['n_nodes']}\nNumber of edges: {st['n_edges']}\n")
-        name = "Louvain algorithm" if algorithm == 1 else "Louvain algorithm with multilevel refinement"
+        name = ("Louvain algorithm" if algorithm == 1 else "Louvain algorithm with multilevel refinement"
+                if algorithm == 2 else "smart local moving algorithm")
         _message(f"Running {name}...")
         if n_start == 1:
             _message(f"Modularity: {st['modularity']:.4f}")

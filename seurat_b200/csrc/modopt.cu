@@ -307,10 +307,11 @@ int check_args(int modularity_function, double resolution, int algorithm, int n_
     b200nn_set_error("error: resolution<1 for alternative modularity");
     return B200NN_ERR_INVALID;
   }
-  if (algorithm == 3 || algorithm == 4) {
-    b200nn_set_error("modularity optimiser: algorithm %d (%s) is not available on the device; 1 = Louvain and "
-                     "2 = Louvain with multilevel refinement are",
-                     algorithm, algorithm == 3 ? "smart local moving" : "Leiden, an R-side package in the reference");
+  if (algorithm == 4) {
+    // FindClusters sends algorithm 4 to RunLeiden (R/clustering.R:364-375, an R-side package), never
+    // to this entry point; the wrapper itself would run nothing for it
+    b200nn_set_error("modularity optimiser: algorithm 4 (Leiden) is not part of RunModularityClusteringCpp; "
+                     "1 = Louvain, 2 = Louvain with multilevel refinement, 3 = smart local moving");
     return B200NN_ERR_INVALID;
   }
   return B200NN_OK;
@@ -336,6 +337,7 @@ void fill_stats(const modopt::Stats &s, int64_t n, int64_t edges, int32_t n_clus
   out->ms_local_moving = s.ms_local_moving;
   out->ms_reduce = s.ms_reduce;
   out->ms_quality = s.ms_quality;
+  out->ms_subnetworks = s.ms_subnetworks;
   out->gpu_launches = launches;
 }
 

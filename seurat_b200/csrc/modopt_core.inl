@@ -111,7 +111,7 @@ struct Net {
 struct Stats {
   i64 windows = 0, rounds = 0, seq_steps = 0, shrinks = 0, local_moving_calls = 0, levels = 0;
   i64 max_window = 0;
-  double ms_local_moving = 0, ms_reduce = 0, ms_quality = 0, ms_build = 0;
+  double ms_local_moving = 0, ms_reduce = 0, ms_quality = 0, ms_build = 0, ms_subnetworks = 0;
 };
 
 MO_HD inline u32 hash_cluster(i32 c) { return (u32)c * 0x9E3779B1u; }
@@ -268,11 +268,12 @@ struct LocalMoving {
   }
 
   // returns true when any node changed its cluster (the reference's `update`)
-  bool run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng);
+  // host_perm: the visiting order when the caller drew it already (subnetworks of the SLM step)
+  bool run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng, const i32 *host_perm = nullptr);
 };
 
 template <class B>
-bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
+bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng, const i32 *host_perm) {
   const i32 n = net.n;
   if (n == 1) return false;
   if (stats) stats->local_moving_calls++;
@@ -336,8 +337,8 @@ bool LocalMoving<B>::run(i32 *cl_io, i32 *n_clusters_io, JavaRandom &rng) {
   // ---- the visiting order (host control data) and its inverse
   {
     std::vector<i32> hp;
-    random_permutation(rng, n, hp);
-    be.h2d(perm, hp.data(), sizeof(i32) * (size_t)n);
+    if (!host_perm) random_permutation(rng, n, hp);
+    be.h2d(perm, host_perm ? host_perm : hp.data(), sizeof(i32) * (size_t)n);
     i32 *perm_ = perm, *pos_ = pos;
     be.pfor(n, [=] MO_HD(i64 t) { pos_[perm_[t]] = (i32)t; });
   }
@@ -1035,6 +1036,8 @@ struct Optimizer {
     return u;
   }
 
+  bool slm(const Net &nt, i32 *cl, i32 *nC, int depth = 0);  // algorithm 3
+
   // algorithm 1 (refine = false) and 2 (refine = true)
   bool louvain(const Net &nt, i32 *cl, i32 *nC, bool refine, int depth = 0) {
     if (nt.n <= 1 || be.failed()) return false;
@@ -1062,6 +1065,260 @@ struct Optimizer {
   }
 };
 
+// =================================================================================================
+// Smart local moving (ModularityOptimizer.cpp:649-692): local moving, then local moving INSIDE every
+// cluster (its subnetwork, from singletons), then the same on the reduced network of the refined
+// clusters, started from the unrefined partition.
+// =================================================================================================
+constexpr i32 SLM_SMALL_MAX = 1024;  // subnetworks up to this size: one thread each runs the reference loop
+
+// Network::createSubnetworks (:296-306, :397-440) for all clusters at once: nodes in (cluster, index)
+// order = position g; cluster c owns positions [off[c], off[c+1]); edges that stay inside the
+// cluster, in adjacency order, with LOCAL neighbour ids; node weights copied (not recomputed, :421).
+struct SubNets {
+  i64 *off = nullptr;   // [nC + 1]
+  i32 *node = nullptr;  // [n] position -> node
+  i64 *first = nullptr; // [n + 1]
+  i32 *nbr = nullptr;
+  double *ew = nullptr, *nw = nullptr;
+  i64 m = 0;
+};
+
+template <class B>
+void build_subnets(B &be, const Net &nt, const i32 *cl, i32 nC, SubNets &S) {
+  const i32 n = nt.n;
+  const Net c = nt;
+  u64 *k1 = be.template alloc<u64>(n), *k2 = be.template alloc<u64>(n);
+  i32 *rank = be.template alloc<i32>(n);
+  i64 *dg = be.template alloc<i64>((i64)n + 1);
+  S.off = be.template alloc<i64>((i64)nC + 1);
+  S.node = be.template alloc<i32>(n);
+  S.first = be.template alloc<i64>((i64)n + 1);
+  S.nw = be.template alloc<double>(n);
+  be.pfor(n, [=] MO_HD(i64 v) { k1[v] = ((u64)(u32)cl[v] << 32) | (u64)(u32)v; });
+  be.sort_keys(k1, k2, n, 64);
+  first_from_sorted(be, k2, n, 32, S.off, nC);
+  {
+    i32 *node = S.node;
+    double *nw = S.nw;
+    be.pfor(n, [=] MO_HD(i64 g) {
+      const i32 v = (i32)(u32)k2[g];
+      node[g] = v;
+      rank[v] = (i32)g;
+      nw[g] = c.nw[v];
+      const i32 cv = cl[v];
+      i64 k = 0;
+      for (i64 e = c.first[v]; e < c.first[v + 1]; ++e) k += cl[c.nbr[e]] == cv ? 1 : 0;
+      dg[g] = k;
+    });
+  }
+  be.excl_scan(dg, S.first, n);
+  be.d2h(&S.m, S.first + n, sizeof(i64));
+  S.nbr = be.template alloc<i32>(S.m > 0 ? S.m : 1);
+  S.ew = be.template alloc<double>(S.m > 0 ? S.m : 1);
+  {
+    const SubNets T = S;
+    be.pfor(n, [=] MO_HD(i64 g) {
+      const i32 v = T.node[g];
+      const i32 cv = cl[v];
+      const i64 o = T.off[cv];
+      i64 q = T.first[g];
+      for (i64 e = c.first[v]; e < c.first[v + 1]; ++e) {
+        const i32 u = c.nbr[e];
+        if (cl[u] != cv) continue;
+        T.nbr[q] = (i32)(rank[u] - o);
+        T.ew[q] = c.ew[e];
+        ++q;
+      }
+    });
+  }
+  be.free(k1); be.free(k2); be.free(rank); be.free(dg);
+}
+
+template <class B>
+void free_subnets(B &be, SubNets &S) {
+  be.free(S.off); be.free(S.node); be.free(S.first); be.free(S.nbr); be.free(S.ew); be.free(S.nw);
+  S = SubNets();
+}
+
+// scratch of the one-thread-per-subnetwork local moving, all [n], addressed at the subnetwork's offset
+struct SmallScratch {
+  i32 *clus, *nn, *unused, *nbc, *newc, *perm, *sub_nc;
+  double *cw, *ewpc;
+};
+
+// runLocalMovingAlgorithm (:474-581) of ONE subnetwork, from singletons, exactly as the reference
+// loops (these networks are small; many of them run side by side, one thread each)
+MO_HD inline void lm_small(const SubNets &S, const SmallScratch &W, double res, i32 c) {
+  const i64 o = S.off[c];
+  const i32 ns = (i32)(S.off[c + 1] - o);
+  if (ns == 1) {  // "if (network->getNNodes() == 1) return false" -- no draw, one cluster
+    W.clus[o] = 0;
+    W.sub_nc[c] = 1;
+    return;
+  }
+  i32 *clus = W.clus + o, *nn = W.nn + o, *unused = W.unused + o, *nbc = W.nbc + o, *newc = W.newc + o;
+  const i32 *perm = W.perm + o;
+  double *cw = W.cw + o, *ewpc = W.ewpc + o;
+  const double *nw = S.nw + o;
+  const i64 *first = S.first + o;
+  for (i32 j = 0; j < ns; ++j) {
+    clus[j] = j;
+    cw[j] = dadd(0.0, nw[j]);
+    nn[j] = 1;
+    ewpc[j] = 0.0;
+  }
+  i32 nUnused = 0, nStable = 0, i = 0;
+  do {
+    const i32 j = perm[i];
+    i32 k = 0;
+    for (i64 e = first[j]; e < first[j + 1]; ++e) {
+      const i32 l = clus[S.nbr[e]];
+      if (ewpc[l] == 0.0) nbc[k++] = l;
+      ewpc[l] = dadd(ewpc[l], S.ew[e]);
+    }
+    const i32 own = clus[j];
+    cw[own] = dsub(cw[own], nw[j]);
+    if (--nn[own] == 0) unused[nUnused++] = own;
+    i32 best = -1;
+    double mx = 0.0;
+    for (i32 q = 0; q < k; ++q) {
+      const i32 l = nbc[q];
+      const double qf = dsub(ewpc[l], dmul(dmul(nw[j], cw[l]), res));
+      if (qf > mx || (qf == mx && l < best)) {
+        best = l;
+        mx = qf;
+      }
+      ewpc[l] = 0.0;
+    }
+    if (mx == 0.0) best = unused[--nUnused];
+    cw[best] = dadd(cw[best], nw[j]);
+    nn[best]++;
+    if (best == own) {
+      nStable++;
+    } else {
+      clus[j] = best;
+      nStable = 1;
+    }
+    i = (i < ns - 1) ? i + 1 : 0;
+  } while (nStable < ns);
+  i32 cnt = 0;
+  for (i32 q = 0; q < ns; ++q)
+    if (nn[q] > 0) newc[q] = cnt++;
+  for (i32 j = 0; j < ns; ++j) clus[j] = newc[clus[j]];
+  W.sub_nc[c] = cnt;
+}
+
+template <class B>
+bool Optimizer<B>::slm(const Net &nt, i32 *cl, i32 *nC, int depth) {
+  if (nt.n <= 1 || be.failed()) return false;
+  if (stats) stats->levels = std::max<i64>(stats->levels, depth + 1);
+  bool update = local_moving(nt, cl, nC);
+  if (*nC >= nt.n) return update;
+  const i32 n = nt.n, nC0 = *nC;
+  const double t0 = be.now_ms();
+  SubNets S;
+  build_subnets(be, nt, cl, nC0, S);
+  std::vector<i64> hoff((size_t)nC0 + 1);
+  be.d2h(hoff.data(), S.off, sizeof(i64) * ((size_t)nC0 + 1));
+  // the visiting orders, drawn cluster by cluster as the reference does (:660-663 -> :500)
+  std::vector<i32> hperm((size_t)n), one;
+  for (i32 c = 0; c < nC0; ++c) {
+    const i32 ns = (i32)(hoff[c + 1] - hoff[c]);
+    if (ns <= 1) {
+      if (ns == 1) hperm[hoff[c]] = 0;
+      continue;
+    }
+    random_permutation(rng, ns, one);
+    std::copy(one.begin(), one.end(), hperm.begin() + hoff[c]);
+  }
+  SmallScratch W;
+  W.clus = be.template alloc<i32>(n); W.nn = be.template alloc<i32>(n); W.unused = be.template alloc<i32>(n);
+  W.nbc = be.template alloc<i32>(n); W.newc = be.template alloc<i32>(n); W.perm = be.template alloc<i32>(n);
+  W.sub_nc = be.template alloc<i32>(nC0); W.cw = be.template alloc<double>(n); W.ewpc = be.template alloc<double>(n);
+  be.h2d(W.perm, hperm.data(), sizeof(i32) * (size_t)n);
+  {
+    const SubNets T = S;
+    const SmallScratch V = W;
+    const double res = resolution;
+    be.pfor(nC0, [=] MO_HD(i64 c) {
+      if (T.off[c + 1] - T.off[c] <= SLM_SMALL_MAX) lm_small(T, V, res, (i32)c);
+    });
+  }
+  // the large subnetworks through the windowed local moving, one after the other
+  for (i32 c = 0; c < nC0 && !be.failed(); ++c) {
+    const i64 o = hoff[c];
+    const i32 ns = (i32)(hoff[c + 1] - o);
+    if (ns <= SLM_SMALL_MAX) continue;
+    i64 fe[2];
+    be.d2h(&fe[0], S.first + o, sizeof(i64));
+    be.d2h(&fe[1], S.first + o + ns, sizeof(i64));
+    Net sub;
+    sub.n = ns;
+    sub.m2 = fe[1] - fe[0];
+    sub.first = be.template alloc<i64>((i64)ns + 1);
+    sub.nbr = S.nbr + fe[0];
+    sub.ew = S.ew + fe[0];
+    sub.nw = S.nw + o;
+    {
+      i64 *f = sub.first;
+      const i64 *sf = S.first + o;
+      const i64 b0 = fe[0];
+      be.pfor((i64)ns + 1, [=] MO_HD(i64 j) { f[j] = sf[j] - b0; });
+    }
+    finish_net(be, sub);
+    i32 *cls = W.clus + o;
+    be.pfor(ns, [=] MO_HD(i64 j) { cls[j] = (i32)j; });
+    i32 snc = ns;
+    LocalMoving<B> lm(be, sub, resolution, stats);
+    lm.run(cls, &snc, rng, hperm.data() + o);
+    be.h2d(W.sub_nc + c, &snc, sizeof(i32));
+    be.free(sub.first);
+  }
+  // refined clustering: the sub-clusters of cluster c follow those of the clusters before it (:664-667)
+  i64 *cin = be.template alloc<i64>((i64)nC0 + 1), *base = be.template alloc<i64>((i64)nC0 + 1);
+  {
+    const i32 *snc = W.sub_nc;
+    be.pfor(nC0, [=] MO_HD(i64 c) { cin[c] = snc[c]; });
+  }
+  be.excl_scan(cin, base, nC0);
+  i64 nRef = 0;
+  be.d2h(&nRef, base + nC0, sizeof(i64));
+  {
+    const SubNets T = S;
+    const i32 *clus = W.clus;
+    be.pfor(n, [=] MO_HD(i64 g) {
+      const i32 v = T.node[g];
+      cl[v] = (i32)(base[cl[v]] + clus[g]);
+    });
+  }
+  if (stats) stats->ms_subnetworks += be.now_ms() - t0;
+  // the reduced network of the refined clusters, started from the unrefined partition (:670-684)
+  Net red;
+  const double t1 = be.now_ms();
+  reduce_network(be, nt, cl, (i32)nRef, red);
+  if (stats) stats->ms_reduce += be.now_ms() - t1;
+  i32 *cl2 = be.template alloc<i32>(red.n);
+  be.pfor(nRef, [=] MO_HD(i64 r) {
+    i64 lo = 0, hi = nC0;  // the cluster c with base[c] <= r < base[c + 1]
+    while (hi - lo > 1) {
+      const i64 mid = (lo + hi) >> 1;
+      if (base[mid] <= r) lo = mid; else hi = mid;
+    }
+    cl2[r] = (i32)lo;
+  });
+  i32 nC2 = nC0;
+  update |= slm(red, cl2, &nC2, depth + 1);
+  be.pfor(n, [=] MO_HD(i64 v) { cl[v] = cl2[cl[v]]; });  // mergeClusters (:159-163)
+  *nC = nC2;
+  be.free(cl2); be.free(cin); be.free(base);
+  be.free(W.clus); be.free(W.nn); be.free(W.unused); be.free(W.nbc); be.free(W.newc); be.free(W.perm);
+  be.free(W.sub_nc); be.free(W.cw); be.free(W.ewpc);
+  free_subnets(be, S);
+  free_net(be, red);
+  return update;
+}
+
 // RunModularityClusteringCpp (RModularityOptimizer.cpp:21-173) on a built network.
 // cluster_out: host array [n].  Returns the number of clusters; *modularity_out = the best start's value.
 template <class B>
@@ -1088,6 +1345,8 @@ i32 run_clustering(B &be, const Net &net, int algorithm, double resolution, int 
         update = opt.louvain(net, cl, &nC, false);
       else if (algorithm == 2)
         update = opt.louvain(net, cl, &nC, true);
+      else if (algorithm == 3)
+        opt.slm(net, cl, &nC);  // the wrapper does not look at SLM's return value (:122-123)
       ++j;
     } while (j < nIterations && update && !be.failed());
     // only the value after a start's last iteration takes part in the comparison (:134-138)

@@ -91,7 +91,7 @@ extern "C" int emul_modularity_cluster(int n, const int *p, const int *i, const 
   if (stats_out) {
     stats_out[0] = st.windows; stats_out[1] = st.rounds; stats_out[2] = st.seq_steps; stats_out[3] = st.shrinks;
     stats_out[4] = st.local_moving_calls; stats_out[5] = st.levels; stats_out[6] = st.max_window;
-    stats_out[7] = (int64_t)st.ms_local_moving; stats_out[8] = (int64_t)st.ms_reduce; stats_out[9] = (int64_t)st.ms_quality;
+    stats_out[7] = (int64_t)st.ms_local_moving; stats_out[8] = (int64_t)st.ms_reduce; stats_out[9] = (int64_t)st.ms_quality; stats_out[10] = (int64_t)st.ms_subnetworks;
   }
   free_net(be, net);
   return k;

@@ -42,8 +42,8 @@ def main():
                                  "sha256": mc.digest(lab), "labels": lab.tolist() if lab.size <= 1000 else lab[:64].tolist()})
             print(name, params, nc, q)
     for (n, d, seed, centres, k), plist in (((20000, 50, 7, 12, 20), [(1, 0.8, 1, 3, 10, 0), (1, 0.8, 2, 1, 10, 42),
-                                                                       (2, 0.0001, 1, 1, 3, 1)]),
-                                            ((100000, 50, 0, 32, 20), [(1, 0.8, 1, 2, 10, 0)])):
+                                                                       (2, 0.0001, 1, 1, 3, 1), (1, 0.8, 3, 1, 2, 0)]),
+                                            ((100000, 50, 0, 32, 20), [(1, 0.8, 1, 2, 10, 0), (1, 0.8, 3, 1, 2, 0)])):
         p, i, x = snn_case(n, d, seed, centres, k)
         for params in plist:
             lab, nc, q = oracle.modularity_cluster_ref(p, i, x, *params)

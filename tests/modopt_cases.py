@@ -21,7 +21,7 @@ KARATE_KAT = [
     ((1, 1.0, 2, 1, 1, 2), [1, 1, 1, 1, 3, 3, 3, 1, 0, 0, 3, 1, 1, 1, 0, 0, 3, 1, 0, 1, 0, 1, 0, 2, 2, 2, 0, 2, 2, 0, 0,
                             2, 0, 0]),
 ]
-# SLM known answers of the same file (:56-110) -- algorithm 3 is not on the device; they pin oracle/_ref only
+# SLM known answers of the same file (:56-110)
 KARATE_KAT_SLM = [
     ((1, 1.0, 3, 1, 1, 56464), [1, 1, 1, 1, 3, 3, 3, 1, 0, 0, 3, 1, 1, 1, 0, 0, 3, 1, 0, 1, 0, 1, 0, 2, 2, 2, 0, 2, 2,
                                 0, 0, 2, 0, 0]),
@@ -83,11 +83,15 @@ def digest(labels) -> str:
 def small_cases():
     return [
         ("karate", karate, [(1, 1.0, 1, 1, 1, 564), (1, 1.0, 2, 1, 1, 2), (1, 0.05, 1, 1, 10, 10), (2, 0.05, 2, 1, 10, 10),
-                            (1, 1.0, 1, 10, 10, 0), (1, 0.5, 2, 5, 3, 7), (2, 1.0, 1, 3, 4, 99), (1, 3.0, 1, 2, 2, 5)]),
-        ("karate_weighted", karate_weighted, [(1, 1.0, 1, 1, 10, 40), (1, 1.0, 2, 1, 10, 40), (2, 0.3, 1, 4, 5, 1)]),
+                            (1, 1.0, 1, 10, 10, 0), (1, 0.5, 2, 5, 3, 7), (2, 1.0, 1, 3, 4, 99), (1, 3.0, 1, 2, 2, 5),
+                            (1, 1.0, 3, 1, 1, 56464), (1, 0.05, 3, 1, 10, 10), (2, 0.05, 3, 1, 10, 10), (1, 1.3, 3, 4, 3, 77)]),
+        ("karate_weighted", karate_weighted, [(1, 1.0, 1, 1, 10, 40), (1, 1.0, 2, 1, 10, 40), (2, 0.3, 1, 4, 5, 1),
+                                              (1, 1.0, 3, 1, 10, 40)]),
         ("rand300_w_sym", lambda: random_graph(300, 8, 1), [(1, 0.8, 1, 3, 10, 0), (1, 1.5, 2, 2, 5, 11),
-                                                            (2, 0.02, 1, 2, 3, 4), (1, 25.0, 1, 1, 2, 3)]),
+                                                            (2, 0.02, 1, 2, 3, 4), (1, 25.0, 1, 1, 2, 3),
+                                                            (1, 0.8, 3, 2, 4, 9), (2, 0.05, 3, 1, 2, 6)]),
         ("rand1000_unw_lower_iso", lambda: random_graph(1000, 6, 2, weighted=False, symmetric=False, isolated=7),
-         [(1, 1.0, 1, 2, 10, 123456789), (1, 0.3, 2, 1, 10, 8), (2, 0.004, 2, 2, 2, 2)]),
-        ("rand5000_w_sym", lambda: random_graph(5000, 14, 3), [(1, 0.8, 1, 2, 10, 0), (1, 2.0, 2, 1, 4, 17)]),
+         [(1, 1.0, 1, 2, 10, 123456789), (1, 0.3, 2, 1, 10, 8), (2, 0.004, 2, 2, 2, 2), (1, 1.0, 3, 2, 3, 31)]),
+        ("rand5000_w_sym", lambda: random_graph(5000, 14, 3), [(1, 0.8, 1, 2, 10, 0), (1, 2.0, 2, 1, 4, 17),
+                                                               (1, 0.8, 3, 1, 3, 5)]),
     ]

@@ -35,9 +35,10 @@ def ctx():
 
 
 def test_reference_tests_known_answers(ctx):
-    """tests/testthat/test_modularity_optimizer.R: 'Algorithm 1' and 'Algorithm 2' on the karate club"""
+    """tests/testthat/test_modularity_optimizer.R: 'Algorithm 1', 'Algorithm 2', 'Algorithm 3' and 'Low
+    Resolution' on the karate club"""
     p, i, x = mc.slots(mc.karate())
-    for params, want in mc.KARATE_KAT:
+    for params, want in mc.KARATE_KAT + mc.KARATE_KAT_SLM:
         got, st = ctx.modularity_cluster(p, i, x, *params)
         assert got.tolist() == want and st["n_clusters"] == max(want) + 1
 
@@ -73,7 +74,7 @@ def test_matches_the_reference_on_random_graphs(ctx, seed):
     for _ in range(3):
         mf = int(rng.integers(1, 3))
         res = float(rng.choice([0.01, 0.2, 1.0])) if mf == 2 else float(rng.choice([0.1, 0.8, 1.0, 4.0, 40.0]))
-        params = (mf, res, int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(1, 6)),
+        params = (mf, res, int(rng.integers(1, 4)), int(rng.integers(1, 4)), int(rng.integers(1, 6)),
                   int(rng.integers(0, 2 ** 40)))
         want, wc, wq = oracle.modularity_cluster_ref(p, i, x, *params)
         got, st = ctx.modularity_cluster(p, i, x, *params)
@@ -104,11 +105,11 @@ def test_resident_snn_config_b(ctx):
     cfg = CONFIGS["B"]
     X, _ = gaussian_mixture(cfg["n"], cfg["d"], cfg["seed"])
     ctx.find_neighbors(X, cfg["k"], PRUNE, True, _lib.ROW_MAJOR)
-    c = [c for c in GOLD if c["graph"] == "snn:100000:50:0:32:20"][0]
-    lab, st = ctx.modularity_cluster_resident(cfg["n"], *c["params"])
-    assert st["n_clusters"] == c["n_clusters"] and mc.digest(lab) == c["sha256"], st
-    assert st["modularity"] == float.fromhex(c["modularity"])
-    assert st["rounds"] <= 12 * st["windows"] + 50, st
+    for c in [c for c in GOLD if c["graph"] == "snn:100000:50:0:32:20"]:      # Louvain and SLM
+        lab, st = ctx.modularity_cluster_resident(cfg["n"], *c["params"])
+        assert st["n_clusters"] == c["n_clusters"] and mc.digest(lab) == c["sha256"], st
+        assert st["modularity"] == float.fromhex(c["modularity"])
+        assert st["rounds"] <= 12 * st["windows"] + 50, st
     with pytest.raises(sb.B200Error, match="expected"):
         ctx.modularity_cluster_resident(cfg["n"] + 1, *c["params"])
 
@@ -120,7 +121,7 @@ def test_argument_errors_carry_the_wrappers_messages(ctx):
                     ({"n_random_starts": 0}, "Have to have at least one start"),
                     ({"n_iterations": 0}, "Need at least one interation"),
                     ({"modularity_function": 2, "resolution": 1.5}, "resolution<1 for alternative modularity"),
-                    ({"algorithm": 3}, "not available on the device")):
+                    ({"algorithm": 4}, "Leiden")):
         with pytest.raises(sb.B200Error, match=msg):
             ctx.modularity_cluster(p, i, x, **kw)
     with pytest.raises(sb.B200Error, match="Matrix contained no network data"):

@@ -35,7 +35,7 @@ def test_ref_build_reproduces_the_reference_tests_known_answers():
 
 def test_emulated_device_steps_reproduce_the_reference_tests_known_answers():
     p, i, x = mc.slots(mc.karate())
-    for params, want in mc.KARATE_KAT:
+    for params, want in mc.KARATE_KAT + mc.KARATE_KAT_SLM:
         for w0 in (1, 2, 5, 34):
             got, nc, _, _ = emul_modopt.cluster(p, i, x, *params, win0=w0, winmax=34)
             assert got.tolist() == want and nc == max(want) + 1
@@ -60,7 +60,7 @@ def test_emulated_device_steps_match_golden_snn_20k():
     case = [c for c in GOLD if c["graph"] == "snn:20000:50:7:12:20"]
     X, _ = gaussian_mixture(20000, 50, seed=7, n_centres=12)
     p, i, x = oracle.find_neighbors(X, k=20, prune=1 / 15, method="kdtree")["snn"]
-    for c in case[:2]:
+    for c in [case[0], case[1], case[3]]:       # Louvain, refinement, SLM (subnetworks above the one-thread size)
         lab, nc, q, st = emul_modopt.cluster(p, i, x, *c["params"])
         assert nc == c["n_clusters"] and mc.digest(lab) == c["sha256"] and q == float.fromhex(c["modularity"])
         assert st["rounds"] < 12 * max(1, st["windows"]), "the fixed point should need few rounds per window"
@@ -77,7 +77,7 @@ def test_emulated_device_steps_match_the_reference_on_random_graphs(seed):
     for _ in range(4):
         mf = int(rng.integers(1, 3))
         res = float(rng.choice([0.01, 0.2, 0.8, 1.0])) if mf == 2 else float(rng.choice([0.1, 0.8, 1.0, 4.0, 40.0]))
-        params = (mf, res, int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(1, 6)),
+        params = (mf, res, int(rng.integers(1, 4)), int(rng.integers(1, 4)), int(rng.integers(1, 6)),
                   int(rng.integers(0, 2 ** 40)))
         want, wc, wq = oracle.modularity_cluster_ref(p, i, x, *params)
         got, gc, gq, st = emul_modopt.cluster(p, i, x, *params, win0=int(rng.integers(1, 64)), winmax=n)
