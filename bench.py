@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-extra-workload", action="store_true")
+    ap.add_argument("--no-clustering", action="store_true",
+                    help="skip the FindClusters leg (modularity optimiser on the resident SNN graph, outside the metric)")
     ap.add_argument("--e2e-deadline", type=float, default=150.0,
                     help="N > 1: seconds the single-process multi-device e2e leg may take before it is abandoned")
     args = ap.parse_args()
@@ -433,6 +435,37 @@ def main():
     else:
         e2e = e2e_multi(args, cfg, X, rank, world, local, dev, cpu_group, main_last)
 
+    # ---- the step after FindNeighbors: FindClusters on the SNN graph still in HBM --------
+    # outside the metric; beside it the REAL reference optimiser (oracle/_ref, the reference's own
+    # ModularityOptimizer.cpp, single-threaded as in R) on the same graph, when the prebuilt file is there
+    clustering = None
+    if world == 1 and not args.no_clustering and not args.no_verify:
+        try:
+            step(False)                                   # the SNN of all rows is resident again
+            t0 = time.perf_counter()
+            lab, cst = ctx.modularity_cluster_resident(n, 1, 0.8, 1, 1, 10, 0)
+            t_gpu = time.perf_counter() - t0
+            clustering = {"workload": "FindClusters: Louvain (algorithm 1), resolution 0.8, n.start 1, n.iter 10, seed 0 on "
+                                      "the SNN graph resident in HBM", "seconds": t_gpu, "n_clusters": cst["n_clusters"],
+                          "modularity": cst["modularity"], "stats": cst}
+            import oracle
+            if oracle.have_ref():
+                r = ctx.dev_result(1)
+                P_ = torch.empty(r.n_rows + 1, dtype=torch.int64, device=dev)
+                I_ = torch.empty(r.nnz, dtype=torch.int32, device=dev)
+                X_ = torch.empty(r.nnz, dtype=torch.float64, device=dev)
+                ctx.dev_copy_result(1, P_, I_, X_)
+                t0 = time.perf_counter()
+                want, wc, wq = oracle.modularity_cluster_ref(P_.cpu().numpy().astype(np.int32), I_.cpu().numpy(),
+                                                             X_.cpu().numpy(), 1, 0.8, 1, 1, 10, 0)
+                clustering["reference"] = {"kind": "reference", "cores": 1, "seconds": time.perf_counter() - t0,
+                                           "what": "oracle/_ref: the reference's ModularityOptimizer.cpp on the same graph",
+                                           "identical_labels": bool((want == lab).all()),
+                                           "identical_modularity": bool(wq == cst["modularity"])}
+                del P_, I_, X_
+        except Exception as ex:                       # never lose the metric line over the extra leg
+            clustering = {"error": repr(ex)}
+
     # ---- a second workload without the mixture's coarse cluster structure (1 GPU only) ------
     other = None
     if world == 1 and not args.no_extra_workload and args.config == "C":
@@ -512,7 +545,8 @@ def main():
             "data": "synthetic", "config": workload_config(cfg, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "roofline_snn": roofline_snn, "cpu_baseline": cpu,
             "verify": verify, "stage_ms_per_step": st, "n_uncertified": ks.get("n_uncertified"),
-            "nnz_snn": g["nnz_snn"], "max_indegree": g.get("max_indegree"), "other_workloads": other}
+            "nnz_snn": g["nnz_snn"], "max_indegree": g.get("max_indegree"), "other_workloads": other,
+            "find_clusters": clustering}
     hung = bool(e2e and e2e.pop("_hung", False))
     print(json.dumps(line))
     sys.stdout.flush()

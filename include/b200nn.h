@@ -325,6 +325,35 @@ B200NN_API int b200nn_modularity_cluster_resident(b200nn_ctx *ctx, int32_t modul
                                                   int32_t *cluster_out, int64_t n_expected,
                                                   b200nn_modopt_stats *stats);
 
+/* ---- SNN side consumers ----------------------------------- */
+/*
+ * WriteEdgeFile, /root/reference/src/snn.cpp:40-59 (and the file half of DirectSNNToFile, :63-69):
+ * the strict lower triangle of the dgCMatrix (p, i, x) as lines "col<TAB>row<TAB>value", columns
+ * in order, value with 15 significant digits ("%.15g" = std::setprecision(15)).  Host I/O only.
+ * n_written (may be NULL) receives the number of lines.
+ */
+B200NN_API int b200nn_write_edge_file(const int32_t *p, const int32_t *i, const double *x, int64_t n,
+                                      const char *filename, int64_t *n_written);
+/*
+ * fast_dist, /root/reference/src/fast_NN_dist.cpp:34-69: Euclidean distance between row r of x
+ * [nx x d] and every row of y [ny x d] listed for it; the lists are given as ptr [nx + 1] /
+ * nbr [ptr[nx]] (1-based rows of y, R's list of index vectors flattened); out [ptr[nx]].
+ * Arithmetic as the reference's: squares summed in dimension order, sqrt at the end (bit-exact).
+ */
+B200NN_API int b200nn_fast_dist(b200nn_ctx *ctx, const double *x, int64_t nx, const double *y, int64_t ny,
+                                int32_t d, int32_t layout, const int64_t *ptr, const int32_t *nbr, double *out);
+/*
+ * SNN_SmallestNonzero_Dist, /root/reference/src/snn.cpp:82-126: for every column of the SNN graph
+ * the mean distance (minus nearest_dist, floored at 0) to the n_small cells with the smallest
+ * non-zero weights (all cells tied with the n_small-th are included; if that makes more than
+ * n_small, the n_small largest distances are averaged).  mat [n x d] in `layout`; out [n].
+ * Distances agree with the reference's Eigen norm to rounding (1e-12 relative), see extras_core.inl.
+ */
+B200NN_API int b200nn_snn_smallest_nonzero_dist(b200nn_ctx *ctx, const int32_t *p, const int32_t *i,
+                                                const double *x, int64_t n, const double *mat, int32_t d,
+                                                int32_t layout, int32_t n_small, const double *nearest_dist,
+                                                double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,12 @@ def lib() -> C.CDLL:
         L.oracle_l2norm.argtypes = [vp, i64, i32]
         L.oracle_l2norm.restype = None
         L.oracle_num_threads.restype = i32
+        L.oracle_write_edge_file.argtypes = [vp, vp, vp, i64, C.c_char_p]
+        L.oracle_write_edge_file.restype = i64
+        L.oracle_fast_dist.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp]
+        L.oracle_fast_dist.restype = i32
+        L.oracle_snn_smallest_nonzero_dist.argtypes = [vp, vp, vp, i64, vp, i32, i32, vp, vp]
+        L.oracle_snn_smallest_nonzero_dist.restype = None
         _lib = L
     return _lib
 
@@ -220,3 +226,40 @@ def modularity_cluster_ref(p, i, x, modularity_function=1, resolution=0.8, algor
         raise ValueError({-1: "invalid argument", -2: "Matrix contained no network data.  Check format.",
                           -3: "Clustering step failed.", -4: "C++ exception"}.get(rc, str(rc)))
     return out, rc, q.value
+
+
+# ----------------------------------------------------------------------------------------------
+# SNN side consumers (src/snn.cpp:40-126, src/fast_NN_dist.cpp)
+# ----------------------------------------------------------------------------------------------
+def write_edge_file(p, i, x, filename: str) -> int:
+    p = np.ascontiguousarray(p, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return int(lib().oracle_write_edge_file(_p(p), _p(i), _p(x), p.size - 1, filename.encode()))
+
+
+def fast_dist(x, y, lists):
+    """lists: one 1-based index vector per row of x -> list of distance vectors (fast_dist)"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    ptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(v) for v in lists])
+    nbr = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.int32) for v in lists]) if ptr[-1] else
+                               np.zeros(0, np.int32), dtype=np.int32)
+    out = np.empty(int(ptr[-1]), dtype=np.float64)
+    if lib().oracle_fast_dist(_p(x), x.shape[0], _p(y), y.shape[0], x.shape[1], _p(ptr), _p(nbr), _p(out)) != 0:
+        raise ValueError("neighbour index out of range")
+    return [out[ptr[r]:ptr[r + 1]] for r in range(len(lists))]
+
+
+def snn_smallest_nonzero_dist(p, i, x, mat, n_small: int, nearest_dist):
+    p = np.ascontiguousarray(p, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    mat = np.ascontiguousarray(mat, dtype=np.float64)
+    nearest = np.ascontiguousarray(nearest_dist, dtype=np.float64)
+    n = p.size - 1
+    out = np.empty(n, dtype=np.float64)
+    lib().oracle_snn_smallest_nonzero_dist(_p(p), _p(i), _p(x), n, _p(mat), mat.shape[1], int(n_small), _p(nearest),
+                                           _p(out))
+    return out

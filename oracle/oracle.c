@@ -30,6 +30,8 @@
  *                          description; RANN is an un-vendored, un-pinned CRAN
  *                          dependency (/root/reference/DESCRIPTION:72).
  *   oracle_l2norm          /root/reference/R/utilities.R:2107-2122 (L2Norm)
+ *   oracle_write_edge_file / oracle_fast_dist / oracle_snn_smallest_nonzero_dist
+ *                          /root/reference/src/snn.cpp:40-59, 82-126; src/fast_NN_dist.cpp:8-69
  *
  * Build:  make -C oracle        (gcc -O2 -ffp-contract=off -fopenmp)
  * All matrices are row-major (one cell per row) unless stated otherwise.
@@ -600,6 +602,103 @@ ORACLE_API void oracle_l2norm(double *m, int64_t n, int d) {
       double v = m[i * d + j] / s;
       m[i * d + j] = isfinite(v) ? v : 0.0;
     }
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* SNN side consumers                                     */
+/* ------------------------------------------------------------------ */
+
+/* WriteEdgeFile, /root/reference/src/snn.cpp:40-59: strict lower triangle, "col\trow\tvalue" with
+ * std::setprecision(15) on the default float format, i.e. "%.15g". */
+#include <stdio.h>
+ORACLE_API int64_t oracle_write_edge_file(const int32_t *p, const int32_t *i, const double *x, int64_t n,
+                                          const char *filename) {
+  FILE *f = fopen(filename, "w");
+  if (!f) return -1;
+  int64_t lines = 0;
+  for (int64_t k = 0; k < n; ++k)
+    for (int64_t e = p[k]; e < p[k + 1]; ++e) {
+      if (k >= i[e]) continue; /* it.col() >= it.row() */
+      fprintf(f, "%lld\t%d\t%.15g\n", (long long)k, i[e], x[e]);
+      ++lines;
+    }
+  fclose(f);
+  return lines;
+}
+
+/* fast_dist, /root/reference/src/fast_NN_dist.cpp:8-69: rval += pow(d1 - d2, 2) over the columns,
+ * sqrt(rval).  x [nx x d], y [ny x d] row-major; lists flattened as ptr / nbr (1-based). */
+ORACLE_API int oracle_fast_dist(const double *x, int64_t nx, const double *y, int64_t ny, int d, const int64_t *ptr,
+                                const int32_t *nbr, double *out) {
+  for (int64_t r = 0; r < nx; ++r)
+    for (int64_t q = ptr[r]; q < ptr[r + 1]; ++q) {
+      const int64_t j = (int64_t)nbr[q] - 1;
+      if (j < 0 || j >= ny) return -1;
+      double rval = 0;
+      for (int c = 0; c < d; ++c) rval += pow(x[r * d + c] - y[j * d + c], 2);
+      out[q] = sqrt(rval);
+    }
+  return 0;
+}
+
+/* SNN_SmallestNonzero_Dist, /root/reference/src/snn.cpp:82-126.  The row distance is Eigen's
+ * (a - b).norm() there; restated as the square root of the squares summed in column order. */
+static int cmp_desc(const void *a, const void *b) {
+  const double u = *(const double *)a, v = *(const double *)b;
+  return u < v ? 1 : (u > v ? -1 : 0);
+}
+ORACLE_API void oracle_snn_smallest_nonzero_dist(const int32_t *p, const int32_t *ri, const double *x, int64_t n,
+                                                 const double *mat, int d, int n_small, const double *nearest,
+                                                 double *out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = p[i], cnt = p[i + 1] - b;
+    int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)(cnt > 0 ? cnt : 1));
+    double *dists = (double *)malloc(sizeof(double) * (size_t)(cnt > 0 ? cnt : 1));
+    /* sort_indexes (:70-79): std::stable_sort of 0..cnt-1 by value */
+    for (int64_t a = 0; a < cnt; ++a) order[a] = a;
+    for (int64_t a = 1; a < cnt; ++a) { /* stable insertion sort */
+      const int64_t o = order[a];
+      int64_t q = a;
+      while (q > 0 && x[b + o] < x[b + order[q - 1]]) {
+        order[q] = order[q - 1];
+        --q;
+      }
+      order[q] = o;
+    }
+    int64_t n_i = n_small;
+    if (n_i > cnt) n_i = cnt;
+    int64_t nd = 0;
+    for (int64_t j = 0; j < cnt; ++j) {
+      const int64_t cell = ri[b + order[j]];
+      if (nd < n_i || x[b + order[j]] == x[b + order[n_i - 1]]) {
+        double acc = 0;
+        for (int c = 0; c < d; ++c) {
+          const double t = mat[cell * d + c] - mat[i * d + c];
+          acc += t * t;
+        }
+        double res = sqrt(acc);
+        if (nearest[i] > 0) {
+          res = res - nearest[i];
+          if (res < 0) res = 0;
+        }
+        dists[nd++] = res;
+      } else {
+        break;
+      }
+    }
+    double avg = 0;
+    if (nd > n_i) {
+      qsort(dists, (size_t)nd, sizeof(double), cmp_desc);
+      for (int64_t a = 0; a < n_i; ++a) avg += dists[a];
+      avg /= (double)n_i;
+    } else {
+      for (int64_t a = 0; a < nd; ++a) avg += dists[a];
+      avg /= (double)nd;
+    }
+    out[i] = avg;
+    free(order);
+    free(dists);
   }
 }
 

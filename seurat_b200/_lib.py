@@ -31,6 +31,7 @@ SYMBOLS = [
     "b200nn_multi_create", "b200nn_multi_destroy", "b200nn_multi_size", "b200nn_multi_knn",
     "b200nn_multi_find_neighbors_count", "b200nn_multi_find_neighbors_fill",
     "b200nn_modularity_cluster", "b200nn_modularity_cluster_resident",
+    "b200nn_write_edge_file", "b200nn_fast_dist", "b200nn_snn_smallest_nonzero_dist",
 ]
 
 
@@ -134,6 +135,9 @@ def load() -> C.CDLL:
                                                 C.POINTER(ModoptStats)]
         L.b200nn_modularity_cluster_resident.argtypes = [vp, i32, dbl, i32, i32, i32, C.c_uint64, vp, i64,
                                                          C.POINTER(ModoptStats)]
+        L.b200nn_write_edge_file.argtypes = [vp, vp, vp, i64, C.c_char_p, C.POINTER(i64)]
+        L.b200nn_fast_dist.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]
+        L.b200nn_snn_smallest_nonzero_dist.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp]
         _lib = L
         return L
 
@@ -141,6 +145,18 @@ def load() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != OK:
         raise B200Error(rc, load().b200nn_last_error().decode("utf-8", "replace"))
+
+
+def write_edge_file(p, i, x, filename: str) -> int:
+    """WriteEdgeFile (src/snn.cpp:40-59): strict lower triangle as "col\\trow\\tvalue" lines; host I/O,
+    needs no device.  Returns the number of lines written."""
+    p = np.ascontiguousarray(p, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n_lines = C.c_int64(0)
+    check(load().b200nn_write_edge_file(_ptr(p), _ptr(i), _ptr(x), p.size - 1, str(filename).encode(),
+                                        C.byref(n_lines)))
+    return int(n_lines.value)
 
 
 def device_count() -> int:
@@ -216,6 +232,27 @@ class Context:
                                                          int(random_seed) & (2 ** 64 - 1), _ptr(out), n,
                                                          C.byref(st)))
         return out, st.as_dict()
+
+    # ---- SNN side consumers (src/snn.cpp:40-126, src/fast_NN_dist.cpp) ---------------
+    def fast_dist(self, x, y, ptr, nbr, layout: int):
+        """distances between row r of x and the rows of y listed (1-based) in nbr[ptr[r]:ptr[r+1]]"""
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+        out = np.empty(int(ptr[-1]), dtype=np.float64)
+        check(self._L.b200nn_fast_dist(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[1], layout,
+                                       _ptr(ptr), _ptr(nbr), _ptr(out)))
+        return out
+
+    def snn_smallest_nonzero_dist(self, p, i, x, mat, layout: int, n_small: int, nearest_dist):
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nearest = np.ascontiguousarray(nearest_dist, dtype=np.float64)
+        n = p.size - 1
+        out = np.empty(n, dtype=np.float64)
+        check(self._L.b200nn_snn_smallest_nonzero_dist(self._h, _ptr(p), _ptr(i), _ptr(x), n, _ptr(mat), mat.shape[1],
+                                                       layout, int(n_small), _ptr(nearest), _ptr(out)))
+        return out
 
     def index(self, ref, layout: int) -> "Index":
         """Keep the reference embedding `ref` [nr, d] on the device for repeated queries."""
@@ -507,6 +544,27 @@ class MultiContext:
                                                          int(random_seed) & (2 ** 64 - 1), _ptr(out), n,
                                                          C.byref(st)))
         return out, st.as_dict()
+
+    # ---- SNN side consumers (src/snn.cpp:40-126, src/fast_NN_dist.cpp) ---------------
+    def fast_dist(self, x, y, ptr, nbr, layout: int):
+        """distances between row r of x and the rows of y listed (1-based) in nbr[ptr[r]:ptr[r+1]]"""
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+        out = np.empty(int(ptr[-1]), dtype=np.float64)
+        check(self._L.b200nn_fast_dist(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[1], layout,
+                                       _ptr(ptr), _ptr(nbr), _ptr(out)))
+        return out
+
+    def snn_smallest_nonzero_dist(self, p, i, x, mat, layout: int, n_small: int, nearest_dist):
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nearest = np.ascontiguousarray(nearest_dist, dtype=np.float64)
+        n = p.size - 1
+        out = np.empty(n, dtype=np.float64)
+        check(self._L.b200nn_snn_smallest_nonzero_dist(self._h, _ptr(p), _ptr(i), _ptr(x), n, _ptr(mat), mat.shape[1],
+                                                       layout, int(n_small), _ptr(nearest), _ptr(out)))
+        return out
 
     def index(self, ref, layout: int) -> "Index":
         return self._first().index(ref, layout)

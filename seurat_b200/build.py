@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libb200nn.so")
-SOURCES = ["util.cu", "knn_exact.cu", "knn_tc.cu", "snn.cu", "api.cu", "multi.cu", "modopt.cu"]
+SOURCES = ["util.cu", "knn_exact.cu", "knn_tc.cu", "snn.cu", "api.cu", "multi.cu", "modopt.cu", "extras.cu"]
 HEADERS = [os.path.join(CSRC, "internal.cuh"), os.path.join(HERE, "..", "include", "b200nn.h")]
 
 NVCC_FLAGS = [

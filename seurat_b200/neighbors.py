@@ -25,7 +25,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["Embedding", "Neighbor", "Graph", "L2Norm", "NNHelper", "ComputeSNN", "FindNeighbors",
+__all__ = ["WriteEdgeFile", "DirectSNNToFile", "fast_dist", "SNN_SmallestNonzero_Dist",
+           "Embedding", "Neighbor", "Graph", "L2Norm", "NNHelper", "ComputeSNN", "FindNeighbors",
            "FindNeighborsSeurat", "SeuratLite", "Indices", "Distances", "Cells"]
 
 
@@ -271,6 +272,52 @@ def ComputeSNN(nn_ranked, prune: float, ctx: _lib.Context | None = None,
         stats_out.update(st)
     n = nn.shape[0]
     return Graph(p, i, x, (n, n))
+
+
+def WriteEdgeFile(snn: Graph, filename: str, display_progress: bool = False) -> None:
+    """``WriteEdgeFile(snn, filename, display_progress)`` -- src/snn.cpp:40-59: the strict lower triangle
+    of the graph, one ``col<TAB>row<TAB>value`` line per entry, 15 significant digits."""
+    if display_progress:
+        _message("Writing SNN as edge file")
+    _lib.write_edge_file(snn.p, snn.i, snn.x, str(filename))
+
+
+def DirectSNNToFile(nn_ranked, prune: float, display_progress: bool, filename: str,
+                    ctx: _lib.Context | None = None) -> Graph:
+    """``DirectSNNToFile`` -- src/snn.cpp:63-69: ComputeSNN, then the edge file, without a trip through R."""
+    snn = ComputeSNN(nn_ranked, prune, ctx=ctx)
+    WriteEdgeFile(snn, filename, display_progress)
+    return snn
+
+
+def fast_dist(x, y, n, ctx: _lib.Context | None = None) -> list:
+    """``fast_dist(x, y, n)`` -- src/fast_NN_dist.cpp:34-69: for every row r of ``x`` the Euclidean distances
+    to the rows of ``y`` listed (1-based) in ``n[r]``.  Returns a list of vectors shaped like ``n``;
+    an empty list when ``len(n) != nrow(x)``, like the reference."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if x.shape[0] != len(n):
+        return []
+    if not (x.flags.c_contiguous or x.flags.f_contiguous):
+        x = np.ascontiguousarray(x)
+    if _layout_of(y) != _layout_of(x) or not (y.flags.c_contiguous or y.flags.f_contiguous):
+        y = np.asarray(y, order="C" if _layout_of(x) == _lib.ROW_MAJOR else "F")
+    ptr = np.zeros(len(n) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(v) for v in n])
+    nbr = (np.concatenate([np.asarray(v).astype(np.int32) for v in n]) if ptr[-1] else np.zeros(0, np.int32))
+    ctx = ctx or _lib.default_context()
+    out = ctx.fast_dist(x, y, ptr, nbr, _layout_of(x))
+    return [out[ptr[r]:ptr[r + 1]] for r in range(len(n))]
+
+
+def SNN_SmallestNonzero_Dist(snn: Graph, mat, n: int, nearest_dist, ctx: _lib.Context | None = None) -> np.ndarray:
+    """``SNN_SmallestNonzero_Dist(snn, mat, n, nearest_dist)`` -- src/snn.cpp:82-126 (the WNN kernel-bandwidth
+    helper): per cell the mean distance to its ``n`` weakest SNN neighbours, minus ``nearest_dist``."""
+    mat = np.asarray(mat, dtype=np.float64)
+    if not (mat.flags.c_contiguous or mat.flags.f_contiguous):
+        mat = np.ascontiguousarray(mat)
+    ctx = ctx or _lib.default_context()
+    return ctx.snn_smallest_nonzero_dist(snn.p, snn.i, snn.x, mat, _layout_of(mat), int(n), nearest_dist)
 
 
 def _nn_graph(nn_ranked: np.ndarray, n: int, ctx: _lib.Context) -> Graph:

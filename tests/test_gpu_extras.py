@@ -1,0 +1,63 @@
+"""GPU suite (-m gpu): SNN side consumers through the C ABI against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+import seurat_b200 as sb
+from seurat_b200 import _lib
+from seurat_b200.synthetic import gaussian_mixture
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sb.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_fast_dist_bit_exact(ctx, order):
+    rng = np.random.default_rng(2)
+    x = np.asarray(rng.normal(size=(3000, 30)), order=order)
+    y = np.asarray(rng.normal(size=(5000, 30)), order=order)
+    lists = [rng.integers(1, 5001, rng.integers(0, 40)) for _ in range(3000)]
+    want = oracle.fast_dist(x, y, lists)
+    got = sb.fast_dist(x, y, lists, ctx=ctx)
+    assert len(got) == 3000 and all((a == b).all() for a, b in zip(got, want))
+    assert sb.fast_dist(x, y, lists[:10], ctx=ctx) == []                 # length mismatch: empty list
+    with pytest.raises(sb.B200Error):
+        sb.fast_dist(x[:2], y, [np.array([1, 5001]), np.array([2])], ctx=ctx)
+    # the kNN distances themselves are such distances
+    X, _ = gaussian_mixture(4000, 20, seed=3, n_centres=4)
+    nb = sb.FindNeighbors(sb.Embedding(X, [f"c{i}" for i in range(4000)]), k_param=10, return_neighbor=True,
+                          verbose=False, ctx=ctx)
+    d = sb.fast_dist(X, X, list(nb.nn_idx), ctx=ctx)
+    assert (np.stack(d) == nb.nn_dist).all()
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_snn_smallest_nonzero_dist(ctx, order):
+    X, _ = gaussian_mixture(6000, 15, seed=4, n_centres=5)
+    X[11] = X[10]
+    r = oracle.find_neighbors(X, k=20, prune=1 / 15, method="kdtree")
+    p, i, x = r["snn"]
+    g = sb.Graph(p, i, x, (6000, 6000))
+    nearest = r["nn_dist"][:, 1].copy()
+    nearest[::5] = 0.0
+    Xo = np.asarray(X, order=order)
+    for n_small in (1, 20, 100000):
+        want = oracle.snn_smallest_nonzero_dist(p, i, x, X, n_small, nearest)
+        got = sb.SNN_SmallestNonzero_Dist(g, Xo, n_small, nearest, ctx=ctx)
+        assert (got == want).all()        # same summation order as the oracle: bit-identical
+
+
+def test_direct_snn_to_file(ctx, tmp_path):
+    X, _ = gaussian_mixture(5000, 10, seed=6, n_centres=3)
+    r = oracle.find_neighbors(X, k=15, prune=1 / 15)
+    f1, f2 = str(tmp_path / "gpu.txt"), str(tmp_path / "oracle.txt")
+    g = sb.DirectSNNToFile(r["nn_idx"], 1 / 15, False, f1, ctx=ctx)
+    oracle.write_edge_file(*r["snn"], f2)
+    assert open(f1, "rb").read() == open(f2, "rb").read()
+    assert (g.p == r["snn"][0]).all() and (g.x == r["snn"][2]).all()
