@@ -175,7 +175,7 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
       b200nn_set_error("knn: a sharded call must be a self search (d_qry = NULL) with 0 <= rank < world <= 64");
       return B200NN_ERR_INVALID;
     }
-    const bool tc = algo != B200NN_KNN_EXACT && knn_tc_applicable(nr, nq, d, k);
+    const bool tc = algo != B200NN_KNN_EXACT && knn_tc_applicable(nr, nq, d, k, o.scan_mode & 3);
     if (!(tc && knn_tc_grouped(nr, o.scan_mode & 3))) {
       // no grouping to align the shares with: contiguous rows [b, e) of the full-size outputs
       const int64_t per = ceil_div64(nr, o.shard_world);
@@ -193,9 +193,9 @@ int knn_dispatch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
     }
   }
   if (algo == B200NN_KNN_AUTO)
-    algo = knn_tc_applicable(nr, nq, d, k) ? B200NN_KNN_TENSOR : B200NN_KNN_EXACT;
+    algo = knn_tc_applicable(nr, nq, d, k, o.scan_mode & 3) ? B200NN_KNN_TENSOR : B200NN_KNN_EXACT;
   if (algo == B200NN_KNN_TENSOR) {
-    if (!knn_tc_applicable(nr, nq, d, k)) {
+    if (!knn_tc_applicable(nr, nq, d, k, o.scan_mode & 3)) {
       b200nn_set_error("tensor-core kNN path does not cover nr=%lld d=%d k=%d", (long long)nr, d, k);
       return B200NN_ERR_INVALID;
     }

@@ -219,7 +219,7 @@ int knn_exact_grouped_launch(b200nn_ctx *ctx, const double *d_ref, const double 
 
 // knn_tc.cu : tcgen05 candidate generation + FP64 re-rank + certificate
 // scan_mode: 0 = auto, 1 = exhaustive scan of every key tile, 2 = grouped (tile-pruned) search
-bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k);
+bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k, int scan_mode);
 struct TcRefCache;  // reference-side state of the grouped search, kept by a resident index
 TcRefCache *tc_ref_cache_create();
 void tc_ref_cache_destroy(TcRefCache *c);

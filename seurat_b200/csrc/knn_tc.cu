@@ -62,7 +62,13 @@ constexpr int EPI_WARPS = 8;        // one thread per row of the two resident qu
 constexpr int NUM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;  // 16 KB (A tile == B tile)
 constexpr int MAX_D = BK - 3;       // 61
-constexpr int MAX_KP = 48;          // shared-memory budget of the candidate lists
+constexpr int MAX_KP = 48;          // shared-memory budget of the candidate lists (one list per query row)
+// Larger k' (k > 32): the grouped search runs once per COLUMN SPLIT of the reference set -- split s of S
+// holds tiles s, s + S, ... of every group -- each with its own list of k'/S entries per row and its
+// own threshold; the row's candidates are the union, its threshold the minimum (every non-candidate
+// was rejected by the list of its split, or pruned against that split's bound).  Every tile is still
+// visited once in total.
+constexpr int MAX_SPLITS = 16;      // k <= 256 (see plan_kp)
 // FP32 accumulation error of one key: each of the `ksteps` K = 16 MMAs adds 16 products to the
 // running sum; with a truncating aligned adder every partial result is within 2^-23 of the
 // largest magnitude M involved, so |error| <= ksteps * 17 * 2^-23 * M (provable, not
@@ -277,7 +283,8 @@ struct TcParams {
   int32_t ksteps;      // ceil((d + 3) / 16)
   int32_t kp;          // candidates kept per query
   int32_t stages;      // B ring depth (<= MAX_STAGES)
-  int32_t *cand;       // [nq x kp]
+  int32_t *cand;       // row q's kp candidates at cand + q * cand_stride
+  int64_t cand_stride; // >= kp (column splits of the reference set share one [nq x splits*kp] matrix)
   float *tau;          // [nq]
   float *dbg_keys;     // optional [QT*BM x BN]: keys of item 0 / B tile 0
   TcMisc *misc;
@@ -590,7 +597,7 @@ k_knn_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUte
           T = T > 0.f ? T * 1.0001f + 1e-3f : 1e-3f;
           atomicMax(reinterpret_cast<int *>(P.item_T + item), __float_as_int(T));
         } else {
-          int32_t *dst = P.cand + oq * kp;
+          int32_t *dst = P.cand + oq * P.cand_stride;
           for (int e = 0; e < kp; ++e) {
             int id = e < S.cnt_list ? li[e * LSTRIDE] : -1;
             if (id >= 0 && P.rperm) id = P.rperm[id];
@@ -978,16 +985,17 @@ k_km_accum(const __half *__restrict__ y16, int64_t m, int64_t stride, int d, int
                 (unsigned long long)(long long)(y[j] * 16777216.f));
 }
 
-// padded reference offsets (multiples of BN) and query offsets (multiples of an item); zeroes the cursors
+// padded reference offsets (multiples of BN * rtiles) and query offsets (multiples of an item); zeroes the cursors
 __global__ void k_group_offsets(const int32_t *__restrict__ rcount, const int32_t *__restrict__ qcount, int G,
                                 int32_t *__restrict__ goff, int32_t *__restrict__ qoff,
-                                int32_t *__restrict__ rcursor, int32_t *__restrict__ qcursor) {
+                                int32_t *__restrict__ rcursor, int32_t *__restrict__ qcursor, int rtiles) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int ro = 0, qo = 0;
+  const int rm = BN * rtiles;  // column splits: every group holds the same number of tiles of every split
   for (int g = 0; g < G; ++g) {
     goff[g] = ro;
     qoff[g] = qo;
-    ro += ((rcount[g] + BN - 1) / BN) * BN;
+    ro += ((rcount[g] + rm - 1) / rm) * rm;
     qo += ((qcount[g] + QT * BM - 1) / (QT * BM)) * (QT * BM);  // items never straddle two groups
     rcursor[g] = 0;
     qcursor[g] = 0;
@@ -1124,13 +1132,23 @@ k_fine_offsets(const int32_t *__restrict__ fcount, const int32_t *__restrict__ o
 __global__ void __launch_bounds__(256)
 k_fine_scatter(const int32_t *__restrict__ gid, const float *__restrict__ anorm, int64_t n,
                const float *__restrict__ gstat, const int32_t *__restrict__ foff, int32_t *__restrict__ fcursor,
-               int32_t *__restrict__ perm, const int32_t *__restrict__ owner, int rank) {
+               int32_t *__restrict__ perm, const int32_t *__restrict__ owner, int rank,
+               const int32_t *__restrict__ goff = nullptr, int deal = 1) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int g = gid[i];
   if (owner && owner[g] != rank) return;  // a query row of another share
   const int f = g * FINE_NB + fine_bucket(anorm[i], gstat[2 * g], gstat[2 * g + 1]);
-  perm[foff[f] + atomicAdd(&fcursor[f], 1)] = (int32_t)i;
+  int p = foff[f] + atomicAdd(&fcursor[f], 1);
+  if (deal > 1) {
+    // column splits: the hub-first sequence of the group is dealt round-robin into `deal` sub-sequences
+    // stored one after the other (each a whole number of tiles, itself hub-first), so that every split
+    // is a uniform sample of the group -- a row's near neighbours, which crowd into the first tiles
+    // of the hub-first order, then fall into the splits binomially (see plan_kp)
+    const int g0 = goff[g], sub = (goff[g + 1] - g0) / deal, pl = p - g0;
+    p = g0 + (pl % deal) * sub + pl / deal;
+  }
+  perm[p] = (int32_t)i;
 }
 
 // annulus [lo, hi] of |yh_r - c_g| over the rows of every 128-row tile (one warp per tile);
@@ -1344,7 +1362,8 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
               const float *__restrict__ item_T, int G, const float *__restrict__ cent,
               const float *__restrict__ grad, const int32_t *__restrict__ goff,
               const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, int pass1,
-              int64_t list_stride, int32_t *__restrict__ tiles, int32_t *__restrict__ list_cnt) {
+              int64_t list_stride, int32_t *__restrict__ tiles, int32_t *__restrict__ list_cnt,
+              int nsplit, int split) {
   __shared__ float cs[BK];
   __shared__ float s_min[LIST_THREADS / 32];
   __shared__ int s_scan[LIST_THREADS / 32];
@@ -1406,7 +1425,9 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
         float lb = dist[u] * 0.99999f - ri - grad[g];
         keep = !(lb > 0.f && lb * lb > T);  // also keeps everything when T is +inf / NaN
       }
-      if (keep) ntile[u] = (goff[g + 1] - goff[g]) / BN;
+      // column split `split` of `nsplit` (k' beyond one shared-memory list): the split-th of the group's
+      // nsplit equally long runs of tiles (k_fine_scatter deals the rows; groups hold multiples of nsplit tiles)
+      if (keep) ntile[u] = (goff[g + 1] - goff[g]) / (BN * nsplit);
       // pass 1 only needs an upper bound of tau: a few tiles of the own group suffice
       if (pass1 && ntile[u] > PASS1_TILES) ntile[u] = PASS1_TILES;
     }
@@ -1433,7 +1454,7 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
     for (int u = 0; u < GPT; ++u) {
       const int g = tid * GPT + u;
       if (ntile[u] > 0) {
-        const int t0 = goff[g] / BN;
+        const int t0 = goff[g] / BN + split * ((goff[g + 1] - goff[g]) / (BN * nsplit));
         for (int t = 0; t < ntile[u]; ++t) dst[pos + t] = t0 + t;
       }
       pos += ntile[u];
@@ -1454,11 +1475,12 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
       for (int u = 0; u < GPT; ++u) {
         const int g = tid * GPT + u;
         if (ntile[u] <= 0) continue;
-        const int t0 = goff[g] / BN;
+        const int t0 = goff[g] / BN + split * ((goff[g + 1] - goff[g]) / (BN * nsplit));
         const float D = dist[u];
         const bool nearest = D <= dmin;
         for (int t = 0; t < ntile[u]; ++t) {
-          const float lo = tile_lo[t0 + t], hi = tile_hi[t0 + t];
+          const int tile = t0 + t;
+          const float lo = tile_lo[tile], hi = tile_hi[tile];
           bool keep_t = true;
           if (!(nearest && t < PASS1_TILES)) {
             const float lb = fmaxf(lo - (D * 1.00001f + ri), (D * 0.99999f - ri) - hi);
@@ -1470,7 +1492,7 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
           if (phase == 0)
             atomicAdd(&s_hist[b], 1);
           else
-            dst[atomicAdd(&s_cur[b], 1)] = t0 + t;
+            dst[atomicAdd(&s_cur[b], 1)] = tile;
         }
       }
       __syncthreads();
@@ -1494,7 +1516,7 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
 // items ordered by decreasing list length (counting sort; one block of 1024 threads)
 __global__ void __launch_bounds__(1024)
 k_order_items(const int32_t *__restrict__ list_cnt, int n_items, int max_cnt, int32_t *__restrict__ bins,
-              int32_t *__restrict__ order, TcMisc *__restrict__ misc) {
+              int32_t *__restrict__ order, TcMisc *__restrict__ misc, int accumulate) {
   __shared__ int s_part[1024];
   __shared__ long long s_vis[32];
   const int tid = threadIdx.x;
@@ -1540,7 +1562,7 @@ k_order_items(const int32_t *__restrict__ list_cnt, int n_items, int max_cnt, in
   if (tid == 0) {
     long long v = 0;
     for (int w = 0; w < 32; ++w) v += s_vis[w];
-    misc->tiles_visited = v;
+    misc->tiles_visited = accumulate ? misc->tiles_visited + v : v;
     misc->tiles_total = (long long)n_items * max_cnt;
   }
   __syncthreads();
@@ -1556,8 +1578,9 @@ constexpr int RR_WARPS = 4;
 // and read 16 bytes at a time, and a stride of an odd number of 16-byte units keeps the
 // per-lane row reads conflict-free; odd d: 8-byte accesses with an odd stride.
 __host__ __device__ inline int rr_stride(int d) { return (d & 1) ? d + 2 : ((d & 3) == 2 ? d : d + 2); }
-__host__ __device__ inline size_t rr_per_warp(int d) {
-  size_t b = sizeof(double) * ((size_t)32 * rr_stride(d) + ((d + 1) & ~1)) + 64 * 8 + 64 * 4;
+__host__ __device__ inline int rr_kp_round(int kp) { return kp <= 64 ? 64 : (kp + 31) & ~31; }
+__host__ __device__ inline size_t rr_per_warp(int d, int kp) {
+  size_t b = sizeof(double) * ((size_t)32 * rr_stride(d) + ((d + 1) & ~1)) + (size_t)rr_kp_round(kp) * (8 + 4);
   return (b + 15) & ~(size_t)15;
 }
 
@@ -1579,12 +1602,12 @@ k_rerank(const double *__restrict__ ref, const double *__restrict__ qry, int64_t
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ds = rr_stride(d);
-  // per warp: rows[32][ds] doubles, q[d] doubles, key[64] u64, id[64] i32
-  unsigned char *wbase = rr_smem + (size_t)warp * rr_per_warp(d);
+  // per warp: rows[32][ds] doubles, q[d] doubles, key[kp rounded] u64, id[kp rounded] i32
+  unsigned char *wbase = rr_smem + (size_t)warp * rr_per_warp(d, kp);
   double *rows = reinterpret_cast<double *>(wbase);
   double *qv = rows + 32 * ds;
   unsigned long long *skey = reinterpret_cast<unsigned long long *>(qv + ((d + 1) & ~1));
-  int32_t *sid = reinterpret_cast<int32_t *>(skey + 64);
+  int32_t *sid = reinterpret_cast<int32_t *>(skey + rr_kp_round(kp));
 
   // queries are visited in the group-sorted order of the candidate stage when available:
   // neighbouring warps then gather overlapping candidate rows (L2 hits instead of HBM)
@@ -1728,6 +1751,40 @@ int pick_kp(int k, int n_cand) {
   return kp;
 }
 
+// k' candidates per row as `splits` lists of `per` entries.  A row's certificate needs about `want`
+// (~1.5 k) keys below its threshold, and the threshold is the SMALLEST of the splits' thresholds: the
+// want keys fall into the splits binomially (mean m = want / S, deviation ~ sqrt(m)), so every list
+// gets four deviations of head room -- measured with per = want / S: 64 % of the rows of a 1M-cell
+// input lost their certificate at k = 100 to the one unlucky split.  splits == 0: no plan.
+struct KpPlan {
+  int splits, per, total;
+};
+KpPlan plan_kp(int want) {
+  KpPlan p = {1, want, want};
+  if (want <= MAX_KP) return p;
+  for (int S = 2; S <= MAX_SPLITS; ++S) {
+    const double m = (double)want / S;
+    const int per = ((int)ceil(m + 4.0 * sqrt(m)) + 7) & ~7;
+    if (per <= MAX_KP) {
+      p.splits = S;
+      p.per = per;
+      p.total = S * per;
+      return p;
+    }
+  }
+  p.splits = 0;
+  return p;
+}
+
+// tau[q] = min over the splits' thresholds tau[s * nq + q]
+__global__ void k_tau_min(float *__restrict__ tau, int64_t nq, int splits) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  float m = tau[q];
+  for (int s = 1; s < splits; ++s) m = fminf(m, tau[(int64_t)s * nq + q]);
+  tau[q] = m;
+}
+
 size_t tc_smem_bytes(int kp, int stages) {
   return 1024 + (size_t)(QT + stages) * TILE_BYTES +
          (size_t)(2 * kp + 2 * (PEND + 1)) * EPI_WARPS * 32 * 4 +
@@ -1756,9 +1813,13 @@ struct TcCandidates {
   GroupedRefs groups;
 };
 
-bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k) {
+bool knn_tc_grouped(int64_t nr, int scan_mode);
+
+bool knn_tc_applicable(int64_t nr, int64_t nq, int d, int k, int scan_mode) {
   if (d > MAX_D || d < 1) return false;
-  if (pick_kp(k, 0) > MAX_KP) return false;
+  const int kp = pick_kp(k, 0);
+  // one list per row covers k <= 32; beyond that the grouped search runs per column split
+  if (kp > MAX_KP && !(knn_tc_grouped(nr, scan_mode) && plan_kp(kp).splits > 0)) return false;
   if (nr < 2048 || nq < 1) return false;          // tiny problems: the exact scan is faster
   if (nr >= 0x7fffffffLL - BN || nq >= 0x7fffffffLL - QT * BM) return false;
   return true;
@@ -1840,7 +1901,7 @@ bool knn_tc_grouped(int64_t nr, int scan_mode) { return scan_mode == 2 || (scan_
 struct TcRefCache {
   bool valid = false;
   int64_t nr = 0;
-  int d = 0, G = 0;
+  int d = 0, G = 0, splits = 1;
   void *blob = nullptr;
   size_t bytes = 0;
 };
@@ -1862,7 +1923,7 @@ __global__ void k_misc_reset(TcMisc *misc) {
 }
 
 static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double *d_qry,
-                             int64_t nq, int d, int kp, int mode, TcCandidates *out,
+                             int64_t nq, int d, KpPlan kpl, int mode, TcCandidates *out,
                              float *d_dbg_keys, b200nn_stats *stats, int shard_rank = 0, int shard_world = 0,
                              TcRefCache *cache = nullptr) {
   cudaStream_t st = ctx->stream;
@@ -1870,7 +1931,8 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
   const bool grouped = d_dbg_keys == nullptr && knn_tc_grouped(nr, mode);
   const bool sharded = shard_world > 1;
   if (!grouped || sharded) cache = nullptr;  // only the grouped search has reference-side state worth keeping
-  const bool cached = cache && cache->valid && cache->nr == nr && cache->d == d;
+  // (the layout of the prepared reference side depends on the number of column splits)
+  const bool cached = cache && cache->valid && cache->nr == nr && cache->d == d && cache->splits == kpl.splits;
   // with restored reference-side state the queries are prepared on their own, also for a self search
   const bool self = (d_qry == d_ref) && (nq == nr) && !cached;
   if (sharded && !(grouped && self && shard_world <= 64 && shard_rank >= 0 && shard_rank < shard_world)) {
@@ -1889,8 +1951,14 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
   RC_TRY(ws_get(ctx, WS_TC_QRY16, (size_t)nq * BK, &q16));
   RC_TRY(ws_get(ctx, WS_TC_QRYERR, (size_t)nq * 2, &q_n2));
   q_err = q_n2 + nq;
+  const int kp = kpl.total;
+  if (kpl.splits < 1 || kpl.splits > MAX_SPLITS || kpl.per > MAX_KP || kpl.total != kpl.splits * kpl.per ||
+      (kpl.splits > 1 && !grouped)) {
+    b200nn_set_error("candidate lists of %d entries need %d column splits of the grouped search", kp, kpl.splits);
+    return B200NN_ERR_INVALID;
+  }
   RC_TRY(ws_get(ctx, WS_TC_CAND, (size_t)nq * kp, &cand));
-  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq, &tau));
+  RC_TRY(ws_get(ctx, WS_TC_CANDKEY, (size_t)nq * kpl.splits, &tau));
 
   cudaEvent_t e0 = ctx->ev[8], e1 = ctx->ev[9], e2 = ctx->ev[10];
   CU_TRY(cudaEventRecord(e0, st));
@@ -1925,9 +1993,10 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
   P.nr = nr;
   P.n_items = (int32_t)ceil_div64(nq, QT * BM);
   P.ksteps = (d + 3 + 15) / 16;
-  P.kp = kp;
-  P.stages = pick_stages(kp);
+  P.kp = kpl.per;
+  P.stages = pick_stages(kpl.per);
   P.cand = cand;
+  P.cand_stride = kp;
   P.tau = tau;
   P.dbg_keys = d_dbg_keys;
   P.misc = misc;
@@ -1961,7 +2030,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
   } else {
     // ---- grouped search ------------------------------------------------------------
     const int G = pick_groups(nr);
-    const int64_t nr_pad = ((nr + BN - 1) / BN + G) * BN;  // upper bound of the padded length
+    const int64_t nr_pad = ((nr + BN - 1) / BN + (int64_t)G * kpl.splits) * BN;  // upper bound of the padded length
     const int64_t n_tiles_max = nr_pad / BN;
     const int64_t nq_pad = ((nq + QT * BM - 1) / (QT * BM) + G) * (QT * BM);
     const int64_t list_stride = (n_tiles_max + 3) & ~(int64_t)3;
@@ -2075,6 +2144,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       A.kp = 8;
       A.stages = pick_stages(8);
       A.cand = cand;
+      A.cand_stride = 8;
       A.tau = tau;
       A.misc = misc;
       A.argmin_out = gid_out;
@@ -2128,7 +2198,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     } else {
       RC_TRY(assign_tc(yq16, nq, 1, gid_q, qcount));
     }
-    k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor);
+    k_group_offsets<<<1, 32, 0, st>>>(rcount, qcount, G, goff, qoff, rcursor, qcursor, kpl.splits);
     KERNEL_CHECK(ctx);
     if (cached)  // rperm was restored
       CU_TRY(cudaMemsetAsync(qperm, 0xff, sizeof(int32_t) * (size_t)nq_pad, st));
@@ -2147,7 +2217,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       k_row_anorm<<<(unsigned)ceil_div64(nq, 128), 128, 0, st>>>(yq16, gid_q, nq, d, G, cent, anorm_q, nullptr);
       KERNEL_CHECK(ctx);
     }
-    if (no_hub) {
+    if (no_hub && kpl.splits == 1) {
       if (!cached) {
         k_group_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, nr, G, goff, rcursor, rperm);
         KERNEL_CHECK(ctx);
@@ -2176,7 +2246,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
       }
       if (!cached) {
         k_fine_scatter<<<(unsigned)ceil_div64(nr, 256), 256, 0, st>>>(gid_r, anorm_r, nr, gstat, foff_r, fcur_r, rperm,
-                                                                       nullptr, 0);
+                                                                       nullptr, 0, goff, kpl.splits);
         KERNEL_CHECK(ctx);
       }
       k_fine_scatter<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(gid_q, anorm_q, nq, gstat, foff_q, fcur_q, qperm,
@@ -2215,14 +2285,21 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     P.rperm = rperm;
     P.qperm = qperm;
     P.item_T = item_T;
+    // one round per column split (a single round for k' <= MAX_KP): pass 1, lists, pass 2
+    for (int sp = 0; sp < kpl.splits; ++sp) {
+    if (sp > 0) CU_TRY(cudaMemsetAsync(item_T, 0, sizeof(float) * nI, st));
+    P.cand = cand + (size_t)sp * kpl.per;
+    P.tau = tau + (size_t)sp * nq;
+    P.tau_init = nullptr;
+    P.order = nullptr;
     k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, tile_lo, tile_hi,
-                                                      1, P.list_stride, tiles, list_cnt);
+                                                      1, P.list_stride, tiles, list_cnt, kpl.splits, sp);
     KERNEL_CHECK(ctx);
     P.pass1 = 1;
     RC_TRY(debug_list_stats(ctx, "pass 1", list_cnt, P.n_items));
     RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
     k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, tile_lo, tile_hi,
-                                                      0, P.list_stride, tiles, list_cnt);
+                                                      0, P.list_stride, tiles, list_cnt, kpl.splits, sp);
     KERNEL_CHECK(ctx);
     out->visit = qperm;
     out->n_visit = nq_pad;
@@ -2238,14 +2315,19 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     out->groups.e_max = &misc->e_max;
     out->have_groups = true;
     P.pass1 = 0;
-    P.tau_init = tau;  // written by pass 1, read at the start of every pass-2 row
-    k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc);
+    P.tau_init = P.tau;  // written by pass 1, read at the start of every pass-2 row
+    k_order_items<<<1, 1024, 0, st>>>(list_cnt, P.n_items, (int)n_tiles_max, bins, order, misc, sp > 0);
     KERNEL_CHECK(ctx);
     P.order = order;
     RC_TRY(debug_list_stats(ctx, "pass 2", list_cnt, P.n_items, item_T, item_rad));
-    CU_TRY(cudaEventRecord(ctx->ev[14], st));
+    if (sp == 0) CU_TRY(cudaEventRecord(ctx->ev[14], st));  // several splits: from the first pass 2 to the last
     RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
-    CU_TRY(cudaEventRecord(ctx->ev[15], st));
+    if (sp + 1 == kpl.splits) CU_TRY(cudaEventRecord(ctx->ev[15], st));
+    }  // column splits
+    if (kpl.splits > 1) {
+      k_tau_min<<<(unsigned)ceil_div64(nq, 256), 256, 0, st>>>(tau, nq, kpl.splits);
+      KERNEL_CHECK(ctx);
+    }
     timed_pass2 = true;
     if (cache && !cached) {
       // first call on a resident index: keep the reference-side state (stream-ordered copies)
@@ -2271,6 +2353,7 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
         cache->nr = nr;
         cache->d = d;
         cache->G = G;
+        cache->splits = kpl.splits;
         cache->valid = true;
       }
     }
@@ -2302,14 +2385,17 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
                   int d, int k, int n_cand, int scan_mode, int32_t *d_idx0, double *d_dist,
                   b200nn_stats *stats, int shard_rank, int shard_world, TcRefCache *cache) {
   cudaStream_t st = ctx->stream;
-  int kp = pick_kp(k, n_cand);
-  if (kp > MAX_KP) kp = MAX_KP;
-  if (kp <= k) {
-    b200nn_set_error("k = %d leaves no room for a widened candidate set (max %d)", k, MAX_KP);
+  int want = pick_kp(k, n_cand);
+  if (!knn_tc_grouped(nr, scan_mode) && want > MAX_KP) want = MAX_KP;  // one list per row is all there is
+  KpPlan kpl = plan_kp(want);
+  if (kpl.splits == 0) kpl = plan_kp(pick_kp(k, 0));  // an oversized n_cand: the default width
+  const int kp = kpl.total;
+  if (kpl.splits == 0 || kp <= k) {
+    b200nn_set_error("k = %d leaves no room for a widened candidate set", k);
     return B200NN_ERR_INVALID;
   }
   TcCandidates C;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kp, scan_mode, &C, nullptr, stats, shard_rank,
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry, nq, d, kpl, scan_mode, &C, nullptr, stats, shard_rank,
                            shard_world, cache));
   if (shard_world > 1) {  // the rows this share wrote (the group-sorted query order, -1 = padding)
     ctx->owned_rows = C.visit;
@@ -2327,7 +2413,7 @@ int knn_tc_launch(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double
 
   cudaEvent_t e0 = ctx->ev[11], e1 = ctx->ev[12], e2 = ctx->ev[13];
   CU_TRY(cudaEventRecord(e0, st));
-  const size_t smem = rr_per_warp(d) * RR_WARPS;
+  const size_t smem = rr_per_warp(d, kp) * RR_WARPS;
   const int64_t n_visit = C.visit ? C.n_visit : nq;
   const bool vec = (d % 2 == 0) && (reinterpret_cast<uintptr_t>(d_ref) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(d_qry) % 16 == 0);
@@ -2378,7 +2464,8 @@ int knn_tc_debug(b200nn_ctx *ctx, const double *d_ref, int64_t nr, const double 
                  int d, int kp, int scan_mode, float *d_keys_out, int32_t *d_cand_out, float *d_tau_out,
                  double *h_scale_mu /* [1 + 64] */) {
   TcCandidates C;
-  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, kp, d_keys_out ? 1 : scan_mode, &C,
+  const KpPlan one = {1, kp, kp};
+  RC_TRY(knn_tc_candidates(ctx, d_ref, nr, d_qry ? d_qry : d_ref, nq, d, one, d_keys_out ? 1 : scan_mode, &C,
                            d_keys_out, nullptr));
   int32_t *cand = C.cand;
   float *tau = C.tau;

@@ -128,7 +128,8 @@ def test_resident_index_keeps_prepared_reference(ctx):
     Q2[5] *= 40.0                                   # far outside the reference's range: still exact
     ix = ctx.index(R, _lib.ROW_MAJOR)
     stats = []
-    for q, k in ((Q1, 20), (Q2, 20), (Q1, 7), (None, 20), (Q2, 31)):
+    # k = 50 needs three column splits: the prepared layout changes, the index re-prepares once and again for k = 31
+    for q, k in ((Q1, 20), (Q2, 20), (Q1, 7), (None, 20), (Q2, 50), (Q2[:3000], 50), (Q2, 31)):
         gi, gd, st = ix.knn(q, k)
         stats.append(st)
         wi, wd, _ = ctx.knn(R, q, k, _lib.ROW_MAJOR)      # a fresh call (also disturbs the shared workspace)

@@ -170,3 +170,67 @@ def test_many_uncertified_rows_take_the_exact_fallback(ctx, mode):
     idx, dist, st = ctx.knn(X, Q, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR, k + 2, mode)
     assert (idx == wi).all() and (dist == wd).all()
     print("mode", mode, "uncertified of 300:", st["n_uncertified"])
+
+
+# ---------------------------------------------------------------- k > 32: column splits
+@pytest.mark.parametrize("n,d,k", [(33000, 50, 33), (60000, 30, 50), (40000, 50, 64), (50000, 20, 100),
+                                   (45000, 10, 200), (36000, 40, 256)])
+def test_large_k_runs_per_column_split(ctx, n, d, k):
+    """k > 32 (k' > 48) no longer fits one shared-memory list per row: the grouped search runs once per
+    column split of the reference set and the re-rank sees the union of the splits' candidates.
+    FindNeighbors takes any k.param (R/clustering.R:586); WNN asks for knn.range = 200 (R/clustering.R:55)"""
+    X, _ = gaussian_mixture(n, d, seed=k, n_centres=12)
+    rows = np.sort(np.random.default_rng(k).choice(n, 2500, replace=False))
+    wi, wd = oracle.knn(X, X[rows], k, method="kdtree")
+    idx, dist, st = ctx.knn(X, None, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert st["ms_knn_cand"] > 0
+    assert (dist[rows] == wd).all()
+    assert (idx[rows] == wi).all()
+    print(f"n={n} d={d} k={k}: uncertified rows {st['n_uncertified']} / {n}, tiles visited "
+          f"{st['knn_tiles_visited']} of {st['knn_tiles_total']}")
+    assert st["n_uncertified"] < 0.05 * n, "the certificate should pass for almost every row"
+    # every row is a valid neighbour list: self first (distance 0), ascending distances, no repeats
+    assert (dist[:, 0] == 0).all() and (np.diff(dist, axis=1) >= 0).all()
+    srt = np.sort(idx, axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all() and srt.min() >= 1 and srt.max() <= n
+
+
+def test_large_k_query_path_shares_and_small_sets(ctx):
+    ref, c = gaussian_mixture(48000, 30, seed=31, n_centres=8)
+    qry, _ = gaussian_mixture(5000, 30, seed=32, centres=c)
+    k = 50
+    wi, wd = oracle.knn(ref, qry, k, method="kdtree")
+    idx, dist, st = ctx.knn(ref, qry, k, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    assert st["ms_knn_cand"] > 0 and (idx == wi).all() and (dist == wd).all()
+    # group-aligned shares of a self search (the multi-GPU path) with two column splits
+    n = len(ref)
+    rows = np.sort(np.random.default_rng(3).choice(n, 2000, replace=False))
+    wi, wd = oracle.knn(ref, ref[rows], 40, method="kdtree")
+    r = torch.from_numpy(ref).cuda()
+    tot = torch.zeros((n, 40), dtype=torch.int32, device="cuda")
+    for rank in range(3):
+        i0 = torch.zeros((n, 40), dtype=torch.int32, device="cuda")
+        dd = torch.full((n, 40), float("nan"), dtype=torch.float64, device="cuda")
+        ctx.dev_knn(r, n, None, n, 30, 40, i0, dd, shard_rank=rank, shard_world=3)
+        tot += i0
+    assert (tot.cpu().numpy()[rows] + 1 == wi).all()
+    # below the grouped regime one list per row is all there is: the tensor path refuses, auto takes the FP64 scan
+    X = ref[:6000]
+    with pytest.raises(sb.B200Error):
+        ctx.knn(X, None, 50, _lib.ROW_MAJOR, _lib.KNN_TENSOR)
+    idx, dist, st = ctx.knn(X, None, 50, _lib.ROW_MAJOR, _lib.KNN_AUTO)
+    assert st["ms_knn_cand"] == 0
+    wi, wd = oracle.knn(X, k=50, method="kdtree")
+    assert (idx == wi).all() and (dist == wd).all()
+
+
+def test_find_neighbors_k50_graphs(ctx):
+    """the whole path at k.param = 50: kNN through two column splits, nn Graph, SNN (s_min = 7)"""
+    X, _ = gaussian_mixture(40000, 30, seed=77, n_centres=10)
+    got = ctx.find_neighbors(X, 50, 1 / 15, True, _lib.ROW_MAJOR)
+    assert got["stats"]["ms_knn_cand"] > 0
+    want = oracle.find_neighbors(X, k=50, prune=1 / 15, method="kdtree")
+    assert (got["idx"] == want["nn_idx"]).all() and (got["dist"] == want["nn_dist"]).all()
+    for name in ("nn", "snn"):
+        for a, b in zip(got[name], want[name]):
+            assert a.shape == b.shape and (np.asarray(a) == np.asarray(b)).all(), name
