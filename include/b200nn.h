@@ -316,6 +316,25 @@ B200NN_API int b200nn_modularity_cluster(b200nn_ctx *ctx, int64_t n, const int32
                                          const double *x, int32_t modularity_function, double resolution,
                                          int32_t algorithm, int32_t n_random_starts, int32_t n_iterations,
                                          uint64_t random_seed, int32_t *cluster_out, b200nn_modopt_stats *stats);
+/* The same on an edge list in host memory: edge e joins the 0-based nodes node1[e] and node2[e] with
+ * weight[e] (NULL: 1).  As in the reference (matrixToNetwork, ModularityOptimizer.cpp:759-803) only
+ * edges with node1 < node2 count, and every node's neighbours keep the order of the list. */
+B200NN_API int b200nn_modularity_cluster_edges(b200nn_ctx *ctx, int64_t n_nodes, const int32_t *node1,
+                                               const int32_t *node2, const double *weight, int64_t n_edges,
+                                               int32_t modularity_function, double resolution, int32_t algorithm,
+                                               int32_t n_random_starts, int32_t n_iterations, uint64_t random_seed,
+                                               int32_t *cluster_out, b200nn_modopt_stats *stats);
+/* The edge.file.name input of RunModularityClusteringCpp (RModularityOptimizer.cpp:55-63; file format of
+ * readInputFile, ModularityOptimizer.cpp:806-838 = what b200nn_write_edge_file writes): lines
+ * "node1<TAB>node2[<TAB>weight]", the number of nodes is the largest id + 1 (*n_nodes_out).  Call with
+ * cluster_out = NULL to learn n_nodes, then with cluster_capacity >= n_nodes.  A file that cannot be opened
+ * or parsed gives B200NN_ERR_INVALID with the wrapper's "Could not parse edge file.". */
+B200NN_API int b200nn_modularity_cluster_edge_file(b200nn_ctx *ctx, const char *filename,
+                                                   int32_t modularity_function, double resolution,
+                                                   int32_t algorithm, int32_t n_random_starts,
+                                                   int32_t n_iterations, uint64_t random_seed,
+                                                   int32_t *cluster_out, int64_t cluster_capacity,
+                                                   int64_t *n_nodes_out, b200nn_modopt_stats *stats);
 /* The same on the SNN graph the context still holds in HBM after b200nn_find_neighbors_count /
  * b200nn_dev_graphs (all rows): no D2H + H2D of the graph between FindNeighbors and FindClusters.
  * n_expected > 0 is checked against the resident graph's size. */

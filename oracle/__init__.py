@@ -228,6 +228,28 @@ def modularity_cluster_ref(p, i, x, modularity_function=1, resolution=0.8, algor
     return out, rc, q.value
 
 
+def modularity_cluster_file_ref(filename, modularity_function=1, resolution=0.8, algorithm=1, n_random_starts=10,
+                                n_iterations=10, random_seed=0, capacity=1 << 22):
+    """RunModularityClusteringCpp(edgefilename = filename) of the reference itself (its own readInputFile).
+    Returns (cluster ids int32 [n_nodes], n_clusters, modularity)."""
+    modularity_cluster_ref(np.array([0, 1, 2]), np.array([1, 0]), np.array([1.0, 1.0]), n_random_starts=1,
+                           n_iterations=1)                    # loads the library
+    L = _ref_lib
+    L.ref_modularity_cluster_file.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_modularity_cluster_file.restype = C.c_int
+    out = np.zeros(capacity, dtype=np.int32)
+    n = C.c_int(0)
+    q = C.c_double(0.0)
+    rc = L.ref_modularity_cluster_file(str(filename).encode(), int(modularity_function), float(resolution),
+                                       int(algorithm), int(n_random_starts), int(n_iterations), int(random_seed),
+                                       _p(out), capacity, C.addressof(n), C.addressof(q))
+    if rc < 0:
+        raise ValueError({-1: "invalid argument", -3: "Clustering step failed.", -4: "C++ exception",
+                          -5: "Could not parse edge file."}.get(rc, str(rc)))
+    return out[:n.value].copy(), rc, q.value
+
+
 # ----------------------------------------------------------------------------------------------
 # SNN side consumers (src/snn.cpp:40-126, src/fast_NN_dist.cpp)
 # ----------------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ SYMBOLS = [
     "b200nn_multi_create", "b200nn_multi_destroy", "b200nn_multi_size", "b200nn_multi_knn",
     "b200nn_multi_find_neighbors_count", "b200nn_multi_find_neighbors_fill",
     "b200nn_modularity_cluster", "b200nn_modularity_cluster_resident",
+    "b200nn_modularity_cluster_edges", "b200nn_modularity_cluster_edge_file",
     "b200nn_write_edge_file", "b200nn_fast_dist", "b200nn_snn_smallest_nonzero_dist",
 ]
 
@@ -135,6 +136,10 @@ def load() -> C.CDLL:
                                                 C.POINTER(ModoptStats)]
         L.b200nn_modularity_cluster_resident.argtypes = [vp, i32, dbl, i32, i32, i32, C.c_uint64, vp, i64,
                                                          C.POINTER(ModoptStats)]
+        L.b200nn_modularity_cluster_edges.argtypes = [vp, i64, vp, vp, vp, i64, i32, dbl, i32, i32, i32, C.c_uint64, vp,
+                                                      C.POINTER(ModoptStats)]
+        L.b200nn_modularity_cluster_edge_file.argtypes = [vp, C.c_char_p, i32, dbl, i32, i32, i32, C.c_uint64, vp, i64,
+                                                          C.POINTER(i64), C.POINTER(ModoptStats)]
         L.b200nn_write_edge_file.argtypes = [vp, vp, vp, i64, C.c_char_p, C.POINTER(i64)]
         L.b200nn_fast_dist.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]
         L.b200nn_snn_smallest_nonzero_dist.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp]
@@ -231,6 +236,36 @@ class Context:
                                                          int(algorithm), int(n_random_starts), int(n_iterations),
                                                          int(random_seed) & (2 ** 64 - 1), _ptr(out), n,
                                                          C.byref(st)))
+        return out, st.as_dict()
+
+    def modularity_cluster_edges(self, node1, node2, weight, n_nodes: int, modularity_function: int = 1,
+                                 resolution: float = 0.8, algorithm: int = 1, n_random_starts: int = 10,
+                                 n_iterations: int = 10, random_seed: int = 0):
+        """edge list (0-based node ids, weight may be None = 1) -> (cluster ids int32 [n_nodes], stats)"""
+        node1 = np.ascontiguousarray(node1, dtype=np.int32)
+        node2 = np.ascontiguousarray(node2, dtype=np.int32)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        out = np.empty(max(int(n_nodes), 0), dtype=np.int32)
+        st = ModoptStats()
+        check(self._L.b200nn_modularity_cluster_edges(self._h, int(n_nodes), _ptr(node1), _ptr(node2), _ptr(w),
+                                                      node1.size, int(modularity_function), float(resolution),
+                                                      int(algorithm), int(n_random_starts), int(n_iterations),
+                                                      int(random_seed) & (2 ** 64 - 1), _ptr(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def modularity_cluster_edge_file(self, filename: str, modularity_function: int = 1, resolution: float = 0.8,
+                                     algorithm: int = 1, n_random_starts: int = 10, n_iterations: int = 10,
+                                     random_seed: int = 0):
+        """the edge.file.name input of RunModularityClusteringCpp: "node1<TAB>node2[<TAB>weight]" lines"""
+        n = C.c_int64(0)
+        args = (int(modularity_function), float(resolution), int(algorithm), int(n_random_starts), int(n_iterations),
+                int(random_seed) & (2 ** 64 - 1))
+        fn = str(filename).encode()
+        check(self._L.b200nn_modularity_cluster_edge_file(self._h, fn, *args, None, 0, C.byref(n), None))
+        out = np.empty(n.value, dtype=np.int32)
+        st = ModoptStats()
+        check(self._L.b200nn_modularity_cluster_edge_file(self._h, fn, *args, _ptr(out), n.value, C.byref(n),
+                                                          C.byref(st)))
         return out, st.as_dict()
 
     # ---- SNN side consumers (src/snn.cpp:40-126, src/fast_NN_dist.cpp) ---------------

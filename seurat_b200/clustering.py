@@ -39,11 +39,22 @@ def RunModularityClustering(SNN, modularity: int = 1, resolution: float = 0.8, a
     """``RunModularityClustering`` (R/clustering.R:1881-1906): cluster ids (0-based, largest cluster
     first) of every column of the SNN graph.  ``resident=True`` clusters the SNN graph the context
     still holds in HBM from the preceding FindNeighbors call instead of uploading ``SNN`` again."""
-    if edge_file_name:
-        raise NotImplementedError("edge.file.name: reading the graph from an edge file stays with the reference")
     ctx = ctx or _lib.default_context()
-    p, i, x, n, _ = _slots(SNN)
-    if resident:
+    if edge_file_name:
+        # edge_file <- edge.file.name %||% '' (R/clustering.R:1893): a non-empty name replaces the matrix
+        # (RModularityOptimizer.cpp:55-63); the number of nodes is then the largest id in the file + 1
+        first = ctx._first() if hasattr(ctx, "_first") else ctx
+        ids, st = first.modularity_cluster_edge_file(edge_file_name, modularity, resolution, algorithm, n_start,
+                                                     n_iter, random_seed)
+        if print_output:
+            _message("Reading input file...\n")
+        p = i = x = None
+        n = ids.size
+    else:
+        p, i, x, n, _ = _slots(SNN)
+    if edge_file_name:
+        pass
+    elif resident:
         ids, st = ctx.modularity_cluster_resident(n, modularity, resolution, algorithm, n_start, n_iter, random_seed)
     else:
         ids, st = ctx.modularity_cluster(p, i, x, modularity, resolution, algorithm, n_start, n_iter, random_seed)

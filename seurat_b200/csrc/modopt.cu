@@ -10,6 +10,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <errno.h>
+#include <stdio.h>
+#include <string.h>
 #include <time.h>
 
 #include <string>
@@ -373,6 +376,89 @@ int cluster_device_csc(b200nn_ctx *ctx, int64_t n, const PT *d_p, const int32_t 
   return B200NN_OK;
 }
 
+// the same on an edge list in device memory (the edge.file.name input)
+int cluster_device_edges(b200nn_ctx *ctx, int64_t n, const int32_t *d_n1, const int32_t *d_n2, const double *d_w,
+                         int64_t m, int modularity_function, double resolution, int algorithm, int n_random_starts,
+                         int n_iterations, uint64_t seed, int32_t *cluster_out, b200nn_modopt_stats *stats) {
+  CudaBackend be(ctx);
+  const int64_t l0 = ctx->launches;
+  const double t0 = be.now_ms();
+  modopt::Net net;
+  modopt::Stats st;
+  const int64_t E = modopt::build_network_edges(be, (int32_t)n, d_n1, d_n2, d_w, m, modularity_function, net);
+  st.ms_build = be.now_ms() - t0;
+  if (be.rc != B200NN_OK) return be.rc;
+  if (E == 0) {
+    b200nn_set_error("Matrix contained no network data.  Check format.");
+    return B200NN_ERR_INVALID;
+  }
+  double q = 0;
+  const int32_t k = modopt::run_clustering(be, net, algorithm, resolution, modularity_function, n_random_starts,
+                                           n_iterations, seed, cluster_out, &q, &st);
+  modopt::free_net(be, net);
+  be.free(be.d_scalar);
+  be.report();
+  const double t1 = be.now_ms();
+  if (be.rc != B200NN_OK) return be.rc;
+  if (k < 0) {
+    b200nn_set_error("Clustering step failed.");
+    return B200NN_ERR_STATE;
+  }
+  fill_stats(st, n, E, k, q, t1 - t0, ctx->launches - l0, stats);
+  return B200NN_OK;
+}
+
+// readInputFile (/root/reference/src/ModularityOptimizer.cpp:806-838): one edge per line,
+// "node1<TAB>node2[<TAB>weight]" (weight 1 when absent), node ids 0-based; the number of nodes is the
+// largest id + 1.  std::stoi / std::stod semantics: leading white space skipped, trailing text ignored,
+// no digits -> failure (the wrapper turns every failure into "Could not parse edge file.").
+bool parse_edge_file(const char *fname, std::vector<int32_t> &n1, std::vector<int32_t> &n2, std::vector<double> &w) {
+  FILE *f = fopen(fname, "r");
+  if (!f) return false;
+  std::string line;
+  char buf[4096];
+  bool ok = true;
+  auto take_line = [&]() -> bool {  // std::getline: a last line without '\n' counts, an empty tail does not
+    line.clear();
+    bool any = false;
+    while (fgets(buf, sizeof(buf), f)) {
+      any = true;
+      const size_t len = strlen(buf);
+      if (len && buf[len - 1] == '\n') {
+        line.append(buf, len - 1);
+        return true;
+      }
+      line.append(buf, len);
+    }
+    return any;
+  };
+  while (ok && take_line()) {
+    const char *p = line.c_str();
+    const char *t1 = strchr(p, '\t');
+    if (!t1) {  // splittedLine[1] does not exist: the reference reads out of bounds; refuse
+      ok = false;
+      break;
+    }
+    const char *t2 = strchr(t1 + 1, '\t');
+    char *end = nullptr;
+    errno = 0;
+    const long a = strtol(p, &end, 10);
+    if (end == p || end > t1 || errno == ERANGE || a < 0 || a > 0x7ffffffeL) ok = false;
+    const long b = strtol(t1 + 1, &end, 10);
+    if (end == t1 + 1 || (t2 && end > t2) || errno == ERANGE || b < 0 || b > 0x7ffffffeL) ok = false;
+    double wt = 1.0;
+    if (t2 && t2[1] != '\0') {  // split() drops an empty last token
+      wt = strtod(t2 + 1, &end);
+      if (end == t2 + 1) ok = false;
+    }
+    n1.push_back((int32_t)a);
+    n2.push_back((int32_t)b);
+    w.push_back(wt);
+  }
+  fclose(f);
+  return ok;
+}
+
 }  // namespace
 
 extern "C" {
@@ -413,6 +499,92 @@ int b200nn_modularity_cluster(b200nn_ctx *ctx, int64_t n, const int32_t *p, cons
   cudaFreeAsync(d_x, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   return rc;
+}
+
+int b200nn_modularity_cluster_edges(b200nn_ctx *ctx, int64_t n_nodes, const int32_t *node1, const int32_t *node2,
+                                    const double *weight, int64_t n_edges, int32_t modularity_function,
+                                    double resolution, int32_t algorithm, int32_t n_random_starts,
+                                    int32_t n_iterations, uint64_t random_seed, int32_t *cluster_out,
+                                    b200nn_modopt_stats *stats) {
+  if (!ctx) {
+    b200nn_set_error("NULL context");
+    return B200NN_ERR_INVALID;
+  }
+  if (!node1 || !node2 || !cluster_out || n_nodes <= 0 || n_nodes >= 0x7fffffffLL || n_edges < 0 ||
+      n_edges >= 0xffffffffLL) {
+    b200nn_set_error("modularity_cluster_edges: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  RC_TRY(check_args(modularity_function, resolution, algorithm, n_random_starts, n_iterations));
+  for (int64_t e = 0; e < n_edges; ++e)
+    if (node1[e] < 0 || node2[e] < 0 || node1[e] >= n_nodes || node2[e] >= n_nodes) {
+      b200nn_set_error("modularity_cluster_edges: edge %lld names a node outside [0, %lld)", (long long)e,
+                       (long long)n_nodes);
+      return B200NN_ERR_INVALID;
+    }
+  if (n_edges == 0) {
+    b200nn_set_error("Matrix contained no network data.  Check format.");
+    return B200NN_ERR_INVALID;
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  int32_t *d_1 = nullptr, *d_2 = nullptr;
+  double *d_w = nullptr;
+  CU_TRY(cudaMallocAsync(&d_1, sizeof(int32_t) * (size_t)n_edges, ctx->stream));
+  CU_TRY(cudaMallocAsync(&d_2, sizeof(int32_t) * (size_t)n_edges, ctx->stream));
+  CU_TRY(cudaMallocAsync(&d_w, sizeof(double) * (size_t)n_edges, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_1, node1, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d_2, node2, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+  if (weight) {
+    CU_TRY(cudaMemcpyAsync(d_w, weight, sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+  } else {  // unweighted list: every edge weighs 1 (readInputFile's default)
+    std::vector<double> ones((size_t)n_edges, 1.0);
+    CU_TRY(cudaMemcpyAsync(d_w, ones.data(), sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  int rc = cluster_device_edges(ctx, n_nodes, d_1, d_2, d_w, n_edges, modularity_function, resolution, algorithm,
+                                n_random_starts, n_iterations, random_seed, cluster_out, stats);
+  cudaFreeAsync(d_1, ctx->stream);
+  cudaFreeAsync(d_2, ctx->stream);
+  cudaFreeAsync(d_w, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+int b200nn_modularity_cluster_edge_file(b200nn_ctx *ctx, const char *filename, int32_t modularity_function,
+                                        double resolution, int32_t algorithm, int32_t n_random_starts,
+                                        int32_t n_iterations, uint64_t random_seed, int32_t *cluster_out,
+                                        int64_t cluster_capacity, int64_t *n_nodes_out, b200nn_modopt_stats *stats) {
+  if (!ctx) {
+    b200nn_set_error("NULL context");
+    return B200NN_ERR_INVALID;
+  }
+  if (!filename || !n_nodes_out) {
+    b200nn_set_error("modularity_cluster_edge_file: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  *n_nodes_out = 0;
+  RC_TRY(check_args(modularity_function, resolution, algorithm, n_random_starts, n_iterations));
+  std::vector<int32_t> n1, n2;
+  std::vector<double> w;
+  if (!parse_edge_file(filename, n1, n2, w) || n1.empty()) {
+    b200nn_set_error("Could not parse edge file.");
+    return B200NN_ERR_INVALID;
+  }
+  int32_t mx = 0;
+  for (size_t e = 0; e < n1.size(); ++e) mx = std::max(mx, std::max(n1[e], n2[e]));
+  const int64_t n = (int64_t)mx + 1;
+  *n_nodes_out = n;
+  if (!cluster_out || cluster_capacity < n) {  // size query: the caller allocates n ids and calls again
+    if (cluster_out) {
+      b200nn_set_error("modularity_cluster_edge_file: the file names %lld nodes, cluster_out holds %lld",
+                       (long long)n, (long long)cluster_capacity);
+      return B200NN_ERR_INVALID;
+    }
+    return B200NN_OK;
+  }
+  return b200nn_modularity_cluster_edges(ctx, n, n1.data(), n2.data(), w.data(), (int64_t)n1.size(),
+                                         modularity_function, resolution, algorithm, n_random_starts, n_iterations,
+                                         random_seed, cluster_out, stats);
 }
 
 int b200nn_modularity_cluster_resident(b200nn_ctx *ctx, int32_t modularity_function, double resolution,

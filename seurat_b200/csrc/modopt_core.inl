@@ -878,6 +878,70 @@ i64 build_network(B &be, i32 n, const PT *p, const i32 *ri, const double *x, int
   return E;
 }
 
+// The network of an arbitrary edge list (the edge.file.name input of RunModularityClusteringCpp,
+// RModularityOptimizer.cpp:55-63: readInputFile, ModularityOptimizer.cpp:806-838, then the same
+// matrixToNetwork :759-803).  Only edges with node1 < node2 count (:765, :784); the adjacency of v lists
+// its edges in the order of the list, whichever end v is.  Returns the number of edges kept.
+template <class B>
+i64 build_network_edges(B &be, i32 n, const i32 *node1, const i32 *node2, const double *w, i64 M,
+                        int modularityFunction, Net &out) {
+  if (M <= 0) return 0;
+  i64 *cnt = be.template alloc<i64>(M + 1), *off = be.template alloc<i64>(M + 1);
+  be.pfor(M, [=] MO_HD(i64 e) { cnt[e] = node1[e] < node2[e] ? 1 : 0; });
+  be.excl_scan(cnt, off, M);
+  i64 E = 0;
+  be.d2h(&E, off + M, sizeof(i64));
+  if (E == 0) {
+    be.free(cnt); be.free(off);
+    return 0;
+  }
+  u64 *k1 = be.template alloc<u64>(2 * E), *k2 = be.template alloc<u64>(2 * E);
+  be.pfor(M, [=] MO_HD(i64 e) {
+    if (!(node1[e] < node2[e])) return;
+    const i64 o = off[e];  // rank among the kept edges (o < 2^32)
+    k1[2 * o] = ((u64)(u32)node1[e] << 33) | ((u64)o << 1) | 1ull;   // v = node1: neighbour node2
+    k1[2 * o + 1] = ((u64)(u32)node2[e] << 33) | ((u64)o << 1);      // v = node2: neighbour node1
+  });
+  // kept rank -> position in the list
+  i64 *src = be.template alloc<i64>(E);
+  be.pfor(M, [=] MO_HD(i64 e) { if (node1[e] < node2[e]) src[off[e]] = e; });
+  be.sort_keys(k1, k2, 2 * E, 64);
+  out = Net();
+  out.n = n;
+  out.m2 = 2 * E;
+  out.owned = true;
+  out.first = be.template alloc<i64>((i64)n + 1);
+  out.nbr = be.template alloc<i32>(2 * E);
+  out.ew = be.template alloc<double>(2 * E);
+  out.nw = be.template alloc<double>(n);
+  first_from_sorted(be, k2, 2 * E, 33, out.first, n);
+  {
+    i32 *nbr = out.nbr;
+    double *ew = out.ew;
+    be.pfor(2 * E, [=] MO_HD(i64 s) {
+      const u64 k = k2[s];
+      const i64 e = src[(i64)((k >> 1) & 0xffffffffull)];
+      nbr[s] = (k & 1ull) ? node2[e] : node1[e];
+      ew[s] = w[e];
+    });
+  }
+  {
+    const Net c = out;
+    double *nw = out.nw;
+    if (modularityFunction == 1)
+      be.pfor(n, [=] MO_HD(i64 v) {
+        double acc = 0.0;
+        for (i64 e = c.first[v]; e < c.first[v + 1]; ++e) acc = dadd(acc, c.ew[e]);
+        nw[v] = acc;
+      });
+    else
+      be.pfor(n, [=] MO_HD(i64 v) { nw[v] = 1.0; });
+  }
+  be.free(cnt); be.free(off); be.free(k1); be.free(k2); be.free(src);
+  finish_net(be, out);
+  return E;
+}
+
 // Network::createReducedNetwork (ModularityOptimizer.cpp:315-367).  The reference scans cluster by
 // cluster, node by node (ascending), edge by edge, adds every edge weight to a per-target running
 // sum and lists the targets in order of first appearance.  Here: every adjacency entry gets its

@@ -49,4 +49,33 @@ ComputeSNN <- function(nn_ranked, prune) {
 #                          g[[nm]] <- as.Graph(g[[nm]]) }
 #   return(g)
 
+# The step after FindNeighbors and the SNN side consumers (R/RcppExports.R): same arguments, same values.
+b200_backend <- function() identical(getOption("Seurat.nn.backend"), "b200")
+RunModularityClusteringCpp <- function(SNN, modularityFunction, resolution, algorithm, nRandomStarts, nIterations,
+                                       randomSeed, printOutput, edgefilename) {
+  if (b200_backend())
+    return(.Call("b200_RunModularityClusteringCpp", SNN, modularityFunction, resolution, algorithm, nRandomStarts,
+                 nIterations, randomSeed, printOutput, edgefilename, PACKAGE = "b200nn"))
+  .Call('_Seurat_RunModularityClusteringCpp', PACKAGE = 'Seurat', SNN, modularityFunction, resolution, algorithm,
+        nRandomStarts, nIterations, randomSeed, printOutput, edgefilename)
+}
+WriteEdgeFile <- function(snn, filename, display_progress) {
+  if (b200_backend()) return(invisible(.Call("b200_WriteEdgeFile", snn, filename, display_progress, PACKAGE = "b200nn")))
+  invisible(.Call('_Seurat_WriteEdgeFile', PACKAGE = 'Seurat', snn, filename, display_progress))
+}
+DirectSNNToFile <- function(nn_ranked, prune, display_progress, filename) {
+  if (b200_backend())
+    return(.Call("b200_DirectSNNToFile", nn_ranked, as.double(prune), display_progress, filename, PACKAGE = "b200nn"))
+  .Call('_Seurat_DirectSNNToFile', PACKAGE = 'Seurat', nn_ranked, prune, display_progress, filename)
+}
+fast_dist <- function(x, y, n) {
+  if (b200_backend()) return(.Call("b200_fast_dist", x, y, n, PACKAGE = "b200nn"))
+  .Call('_Seurat_fast_dist', PACKAGE = 'Seurat', x, y, n)
+}
+SNN_SmallestNonzero_Dist <- function(snn, mat, n, nearest_dist) {
+  if (b200_backend())
+    return(.Call("b200_SNN_SmallestNonzero_Dist", snn, mat, as.integer(n), nearest_dist, PACKAGE = "b200nn"))
+  .Call('_Seurat_SNN_SmallestNonzero_Dist', PACKAGE = 'Seurat', snn, mat, n, nearest_dist)
+}
+
 .onUnload <- function(libpath) .Call("b200_release", PACKAGE = "b200nn")

@@ -23,6 +23,15 @@
  *                                   arguments of NNHelper / FindNeighbors, R/clustering.R:596-597,
  *                                   :1686-1688: the reference embedding stays on the GPU behind an
  *                                   external pointer (finaliser pattern of src/valid_pointer.c:4-6)
+ *   The step after FindNeighbors and the SNN side consumers, same arguments as the
+ *   Rcpp wrappers they stand in for:
+ *   b200_RunModularityClusteringCpp(SNN, modularityFunction, resolution, algorithm, nRandomStarts,
+ *                                   nIterations, randomSeed, printOutput, edgefilename)
+ *                                   _Seurat_RunModularityClusteringCpp, src/RcppExports.cpp:14-32
+ *   b200_WriteEdgeFile(snn, filename, display_progress)        src/RcppExports.cpp:324-333
+ *   b200_DirectSNNToFile(nn_ranked, prune, display_progress, filename)      :335-346
+ *   b200_fast_dist(x, y, n)                                    :253-264
+ *   b200_SNN_SmallestNonzero_Dist(snn, mat, n, nearest_dist)   :348-360
  * Registration follows src/RcppExports.cpp:407-445 (R_CallMethodDef table,
  * R_registerRoutines, R_useDynamicSymbols(dll, FALSE)).
  *
@@ -244,6 +253,138 @@ SEXP b200_index_nn2(SEXP index, SEXP query_, SEXP k_) {
   return res;
 }
 
+/* ---- the step after FindNeighbors and the SNN side consumers ------------------------------------- */
+static void dgc_slots(SEXP m, int *n, const int **p, const int **i, const double **x) {
+  SEXP dim = R_do_slot(m, Rf_install("Dim"));
+  *n = INTEGER(dim)[1];
+  *p = INTEGER(R_do_slot(m, Rf_install("p")));
+  *i = INTEGER(R_do_slot(m, Rf_install("i")));
+  *x = REAL(R_do_slot(m, Rf_install("x")));
+}
+
+/* RunModularityClusteringCpp drop-in (src/RModularityOptimizer.cpp:21-173): SNN dgCMatrix (only its strict
+ * lower triangle is read) or, with a non-empty edgefilename, the edge file; returns the integer vector of
+ * 0-based cluster ids, clusters ordered by decreasing size.  The wrapper's console lines are kept. */
+SEXP b200_RunModularityClusteringCpp(SEXP SNN, SEXP modularityFunction, SEXP resolution, SEXP algorithm,
+                                     SEXP nRandomStarts, SEXP nIterations, SEXP randomSeed, SEXP printOutput,
+                                     SEXP edgefilename) {
+  const int mf = Rf_asInteger(modularityFunction), alg = Rf_asInteger(algorithm);
+  const int ns = Rf_asInteger(nRandomStarts), ni = Rf_asInteger(nIterations), print = Rf_asLogical(printOutput);
+  const double res = Rf_asReal(resolution);
+  const uint64_t seed = (uint64_t)(int64_t)Rf_asInteger(randomSeed); /* JavaRandom(int) sign-extends */
+  const char *file = Rf_isNull(edgefilename) ? "" : CHAR(STRING_ELT(edgefilename, 0));
+  b200nn_modopt_stats st;
+  SEXP out;
+  int rc;
+  if (print) Rprintf("Modularity Optimizer version 1.3.0 by Ludo Waltman and Nees Jan van Eck\n\n");
+  if (file[0] != '\0') {
+    int64_t n = 0;
+    if (print) Rprintf("Reading input file...\n\n");
+    rc = b200nn_modularity_cluster_edge_file(get_ctx(), file, mf, res, alg, ns, ni, seed, NULL, 0, &n, NULL);
+    if (rc != B200NN_OK) Rf_error("%s", b200nn_last_error());
+    out = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)n));
+    rc = b200nn_modularity_cluster_edge_file(get_ctx(), file, mf, res, alg, ns, ni, seed, INTEGER(out), n, &n, &st);
+  } else {
+    int n;
+    const int *p, *i;
+    const double *x;
+    dgc_slots(SNN, &n, &p, &i, &x);
+    out = PROTECT(Rf_allocVector(INTSXP, n));
+    rc = b200nn_modularity_cluster(get_ctx(), n, p, i, x, mf, res, alg, ns, ni, seed, INTEGER(out), &st);
+  }
+  if (rc != B200NN_OK) {
+    UNPROTECT(1);
+    Rf_error("%s", b200nn_last_error()); /* the wrapper's stop() texts */
+  }
+  if (print) {
+    Rprintf("Number of nodes: %d\nNumber of edges: %d\n\n", (int)st.n_nodes, (int)st.n_edges);
+    Rprintf("Running %s...\n", alg == 1 ? "Louvain algorithm"
+                               : alg == 2 ? "Louvain algorithm with multilevel refinement"
+                                          : "smart local moving algorithm");
+    if (ns == 1) Rprintf("Modularity: %.4f\n", st.modularity);
+    else Rprintf("Maximum modularity in %d random starts: %.4f\n", ns, st.modularity);
+    Rprintf("Number of communities: %d\nElapsed time: %d seconds\n", (int)st.n_clusters, (int)(st.ms_total / 1000.0));
+  }
+  UNPROTECT(1);
+  return out;
+}
+
+/* WriteEdgeFile drop-in (src/snn.cpp:40-59) */
+SEXP b200_WriteEdgeFile(SEXP snn, SEXP filename, SEXP display_progress) {
+  int n;
+  const int *p, *i;
+  const double *x;
+  dgc_slots(snn, &n, &p, &i, &x);
+  if (Rf_asLogical(display_progress) == TRUE) REprintf("Writing SNN as edge file\n");
+  if (b200nn_write_edge_file(p, i, x, n, CHAR(STRING_ELT(filename, 0)), NULL) != B200NN_OK)
+    Rf_error("%s", b200nn_last_error());
+  return R_NilValue;
+}
+
+SEXP b200_ComputeSNN(SEXP nn_ranked, SEXP prune_);
+/* DirectSNNToFile drop-in (src/snn.cpp:63-69): ComputeSNN, then the edge file, the graph is returned */
+SEXP b200_DirectSNNToFile(SEXP nn_ranked, SEXP prune, SEXP display_progress, SEXP filename) {
+  SEXP g = PROTECT(b200_ComputeSNN(nn_ranked, prune));
+  b200_WriteEdgeFile(g, filename, display_progress);
+  UNPROTECT(1);
+  return g;
+}
+
+/* fast_dist drop-in (src/fast_NN_dist.cpp:34-69): n is a list of (1-based) row indices of y, one vector per
+ * row of x; returns the list of distance vectors (an empty list when the shapes do not fit, as the reference) */
+SEXP b200_fast_dist(SEXP x_, SEXP y_, SEXP n_) {
+  SEXP x = PROTECT(as_real_matrix(x_, "x"));
+  SEXP y = PROTECT(as_real_matrix(y_, "y"));
+  const R_xlen_t nx = Rf_nrows(x), m = Rf_xlength(n_);
+  if (nx != m || Rf_ncols(x) != Rf_ncols(y)) {
+    UNPROTECT(2);
+    return Rf_allocVector(VECSXP, 0);
+  }
+  int64_t *ptr = (int64_t *)R_alloc((size_t)m + 1, sizeof(int64_t));
+  ptr[0] = 0;
+  for (R_xlen_t r = 0; r < m; ++r) ptr[r + 1] = ptr[r] + Rf_xlength(VECTOR_ELT(n_, r));
+  int32_t *nbr = (int32_t *)R_alloc((size_t)(ptr[m] > 0 ? ptr[m] : 1), sizeof(int32_t));
+  for (R_xlen_t r = 0; r < m; ++r) {
+    SEXP v = VECTOR_ELT(n_, r);
+    const R_xlen_t len = Rf_xlength(v);
+    for (R_xlen_t j = 0; j < len; ++j)
+      nbr[ptr[r] + j] = Rf_isInteger(v) ? INTEGER(v)[j] : (int32_t)REAL(v)[j];
+  }
+  double *flat = (double *)R_alloc((size_t)(ptr[m] > 0 ? ptr[m] : 1), sizeof(double));
+  int rc = b200nn_fast_dist(get_ctx(), REAL(x), nx, REAL(y), Rf_nrows(y), Rf_ncols(x), B200NN_COL_MAJOR, ptr, nbr,
+                            flat);
+  if (rc != B200NN_OK) {
+    UNPROTECT(2);
+    Rf_error("%s", b200nn_last_error());
+  }
+  SEXP res = PROTECT(Rf_duplicate(n_)); /* clone(n): names are kept */
+  for (R_xlen_t r = 0; r < m; ++r) {
+    const R_xlen_t len = (R_xlen_t)(ptr[r + 1] - ptr[r]);
+    SEXP d = PROTECT(Rf_allocVector(REALSXP, len));
+    for (R_xlen_t j = 0; j < len; ++j) REAL(d)[j] = flat[ptr[r] + j];
+    SET_VECTOR_ELT(res, r, d);
+    UNPROTECT(1);
+  }
+  UNPROTECT(3);
+  return res;
+}
+
+/* SNN_SmallestNonzero_Dist drop-in (src/snn.cpp:82-126) */
+SEXP b200_SNN_SmallestNonzero_Dist(SEXP snn, SEXP mat_, SEXP n_, SEXP nearest_dist) {
+  int n;
+  const int *p, *i;
+  const double *x;
+  dgc_slots(snn, &n, &p, &i, &x);
+  SEXP mat = PROTECT(as_real_matrix(mat_, "mat"));
+  SEXP nd = PROTECT(Rf_coerceVector(nearest_dist, REALSXP));
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+  int rc = b200nn_snn_smallest_nonzero_dist(get_ctx(), p, i, x, n, REAL(mat), Rf_ncols(mat), B200NN_COL_MAJOR,
+                                            Rf_asInteger(n_), REAL(nd), REAL(out));
+  UNPROTECT(3);
+  if (rc != B200NN_OK) Rf_error("%s", b200nn_last_error());
+  return out;
+}
+
 /* Frees the device state.  Resident indexes live inside the single-device context: while any
  * external pointer to one is still alive the context stays (their finaliser needs it). */
 SEXP b200_release(void) {
@@ -264,6 +405,11 @@ static const R_CallMethodDef CallEntries[] = {
     {"b200_FindNeighbors", (DL_FUNC)&b200_FindNeighbors, 4},
     {"b200_index", (DL_FUNC)&b200_index, 1},
     {"b200_index_nn2", (DL_FUNC)&b200_index_nn2, 3},
+    {"b200_RunModularityClusteringCpp", (DL_FUNC)&b200_RunModularityClusteringCpp, 9},
+    {"b200_WriteEdgeFile", (DL_FUNC)&b200_WriteEdgeFile, 3},
+    {"b200_DirectSNNToFile", (DL_FUNC)&b200_DirectSNNToFile, 4},
+    {"b200_fast_dist", (DL_FUNC)&b200_fast_dist, 3},
+    {"b200_SNN_SmallestNonzero_Dist", (DL_FUNC)&b200_SNN_SmallestNonzero_Dist, 4},
     {"b200_release", (DL_FUNC)&b200_release, 0},
     {NULL, NULL, 0}};
 

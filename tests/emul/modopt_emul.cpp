@@ -97,6 +97,22 @@ extern "C" int emul_modularity_cluster(int n, const int *p, const int *i, const 
   return k;
 }
 
+extern "C" int emul_modularity_cluster_edges(int n, const int *node1, const int *node2, const double *w, int64_t m,
+                                             int modularityFunction, double resolution, int algorithm,
+                                             int nRandomStarts, int nIterations, uint64_t seed, int *cluster_out,
+                                             double *modularity_out) {
+  using namespace modopt;
+  EmulBackend be;
+  Net net;
+  const i64 E = build_network_edges(be, n, node1, node2, w, m, modularityFunction, net);
+  if (E == 0) return -2;
+  Stats st;
+  const i32 k = run_clustering(be, net, algorithm, resolution, modularityFunction, nRandomStarts, nIterations, seed,
+                               cluster_out, modularity_out, &st);
+  free_net(be, net);
+  return k;
+}
+
 extern "C" double emul_seq_sum(const double *x, int64_t n, double init) {
   EmulBackend be;
   return modopt::seq_sum(be, x, n, init);

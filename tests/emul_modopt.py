@@ -42,6 +42,22 @@ def cluster(p, i, x, mf, res, alg, ns, ni, seed, win0=0, winmax=0):
     return out, rc, q.value, dict(zip(names, st.tolist()))
 
 
+def cluster_edges(node1, node2, w, n, mf, res, alg, ns, ni, seed):
+    """-> (labels, n_clusters, modularity) from an edge list (build_network_edges of modopt_core.inl)"""
+    node1 = np.ascontiguousarray(node1, dtype=np.int32)
+    node2 = np.ascontiguousarray(node2, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = np.zeros(n, np.int32)
+    q = C.c_double()
+    L = lib()
+    vp = C.c_void_p
+    L.emul_modularity_cluster_edges.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int,
+                                                C.c_int, C.c_uint64, vp, vp]
+    rc = L.emul_modularity_cluster_edges(n, node1.ctypes.data, node2.ctypes.data, w.ctypes.data, node1.size, mf,
+                                         float(res), alg, ns, ni, seed, out.ctypes.data, C.addressof(q))
+    return out, rc, q.value
+
+
 def seq_sum(x, init=0.0):
     """the order-fixed running sum of modopt_core.inl (binade-wise integer prefix sums)"""
     x = np.ascontiguousarray(x, dtype=np.float64)

@@ -61,3 +61,24 @@ def test_product_never_imports_the_oracle():
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in txt and "liboracle" not in txt and "oracle_" not in txt, \
                         f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def test_r_shim_compiles_against_the_documented_r_api():
+    """R is not in the image, so the .Call shim cannot be built for real; it is at least compiled
+    (gcc -fsyntax-only -Wall -Werror) against declarations of the R API entry points it uses
+    (tests/stubs/r_api, written from "Writing R Extensions") and the real include/b200nn.h: argument
+    counts and types of every R API and every C-ABI call are checked, and the registration table must
+    list every .Call entry point with its arity (src/RcppExports.cpp:407-445 pattern)."""
+    import subprocess
+    shim = os.path.join(ROOT, "shim", "b200nn_r.c")
+    r = subprocess.run(["/usr/bin/gcc", "-std=gnu11", "-fsyntax-only", "-Wall", "-Werror",
+                        "-I" + os.path.join(ROOT, "tests", "stubs", "r_api"), "-I" + os.path.join(ROOT, "include"),
+                        shim], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(shim).read()
+    defined = {m.group(1): m.group(2).count("SEXP") for m in re.finditer(r"^SEXP (b200_\w+)\(([^)]*)\)\s*\{", src, re.M)}
+    table = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(b200_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', src)}
+    assert defined == table, "every .Call entry point is registered with its number of arguments"
+    rsrc = open(os.path.join(ROOT, "shim", "b200nn.R")).read()
+    for name in re.findall(r'\.Call\("(b200_\w+)"', rsrc):
+        assert name in table, f"{name} is called from b200nn.R but not registered"

@@ -128,3 +128,42 @@ def test_argument_errors_carry_the_wrappers_messages(ctx):
         ctx.modularity_cluster(np.zeros(5, np.int32), np.zeros(0, np.int32), np.zeros(0))
     lab, _ = ctx.modularity_cluster(p, i, x, 1, 1.0, 1, 1, 1, 564)      # the context keeps working
     assert lab.tolist() == mc.KARATE_KAT[0][1]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref/libmodopt_ref.so missing")
+def test_edge_file_input_matches_the_reference_reading_the_same_file(ctx, tmp_path):
+    """edge.file.name of RunModularityClusteringCpp (RModularityOptimizer.cpp:55-63) through
+    b200nn_modularity_cluster_edge_file / _edges and through the host mirror"""
+    rng = np.random.default_rng(5)
+    n, m = 3000, 20000
+    n1, n2 = rng.integers(0, n, m), rng.integers(0, n, m)
+    w = np.round(rng.random(m) + 0.01, 6)
+    path = str(tmp_path / "edges.txt")
+    with open(path, "w") as f:
+        for e in range(m):
+            f.write(f"{n1[e]}\t{n2[e]}\t{float(w[e])!r}\n")
+    for alg in (1, 2, 3):
+        params = (1, 0.8, alg, 2, 5, 42)
+        want, wc, wq = oracle.modularity_cluster_file_ref(path, *params)
+        got, st = ctx.modularity_cluster_edge_file(path, *params)
+        assert (got == want).all() and st["n_clusters"] == wc and st["modularity"] == wq
+        got2, st2 = ctx.modularity_cluster_edges(n1, n2, w, want.size, *params)
+        assert (got2 == want).all() and st2["modularity"] == wq
+    ids = sb.RunModularityClustering(None, 1, 0.8, 1, 2, 5, 42, print_output=False, edge_file_name=path, ctx=ctx)
+    want, _, _ = oracle.modularity_cluster_file_ref(path, 1, 0.8, 1, 2, 5, 42)
+    assert (ids == want).all()
+    # unweighted file (weight 1), and the failures the wrapper reports
+    path2 = str(tmp_path / "unweighted.txt")
+    with open(path2, "w") as f:
+        for e in range(m):
+            f.write(f"{n1[e]}\t{n2[e]}\n")
+    want, wc, wq = oracle.modularity_cluster_file_ref(path2, 1, 0.8, 1, 1, 3, 7)
+    got, st = ctx.modularity_cluster_edge_file(path2, 1, 0.8, 1, 1, 3, 7)
+    assert (got == want).all() and st["modularity"] == wq
+    with pytest.raises(sb.B200Error, match="Could not parse edge file"):
+        ctx.modularity_cluster_edge_file(str(tmp_path / "missing.txt"))
+    bad = str(tmp_path / "bad.txt")
+    with open(bad, "w") as f:
+        f.write("0\t1\t0.5\nx\t2\t0.1\n")
+    with pytest.raises(sb.B200Error, match="Could not parse edge file"):
+        ctx.modularity_cluster_edge_file(bad)

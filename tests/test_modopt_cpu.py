@@ -129,3 +129,53 @@ def test_order_fixed_running_sum_is_exact():
             x[n // 3] = 1e18
         init = 0.0 if trial % 2 else float(rng.random() * 1000)
         assert emul_modopt.seq_sum(x, init) == plain(x, init), trial
+
+
+def _write_edges(path, n1, n2, w=None):
+    with open(path, "w") as f:
+        for e in range(len(n1)):
+            f.write(f"{n1[e]}\t{n2[e]}" + ("" if w is None else f"\t{float(w[e])!r}") + "\n")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(5))
+def test_emulated_edge_list_input_matches_the_reference_reading_the_same_file(seed, tmp_path):
+    """edge.file.name (RModularityOptimizer.cpp:55-63): the reference reads the file with its own readInputFile;
+    the device steps get the parsed list (build_network_edges).  Lists in arbitrary order, with reversed pairs,
+    self pairs and repeated pairs (only node1 < node2 counts, repeats stay separate edges)"""
+    rng = np.random.default_rng(77 + seed)
+    n = int(rng.integers(30, 600))
+    m = int(n * rng.uniform(2, 9))
+    n1 = rng.integers(0, n, m)
+    n2 = rng.integers(0, n, m)
+    if seed % 2 == 0:                       # the format WriteEdgeFile produces: col < row, column-major order
+        lo, hi = np.minimum(n1, n2), np.maximum(n1, n2)
+        keep = lo < hi
+        order = np.lexsort((hi[keep], lo[keep]))
+        n1, n2 = lo[keep][order], hi[keep][order]
+    w = None if seed == 1 else np.round(rng.random(len(n1)) + 0.01, 6)
+    path = str(tmp_path / "edges.txt")
+    _write_edges(path, n1, n2, w)
+    n_nodes = int(max(n1.max(), n2.max())) + 1
+    for alg in (1, 2, 3):
+        params = (1 + seed % 2, 0.8 if seed % 2 == 0 else 0.5, alg, 2, 4, 12345 + seed)
+        want, wc, wq = oracle.modularity_cluster_file_ref(path, *params)
+        assert want.size == n_nodes
+        got, gc, gq = emul_modopt.cluster_edges(n1, n2, np.ones(len(n1)) if w is None else w, n_nodes, *params)
+        assert gc == wc and (got == want).all() and gq == wq, (alg, params)
+
+
+@needs_ref
+def test_edge_file_round_trip_of_an_snn_graph(tmp_path):
+    """WriteEdgeFile -> edge.file.name gives what the matrix input gives when the weights survive the
+    15-digit text form (Jaccard values of k = 10: s / (20 - s))"""
+    X = np.random.default_rng(3).normal(size=(700, 8))
+    p, i, x = oracle.find_neighbors(X, k=10, prune=1 / 15)["snn"]
+    path = str(tmp_path / "snn_edges.txt")
+    oracle.write_edge_file(p, i, x, path)
+    a, ac, aq = oracle.modularity_cluster_ref(p, i, x, 1, 0.8, 1, 3, 5, 9)
+    b, bc, bq = oracle.modularity_cluster_file_ref(path, 1, 0.8, 1, 3, 5, 9)
+    assert b.size <= a.size
+    e1, e2, ew = np.loadtxt(path, delimiter="\t", unpack=True)
+    got, gc, gq = emul_modopt.cluster_edges(e1.astype(np.int32), e2.astype(np.int32), ew, b.size, 1, 0.8, 1, 3, 5, 9)
+    assert gc == bc and (got == b).all() and gq == bq
