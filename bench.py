@@ -502,7 +502,9 @@ def main():
         roofline = {"kernel": "k_knn_tc (tcgen05; the pass-2 launch of the grouped search)", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " bf16 sustained",
-                    "traffic": traffic_from_profiles("k_knn_tc", world),
+                    "traffic": traffic_from_profiles("k_knn_tc_pass2_launch", world) or traffic_from_profiles("k_knn_tc", world),
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the pass-2 launch, committed ncu launch "
+                                      "list of this command on one B200 (profiles/r02_traffic.json); null for N > 1",
                     "executed_flops_per_launch": exec_flops, "ms_per_launch": k1_ms,
                     "tiles_visited": tv, "tiles_total": tt, "tiles_visited_frac": tv / tt if tt else None,
                     "algorithmic_equiv_tflops": 2.0 * nq_local * n * d / (st["knn_cand"] * 1e-3) / 1e12,

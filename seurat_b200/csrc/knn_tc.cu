@@ -1363,11 +1363,12 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
               const float *__restrict__ grad, const int32_t *__restrict__ goff,
               const float *__restrict__ tile_lo, const float *__restrict__ tile_hi, int pass1,
               int64_t list_stride, int32_t *__restrict__ tiles, int32_t *__restrict__ list_cnt,
-              int nsplit, int split) {
+              int nsplit, int split, const int32_t *__restrict__ rcount, int min_rows) {
   __shared__ float cs[BK];
   __shared__ float s_min[LIST_THREADS / 32];
   __shared__ int s_scan[LIST_THREADS / 32];
-  __shared__ float s_dmin;
+  __shared__ float s_big[LIST_THREADS / 32];
+  __shared__ float s_dmin, s_dbig;
   __shared__ int s_hist[LIST_NBK];
   __shared__ int s_cur[LIST_NBK];
   __shared__ int s_total;
@@ -1380,11 +1381,21 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
   __syncthreads();
   constexpr int GPT = 4;  // groups per thread (G <= 1024)
   float dist[GPT];
-  float dmin = CUDART_INF_F;
+  bool big[GPT];
+  // The ANCHOR group of an item -- pass 1 scans its first tiles to get a threshold, pass 2 always visits
+  // them again -- is the nearest group that can fill a k'-entry list: at least ANCHOR_TILES tiles of this
+  // split (pass 1 then works on 8-key bucket minima of >= 3 full tiles) or at least min_rows = 2 k' rows per
+  // split (plain keys).  A tiny group (k-means leaves a few with a handful of points) cannot: the item's
+  // bound would stay +inf and the item would visit EVERY tile -- one such item of 7 942 tiles among items of
+  // ~250 made its CTA the tail of the whole launch (pass 2 of config C: 16.0 -> 12.3 ms once it was gone).
+  // Without any sufficient group the nearest group of all is the anchor.
+  constexpr int ANCHOR_TILES = 4;
+  float dmin = CUDART_INF_F, dbig = CUDART_INF_F;
 #pragma unroll
   for (int u = 0; u < GPT; ++u) {
     const int g = tid * GPT + u;
     dist[u] = CUDART_INF_F;
+    big[u] = false;
     if (g < G && goff[g + 1] > goff[g]) {
       const float4 *cv = reinterpret_cast<const float4 *>(cent + (size_t)g * BK);
       float s = 0.f;
@@ -1399,19 +1410,32 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
       }
       dist[u] = sqrtf(s);
       dmin = fminf(dmin, dist[u]);
+      big[u] = (goff[g + 1] - goff[g]) / (BN * nsplit) >= ANCHOR_TILES || rcount[g] / nsplit >= min_rows;
+      if (big[u]) dbig = fminf(dbig, dist[u]);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-  if (lane == 0) s_min[w] = dmin;
-  __syncthreads();
-  if (tid == 0) {
-    float m = s_min[0];
-    for (int i = 1; i < LIST_THREADS / 32; ++i) m = fminf(m, s_min[i]);
-    s_dmin = m;
+  for (int o = 16; o > 0; o >>= 1) {
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    dbig = fminf(dbig, __shfl_xor_sync(0xffffffffu, dbig, o));
+  }
+  if (lane == 0) {
+    s_min[w] = dmin;
+    s_big[w] = dbig;
   }
   __syncthreads();
-  dmin = s_dmin;
+  if (tid == 0) {
+    float m = s_min[0], b = s_big[0];
+    for (int i = 1; i < LIST_THREADS / 32; ++i) {
+      m = fminf(m, s_min[i]);
+      b = fminf(b, s_big[i]);
+    }
+    s_dmin = m;
+    s_dbig = b;
+  }
+  __syncthreads();
+  const bool any_big = s_dbig < CUDART_INF_F;
+  dmin = any_big ? s_dbig : s_dmin;  // distance of the anchor group
   const float T = pass1 ? 0.f : item_T[item];
   const float ri = item_rad[item];
   int ntile[GPT], mine = 0;
@@ -1420,7 +1444,7 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
     const int g = tid * GPT + u;
     ntile[u] = 0;
     if (dist[u] < CUDART_INF_F) {
-      bool keep = dist[u] <= dmin;  // the nearest group is always visited (pass 1 == subset of pass 2)
+      bool keep = dist[u] <= dmin && (big[u] || !any_big);  // the anchor group is always visited (pass 1 == subset of pass 2)
       if (!pass1 && !keep) {
         float lb = dist[u] * 0.99999f - ri - grad[g];
         keep = !(lb > 0.f && lb * lb > T);  // also keeps everything when T is +inf / NaN
@@ -1477,7 +1501,7 @@ k_build_lists(const float *__restrict__ item_c, const float *__restrict__ item_r
         if (ntile[u] <= 0) continue;
         const int t0 = goff[g] / BN + split * ((goff[g + 1] - goff[g]) / (BN * nsplit));
         const float D = dist[u];
-        const bool nearest = D <= dmin;
+        const bool nearest = D <= dmin && (big[u] || !any_big);
         for (int t = 0; t < ntile[u]; ++t) {
           const int tile = t0 + t;
           const float lo = tile_lo[tile], hi = tile_hi[tile];
@@ -2293,13 +2317,13 @@ static int knn_tc_candidates(b200nn_ctx *ctx, const double *d_ref, int64_t nr, c
     P.tau_init = nullptr;
     P.order = nullptr;
     k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, tile_lo, tile_hi,
-                                                      1, P.list_stride, tiles, list_cnt, kpl.splits, sp);
+                                                      1, P.list_stride, tiles, list_cnt, kpl.splits, sp, rcount, 2 * kpl.per);
     KERNEL_CHECK(ctx);
     P.pass1 = 1;
     RC_TRY(debug_list_stats(ctx, "pass 1", list_cnt, P.n_items));
     RC_TRY(launch_tc(ctx, map_q, map_r, P, false));
     k_build_lists<<<P.n_items, LIST_THREADS, 0, st>>>(item_c, item_rad, item_T, G, cent, grad, goff, tile_lo, tile_hi,
-                                                      0, P.list_stride, tiles, list_cnt, kpl.splits, sp);
+                                                      0, P.list_stride, tiles, list_cnt, kpl.splits, sp, rcount, 2 * kpl.per);
     KERNEL_CHECK(ctx);
     out->visit = qperm;
     out->n_visit = nq_pad;

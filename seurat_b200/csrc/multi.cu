@@ -246,10 +246,11 @@ int shard_count_phase(b200nn_multi *m, int g, const Job &J, Gate &gate) {
   bool ok = true;
   static const bool trace = getenv("B200NN_TRACE") != nullptr;  // phase progress of every shard on stderr
   int phase_no = 0;
+  const double t_call = now_ms();
   auto phase = [&](int rc) {  // all shards leave a phase together; a failure anywhere ends the call
-    if (trace) fprintf(stderr, "[b200nn multi] shard %d/%d (device %d) finished phase %d rc=%d, waits\n", g, G, s.dev, phase_no, rc);
+    if (trace) fprintf(stderr, "[b200nn multi] shard %d/%d (device %d) finished phase %d rc=%d at %.2f ms, waits\n", g, G, s.dev, phase_no, rc, now_ms() - t_call);
     ok = gate.wait(rc == B200NN_OK) && rc == B200NN_OK;
-    if (trace) fprintf(stderr, "[b200nn multi] shard %d/%d leaves phase %d (%s)\n", g, G, phase_no, ok ? "ok" : "failed");
+    if (trace) fprintf(stderr, "[b200nn multi] shard %d/%d leaves phase %d (%s) at %.2f ms\n", g, G, phase_no, ok ? "ok" : "failed", now_ms() - t_call);
     ++phase_no;
     return ok;
   };
