@@ -43,6 +43,10 @@ def main(path):
     if len(src) > 2:
         hdr, data = src[1], src[2:]
         ci = {h: i for i, h in enumerate(hdr)}
+        # a multi-kernel report repeats title + header lines per kernel: keep the rows of the LAST kernel
+        data = [r for r in data if len(r) >= len(hdr)]
+        last = max([i for i, r in enumerate(data) if r[ci["# Samples"]] == "# Samples"], default=-1)
+        data = data[last + 1:]
         stalls = [h for h in hdr if h.startswith("stall_") and "Not" not in h]
         tot = sum(int(r[ci["# Samples"]] or 0) for r in data)
         inst = sum(int(r[ci["Instructions Executed"]] or 0) for r in data)
