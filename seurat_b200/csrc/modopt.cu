@@ -344,6 +344,20 @@ void fill_stats(const modopt::Stats &s, int64_t n, int64_t edges, int32_t n_clus
   out->gpu_launches = launches;
 }
 
+// stream-ordered device buffer released on every exit path of an entry point
+struct PoolBuf {
+  void *p = nullptr;
+  cudaStream_t st;
+  explicit PoolBuf(cudaStream_t s) : st(s) {}
+  ~PoolBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  PoolBuf(const PoolBuf &) = delete;
+  PoolBuf &operator=(const PoolBuf &) = delete;
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
 template <typename PT>
 int cluster_device_csc(b200nn_ctx *ctx, int64_t n, const PT *d_p, const int32_t *d_i, const double *d_x,
                        int modularity_function, double resolution, int algorithm, int n_random_starts,
@@ -482,21 +496,20 @@ int b200nn_modularity_cluster(b200nn_ctx *ctx, int64_t n, const int32_t *p, cons
     return B200NN_ERR_INVALID;
   }
   CU_TRY(cudaSetDevice(ctx->device));
-  int32_t *d_p = nullptr, *d_i = nullptr;
-  double *d_x = nullptr;
-  CU_TRY(cudaMallocAsync(&d_p, sizeof(int32_t) * (size_t)(n + 1), ctx->stream));
-  CU_TRY(cudaMallocAsync(&d_i, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), ctx->stream));
-  CU_TRY(cudaMallocAsync(&d_x, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1), ctx->stream));
-  CU_TRY(cudaMemcpyAsync(d_p, p, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
-  if (nnz > 0) {
-    CU_TRY(cudaMemcpyAsync(d_i, i, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  {
+    PoolBuf bp(ctx->stream), bi(ctx->stream), bx(ctx->stream);  // freed on every path, error returns included
+    CU_TRY(cudaMallocAsync(&bp.p, sizeof(int32_t) * (size_t)(n + 1), ctx->stream));
+    CU_TRY(cudaMallocAsync(&bi.p, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), ctx->stream));
+    CU_TRY(cudaMallocAsync(&bx.p, sizeof(double) * (size_t)(nnz > 0 ? nnz : 1), ctx->stream));
+    CU_TRY(cudaMemcpyAsync(bp.p, p, sizeof(int32_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz > 0) {
+      CU_TRY(cudaMemcpyAsync(bi.p, i, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(cudaMemcpyAsync(bx.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = cluster_device_csc(ctx, n, bp.as<int32_t>(), bi.as<int32_t>(), bx.as<double>(), modularity_function,
+                            resolution, algorithm, n_random_starts, n_iterations, random_seed, cluster_out, stats);
   }
-  int rc = cluster_device_csc(ctx, n, d_p, d_i, d_x, modularity_function, resolution, algorithm, n_random_starts,
-                              n_iterations, random_seed, cluster_out, stats);
-  cudaFreeAsync(d_p, ctx->stream);
-  cudaFreeAsync(d_i, ctx->stream);
-  cudaFreeAsync(d_x, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   return rc;
 }
@@ -527,25 +540,25 @@ int b200nn_modularity_cluster_edges(b200nn_ctx *ctx, int64_t n_nodes, const int3
     return B200NN_ERR_INVALID;
   }
   CU_TRY(cudaSetDevice(ctx->device));
-  int32_t *d_1 = nullptr, *d_2 = nullptr;
-  double *d_w = nullptr;
-  CU_TRY(cudaMallocAsync(&d_1, sizeof(int32_t) * (size_t)n_edges, ctx->stream));
-  CU_TRY(cudaMallocAsync(&d_2, sizeof(int32_t) * (size_t)n_edges, ctx->stream));
-  CU_TRY(cudaMallocAsync(&d_w, sizeof(double) * (size_t)n_edges, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(d_1, node1, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(cudaMemcpyAsync(d_2, node2, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
-  if (weight) {
-    CU_TRY(cudaMemcpyAsync(d_w, weight, sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
-  } else {  // unweighted list: every edge weighs 1 (readInputFile's default)
-    std::vector<double> ones((size_t)n_edges, 1.0);
-    CU_TRY(cudaMemcpyAsync(d_w, ones.data(), sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
+  int rc;
+  {
+    PoolBuf b1(ctx->stream), b2(ctx->stream), bw(ctx->stream);
+    CU_TRY(cudaMallocAsync(&b1.p, sizeof(int32_t) * (size_t)n_edges, ctx->stream));
+    CU_TRY(cudaMallocAsync(&b2.p, sizeof(int32_t) * (size_t)n_edges, ctx->stream));
+    CU_TRY(cudaMallocAsync(&bw.p, sizeof(double) * (size_t)n_edges, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(b1.p, node1, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(b2.p, node2, sizeof(int32_t) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+    if (weight) {
+      CU_TRY(cudaMemcpyAsync(bw.p, weight, sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+    } else {  // unweighted list: every edge weighs 1 (readInputFile's default)
+      std::vector<double> ones((size_t)n_edges, 1.0);
+      CU_TRY(cudaMemcpyAsync(bw.p, ones.data(), sizeof(double) * (size_t)n_edges, cudaMemcpyHostToDevice, ctx->stream));
+      CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    rc = cluster_device_edges(ctx, n_nodes, b1.as<int32_t>(), b2.as<int32_t>(), bw.as<double>(), n_edges,
+                              modularity_function, resolution, algorithm, n_random_starts, n_iterations, random_seed,
+                              cluster_out, stats);
   }
-  int rc = cluster_device_edges(ctx, n_nodes, d_1, d_2, d_w, n_edges, modularity_function, resolution, algorithm,
-                                n_random_starts, n_iterations, random_seed, cluster_out, stats);
-  cudaFreeAsync(d_1, ctx->stream);
-  cudaFreeAsync(d_2, ctx->stream);
-  cudaFreeAsync(d_w, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   return rc;
 }
