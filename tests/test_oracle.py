@@ -133,3 +133,22 @@ def test_oracle_selftest_under_asan_ubsan():
     r = subprocess.run([os.path.join(root, "selftest_asan")], capture_output=True, text=True, timeout=300,
                        env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0 and "oracle selftest ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+def test_knn_against_scipy_ckdtree_20k():
+    """a third, independent exact search (scipy.spatial.cKDTree: its own kd-tree and distance loop) on the
+    benchmark's kind of input at 20k x 50 and on a query != reference case: same neighbours wherever the
+    distances are distinct, distances equal to the last few bits"""
+    from scipy.spatial import cKDTree
+    from seurat_b200.synthetic import gaussian_mixture
+    X, cen = gaussian_mixture(20_000, 50, seed=5, n_centres=12)
+    Q, _ = gaussian_mixture(3_000, 50, seed=6, centres=cen)
+    for qry in (None, Q):
+        idx, dist = oracle.knn(X, qry, 20, method="kdtree")
+        d2, i2 = cKDTree(X, leafsize=8).query(X if qry is None else qry, k=20)
+        assert np.allclose(d2, dist, rtol=1e-12, atol=0)
+        gap_ok = np.ones_like(dist, dtype=bool)           # positions whose neighbours in the list are not tied
+        gap_ok[:, 1:] &= (dist[:, 1:] - dist[:, :-1]) > 1e-9 * dist[:, 1:]
+        gap_ok[:, :-1] &= (dist[:, 1:] - dist[:, :-1]) > 1e-9 * dist[:, 1:]
+        assert (idx[gap_ok] == i2[gap_ok] + 1).all()
+        assert gap_ok.mean() > 0.999
