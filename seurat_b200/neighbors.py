@@ -320,6 +320,39 @@ def SNN_SmallestNonzero_Dist(snn: Graph, mat, n: int, nearest_dist, ctx: _lib.Co
     return ctx.snn_smallest_nonzero_dist(snn.p, snn.i, snn.x, mat, _layout_of(mat), int(n), nearest_dist)
 
 
+def ComputeSNNwidth(snn_graph: Graph, embeddings, k_nn: int, l2_norm: bool = True, nearest_dist=None,
+                    ctx: _lib.Context | None = None) -> np.ndarray:
+    """``ComputeSNNwidth`` (R/clustering.R:1027-1049), the R-level caller of ``SNN_SmallestNonzero_Dist``
+    (WNN's kernel bandwidth): optional row L2 normalisation, ``nearest.dist`` defaults to zeros and must
+    have one entry per column of the graph."""
+    emb = np.asarray(embeddings, dtype=np.float64)
+    if l2_norm:
+        emb = L2Norm(emb)
+    ncol = snn_graph.Dim[1]
+    nearest = np.zeros(ncol, dtype=np.float64) if nearest_dist is None else np.asarray(nearest_dist, dtype=np.float64)
+    if nearest.size != ncol:
+        raise ValueError("Please provide a vector for nearest.dist that has as many elements as"
+                         f" there are columns in the snn.graph ({ncol}).")
+    return SNN_SmallestNonzero_Dist(snn_graph, emb, k_nn, nearest, ctx=ctx)
+
+
+def NNdist(nn_idx, embeddings, metric: str = "euclidean", query_embeddings=None, nearest_dist=None,
+           ctx: _lib.Context | None = None) -> list:
+    """``NNdist`` (R/clustering.R:1620-1644), the R-level caller of ``fast_dist``: distances from every
+    (query) cell to the cells listed for it (a matrix of 1-based indices, one row per cell, or a list of
+    index vectors); with ``nearest.dist`` the distance to the nearest neighbour is subtracted and the
+    result floored at 0."""
+    emb = np.asarray(embeddings, dtype=np.float64)
+    if not isinstance(nn_idx, (list, tuple)):
+        nn_idx = list(np.asarray(nn_idx))
+    q = emb if query_embeddings is None else np.asarray(query_embeddings, dtype=np.float64)
+    d = fast_dist(q, emb, nn_idx, ctx=ctx)
+    if nearest_dist is not None:
+        nearest = np.asarray(nearest_dist, dtype=np.float64)
+        d = [np.maximum(d[r] - nearest[r], 0.0) for r in range(q.shape[0])]
+    return d
+
+
 def _nn_graph(nn_ranked: np.ndarray, n: int, ctx: _lib.Context) -> Graph:
     nn = np.asarray(nn_ranked)
     if nn.dtype != np.int32:

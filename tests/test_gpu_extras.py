@@ -61,3 +61,24 @@ def test_direct_snn_to_file(ctx, tmp_path):
     oracle.write_edge_file(*r["snn"], f2)
     assert open(f1, "rb").read() == open(f2, "rb").read()
     assert (g.p == r["snn"][0]).all() and (g.x == r["snn"][2]).all()
+
+
+def test_r_level_callers_of_the_side_consumers(ctx):
+    """ComputeSNNwidth (R/clustering.R:1027-1049) and NNdist (R/clustering.R:1620-1644)"""
+    X, _ = gaussian_mixture(3000, 12, seed=9, n_centres=4)
+    r = oracle.find_neighbors(X, k=15, prune=0.0, method="kdtree")
+    p, i, x = r["snn"]
+    g = sb.Graph(p, i, x, (3000, 3000))
+    Xn = sb.L2Norm(X)
+    want = oracle.snn_smallest_nonzero_dist(p, i, x, Xn, 15, np.zeros(3000))
+    assert (sb.ComputeSNNwidth(g, X, 15, ctx=ctx) == want).all()
+    nearest = r["nn_dist"][:, 1]
+    want = oracle.snn_smallest_nonzero_dist(p, i, x, X, 15, nearest)
+    assert (sb.ComputeSNNwidth(g, X, 15, l2_norm=False, nearest_dist=nearest, ctx=ctx) == want).all()
+    with pytest.raises(ValueError, match="as many elements as there are columns"):
+        sb.ComputeSNNwidth(g, X, 15, nearest_dist=np.zeros(7), ctx=ctx)
+    d = sb.NNdist(r["nn_idx"], X, ctx=ctx)                     # matrix of indices -> one row per cell
+    assert (np.stack(d) == r["nn_dist"]).all()
+    d0 = sb.NNdist(list(r["nn_idx"][:50]), X, query_embeddings=X[:50], nearest_dist=nearest[:50], ctx=ctx)
+    w0 = np.maximum(r["nn_dist"][:50] - nearest[:50, None], 0.0)
+    assert (np.stack(d0) == w0).all() and (np.stack(d0)[:, :2] == 0).all()

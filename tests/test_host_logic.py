@@ -73,3 +73,10 @@ def test_index_argument_is_type_checked():
     X = sb.Embedding(np.random.default_rng(0).normal(size=(30, 4)), [str(i) for i in range(30)])
     with pytest.raises(TypeError, match="cache_index=True"):
         sb.NNHelper(X, k=3, method="rann", index=object())
+
+
+def test_compute_snn_width_argument_check_needs_no_device():
+    import seurat_b200 as sb
+    g = sb.Graph(np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, 1.0]), (2, 2))
+    with pytest.raises(ValueError, match=r"columns in the snn.graph \(2\)"):
+        sb.ComputeSNNwidth(g, np.ones((2, 3)), 1, nearest_dist=[0.0, 0.0, 0.0])
