@@ -284,6 +284,21 @@ B200NN_API int b200nn_dev_result(b200nn_ctx *ctx, int32_t which, b200nn_dev_csr 
 B200NN_API int b200nn_dev_copy_result(b200nn_ctx *ctx, int32_t which, int64_t *d_p, int32_t *d_i,
                                       double *d_x);
 
+/* ---- device-resident embedding hand-off ------------------- */
+/*
+ * What FindNeighbors does to the embedding on the host before the search, for an embedding that already
+ * lives in HBM (a PCA computed on the device): the column subset Embeddings(object[[reduction]])[, dims]
+ * (/root/reference/R/clustering.R:843-846) and, with l2_norm != 0, L2Norm (R/clustering.R:619-622,
+ * R/utilities.R:2107-2122: rows divided by sqrt(sum(x^2)), R's long-double sum reproduced bit for bit,
+ * non-finite results set to 0).  d_src: [n x n_cols] doubles on the context's device in src_layout;
+ * dims: n_dims 0-based column numbers in HOST memory (NULL = all columns in order); d_out: [n x n_dims]
+ * row-major on the device -- what b200nn_dev_knn / b200nn_dev_graphs take, so no H2D of the embedding
+ * remains.  Must not alias d_src.
+ */
+B200NN_API int b200nn_dev_embedding_prepare(b200nn_ctx *ctx, const double *d_src, int64_t n, int32_t n_cols,
+                                            int32_t src_layout, const int32_t *dims, int32_t n_dims,
+                                            int32_t l2_norm, double *d_out);
+
 /* ---- modularity optimiser (the step after FindNeighbors) --- */
 /*
  * Replaces RunModularityClusteringCpp, /root/reference/src/RModularityOptimizer.cpp:21-173

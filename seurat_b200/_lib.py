@@ -33,6 +33,7 @@ SYMBOLS = [
     "b200nn_modularity_cluster", "b200nn_modularity_cluster_resident",
     "b200nn_modularity_cluster_edges", "b200nn_modularity_cluster_edge_file",
     "b200nn_write_edge_file", "b200nn_fast_dist", "b200nn_snn_smallest_nonzero_dist",
+    "b200nn_dev_embedding_prepare",
 ]
 
 
@@ -140,6 +141,7 @@ def load() -> C.CDLL:
                                                       C.POINTER(ModoptStats)]
         L.b200nn_modularity_cluster_edge_file.argtypes = [vp, C.c_char_p, i32, dbl, i32, i32, i32, C.c_uint64, vp, i64,
                                                           C.POINTER(i64), C.POINTER(ModoptStats)]
+        L.b200nn_dev_embedding_prepare.argtypes = [vp, vp, i64, i32, i32, vp, i32, i32, vp]
         L.b200nn_write_edge_file.argtypes = [vp, vp, vp, i64, C.c_char_p, C.POINTER(i64)]
         L.b200nn_fast_dist.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp]
         L.b200nn_snn_smallest_nonzero_dist.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp, vp]
@@ -406,6 +408,13 @@ class Context:
         check(self._L.b200nn_dev_knn_candidates(self._h, _ptr(d_ref), nr, _ptr(d_qry), nq, d, n_cand,
                                                 scan_mode, _ptr(d_cand), _ptr(d_tau), _ptr(d_keys),
                                                 _ptr(scale_mu)))
+
+    def dev_embedding_prepare(self, d_src, n: int, n_cols: int, layout: int, dims, l2_norm: bool, d_out) -> None:
+        """columns `dims` (0-based, None = all) of a device matrix [n x n_cols] in `layout`, optionally L2
+        normalised like R's L2Norm, as the row-major device matrix the dev_* stages take"""
+        dd = None if dims is None else np.ascontiguousarray(dims, dtype=np.int32)
+        check(self._L.b200nn_dev_embedding_prepare(self._h, _ptr(d_src), n, n_cols, layout, _ptr(dd),
+                                                   0 if dd is None else dd.size, 1 if l2_norm else 0, _ptr(d_out)))
 
     def dev_graphs(self, d_idx0, n: int, k: int, prune: float, compute_snn: bool, row_begin: int,
                    row_end: int) -> dict:

@@ -5,6 +5,11 @@
 //                                    and fwrite; the format is std::setprecision(15) = "%.15g")
 //   b200nn_fast_dist                 fast_dist, /root/reference/src/fast_NN_dist.cpp:34-69
 //   b200nn_snn_smallest_nonzero_dist SNN_SmallestNonzero_Dist, /root/reference/src/snn.cpp:82-126
+//   b200nn_dev_embedding_prepare      what FindNeighbors.Seurat / .default do to the embedding on
+//                                    the host before the search -- Embeddings(...)[, dims]
+//                                    (/root/reference/R/clustering.R:843-846) and L2Norm
+//                                    (R/clustering.R:619-622, R/utilities.R:2107-2122) -- on an embedding that
+//                                    already lives in HBM
 #include <string.h>
 
 #include <string>
@@ -46,6 +51,33 @@ k_smallest_nonzero(const int64_t *__restrict__ p, const int32_t *__restrict__ ri
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   out[i] = extras::smallest_nonzero_dist_col(p, ri, x, mat, d, n_small, nearest, i, ord + p[i], dist + p[i]);
+}
+
+// One thread per cell: gather the selected columns of a row-major or column-major device matrix, optionally
+// divide by the row's L2 norm (R's arithmetic, extras_core.inl), stage 128 rows in shared memory and write them
+// out as one contiguous block of the row-major result.  STAGED = false: rows too wide for shared memory are
+// written directly.
+template <bool STAGED>
+__global__ void __launch_bounds__(128)
+k_embedding_prepare(const double *__restrict__ src, int64_t n, int n_cols, int col_major, const int32_t *__restrict__ dims,
+                    int nd, int l2, double *__restrict__ out) {
+  extern __shared__ double tile[];  // [128][nd | 1]
+  const int64_t r0 = (int64_t)blockIdx.x * 128, row = r0 + threadIdx.x;
+  const int ts = nd | 1;
+  double *mine = STAGED ? tile + (size_t)threadIdx.x * ts : out + row * nd;
+  if (row < n) {
+    const int64_t rs = col_major ? 1 : n_cols, cs = col_major ? n : 1;
+    for (int j = 0; j < nd; ++j) mine[j] = src[row * rs + (int64_t)(dims ? dims[j] : j) * cs];
+    if (l2) {
+      const double norm = extras::l2norm_of_row(mine, 1, nd);
+      for (int j = 0; j < nd; ++j) mine[j] = extras::l2norm_entry(mine[j], norm);
+    }
+  }
+  if (STAGED) {
+    __syncthreads();
+    const int64_t rows = n - r0 < 128 ? n - r0 : 128, total = rows * nd;
+    for (int64_t t = threadIdx.x; t < total; t += 128) out[r0 * nd + t] = tile[(t / nd) * ts + (t % nd)];
+  }
 }
 
 __global__ void k_widen_p(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
@@ -227,6 +259,46 @@ int b200nn_snn_smallest_nonzero_dist(b200nn_ctx *ctx, const int32_t *p, const in
                                                                           ddist, dout);
   KERNEL_CHECK(ctx);
   CU_TRY(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B200NN_OK;
+}
+
+int b200nn_dev_embedding_prepare(b200nn_ctx *ctx, const double *d_src, int64_t n, int32_t n_cols, int32_t src_layout,
+                                 const int32_t *dims, int32_t n_dims, int32_t l2_norm, double *d_out) {
+  if (!ctx) {
+    b200nn_set_error("NULL context");
+    return B200NN_ERR_INVALID;
+  }
+  if (!d_src || !d_out || n <= 0 || n_cols <= 0 || (dims && n_dims <= 0) || (!dims && n_dims != 0 && n_dims != n_cols) ||
+      (src_layout != B200NN_ROW_MAJOR && src_layout != B200NN_COL_MAJOR)) {
+    b200nn_set_error("dev_embedding_prepare: invalid argument");
+    return B200NN_ERR_INVALID;
+  }
+  const int nd = dims ? n_dims : n_cols;
+  for (int j = 0; dims && j < nd; ++j)
+    if (dims[j] < 0 || dims[j] >= n_cols) {
+      b200nn_set_error("dev_embedding_prepare: dimension %d is outside the embedding's %d columns (subscript out of bounds)",
+                       dims[j] + 1, n_cols);
+      return B200NN_ERR_INDEX_RANGE;
+    }
+  CU_TRY(cudaSetDevice(ctx->device));
+  DevBufs B(ctx->stream);
+  int32_t *d_dims = nullptr;
+  if (dims) {
+    RC_TRY(B.get((size_t)nd, &d_dims));
+    CU_TRY(cudaMemcpyAsync(d_dims, dims, sizeof(int32_t) * (size_t)nd, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const size_t smem = sizeof(double) * 128 * (size_t)(nd | 1);
+  const unsigned grid = (unsigned)ceil_div64(n, 128);
+  if (smem <= 200 * 1024) {
+    CU_TRY(cudaFuncSetAttribute(k_embedding_prepare<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_embedding_prepare<true><<<grid, 128, smem, ctx->stream>>>(d_src, n, n_cols, src_layout == B200NN_COL_MAJOR, d_dims,
+                                                               nd, l2_norm != 0, d_out);
+  } else {
+    k_embedding_prepare<false><<<grid, 128, 0, ctx->stream>>>(d_src, n, n_cols, src_layout == B200NN_COL_MAJOR, d_dims, nd,
+                                                             l2_norm != 0, d_out);
+  }
+  KERNEL_CHECK(ctx);
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   return B200NN_OK;
 }

@@ -159,8 +159,12 @@ def L2Norm(mat, MARGIN: int = 1):
     emb = mat if isinstance(mat, Embedding) else None
     m = np.asarray(emb.values if emb is not None else mat, dtype=np.float64)
     axis = 1 if MARGIN == 1 else 0
-    sq = (m * m).astype(np.longdouble)
-    norm = np.sqrt(sq.sum(axis=axis).astype(np.float64))
+    # sum(x^2) term by term in long double, in the order R visits them (numpy's own sum() is pairwise)
+    sq = m * m
+    acc = np.zeros(m.shape[1 - axis], dtype=np.longdouble)
+    for j in range(m.shape[axis]):
+        acc += sq[:, j] if axis == 1 else sq[j, :]
+    norm = np.sqrt(acc.astype(np.float64))
     with np.errstate(divide="ignore", invalid="ignore"):
         out = m / (norm[:, None] if axis == 1 else norm[None, :])
     out[~np.isfinite(out)] = 0.0
@@ -446,6 +450,78 @@ def FindNeighbors(object, query=None, distance_matrix: bool = False, k_param: in
         snn_matrix.colnames = object.rownames
         neighbor_graphs["snn"] = as_Graph(snn_matrix)
     return neighbor_graphs
+
+
+# ---------------------------------------------------------------------------
+# FindNeighbors on an embedding that already lives in HBM
+# ---------------------------------------------------------------------------
+def FindNeighborsResident(embedding, rownames, dims=None, k_param: int = 20, return_neighbor: bool = False,
+                          compute_SNN: bool | None = None, prune_SNN: float = 1 / 15, l2_norm: bool = False,
+                          verbose: bool = True, ctx: _lib.Context | None = None, stats_out: dict | None = None):
+    """``FindNeighbors`` for a device-resident embedding -- e.g. a PCA computed on the GPU: the 400 MB - 1 GB
+    upload of the embedding and the host-side ``[, dims]`` / ``L2Norm`` copies disappear.
+
+    ``embedding``: 2-D float64 CUDA tensor [cells x components], row-major (contiguous) or column-major (the
+    transpose is contiguous, R's layout); ``dims``: 0-based component numbers (``dims = 1:10`` of
+    ``FindNeighbors.Seurat``, R/clustering.R:843-846, is ``range(10)``), None = all; ``l2_norm`` as in
+    ``FindNeighbors.default`` (R/clustering.R:619-622), R's arithmetic bit for bit.  Same return values as
+    :func:`FindNeighbors`: ``{"nn": Graph, "snn": Graph}`` / ``{"nn": Graph}`` / :class:`Neighbor`."""
+    import torch
+    t = embedding
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2):
+        raise TypeError("FindNeighborsResident expects a 2-D float64 CUDA tensor; use FindNeighbors for host matrices")
+    if rownames is None:
+        raise ValueError("Please provide rownames (cell names) with the input object")
+    if compute_SNN is None:
+        compute_SNN = not return_neighbor
+    n, n_cols = int(t.shape[0]), int(t.shape[1])
+    if len(rownames) != n:
+        raise ValueError("rownames must name every row of the embedding")
+    if t.is_contiguous():
+        layout = _lib.ROW_MAJOR
+    elif t.t().is_contiguous():
+        layout = _lib.COL_MAJOR
+    else:
+        t, layout = t.contiguous(), _lib.ROW_MAJOR
+    dims0 = None if dims is None else np.asarray(list(dims), dtype=np.int32)
+    nd = n_cols if dims0 is None else int(dims0.size)
+    if n < k_param:
+        warnings.warn("k.param set larger than number of cells. Setting k.param to number of cells - 1.")
+        k_param = n - 1
+    ctx = ctx or _lib.default_context()
+    with torch.cuda.device(t.device):
+        if dims0 is None and not l2_norm and layout == _lib.ROW_MAJOR:
+            work = t                                        # already what the search takes
+        else:
+            work = torch.empty((n, nd), dtype=torch.float64, device=t.device)
+            ctx.dev_embedding_prepare(t, n, n_cols, layout, dims0, l2_norm, work)
+        _message("Computing nearest neighbors" if return_neighbor else "Computing nearest neighbor graph", verbose)
+        idx0 = torch.empty((n, k_param), dtype=torch.int32, device=t.device)
+        dist = torch.empty((n, k_param), dtype=torch.float64, device=t.device)
+        st = ctx.dev_knn(work, n, None, n, nd, int(k_param), idx0, dist)   # refuses NA / NaN / Inf itself
+        _warn_slow_path(st, n)
+        if return_neighbor:
+            if compute_SNN:
+                warnings.warn("The SNN graph is not computed if return.neighbor is TRUE.")
+            if stats_out is not None:
+                stats_out.update(st)
+            return Neighbor(nn_idx=(idx0 + 1).cpu().numpy(), nn_dist=dist.cpu().numpy(), cell_names=list(rownames))
+        if compute_SNN:
+            _message("Computing SNN", verbose)
+        g = ctx.dev_graphs(idx0, n, int(k_param), float(prune_SNN), bool(compute_SNN), 0, n)
+        if stats_out is not None:
+            stats_out.update(st)
+            stats_out.update(g)
+        out = {}
+        for name, which in (("nn", 0), ("snn", 1)) if compute_SNN else (("nn", 0),):
+            r = ctx.dev_result(which)
+            P = torch.empty(r.n_rows + 1, dtype=torch.int64, device=t.device)
+            I = torch.empty(r.nnz, dtype=torch.int32, device=t.device)
+            X = torch.empty(r.nnz, dtype=torch.float64, device=t.device)
+            ctx.dev_copy_result(which, P, I, X)
+            out[name] = Graph(P.to(torch.int32).cpu().numpy(), I.cpu().numpy(), X.cpu().numpy(), (n, n),
+                              (list(rownames), list(rownames)))
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -19,3 +19,24 @@ extern "C" void emul_smallest_nonzero(const int64_t *p, const int32_t *ri, const
   for (int64_t i = 0; i < n; ++i)
     out[i] = extras::smallest_nonzero_dist_col(p, ri, x, mat, d, n_small, nearest, i, ord.data() + p[i], dist.data() + p[i]);
 }
+
+// L2Norm of a row-major matrix with the integer restatement of the long-double sum (extras_core.inl) ...
+extern "C" void emul_l2norm(const double *m, int64_t n, int d, double *out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const double s = extras::l2norm_of_row(m + i * d, 1, d);
+    for (int j = 0; j < d; ++j) out[i * d + j] = extras::l2norm_entry(m[i * d + j], s);
+  }
+}
+// ... the total alone, and the same total from the compiler's own long double (x87 on x86-64): the pin
+extern "C" double emul_x87_sum(const double *t, int64_t n) {
+  extras::X87Sum s;
+  extras::x87_init(s);
+  for (int64_t i = 0; i < n; ++i) extras::x87_add(s, t[i]);
+  return extras::x87_to_double(s);
+}
+extern "C" double native_long_double_sum(const double *t, int64_t n) {
+  volatile long double acc = 0.0L;
+  for (int64_t i = 0; i < n; ++i) acc = acc + (long double)t[i];
+  return (double)acc;
+}
+extern "C" int native_long_double_mantissa_bits() { return __LDBL_MANT_DIG__; }

@@ -126,3 +126,55 @@ def test_smallest_nonzero_dist_oracle_and_emulation():
     pe = np.array([0, 0, 1, 2], np.int32)
     w = oracle.snn_smallest_nonzero_dist(pe, np.array([2, 1], np.int32), np.array([0.5, 0.5]), X[:3], 2, np.zeros(3))
     assert np.isnan(w[0]) and np.isfinite(w[1:]).all()
+
+
+def test_integer_restatement_of_the_long_double_sum_is_exact():
+    """X87Sum (extras_core.inl) == the compiler's own long double accumulation (x87 extended on x86-64, what R's
+    sum() uses), bit for bit after the final rounding to double: random magnitudes over 600 binades, long
+    sums, ties, subnormals, zeros, huge terms; then L2Norm rows against the oracle's L2Norm"""
+    L = emul()
+    assert L.native_long_double_mantissa_bits() == 64, "the pin needs an x87 long double (x86-64)"
+    for f in (L.emul_x87_sum, L.native_long_double_sum):
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_int64]
+    rng = np.random.default_rng(17)
+
+    def both(t):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        return L.emul_x87_sum(t.ctypes.data, t.size), L.native_long_double_sum(t.ctypes.data, t.size)
+
+    for trial in range(4000):
+        n = int(rng.integers(1, 120))
+        kind = trial % 8
+        if kind == 0:
+            t = rng.random(n) ** 2
+        elif kind == 1:
+            t = (rng.normal(size=n) * 10.0 ** rng.integers(-150, 150, n)) ** 2
+        elif kind == 2:                       # exact ties at the 64-bit rounding position
+            t = np.ldexp(rng.integers(1, 2 ** 53, n).astype(np.float64), rng.integers(-70, 12, n))
+        elif kind == 3:                       # subnormal and tiny terms
+            t = np.ldexp(rng.integers(0, 2 ** 20, n).astype(np.float64), rng.integers(-1074, -1000, n))
+        elif kind == 4:
+            t = np.where(rng.random(n) < 0.3, 0.0, rng.random(n) * 1e-3)
+        elif kind == 5:                       # one dominating term, many that only leave a sticky bit
+            t = rng.random(n) * 1e-25
+            t[rng.integers(0, n)] = 1e12
+        elif kind == 6:
+            t = np.full(n, np.ldexp(1.0, int(rng.integers(-40, 40)))) * (1 + 2.0 ** -52)
+        else:
+            t = np.ldexp(rng.random(n) + 0.5, rng.integers(900, 1023, n))       # near overflow
+        a, b = both(t)
+        assert a == b or (np.isinf(a) and np.isinf(b)), (trial, kind, a, b)
+    big = rng.random(50_000) * 10.0 ** rng.integers(-8, 8, 50_000)
+    a, b = both(big)
+    assert a == b
+    assert np.isinf(both(np.array([1.0, np.inf]))[0])
+    # rows: the emulated device body == the oracle's L2Norm (long double in C), zero rows -> zeros
+    L.emul_l2norm.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    for d in (1, 3, 10, 50, 99):
+        M = rng.normal(size=(2000, d)) * 10.0 ** rng.integers(-6, 6, size=(2000, 1))
+        M[7] = 0.0
+        out = np.empty_like(M)
+        L.emul_l2norm(M.ctypes.data, M.shape[0], d, out.ctypes.data)
+        want = oracle.l2norm(M)
+        assert (out == want).all() and (out[7] == 0).all()

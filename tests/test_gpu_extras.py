@@ -82,3 +82,45 @@ def test_r_level_callers_of_the_side_consumers(ctx):
     d0 = sb.NNdist(list(r["nn_idx"][:50]), X, query_embeddings=X[:50], nearest_dist=nearest[:50], ctx=ctx)
     w0 = np.maximum(r["nn_dist"][:50] - nearest[:50, None], 0.0)
     assert (np.stack(d0) == w0).all() and (np.stack(d0)[:, :2] == 0).all()
+
+
+def test_find_neighbors_on_a_device_resident_embedding(ctx):
+    """an embedding that already lives in HBM goes through dims slicing and L2Norm on the device
+    (b200nn_dev_embedding_prepare) and through the dev_* stages -- same Neighbor / Graphs as the host path"""
+    import torch
+    n, D = 6000, 24
+    X, _ = gaussian_mixture(n, D, seed=41, n_centres=6)
+    X[17] = 0.0                                             # a zero row: L2Norm gives zeros, not NaN
+    names = [f"c{i}" for i in range(n)]
+    dims = [0, 1, 2, 3, 4, 5, 6, 7, 9, 11, 12, 20]          # Embeddings(object[[reduction]])[, dims]
+    row_major = torch.from_numpy(X).cuda()
+    col_major = torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()     # R's layout: the transpose is contiguous
+    assert row_major.is_contiguous() and not col_major.is_contiguous() and col_major.t().is_contiguous()
+    for l2 in (False, True):
+        sub = X[:, dims]
+        want_mat = oracle.l2norm(sub) if l2 else sub
+        for t in (row_major, col_major):
+            work = torch.empty((n, len(dims)), dtype=torch.float64, device="cuda")
+            ctx.dev_embedding_prepare(t, n, D, _lib.ROW_MAJOR if t.is_contiguous() else _lib.COL_MAJOR, dims, l2, work)
+            assert (work.cpu().numpy() == want_mat).all(), "device slice / L2Norm must equal R's arithmetic"
+        assert (sb.L2Norm(sub) == oracle.l2norm(sub)).all()
+        host = sb.FindNeighbors(sb.Embedding(sub, names), k_param=15, l2_norm=l2, verbose=False, ctx=ctx)
+        nb_h = sb.FindNeighbors(sb.Embedding(sub, names), k_param=15, l2_norm=l2, return_neighbor=True,
+                                verbose=False, ctx=ctx)
+        for t in (row_major, col_major):
+            dev = sb.FindNeighborsResident(t, names, dims=dims, k_param=15, l2_norm=l2, verbose=False, ctx=ctx)
+            for name in ("nn", "snn"):
+                a, b = dev[name], host[name]
+                assert (a.p == b.p).all() and (a.i == b.i).all() and (a.x == b.x).all(), (name, l2)
+                assert a.rownames == names and a.Dim == (n, n)
+            nb_d = sb.FindNeighborsResident(t, names, dims=dims, k_param=15, l2_norm=l2, return_neighbor=True,
+                                            verbose=False, ctx=ctx)
+            assert (nb_d.nn_idx == nb_h.nn_idx).all() and (nb_d.nn_dist == nb_h.nn_dist).all()
+    # every component of a row-major tensor, no normalisation: used in place; nn Graph only
+    g = sb.FindNeighborsResident(row_major, names, k_param=10, compute_SNN=False, verbose=False, ctx=ctx)
+    h = sb.FindNeighbors(sb.Embedding(X, names), k_param=10, compute_SNN=False, verbose=False, ctx=ctx)
+    assert set(g) == {"nn"} and (g["nn"].i == h["nn"].i).all() and (g["nn"].p == h["nn"].p).all()
+    with pytest.raises(sb.B200Error, match="subscript out of bounds"):
+        sb.FindNeighborsResident(row_major, names, dims=[0, D], verbose=False, ctx=ctx)
+    with pytest.raises(TypeError):
+        sb.FindNeighborsResident(X, names, ctx=ctx)
