@@ -82,3 +82,15 @@ def test_r_shim_compiles_against_the_documented_r_api():
     rsrc = open(os.path.join(ROOT, "shim", "b200nn.R")).read()
     for name in re.findall(r'\.Call\("(b200_\w+)"', rsrc):
         assert name in table, f"{name} is called from b200nn.R but not registered"
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md lists the whole ABI: a new entry point must be explained to the maintainer who binds it"""
+    docs = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    listed = set(re.findall(r"`(b200nn_\w+)`", docs))
+    # "`b200nn_x_count` / `_fill`" style continuations
+    for stem, tails in re.findall(r"`(b200nn_\w+?)_(?:count|create)`((?:\s*/\s*`_\w+`)+)", docs):
+        for t in re.findall(r"`_(\w+)`", tails):
+            listed.add(f"{stem}_{t}")
+    missing = [s for s in header_symbols() if s not in listed]
+    assert not missing, f"not mentioned in INTEGRATION.md: {missing}"

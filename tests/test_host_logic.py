@@ -80,3 +80,9 @@ def test_compute_snn_width_argument_check_needs_no_device():
     g = sb.Graph(np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([1.0, 1.0]), (2, 2))
     with pytest.raises(ValueError, match=r"columns in the snn.graph \(2\)"):
         sb.ComputeSNNwidth(g, np.ones((2, 3)), 1, nearest_dist=[0.0, 0.0, 0.0])
+
+
+def test_find_neighbors_resident_refuses_host_matrices():
+    import seurat_b200 as sb
+    with pytest.raises(TypeError, match="CUDA tensor"):
+        sb.FindNeighborsResident(np.zeros((5, 2)), [f"c{i}" for i in range(5)])
