@@ -20,6 +20,74 @@ from .neighbors import Graph, _message
 __all__ = ["RunModularityClustering", "FindClusters", "GroupSingletons"]
 
 
+# ---------------------------------------------------------------------------
+# R's random draw, for the one place the reference's result depends on it: GroupSingletons calls
+# set.seed(1) and then sample(tied clusters, 1) (R/clustering.R:1395-1405).  Restated from R's
+# sources (src/main/RNG.c: set.seed's scrambling and the Mersenne-Twister state; R_unif_index with
+# sample.kind = "Rejection", R >= 3.6); pinned in tests/test_modopt_cpu.py by R's well-known outputs
+# (set.seed(1); runif(3) -> 0.2655087 0.3721239 0.5728534; sample(1:10) -> 9 4 7 1 2 5 3 10 6 8).
+# ---------------------------------------------------------------------------
+def _r_unif_rand(seed: int):
+    """generator of unif_rand() values after set.seed(seed) (default RNG kind "Mersenne-Twister")"""
+    m32 = 0xffffffff
+    s = int(seed) & m32
+    for _ in range(50):                      # RNG_Init: initial scrambling
+        s = (69069 * s + 1) & m32
+    st = []
+    for _ in range(625):
+        s = (69069 * s + 1) & m32
+        st.append(s)
+    mt = st[1:]                              # dummy[0] = mti = 624: the first draw regenerates the state
+    n_, m_ = 624, 397
+    mti = n_
+    while True:
+        if mti >= n_:
+            for kk in range(n_):
+                y = (mt[kk] & 0x80000000) | (mt[(kk + 1) % n_] & 0x7fffffff)
+                mt[kk] = mt[(kk + m_) % n_] ^ (y >> 1) ^ (0x9908b0df if y & 1 else 0)
+            mti = 0
+        y = mt[mti]
+        mti += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9d2c5680
+        y ^= (y << 15) & 0xefc60000
+        y ^= y >> 18
+        v = y * 2.3283064365386963e-10       # [0, 1), then fixup() keeps it inside (0, 1)
+        if v <= 0.0:
+            v = 0.5 * 2.328306437080797e-10
+        elif 1.0 - v <= 0.0:
+            v = 1.0 - 0.5 * 2.328306437080797e-10
+        yield v
+
+
+def _r_unif_index(gen, dn: int) -> int:
+    """R_unif_index(dn), rejection sampling from the integers below the next power of two"""
+    if dn <= 0:
+        return 0
+    bits = (dn - 1).bit_length()             # ceil(log2(dn))
+    while True:
+        v, n = 0, 0
+        while n <= bits:                     # rbits(): 16 random bits per unif_rand()
+            v = 65536 * v + int(next(gen) * 65536)
+            n += 16
+        v &= (1 << bits) - 1
+        if v < dn:
+            return v
+
+
+def _r_sample(n: int, size: int | None = None, seed: int = 1) -> list:
+    """sample.int(n, size) without replacement right after set.seed(seed): 0-based positions"""
+    gen = _r_unif_rand(seed)
+    x = list(range(n))
+    out = []
+    for _ in range(n if size is None else size):
+        j = _r_unif_index(gen, n)
+        out.append(x[j])
+        n -= 1
+        x[j] = x[n]
+    return out
+
+
 def _slots(SNN):
     if isinstance(SNN, Graph):
         return SNN.p, SNN.i, SNN.x, SNN.Dim[1], SNN.colnames
@@ -115,11 +183,9 @@ def GroupSingletons(ids, SNN, group_singletons: bool = True, verbose: bool = Tru
         conn = np.array(conn)
         m = np.nanmax(conn)
         best = [c for c, v in zip(cluster_names, conn) if v == m]
-        if len(best) > 1 and verbose:
-            # the reference draws among tied clusters with R's sample() after set.seed(1); R's RNG is
-            # not reproduced here, the first tied cluster is taken
-            _message(f"GroupSingletons: {len(best)} clusters tie for singleton {s}; taking the first")
-        target = best[0]
+        # closest_cluster <- sample(names(connectivity[mi]), 1) right after set.seed(1) (:1395, :1404): R's
+        # draw, reproduced (the first of up to 8 tied clusters, the 9th of 9 - 16, ...)
+        target = best[_r_sample(len(best), 1, seed=1)[0]]
         str_ids[cell] = target
         new_ids[cell] = target if isinstance(ids[cell], str) else type(ids[cell])(target)
     if verbose:

@@ -179,3 +179,20 @@ def test_edge_file_round_trip_of_an_snn_graph(tmp_path):
     e1, e2, ew = np.loadtxt(path, delimiter="\t", unpack=True)
     got, gc, gq = emul_modopt.cluster_edges(e1.astype(np.int32), e2.astype(np.int32), ew, b.size, 1, 0.8, 1, 3, 5, 9)
     assert gc == bc and (got == b).all() and gq == bq
+
+
+def test_r_random_draw_of_group_singletons_is_reproduced():
+    """GroupSingletons breaks ties with set.seed(1); sample(tied, 1) (R/clustering.R:1395-1405).  The restated
+    generator gives R's well-known outputs: set.seed(1); runif(6) and sample(1:10) under seeds 1 and 42"""
+    from seurat_b200 import clustering as cl
+    g = cl._r_unif_rand(1)
+    assert [round(next(g), 7) for _ in range(6)] == [0.2655087, 0.3721239, 0.5728534, 0.9082078, 0.2016819, 0.8983897]
+    assert [v + 1 for v in cl._r_sample(10, seed=1)] == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
+    assert [v + 1 for v in cl._r_sample(10, seed=42)] == [1, 5, 10, 8, 2, 4, 6, 9, 7, 3]
+    assert [cl._r_sample(L, 1)[0] for L in range(1, 10)] == [0, 0, 0, 0, 0, 0, 0, 0, 8]
+    # a singleton equally connected to two clusters joins the first of them (R's draw for two ties)
+    import seurat_b200 as sb
+    import scipy.sparse as sp
+    S = sp.csc_matrix(np.array([[1, .5, 0, 0, .2], [.5, 1, 0, 0, .2], [0, 0, 1, .5, .2], [0, 0, .5, 1, .2],
+                                [.2, .2, .2, .2, 1]]))
+    assert sb.GroupSingletons([0, 0, 1, 1, 2], S, verbose=False) == [0, 0, 1, 1, 0]
