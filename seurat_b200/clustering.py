@@ -75,6 +75,17 @@ def _r_unif_index(gen, dn: int) -> int:
             return v
 
 
+def _r_mean(x) -> float:
+    """R's mean() of a double vector (src/main/summary.c, real_mean): the sum in long double in storage
+    order, divided by n, then one refinement pass s += sum(x - s) / n; rounded to double at the end.
+    GroupSingletons compares such means for equality, so the arithmetic matters."""
+    v = np.asarray(x, dtype=np.float64).astype(np.longdouble)
+    n = np.longdouble(v.size)
+    s = np.cumsum(v)[-1] / n                 # cumsum adds term by term (np.sum is pairwise)
+    s = s + np.cumsum(v - s)[-1] / n
+    return float(s)
+
+
 def _r_sample(n: int, size: int | None = None, seed: int = 1) -> list:
     """sample.int(n, size) without replacement right after set.seed(seed): 0-based positions"""
     gen = _r_unif_rand(seed)
@@ -179,7 +190,7 @@ def GroupSingletons(ids, SNN, group_singletons: bool = True, verbose: bool = Tru
         conn = []
         for c in cluster_names:
             cols = np.nonzero(str_ids == c)[0]
-            conn.append(row[cols].sum() / (1 * len(cols)) if len(cols) else np.nan)
+            conn.append(_r_mean(row[cols]) if len(cols) else np.nan)
         conn = np.array(conn)
         m = np.nanmax(conn)
         best = [c for c, v in zip(cluster_names, conn) if v == m]
